@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI declared in include/fbs_b200.h.
+
+There is NO fallback: if the shared library is missing, or a call returns non-zero, this
+raises.  Nothing here touches ``oracle/``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libfbs_b200.so')
+
+RESAMPLE_MULTINOMIAL, RESAMPLE_KILLING, RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED = 0, 1, 2, 3
+INIT_DEGENERATE, INIT_NORMAL = 0, 1
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+_f32 = C.c_float
+_f64 = C.c_double
+_int = C.c_int
+
+
+class AffineModelStruct(C.Structure):
+    _fields_ = [('K', _i32), ('du', _i32), ('dv', _i32), ('reserved', _i32),
+                ('MT', _p), ('m', _p), ('dt', _p), ('sd', _p), ('lognorm', _p)]
+
+
+_M = C.POINTER(AffineModelStruct)
+
+# name -> (argtypes, restype); every symbol include/fbs_b200.h declares (checked by tests/test_abi.py)
+SIGNATURES = {
+    'fbs_version': ([], _int),
+    'fbs_last_error': ([], C.c_char_p),
+    'fbs_launch_count': ([], _i64),
+    'fbs_reset_launch_count': ([], None),
+    'fbs_random_bits_u32': ([_p, _p, _i64, _i64, _p], _int),
+    'fbs_random_split': ([_p, _p, _i64, _i64, _p], _int),
+    'fbs_random_uniform_f32': ([_p, _p, _i64, _i64, _f32, _f32, _p], _int),
+    'fbs_random_normal_f32': ([_p, _p, _i64, _i64, _p], _int),
+    'fbs_random_randint_i32': ([_p, _p, _i64, _i64, _i32, _i32, _p], _int),
+    'fbs_random_choice_f32': ([_p, _p, _p, _i64, _i64, _i64, _p], _int),
+    'fbs_cond_resample_f32': ([_p, _int, _p, _p, _p, _p, _int, _i64, _i64, _p], _int),
+    'fbs_resample_f32': ([_p, _int, _p, _p, _i64, _i64, _p], _int),
+    'fbs_ou_forward_path_f32': ([_p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _i64, _int, _p, _p], _int),
+    'fbs_em_affine_path_f32': ([_p, _p, _p, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p], _int),
+    'fbs_csmc_step_affine_f32': ([_p, _M, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p], _int),
+    'fbs_affine_eval_f32': ([_p, _M, _i32, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p], _int),
+    'fbs_csmc_forward_affine_f32': ([_p, _M, _p, _p, _p, _p, _int, _f32, _int, _i64, _i64, _p, _p, _p, _p, _p], _int),
+    'fbs_backward_scan_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p], _int),
+    'fbs_pmcmc_filter_affine_f32': ([_p, _M, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p, _p], _int),
+    'fbs_force_move_f32': ([_p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _p, _p, _p], _int),
+    'fbs_pcn_combine_f32': ([_p, _f64, _p, _p, _p, _p, _i64, _i64, _p], _int),
+    'fbs_mh_accept_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p], _int),
+    'fbs_gaussian_ref_sample_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p], _int),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f'{LIB_PATH} is missing: run `python -m fbs_b200.build` (or __graft_entry__.build()). '
+                              'fbs_b200 has no CPU fallback.')
+        handle = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        msg = handle.fbs_last_error().decode('utf-8', 'replace')
+        cls = NotImplementedError if rc == 3 else (ValueError if rc == 1 else NativeError)
+        raise cls(f'{name} failed (code {rc}): {msg}')
+
+
+def launch_count() -> int:
+    return int(lib().fbs_launch_count())
+
+
+def reset_launch_count():
+    lib().fbs_reset_launch_count()

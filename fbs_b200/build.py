@@ -1,0 +1,51 @@
+"""Build the sm_100a C-ABI shared library in-tree (fbs_b200/_lib/libfbs_b200.so).
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box.
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_DIR = os.path.join(_HERE, '_lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libfbs_b200.so')
+SOURCES = ['random_kernels.cu', 'resample_kernels.cu', 'sde_kernels.cu', 'csmc_kernels.cu', 'step_kernels.cu']
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+              '-Xcompiler', '-fPIC', '-shared']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    return 'nvcc'
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(_HERE, '..', 'include', 'fbs_b200.h'))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, '-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd[1:1] = ['-Xptxas', '-v']
+        print(' '.join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,184 @@
+// Warp-cooperative resampling primitives shared by the standalone resampling kernels and the
+// fused CSMC / pMCMC sweep kernels.  One warp works on one chain's N weights.
+//
+// Summation-order contract: every cumulative sum / sum that decides an index is
+// SEQUENTIAL float32, c[i] = fl(c[i-1] + w[i]) -- done by lane 0 -- so that indices are
+// bit-exact against the oracle on identical weights and keys.  max() is order-free.
+//
+// Reference: fbs/samplers/csmc/resamplings.py (conditional), fbs/samplers/resampling.py.
+#pragma once
+#include "fbs_rng.cuh"
+
+namespace fbs {
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// cum[i] = sequential cumsum of w (lane 0).  w and cum may alias.  Returns cum[n-1] to all lanes.
+__device__ __forceinline__ float warp_seq_cumsum(const float* w, float* cum, int n, int lane) {
+  float acc = 0.f;
+  if (lane == 0) {
+    for (int i = 0; i < n; ++i) {
+      acc = __fadd_rn(acc, w[i]);
+      cum[i] = acc;
+    }
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, acc, 0);
+}
+
+// jax.random.choice(key, n, (n_draws,), p=w) given the cumulative sums: draw e.
+__device__ __forceinline__ int choice_from_cum(const float* cum, int n, float u) {
+  float r = __fmul_rn(cum[n - 1], __fsub_rn(1.0f, u));
+  return searchsorted_left(cum, n, r);
+}
+
+// Unconditional part of `killing` (resamplings.py:63-74 / resampling.py:93-101):
+// idx[n] = killed ? choice : n.  cum must hold cumsum(w).  Writes idx for all n.
+__device__ __forceinline__ void warp_killing_unconditional(Key key_1, Key key_2, const float* w, const float* cum,
+                                                           float w_max, int n, int lane, int* idx) {
+  const uint32_t h = ((uint32_t)n + 1u) >> 1;
+  for (uint32_t b = lane; b < h; b += 32) {
+    uint32_t a0, a1, c0, c1;
+    random_bits_block(key_1, n, b, a0, a1);
+    random_bits_block(key_2, n, b, c0, c1);
+    {
+      float u1 = bits_to_unit(a0);
+      bool killed = __fmul_rn(u1, w_max) >= w[b];
+      idx[b] = killed ? choice_from_cum(cum, n, bits_to_unit(c0)) : (int)b;
+    }
+    uint32_t e = b + h;
+    if (e < (uint32_t)n) {
+      float u1 = bits_to_unit(a1);
+      bool killed = __fmul_rn(u1, w_max) >= w[e];
+      idx[e] = killed ? choice_from_cum(cum, n, bits_to_unit(c1)) : (int)e;
+    }
+  }
+  __syncwarp();
+}
+
+// Conditional killing resampling, resamplings.py:40-88.
+//   w     [n] normalised weights (shared or global memory, read only)
+//   cum   [n] scratch            tmp [n] int scratch          out [n] ancestor indices
+// All pointers must be visible to the whole warp.  i = pinned ancestor value, j = pinned slot.
+__device__ __forceinline__ void warp_cond_killing(Key key, const float* w, int n, int i, int j, bool conditional,
+                                                  float* cum, int* tmp, int* out, int lane) {
+  Key key_1, key_2, key_3;
+  split3(key, key_1, key_2, key_3);  // :66
+  float m = -INFINITY;
+  for (int q = lane; q < n; q += 32) m = fmaxf(m, w[q]);
+  const float w_max = warp_max(m);  // :69
+  warp_seq_cumsum(w, cum, n, lane);
+  int* dst = conditional ? tmp : out;
+  warp_killing_unconditional(key_1, key_2, w, cum, w_max, n, lane, dst);
+  if (!conditional) return;
+
+  // J_prob = (1 - w / w_max) / N, J_prob[i] = max(1 - sum(J_prob with J_prob[i] = 0), 0)   (:79-82)
+  const float fn = (float)n;
+  float acc = 0.f;
+  if (lane == 0) {
+    for (int q = 0; q < n; ++q) {
+      float jp = (q == i) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(w[q], w_max)), fn);
+      acc = __fadd_rn(acc, jp);
+    }
+    const float jp_i = fmaxf(__fsub_rn(1.0f, acc), 0.f);
+    acc = 0.f;
+    for (int q = 0; q < n; ++q) {
+      float jp = (q == i) ? jp_i : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(w[q], w_max)), fn);
+      acc = __fadd_rn(acc, jp);
+      cum[q] = acc;
+    }
+  }
+  __syncwarp();
+  // J ~ Cat(J_prob): choice(key_3, N, (), p=J_prob)   (:84) -- random_bits(key_3, 1) = block (0, 0), word 0
+  uint32_t x0 = 0u, x1 = 0u;
+  threefry2x32(key_3.k0, key_3.k1, x0, x1);
+  const int J = choice_from_cum(cum, n, bits_to_unit(x0));
+  // idx = roll(idx, j - J); idx[j] = i   (:85-86):  out[m] = tmp[(m - (j - J)) mod n]
+  int shift = (j - J) % n;
+  if (shift < 0) shift += n;
+  for (int q = lane; q < n; q += 32) {
+    int src = q - shift;
+    if (src < 0) src += n;
+    out[q] = (q == j) ? i : tmp[src];
+  }
+  __syncwarp();
+}
+
+// Conditional multinomial, resamplings.py:10-37.
+__device__ __forceinline__ void warp_cond_multinomial(Key key, const float* w, int n, int i, int j, bool conditional,
+                                                      float* cum, int* out, int lane) {
+  warp_seq_cumsum(w, cum, n, lane);
+  const uint32_t h = ((uint32_t)n + 1u) >> 1;
+  for (uint32_t b = lane; b < h; b += 32) {
+    uint32_t c0, c1;
+    random_bits_block(key, n, b, c0, c1);
+    out[b] = (conditional && (int)b == j) ? i : choice_from_cum(cum, n, bits_to_unit(c0));
+    uint32_t e = b + h;
+    if (e < (uint32_t)n) out[e] = (conditional && (int)e == j) ? i : choice_from_cum(cum, n, bits_to_unit(c1));
+  }
+  __syncwarp();
+}
+
+// systematic / stratified.  clip = true: fbs/samplers/resampling.py:43-59; clip = false with
+// systematic: fbs/samplers/csmc/resamplings.py:120-125.
+__device__ __forceinline__ void warp_systematic_or_stratified(Key key, const float* w, int n, bool is_systematic,
+                                                              bool clip, float* cum, int* out, int lane) {
+  warp_seq_cumsum(w, cum, n, lane);
+  const float fn = (float)n;
+  if (is_systematic) {
+    uint32_t x0 = 0u, x1 = 0u;  // uniform(key, ()) = random_bits(key, 1) word 0
+    threefry2x32(key.k0, key.k1, x0, x1);
+    const float u = bits_to_unit(x0);
+    for (int q = lane; q < n; q += 32) {
+      float pt = __fdiv_rn(__fadd_rn((float)q, u), fn);
+      int id = searchsorted_left(cum, n, pt);
+      out[q] = clip ? min(max(id, 0), n - 1) : id;
+    }
+  } else {
+    const uint32_t h = ((uint32_t)n + 1u) >> 1;
+    for (uint32_t b = lane; b < h; b += 32) {
+      uint32_t c0, c1;
+      random_bits_block(key, n, b, c0, c1);
+      {
+        float pt = __fdiv_rn(__fadd_rn((float)b, bits_to_unit(c0)), fn);
+        int id = searchsorted_left(cum, n, pt);
+        out[b] = clip ? min(max(id, 0), n - 1) : id;
+      }
+      uint32_t e = b + h;
+      if (e < (uint32_t)n) {
+        float pt = __fdiv_rn(__fadd_rn((float)e, bits_to_unit(c1)), fn);
+        int id = searchsorted_left(cum, n, pt);
+        out[e] = clip ? min(max(id, 0), n - 1) : id;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Sorted-uniform multinomial, fbs/samplers/resampling.py:36-40,62-68 ("Not tested." upstream).
+// pts scratch [n + 1].
+__device__ __forceinline__ void warp_sorted_multinomial(Key key, const float* w, int n, float* cum, float* pts, int* out,
+                                                        int lane) {
+  warp_seq_cumsum(w, cum, n, lane);
+  const uint32_t n1 = (uint32_t)n + 1u;
+  const uint32_t h = (n1 + 1u) >> 1;
+  for (uint32_t b = lane; b < h; b += 32) {
+    uint32_t c0, c1;
+    random_bits_block(key, n1, b, c0, c1);
+    pts[b] = -logf(bits_to_unit(c0));
+    if (b + h < n1) pts[b + h] = -logf(bits_to_unit(c1));
+  }
+  __syncwarp();
+  const float z_last = warp_seq_cumsum(pts, pts, (int)n1, lane);
+  for (int q = lane; q < n; q += 32) {
+    int id = searchsorted_left(cum, n, __fdiv_rn(pts[q], z_last));
+    out[q] = min(max(id, 0), n - 1);
+  }
+  __syncwarp();
+}
+
+}  // namespace fbs

@@ -1,0 +1,203 @@
+// Per-timestep CSMC kernels for particle sets held in global memory (large N): the body of
+// fbs/samplers/csmc/csmc.py:132-148 as three launches -- ancestors, fused transition + weight,
+// normalise.  The persistent whole-sweep kernel (csmc_kernels.cu) is the fast path when the
+// particle set of a chain fits in shared memory; this is the general one.
+#include "fbs_common.cuh"
+#include "fbs_resample.cuh"
+
+namespace fbs {
+
+// (1) A = cond_resampling(key_resampling, exp(log_ws), b_star_prev, b_star, True): one warp per chain.
+__global__ void step_ancestors_kernel(int scheme, const uint32_t* __restrict__ step_keys,
+                                      const float* __restrict__ log_ws, const int32_t* __restrict__ b_prev,
+                                      const int32_t* __restrict__ b_cur, int64_t B, int N, int32_t* __restrict__ A_out) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  float* w = smem;
+  float* cum = w + N;
+  int* tmp = reinterpret_cast<int*>(cum + N + 1);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int q = lane; q < N; q += 32) w[q] = expf(log_ws[b * N + q]);
+    __syncwarp();
+    const Key key_k{step_keys[2 * b], step_keys[2 * b + 1]};
+    Key key_res, key_tr;
+    split2(key_k, key_res, key_tr);  // csmc.py:136
+    if (scheme == FBS_RESAMPLE_KILLING)
+      warp_cond_killing(key_res, w, N, b_prev[b], b_cur[b], true, cum, tmp, A_out + b * N, lane);
+    else
+      warp_cond_multinomial(key_res, w, N, b_prev[b], b_cur[b], true, cum, A_out + b * N, lane);
+    __syncwarp();
+  }
+}
+
+// (2) fused transition + weight: one warp per child particle.
+//   parent = us_prev[A[n]];  drift = M_k [parent; v_prev] + m_k
+//   us_out[n] = parent + dt drift_u + sd eps[n]  (reference particle pinned to u_star)
+//   lw_out[n] = -0.5 (sum_v (v - v_prev - dt drift_v)^2 / sd^2 + lognorm)         (unnormalised)
+__global__ void step_transition_kernel(int du, int dv, const float* __restrict__ MTk, const float* __restrict__ mk,
+                                       const float* __restrict__ dtp, const float* __restrict__ sdp,
+                                       const float* __restrict__ lnp, int k, const uint32_t* __restrict__ step_keys,
+                                       int split_first, const float* __restrict__ us_prev,
+                                       const int32_t* __restrict__ A, const float* __restrict__ v,
+                                       const float* __restrict__ v_prev, const float* __restrict__ u_star,
+                                       const int32_t* __restrict__ b_cur, const float* __restrict__ u_eval, int64_t B,
+                                       int N, float* __restrict__ us_out, float* __restrict__ lw_out,
+                                       float* __restrict__ tlp_out) {
+  const int D = du + dv;
+  const float dt = dtp[k], sd = sdp[k], lognorm = lnp[k];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float inv_s2 = 1.0f / (sd * sd);
+  const uint32_t nel = (uint32_t)N * du;
+  for (int64_t row = warp_global; row < B * N; row += nwarps) {
+    const int64_t b = row / N;
+    const int n = (int)(row - b * N);
+    Key key_tr{0u, 0u};
+    if (step_keys) {
+      key_tr = Key{step_keys[2 * b], step_keys[2 * b + 1]};
+      if (split_first) {
+        Key key_res;
+        split2(Key{key_tr.k0, key_tr.k1}, key_res, key_tr);
+      }
+    }
+    const float* parent = us_prev + (b * N + (A ? A[b * N + n] : n)) * du;
+    const float* vp = v_prev + b * dv;
+    const float* vc = v ? v + b * dv : nullptr;
+    const bool pinned = b_cur && (n == b_cur[b]);
+    float ss = 0.f, st = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < du; ++j) acc = fmaf(__ldg(MTk + (size_t)j * D + i), __ldg(parent + j), acc);
+      for (int j = 0; j < dv; ++j) acc = fmaf(__ldg(MTk + (size_t)(du + j) * D + i), __ldg(vp + j), acc);
+      const float drift = acc + mk[i];
+      if (i < du) {
+        const float mean = parent[i] + dt * drift;
+        if (us_out) {
+          const float eps = bits_to_normal(random_bits_elem(key_tr, nel, (uint32_t)n * du + i));
+          us_out[(b * N + n) * du + i] = pinned ? u_star[b * du + i] : mean + sd * eps;
+        }
+        if (u_eval) {
+          const float resid = u_eval[b * du + i] - mean;
+          st = fmaf(resid, resid, st);
+        }
+      } else if (vc) {
+        const int q = i - du;
+        const float resid = (vc[q] - vp[q]) - dt * drift;
+        ss = fmaf(resid, resid, ss);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      st += __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    if (lane == 0) {
+      if (lw_out) lw_out[b * N + n] = -0.5f * (ss * inv_s2 + lognorm);
+      // sum_du logN(u; mean, sd): the normaliser is du * log(2 pi sd^2) = lognorm * du / dv
+      if (tlp_out) tlp_out[b * N + n] = -0.5f * (st * inv_s2 + lognorm * ((float)du / (float)dv));
+    }
+  }
+}
+
+// (3) log_ws -= logsumexp(log_ws): one CTA per chain.
+__global__ void step_normalise_kernel(float* __restrict__ lw, int64_t B, int N) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    float* x = lw + b * N;
+    float m = -INFINITY;
+    for (int q = tid; q < N; q += blockDim.x) m = fmaxf(m, x[q]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = (lane < nw) ? red[lane] : -INFINITY;
+    m = warp_max(m);
+    if (!(fabsf(m) < INFINITY)) m = 0.f;
+    __syncthreads();
+    float s = 0.f;
+    for (int q = tid; q < N; q += blockDim.x) s += expf(x[q] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    s = (lane < nw) ? red[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float lse = logf(s) + m;
+    for (int q = tid; q < N; q += blockDim.x) x[q] -= lse;
+    __syncthreads();
+  }
+}
+
+}  // namespace fbs
+
+using namespace fbs;
+
+extern "C" int fbs_csmc_step_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, int32_t k, int scheme,
+                                        const uint32_t* step_keys, const float* us_prev, const float* log_ws,
+                                        const float* v, const float* v_prev, const float* u_star,
+                                        const int32_t* b_star_prev, const int32_t* b_star, int64_t B, int64_t N,
+                                        int32_t* A_out, float* us_out, float* log_ws_out) {
+  FBS_REQUIRE(model && model->MT && model->m && model->dt && model->sd && model->lognorm, "csmc_step: bad model");
+  FBS_REQUIRE(k >= 0 && k < model->K, "csmc_step: step index %d out of range [0, %d)", k, model->K);
+  FBS_REQUIRE(step_keys && us_prev && log_ws && v && v_prev && u_star && b_star_prev && b_star && A_out && us_out &&
+                  log_ws_out,
+              "csmc_step: null pointer");
+  FBS_REQUIRE(scheme == FBS_RESAMPLE_KILLING || scheme == FBS_RESAMPLE_MULTINOMIAL, "csmc_step: bad scheme %d", scheme);
+  FBS_REQUIRE(B >= 0 && N >= 1 && N < (1ll << 30), "csmc_step: bad sizes");
+  FBS_REQUIRE(us_prev != us_out, "csmc_step: us_out must not alias us_prev");
+  if (B == 0) return FBS_OK;
+  const int du = model->du, dv = model->dv, D = du + dv;
+  const size_t smem = ((size_t)3 * N + 1) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("csmc_step: N=%lld exceeds the single-warp resampling limit (multi-CTA scan not built yet)", (long long)N);
+    return FBS_ERR_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024) cudaFuncSetAttribute(step_ancestors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  step_ancestors_kernel<<<(int)(B > cap ? cap : B), 32, smem, as_stream(s)>>>(scheme, step_keys, log_ws, b_star_prev,
+                                                                           b_star, B, (int)N, A_out);
+  int rc = check_launch("step_ancestors_kernel");
+  if (rc) return rc;
+  const float* MTk = model->MT + (size_t)k * D * D;
+  const float* mk = model->m + (size_t)k * D;
+  int64_t blocks = (B * N + 7) / 8;  // 8 warps (children) per CTA
+  const int64_t cap2 = (int64_t)sm_count() * 8;
+  if (blocks > cap2) blocks = cap2;
+  step_transition_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(du, dv, MTk, mk, model->dt, model->sd, model->lognorm, k,
+                                                                step_keys, 1, us_prev, A_out, v, v_prev, u_star, b_star,
+                                                                nullptr, B, (int)N, us_out, log_ws_out, nullptr);
+  rc = check_launch("step_transition_kernel");
+  if (rc) return rc;
+  step_normalise_kernel<<<(int)(B > cap ? cap : B), 256, 0, as_stream(s)>>>(log_ws_out, B, (int)N);
+  return check_launch("step_normalise_kernel");
+}
+
+// The three closures of the reference drivers evaluated on their own (experiments/toy/gp_gibbs.py:120-135):
+//   us_out  = transition_sampler(us_prev, v_prev, t_k, key)      (needs tr_keys [B,2])
+//   lw_out  = likelihood_logpdf(v, us_prev, v_prev, t_k)         (needs v [B,dv])
+//   tlp_out = transition_logpdf(u_eval, us_prev, v_prev, t_k)    (needs u_eval [B,du])
+// Any output may be NULL.  us_prev [B,N,du], v_prev [B,dv].
+extern "C" int fbs_affine_eval_f32(fbs_stream_t s, const fbs_affine_model_t* model, int32_t k, const uint32_t* tr_keys,
+                                   const float* us_prev, const float* v, const float* v_prev, const float* u_eval,
+                                   int64_t B, int64_t N, float* us_out, float* lw_out, float* tlp_out) {
+  FBS_REQUIRE(model && model->MT && model->m && model->dt && model->sd && model->lognorm, "affine_eval: bad model");
+  FBS_REQUIRE(k >= 0 && k < model->K, "affine_eval: step index %d out of range [0, %d)", k, model->K);
+  FBS_REQUIRE(us_prev && v_prev, "affine_eval: null input");
+  FBS_REQUIRE(!us_out || tr_keys, "affine_eval: us_out needs tr_keys");
+  FBS_REQUIRE(!lw_out || v, "affine_eval: lw_out needs v");
+  FBS_REQUIRE(!tlp_out || u_eval, "affine_eval: tlp_out needs u_eval");
+  FBS_REQUIRE(us_out != us_prev, "affine_eval: us_out must not alias us_prev");
+  FBS_REQUIRE(B >= 0 && N >= 1, "affine_eval: bad sizes");
+  if (B == 0) return FBS_OK;
+  const int du = model->du, dv = model->dv, D = du + dv;
+  int64_t blocks = (B * N + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  step_transition_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(
+      du, dv, model->MT + (size_t)k * D * D, model->m + (size_t)k * D, model->dt, model->sd, model->lognorm, k, tr_keys, 0,
+      us_prev, nullptr, lw_out ? v : nullptr, v_prev, nullptr, nullptr, tlp_out ? u_eval : nullptr, B, (int)N, us_out,
+      lw_out, tlp_out);
+  return check_launch("step_transition_kernel");
+}

@@ -1,0 +1,235 @@
+"""Model objects that stand in for the reference's Python closures.
+
+The reference's samplers are higher-order functions: the experiment scripts hand them closures
+(``transition_sampler``, ``likelihood_logpdf``, ``transition_logpdf``, ``fwd_sampler``, ``unpack``,
+``ref_sampler``; ``experiments/toy/gp_gibbs.py:78-150``, ``experiments/sb/gibbs.py:82-164``).  A CUDA
+kernel cannot call back into Python, so this package provides objects whose *bound methods* satisfy
+the same callable protocol and additionally carry the structured data the fused kernels need.  The
+samplers recognise those bound methods and dispatch a whole sweep to one C-ABI call; an opaque
+closure is an error (no interpreted fallback).
+
+``AffineGaussianModel``: the joint reverse drift is affine, ``drift(uv, t_k) = M_k uv + m_k`` -- true
+for every Gaussian toy / Schroedinger-bridge configuration of the reference.
+"""
+import ctypes
+import math
+import numpy as np
+import torch
+from . import _native as nat
+from ._tensor import dev, empty, ptr, stream, out, is_host
+from .sdes.linear import LinearSDE, step_coefficients, forward_path
+from .sdes.simulators import em_tables, em_path
+
+
+def _host64(x):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=np.float64)
+
+
+class AffineGaussianModel:
+    """Reverse-diffusion closures with an affine joint drift.
+
+    Parameters (host, float64): ``M [K, D, D]``, ``m [K, D]`` with ``drift(uv, ts[k]) = M[k] uv + m[k]``;
+    ``g [K]`` the reverse dispersion at ``ts[k]``; ``dt`` the constant the closures multiply the drift
+    with (the reference uses the Python float ``T / nsteps``, gp_gibbs.py:63,121); ``du`` the size of the
+    unobserved block (``unpack``: first ``du`` coordinates, gp_gibbs.py:89-90).
+    """
+
+    def __init__(self, M, m, g, dt, du, ts, forward=None, ref=None, sde=None):
+        M, m, g = _host64(M), _host64(m), _host64(g)
+        self.K, self.D = M.shape[0], M.shape[1]
+        self.du, self.dv = int(du), self.D - int(du)
+        self.ts = np.asarray(_host64(ts), dtype=np.float32)
+        if self.ts.shape[0] != self.K + 1:
+            raise ValueError('ts must have K + 1 entries')
+        self.dt = float(dt)
+        self.sde = sde
+        self._forward = forward      # ('ou', F, sqrtQ) | ('em', tables)
+        self._ref = ref              # (a, Bm, c, L) of the Gaussian terminal conditional
+        # float32 constants exactly as the float32 reference forms them: sqrt(dt) (python float) * g (f32)
+        sd32 = (np.float32(math.sqrt(self.dt)) * g.astype(np.float32)).astype(np.float32)
+        self.host = dict(
+            MT=np.ascontiguousarray(np.transpose(M, (0, 2, 1))).astype(np.float32),
+            m=m.astype(np.float32),
+            dt=np.full((self.K,), self.dt, dtype=np.float32),
+            sd=sd32,
+            lognorm=(self.dv * np.log(2. * np.pi * sd32.astype(np.float64) ** 2)).astype(np.float32))
+        self._dev = None
+        self._struct = None
+
+    # ---------------------------------------------------------------- construction helpers
+    @classmethod
+    def from_linear_sde(cls, sde: LinearSDE, joint_mean, joint_cov, du, ts, T=None, dt=None):
+        """Jointly Gaussian data (X, Y) ~ N(joint_mean, joint_cov) noised by a scalar linear SDE
+        (gp_gibbs.py:55-109): marginal at forward time s is N(F_s mu, F_s^2 Sigma + Q_s I), the score is
+        linear, hence the reverse drift ``-a(s) z + g(s)^2 score(z, s)`` at ``s = T - t`` is affine."""
+        ts64 = _host64(ts)
+        K = ts64.shape[0] - 1
+        T = float(ts64[-1]) if T is None else float(T)
+        dt = T / K if dt is None else float(dt)
+        mu, Sigma = _host64(joint_mean), _host64(joint_cov)
+        D = mu.shape[0]
+        eye = np.eye(D)
+        ts32 = ts64.astype(np.float32).astype(np.float64)
+        M = np.empty((K, D, D))
+        m = np.empty((K, D))
+        g = np.empty((K,))
+        for k in range(K):
+            s = float(np.float32(T) - np.float32(ts32[k]))           # T - t_prev as the f32 closures see it
+            F, Q = sde.transition(s, ts32[0])
+            prec = np.linalg.solve(F * F * Sigma + Q * eye, eye)
+            gk = float(sde.dispersion(s))
+            M[k] = -float(sde.drift_coef(s)) * eye - gk * gk * prec
+            m[k] = gk * gk * (prec @ (F * mu))
+            g[k] = gk
+        # terminal conditional p(x_T | y_T) of the noised joint (gp_gibbs.py:84-86,138-141)
+        FT, QT = sde.transition(T, ts32[0])
+        mT, cT = FT * mu, FT * FT * Sigma + QT * eye
+        Bm = np.linalg.solve(cT[du:, du:], cT[du:, :du]).T
+        cov_c = cT[:du, :du] - Bm @ cT[du:, :du]
+        ref = (mT[:du], Bm, mT[du:], np.linalg.cholesky(cov_c))
+        F32, sq32 = step_coefficients(sde, ts64)
+        return cls(M, m, g, dt, du, ts64, forward=('ou', F32, sq32), ref=ref, sde=sde)
+
+    @classmethod
+    def from_gaussian_sb(cls, joint_mean, joint_cov, ref_mean, ref_cov, du, ts, sig=1., em_nsteps=10):
+        """Gaussian Schroedinger bridge between the data joint and a Gaussian reference
+        (experiments/sb/gibbs.py:62-150): reverse drift ``-drift_sb(z, T - t) + score(z, T - t)``, unit dispersion."""
+        from .sdes.bridges import make_gaussian_bw_sb
+        ts64 = _host64(ts)
+        K = ts64.shape[0] - 1
+        T = float(ts64[-1])
+        mm, mc, drift = make_gaussian_bw_sb(joint_mean, joint_cov, ref_mean, ref_cov, sig=sig)
+        D = np.asarray(joint_mean).shape[0]
+        ts32 = ts64.astype(np.float32)
+        M = np.empty((K, D, D))
+        m = np.empty((K, D))
+        for k in range(K):
+            s = float(np.float32(T) - ts32[k])
+            A, a = drift.affine(s)
+            prec = np.linalg.inv(mc(s))
+            M[k] = -A - sig ** 2 * prec
+            m[k] = -a + sig ** 2 * prec @ mm(s)
+        rm, rc = _host64(ref_mean), _host64(ref_cov)
+        Bm = np.linalg.solve(rc[du:, du:], rc[du:, :du]).T
+        ref = (rm[:du], Bm, rm[du:], np.linalg.cholesky(rc[:du, :du] - Bm @ rc[du:, :du]))
+        tables = em_tables(ts64, drift, lambda _: sig, em_nsteps)
+        return cls(M, m, np.full((K,), float(sig)), T / K, du, ts64, forward=('em', tables), ref=ref)
+
+    # ---------------------------------------------------------------- device residency
+    def device_arrays(self):
+        if self._dev is None:
+            self._dev = {k: dev(v, torch.float32) for k, v in self.host.items()}
+            st = nat.AffineModelStruct()
+            st.K, st.du, st.dv, st.reserved = self.K, self.du, self.dv, 0
+            for name in ('MT', 'm', 'dt', 'sd', 'lognorm'):
+                setattr(st, name, self._dev[name].data_ptr())
+            self._struct = st
+        return self._dev
+
+    def struct(self):
+        self.device_arrays()
+        return ctypes.byref(self._struct)
+
+    def step_index(self, t_prev) -> int:
+        t = float(t_prev.item() if isinstance(t_prev, torch.Tensor) else t_prev)
+        k = int(np.argmin(np.abs(self.ts[:-1].astype(np.float64) - t)))
+        if abs(float(self.ts[k]) - t) > 1e-6 * max(1., abs(t)):
+            raise ValueError(f't_prev={t} is not one of the model step times ts[:-1]')
+        return k
+
+    # ---------------------------------------------------------------- the closure protocol
+    def unpack(self, xy, **kwargs):
+        return xy[..., :self.du], xy[..., self.du:]
+
+    def _eval(self, k, key, us_prev, v, v_prev, u_eval, want):
+        host = is_host(us_prev)
+        up = dev(us_prev, torch.float32)
+        single = up.dim() == 2
+        if single:
+            up = up.unsqueeze(0)
+        B, N = up.shape[0], up.shape[1]
+
+        def vec(x, d):
+            if x is None:
+                return None
+            t = dev(x, torch.float32).reshape(-1, d)
+            return t.expand(B, d).contiguous() if t.shape[0] == 1 and B > 1 else t
+
+        vp, vv, ue = vec(v_prev, self.dv), vec(v, self.dv), vec(u_eval, self.du)
+        kk = None if key is None else dev(key, torch.uint32).reshape(-1, 2)
+        us_out = empty((B, N, self.du), torch.float32) if want == 'us' else None
+        lw = empty((B, N), torch.float32) if want == 'lw' else None
+        tlp = empty((B, N), torch.float32) if want == 'tlp' else None
+        nat.call('fbs_affine_eval_f32', stream(), self.struct(), int(k), ptr(kk), ptr(up), ptr(vv), ptr(vp), ptr(ue), B,
+                 N, ptr(us_out), ptr(lw), ptr(tlp))
+        res = {'us': us_out, 'lw': lw, 'tlp': tlp}[want]
+        return out(res[0] if single else res, host)
+
+    def transition_sampler(self, us_prev, v_prev, t_prev, key, **kwargs):
+        """(n, du), (dv,), float, key -> (n, du)   -- gp_gibbs.py:120-122."""
+        return self._eval(self.step_index(t_prev), key, us_prev, None, v_prev, None, 'us')
+
+    def likelihood_logpdf(self, v, us_prev, v_prev, t_prev, **kwargs):
+        """(dv,), (n, du), (dv,), float -> (n,)    -- gp_gibbs.py:132-135."""
+        return self._eval(self.step_index(t_prev), None, us_prev, v, v_prev, None, 'lw')
+
+    def transition_logpdf(self, u, us_prev, v_prev, t_prev, **kwargs):
+        """(du,), (n, du), (dv,), float -> (n,)    -- gp_gibbs.py:125-129."""
+        return self._eval(self.step_index(t_prev), None, us_prev, None, v_prev, u, 'tlp')
+
+    def fwd_sampler(self, key, x0, y0, **kwargs):
+        """Forward-noise the joint (x0, y0) over ``ts`` -> path [.., K+1, D] (gp_gibbs.py:144-145; sb/gibbs.py:141-143)."""
+        xy0 = self._joint0(key, x0, y0)
+        if self._forward[0] == 'ou':
+            return forward_path(key, xy0, self._forward[1], self._forward[2])
+        return em_path(key, xy0, self._forward[1])
+
+    def fwd_sampler_reversed(self, key, x0, y0):
+        """Same draw as ``fwd_sampler`` but returned as ``(us, vs) = (path_x[::-1], path_y[::-1])`` (gibbs.py:128-130),
+        written directly in that layout by the kernel."""
+        xy0 = self._joint0(key, x0, y0)
+        if self._forward[0] == 'ou':
+            return forward_path(key, xy0, self._forward[1], self._forward[2], du=self.du, rev=True)
+        return em_path(key, xy0, self._forward[1], du=self.du, rev=True)
+
+    def fwd_ys_sampler(self, key, y0, **kwargs):
+        """Forward-noise y alone (separable forward process; gp_gibbs.py:148-149)."""
+        if self._forward[0] != 'ou':
+            raise NotImplementedError('fwd_ys_sampler needs a separable (scalar linear SDE) forward process')
+        return forward_path(key, y0, self._forward[1], self._forward[2])
+
+    def ref_sampler(self, key, yT, nsamples, **kwargs):
+        """Draw ``nsamples`` from the terminal conditional p(x_T | y_T) (gp_gibbs.py:138-141)."""
+        host = is_host(key)
+        kk = dev(key, torch.uint32)
+        single = kk.dim() == 1
+        kk = kk.reshape(-1, 2)
+        B = kk.shape[0]
+        yt = dev(yT, torch.float32).reshape(-1, self.dv)
+        if yt.shape[0] == 1 and B > 1:
+            yt = yt.expand(B, self.dv).contiguous()
+        if not hasattr(self, '_ref_dev'):
+            self._ref_dev = [dev(np.ascontiguousarray(a), torch.float32) for a in self._ref]
+        a, Bm, c, L = self._ref_dev
+        o = empty((B, int(nsamples), self.du), torch.float32)
+        nat.call('fbs_gaussian_ref_sample_f32', stream(), ptr(kk), ptr(yt), ptr(a), ptr(Bm), ptr(c), ptr(L), B,
+                 int(nsamples), self.du, self.dv, ptr(o))
+        return out(o[0] if single else o, host)
+
+    def _joint0(self, key, x0, y0):
+        host_key = is_host(key)
+        kk_batched = (np.ndim(key) == 2) if host_key else (key.dim() == 2)
+        x = dev(x0, torch.float32)
+        y = dev(y0, torch.float32)
+        if kk_batched:
+            B = key.shape[0]
+            x = x.reshape(-1, self.du)
+            y = y.reshape(-1, self.dv)
+            if x.shape[0] == 1 and B > 1:
+                x = x.expand(B, -1)
+            if y.shape[0] == 1 and B > 1:
+                y = y.expand(B, -1)
+            return torch.cat([x, y], dim=1).contiguous()
+        return torch.cat([x.reshape(-1), y.reshape(-1)]).contiguous()

@@ -1,0 +1,204 @@
+"""Conditional SMC -- API of ``fbs/samplers/csmc/csmc.py`` (``csmc_kernel`` :14-77, ``forward_pass`` :80-164,
+``backward_scanning_pass`` :230-270, ``backward_sampling_pass`` :167-227, ``normalise`` :273-292,
+``barker_move`` :295-297).
+
+``forward_pass`` runs the whole K-step sweep in ONE persistent kernel (``fbs_csmc_forward_affine_f32``)
+when the callables it is given are bound methods of an ``AffineGaussianModel`` plus one of the two init
+objects below.  Anything else raises ``TypeError``: there is no interpreted or CPU fallback.
+
+Batching: the reference ``vmap``s over chains; here every array may carry a leading chain axis ``B``
+(keys ``[B, 2]``) and the kernel's grid runs over it.
+"""
+import math
+import numpy as np
+import torch
+from ... import _native as nat
+from ..._tensor import dev, empty, ptr, stream, out, is_host
+from ...models import AffineGaussianModel
+from ... import random as frandom
+
+
+class DegenerateInit:
+    """``explicit_final=False`` initialisation (gibbs.py:139-144): N copies of the reference start, uniform weights."""
+
+    def __init__(self, nparticles: int):
+        self.nparticles = int(nparticles)
+
+    def sampler(self, *_):
+        raise TypeError('DegenerateInit is consumed by the fused forward_pass; it is not called')
+
+    def likelihood_logpdf(self, *_, **__):
+        raise TypeError('DegenerateInit is consumed by the fused forward_pass; it is not called')
+
+    @property
+    def init_log_w(self) -> float:
+        return float(np.float32(-math.log(self.nparticles)))
+
+
+class NormalInit:
+    """``explicit_final=True`` initialisation (gibbs.py:132-137): N(0, I) particles, weights from the likelihood at ts[0]."""
+
+    def __init__(self, model: AffineGaussianModel):
+        self.model = model
+
+    def sampler(self, key, n):
+        return frandom.normal(key, (n, self.model.du))
+
+    def likelihood_logpdf(self, v0, u0s, v1, **kwargs):
+        return self.model.likelihood_logpdf(v0, u0s, v1, self.model.ts[0], **kwargs)
+
+
+def _model_of(*fns):
+    models = {id(getattr(f, '__self__', None)): getattr(f, '__self__', None) for f in fns}
+    if len(models) != 1:
+        raise TypeError('transition_sampler / likelihood_logpdf must be bound methods of ONE model object')
+    model = next(iter(models.values()))
+    if not isinstance(model, AffineGaussianModel):
+        raise TypeError('fbs_b200 fuses the sweep into a CUDA kernel and cannot call opaque Python closures: pass '
+                        'bound methods of an fbs_b200.AffineGaussianModel (no interpreted fallback exists)')
+    return model
+
+
+def _scheme_of(resampling, family):
+    if getattr(resampling, 'family', None) != family or not hasattr(resampling, 'scheme'):
+        raise TypeError(f'{family} resampling must be one of the fbs_b200 resampling functions')
+    return resampling.scheme
+
+
+def forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples, history=True):
+    """Device-level forward pass on batched device tensors.  Returns a dict of device tensors."""
+    k = dev(key, torch.uint32).reshape(-1, 2)
+    B = k.shape[0]
+    K, du, dv = model.K, model.du, model.dv
+    us = dev(us_star, torch.float32).reshape(B, K + 1, du)
+    bs = dev(bs_star, torch.int32).reshape(B, K + 1)
+    v = dev(vs, torch.float32).reshape(B, K + 1, dv)
+    if isinstance(init, NormalInit):
+        init_mode, N, init_log_w = nat.INIT_NORMAL, int(nsamples) + 1, 0.0      # csmc.py:151: nsamples + 1
+    elif isinstance(init, DegenerateInit):
+        init_mode, N, init_log_w = nat.INIT_DEGENERATE, init.nparticles, init.init_log_w
+    else:
+        raise TypeError('init_sampler / init_likelihood_logpdf must come from DegenerateInit or NormalInit')
+    res = dict(N=N)
+    As = log_wss = uss = None
+    if history:
+        As = empty((B, K, N), torch.int32)
+        log_wss = empty((B, K + 1, N), torch.float32)
+        uss = empty((B, K + 1, N, du), torch.float32)
+    lw_last = empty((B, N), torch.float32)
+    us_last = empty((B, N, du), torch.float32)
+    nat.call('fbs_csmc_forward_affine_f32', stream(), model.struct(), ptr(k), ptr(us), ptr(bs), ptr(v), init_mode,
+             init_log_w, scheme, B, N, ptr(As), ptr(log_wss), ptr(uss), ptr(lw_last), ptr(us_last))
+    res.update(As=As, log_wss=log_wss, uss=uss, log_ws_last=lw_last, us_last=us_last)
+    return res
+
+
+def forward_pass(key, us_star, bs_star, vs, ts, init_sampler, init_likelihood_logpdf, transition_sampler,
+                 likelihood_logpdf, cond_resampling, nsamples, **kwargs):
+    """Forward pass of the CSMC kernel (Algorithm 1 of the paper) -> ``(As, log_wss, uss)``.
+
+    Same arguments as ``fbs.samplers.csmc.csmc.forward_pass``; ``ts`` must be the model's grid.
+    """
+    model = _model_of(transition_sampler, likelihood_logpdf)
+    init = getattr(init_sampler, '__self__', None)
+    if init is None or init is not getattr(init_likelihood_logpdf, '__self__', None):
+        raise TypeError('init_sampler and init_likelihood_logpdf must be the methods of one DegenerateInit/NormalInit')
+    scheme = _scheme_of(cond_resampling, 'conditional')
+    host = is_host(key)
+    single = np.ndim(key) == 1 if host else key.dim() == 1
+    r = forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples, history=True)
+    res = (r['As'], r['log_wss'], r['uss'])
+    if single:
+        res = tuple(t[0] for t in res)
+    return tuple(out(t, host) for t in res)
+
+
+def normalise(log_weights, log_space=False):
+    """csmc.py:273-292 on device tensors / numpy (tiny helper, not on the fused path)."""
+    host = is_host(log_weights)
+    lw = dev(log_weights, torch.float32)
+    lw = lw - torch.logsumexp(lw, dim=-1, keepdim=True)
+    return out(lw if log_space else torch.exp(lw), host)
+
+
+def barker_move(key, ws):
+    return frandom.choice(key, ws.shape[-1], (), p=ws)
+
+
+def backward_scanning_pass(key, As, xss, log_w_T):
+    """csmc.py:230-270 -> ``(xs_star [.., K+1, du], bs_star [.., K+1])``; kernel ``fbs_backward_scan_f32``."""
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B = k.shape[0]
+    A = dev(As, torch.int32)
+    K, N = A.shape[-2], A.shape[-1]
+    A = A.reshape(B, K, N)
+    x = dev(xss, torch.float32)
+    du = x.shape[-1]
+    x = x.reshape(B, K + 1, N, du)
+    lw = dev(log_w_T, torch.float32).reshape(B, N)
+    xs = empty((B, K + 1, du), torch.float32)
+    bs = empty((B, K + 1), torch.int32)
+    nat.call('fbs_backward_scan_f32', stream(), ptr(k), ptr(A), ptr(x), ptr(lw), B, K, N, du, ptr(xs), ptr(bs))
+    if single:
+        xs, bs = xs[0], bs[0]
+    return out(xs, host), out(bs, host)
+
+
+def backward_sampling_pass(key, transition_logpdf, vs, ts, uss, log_ws, *args, **kwargs):
+    """csmc.py:167-227.  Composed step by step from the closure kernels (not a hot path: O(K) launches)."""
+    model = _model_of(transition_logpdf)
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B = k.shape[0]
+    x = dev(uss, torch.float32)
+    du = x.shape[-1]
+    K1, N = (x.shape[-3], x.shape[-2])
+    x = x.reshape(B, K1, N, du)
+    lw = dev(log_ws, torch.float32).reshape(B, K1, N)
+    v = dev(vs, torch.float32).reshape(B, K1, model.dv)
+    keys = frandom.split(k, K1)                                                    # csmc.py:194  [B, K1, 2]
+    W_T = torch.exp(lw[:, -1] - torch.logsumexp(lw[:, -1], dim=-1, keepdim=True))  # csmc.py:200
+    B_t = frandom.choice(keys[:, -1].contiguous(), N, (), p=W_T).reshape(B).long()
+    ar = torch.arange(B, device=x.device)
+    x_t = x[ar, -1, B_t]
+    xs, Bs = [x_t], [B_t]
+    for q, t in enumerate(range(K1 - 2, -1, -1)):                                  # csmc.py:217
+        G = model._eval(t, None, x[:, t].contiguous(), None, v[:, t].contiguous(), x_t.contiguous(), 'tlp')
+        G = G - G.max(dim=-1, keepdim=True).values                                 # csmc.py:207
+        lwt = G + lw[:, t]
+        w = torch.exp(lwt - torch.logsumexp(lwt, dim=-1, keepdim=True))           # csmc.py:208-209
+        B_t = frandom.choice(keys[:, q].contiguous(), N, (), p=w.contiguous()).reshape(B).long()
+        x_t = x[ar, t, B_t]
+        xs.append(x_t)
+        Bs.append(B_t)
+    xs = torch.stack(xs[::-1], dim=1)
+    Bs = torch.stack(Bs[::-1], dim=1).to(torch.int32)
+    if single:
+        xs, Bs = xs[0], Bs[0]
+    return out(xs, host), out(Bs, host)
+
+
+def csmc_kernel(key, us_star, bs_star, vs, ts, init_sampler, init_likelihood_logpdf, transition_sampler,
+                transition_logpdf, measurement_cond_logpdf, cond_resampling, nsamples, backward=False, **kwargs):
+    """Generic cSMC kernel -> ``(xs_star, bs_star)``; same arguments as ``fbs.samplers.csmc.csmc.csmc_kernel``."""
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    keys = frandom.split(k.reshape(-1, 2), 2)                                      # csmc.py:65
+    key_fwd, key_bwd = keys[:, 0].contiguous(), keys[:, 1].contiguous()
+    model = _model_of(transition_sampler, measurement_cond_logpdf)
+    init = getattr(init_sampler, '__self__', None)
+    scheme = _scheme_of(cond_resampling, 'conditional')
+    r = forward_pass_device(key_fwd, us_star, bs_star, vs, model, init, scheme, nsamples, history=True)
+    if backward:
+        xs, bs = backward_sampling_pass(key_bwd, transition_logpdf, dev(vs, torch.float32), ts, r['uss'], r['log_wss'])
+    else:
+        xs, bs = backward_scanning_pass(key_bwd, r['As'], r['uss'], r['log_wss'][:, -1].contiguous())
+    if single:
+        xs, bs = xs[0], bs[0]
+    return out(xs, host), out(bs, host)

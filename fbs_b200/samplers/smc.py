@@ -1,0 +1,177 @@
+"""Bootstrap filter / smoother and the pseudo-marginal kernel -- API of ``fbs/samplers/smc.py``
+(``bootstrap_filter`` :9-88, ``bootstrap_backward_smoother`` :91-112, ``pmcmc_filter_step`` :115-158,
+``pcn_proposal`` :161-168, ``pmcmc_kernel`` :171-258).
+
+``pmcmc_filter_step`` is ONE persistent kernel (``fbs_pmcmc_filter_affine_f32``).  ``pmcmc_kernel`` adds the
+forward-noising, pCN, reference-sampling and MH kernels around it -- seven launches per MCMC step for any
+number of chains.  ``bootstrap_filter`` / ``bootstrap_backward_smoother`` (chain initialisation only) are
+composed step by step from the closure kernels.
+"""
+import math
+import numpy as np
+import torch
+from .. import _native as nat
+from .._tensor import dev, empty, ptr, stream, out, is_host
+from .. import random as frandom
+from .common import MCMCState
+from .csmc.csmc import _model_of, _scheme_of
+
+
+def pmcmc_filter_step(key, vs_bridge, u0s, ts, transition_sampler, likelihood_logpdf, resampling, nparticles,
+                      return_history=False, **kwargs):
+    """smc.py:115-158 -> ``(uT [.., N, du], log_ell [..])``."""
+    model = _model_of(transition_sampler, likelihood_logpdf)
+    scheme = _scheme_of(resampling, 'unconditional')
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B, K, N = k.shape[0], model.K, int(nparticles)
+    v = dev(vs_bridge, torch.float32).reshape(B, K + 1, model.dv)
+    u0 = dev(u0s, torch.float32).reshape(B, N, model.du)
+    uT = empty((B, N, model.du), torch.float32)
+    log_ell = empty((B,), torch.float32)
+    inds = lwh = ush = None
+    if return_history:
+        inds = empty((B, K, N), torch.int32)
+        lwh = empty((B, K, N), torch.float32)
+        ush = empty((B, K, N, model.du), torch.float32)
+    nat.call('fbs_pmcmc_filter_affine_f32', stream(), model.struct(), ptr(k), ptr(v), ptr(u0), scheme, B, N, ptr(uT),
+             ptr(log_ell), ptr(inds), ptr(lwh), ptr(ush))
+    res = (uT, log_ell) + ((inds, lwh, ush) if return_history else ())
+    if single:
+        res = tuple(t[0] for t in res)
+    return tuple(out(t, host) for t in res)
+
+
+def pcn_proposal(key, delta: float, x, mean, sampler):
+    """smc.py:161-168.  ``sampler(key)`` is called on the two split keys (batched when ``key`` is)."""
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    keys = frandom.split(k.reshape(-1, 2), 2)
+    r0 = dev(sampler(keys[:, 0].contiguous() if not single else keys[0, 0].contiguous()), torch.float32)
+    r1 = dev(sampler(keys[:, 1].contiguous() if not single else keys[0, 1].contiguous()), torch.float32)
+    xt = dev(x, torch.float32)
+    B = keys.shape[0]
+    n = xt.numel() // B
+    mt = dev(mean, torch.float32).reshape(-1)
+    if mt.numel() != n:
+        raise ValueError('mean must be shared across chains (shape of one path)')
+    o = torch.empty_like(xt)
+    nat.call('fbs_pcn_combine_f32', stream(), float(delta), ptr(xt), ptr(mt), ptr(r0), ptr(r1), B, n, ptr(o))
+    return out(o, host)
+
+
+def pmcmc_kernel(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler, transition_sampler,
+                 likelihood_logpdf, resampling, nparticles, delta=None, which_u=0, **kwargs):
+    """One pseudo-marginal MCMC step targeting p(u_T | v_T = y0); same arguments as the reference (smc.py:171-184).
+
+    Returns ``(uT, log_ell, ys, MCMCState)``.  With keys ``[B, 2]`` every array carries the chain axis.
+    """
+    model = _model_of(transition_sampler, likelihood_logpdf)
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B, K, N = k.shape[0], model.K, int(nparticles)
+    keys = frandom.split(k, 4)                                                     # smc.py:231
+    key_prop, key_u0, key_filter, key_mh = (keys[:, i].contiguous() for i in range(4))
+    ys_d = dev(ys, torch.float32).reshape(B, K + 1, model.dv).clone()
+    uT_d = dev(uT, torch.float32).reshape(B, model.du).clone()
+    le_d = dev(log_ell, torch.float32).reshape(B).clone()
+    y0_d = dev(y0, torch.float32).reshape(-1, model.dv)
+    if y0_d.shape[0] != 1:
+        raise ValueError('y0 is shared across chains (in_axes=None in the reference driver, gp_pmcmc.py:161)')
+    if delta is None:
+        prop_ys = dev(fwd_ys_sampler(key_prop, y0_d[0]), torch.float32).reshape(B, K + 1, model.dv)   # smc.py:234
+    else:
+        tsh = np.asarray(ts.detach().cpu().numpy() if isinstance(ts, torch.Tensor) else ts, dtype=np.float32)
+        coef = np.asarray(sde.transition(tsh, tsh[0], dtype=np.float32)[0], dtype=np.float32)         # sde.mean, smc.py:236
+        mean = dev(coef, torch.float32)[:, None] * y0_d                                              # [K+1, dv]
+        prop_ys = pcn_proposal(key_prop, delta, ys_d, mean.contiguous(), lambda key_: fwd_ys_sampler(key_, y0_d[0]))
+        prop_ys = prop_ys.reshape(B, K + 1, model.dv)
+    vs = torch.flip(prop_ys, dims=[1]).contiguous()                                # smc.py:239
+    u0s = dev(ref_sampler(key_u0, vs[:, 0].contiguous(), N), torch.float32)        # smc.py:241
+    prop_uTs, prop_log_ell = pmcmc_filter_step(key_filter, vs, u0s, ts, transition_sampler, likelihood_logpdf,
+                                               resampling, N, **kwargs)
+    acc_prob = empty((B,), torch.float32)
+    is_acc = empty((B,), torch.uint8)
+    old_log_ell = le_d.clone()
+    nat.call('fbs_mh_accept_f32', stream(), ptr(key_mh), ptr(prop_uTs), ptr(prop_log_ell), ptr(prop_ys), B, N, model.du,
+             (K + 1) * model.dv, int(which_u), ptr(uT_d), ptr(le_d), ptr(ys_d), ptr(acc_prob), ptr(is_acc))
+    state = MCMCState(acceptance_prob=acc_prob, is_accepted=is_acc.bool(), prop_log_ell=prop_log_ell,
+                      log_ell=old_log_ell)
+    res = [uT_d, le_d, ys_d]
+    if single:
+        res = [t[0] for t in res]
+        state = MCMCState(*[t[0] for t in state])
+    return (*[out(t, host) for t in res], MCMCState(*[out(t, host) for t in state]))
+
+
+def bootstrap_filter(transition_sampler, measurement_cond_pdf, vs, ts, init_sampler, key, nparticles, resampling,
+                     log: bool = True, return_last: bool = True, **kwargs):
+    """smc.py:9-88 -> (samples, negative log-likelihood).  Step-by-step composition (initialisation path)."""
+    if not log:
+        raise NotImplementedError('only the log-domain filter is used by the reference drivers')
+    model = _model_of(transition_sampler, measurement_cond_pdf)
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B, K, N = k.shape[0], model.K, int(nparticles)
+    v = dev(vs, torch.float32).reshape(B, K + 1, model.dv)
+    ks = frandom.split(k, 2)                                                       # smc.py:77
+    key_init, key_steps = ks[:, 0].contiguous(), ks[:, 1].contiguous()
+    us = dev(init_sampler(key_init, v[:, 0].contiguous(), N), torch.float32).reshape(B, N, model.du)
+    step_keys = frandom.split(key_steps, K)                                        # [B, K, 2]
+    log_nell = torch.zeros((B,), dtype=torch.float32, device=us.device)
+    hist = [us]
+    logN = np.float32(math.log(N))
+    ar = torch.arange(B, device=us.device)[:, None]
+    for kk in range(K):
+        pk = frandom.split(step_keys[:, kk].contiguous(), 2)                       # smc.py:61
+        key_proposal, key_resampling = pk[:, 0].contiguous(), pk[:, 1].contiguous()
+        vp, vc = v[:, kk].contiguous(), v[:, kk + 1].contiguous()
+        us_new = model._eval(kk, key_proposal, us, None, vp, None, 'us')           # smc.py:63
+        lw = model._eval(kk, None, us, vc, vp, None, 'lw')                         # smc.py:65
+        c = torch.logsumexp(lw, dim=-1)
+        log_nell = log_nell - (c - logN)                                           # smc.py:67
+        inds = resampling(torch.exp(lw - c[:, None]).contiguous(), key_resampling).long()   # smc.py:68-69
+        us = us_new[ar, inds].contiguous()                                         # smc.py:72
+        if not return_last:
+            hist.append(us)
+    res = (us, log_nell) if return_last else (torch.stack(hist, dim=1), log_nell)
+    if single:
+        res = tuple(t[0] for t in res)
+    return tuple(out(t, host) for t in res)
+
+
+def bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf, *args, **kwargs):
+    """smc.py:91-112 (the unsplit ``key`` draws u_T, as written upstream)."""
+    model = _model_of(transition_logpdf)
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B = k.shape[0]
+    fu = dev(filter_us, torch.float32)
+    N, du = fu.shape[-2], fu.shape[-1]
+    K = model.K
+    fu = fu.reshape(B, K + 1, N, du)
+    v = dev(vs, torch.float32).reshape(B, K + 1, model.dv)
+    ks = frandom.split(k, 2)                                                       # smc.py:108
+    key_smoother = ks[:, 1].contiguous()
+    ar = torch.arange(B, device=fu.device)
+    uT = fu[ar, -1, frandom.randint(k, (), 0, N).reshape(B).long()]               # smc.py:109
+    skeys = frandom.split(key_smoother, K)
+    u = uT
+    traj = []
+    for q, t in enumerate(range(K - 1, -1, -1)):                                   # smc.py:110-111
+        lw = model._eval(t, None, fu[:, t].contiguous(), None, v[:, t].contiguous(), u.contiguous(), 'tlp')
+        w = torch.exp(lw - torch.logsumexp(lw, dim=-1, keepdim=True)).contiguous()
+        idx = frandom.choice(skeys[:, q].contiguous(), N, (), p=w).reshape(B).long()
+        u = fu[ar, t, idx]
+        traj.append(u)
+    res = torch.cat([torch.stack(traj[::-1], dim=1), uT[:, None]], dim=1)
+    return out(res[0] if single else res, host)

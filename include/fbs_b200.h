@@ -1,0 +1,211 @@
+/*
+ * fbs_b200 -- C ABI of the B200-native CSMC / particle-Gibbs / pMCMC hot path.
+ *
+ * Every entry point is `extern "C"`, takes a CUDA stream, DEVICE pointers and sizes, and
+ * returns an int status (FBS_OK == 0).  No entry point allocates, frees, synchronises the
+ * device or retains a pointer; all buffers (inputs, outputs, scratch) are owned by the
+ * caller.  The library keeps no mutable global state besides a thread-local error string,
+ * so it is re-entrant from concurrent host threads (the XLA-FFI threading model).
+ *
+ * The reference (zgbkdlm/fbs, pure JAX) has no FFI of its own; each function below names
+ * the reference Python function (file:line under /root/reference) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the jax.ffi binding a maintainer would add.
+ *
+ * Conventions
+ *   - leading batch dimension B = independent chains (what the reference vmaps over,
+ *     experiments/toy/gp_gibbs.py:172-173); all arrays are dense row-major;
+ *   - keys are jax.random threefry keys, uint32[2] per chain;
+ *   - floats are float32, indices int32 (jax_enable_x64 = False in the experiments);
+ *   - "D" = du + dv, the joint dimension; X (unobserved, u) is the first du coordinates.
+ */
+#ifndef FBS_B200_H_
+#define FBS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fbs_stream_t; /* cudaStream_t */
+
+enum {
+  FBS_OK = 0,
+  FBS_ERR_INVALID_ARGUMENT = 1,
+  FBS_ERR_CUDA = 2,
+  FBS_ERR_UNSUPPORTED = 3
+};
+
+/* Conditional resamplers: fbs/samplers/csmc/resamplings.py.  Unconditional: fbs/samplers/resampling.py. */
+enum {
+  FBS_RESAMPLE_MULTINOMIAL = 0, /* resamplings.py:10-37 / resampling.py:62-68 (sorted uniforms) */
+  FBS_RESAMPLE_KILLING = 1,     /* resamplings.py:40-88 / resampling.py:71-101 */
+  FBS_RESAMPLE_SYSTEMATIC = 2,  /* resamplings.py:120-125 (no clip) / resampling.py:54-55 (clip) */
+  FBS_RESAMPLE_STRATIFIED = 3   /* resampling.py:58-59 */
+};
+
+/* How the CSMC sweep initialises its particle set (fbs/samplers/gibbs.py:132-144). */
+enum {
+  FBS_INIT_DEGENERATE = 0, /* explicit_final=False: N copies of us_star[0], uniform weights (:140-144) */
+  FBS_INIT_NORMAL = 1      /* explicit_final=True: N(0, I) draws, weights = likelihood at ts[0] (:133-137) */
+};
+
+int fbs_version(void);
+/* Thread-local, human-readable description of the last non-OK return on this thread. */
+const char* fbs_last_error(void);
+/* Number of kernel launches issued through this library on this thread since the last reset. */
+int64_t fbs_launch_count(void);
+void fbs_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * jax.random (threefry2x32, jax 0.4.26 non-partitionable) -- third-party semantics the
+ * reference depends on at csmc.py:136,150,157; resamplings.py:66,71,74,84; gibbs.py:126,147,156;
+ * smc.py:142,154,231,248; linear.py:220; simulators.py:81,91.
+ * All are batched over B keys; outputs are [B, n] unless noted.
+ * ---------------------------------------------------------------------------------------- */
+int fbs_random_bits_u32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, uint32_t* out);
+/* jax.random.split(key, num): out [B, num, 2] */
+int fbs_random_split(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t num, uint32_t* out);
+int fbs_random_uniform_f32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, float minval, float maxval,
+                           float* out);
+int fbs_random_normal_f32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, float* out);
+int fbs_random_randint_i32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, int32_t minval,
+                           int32_t maxval, int32_t* out);
+/* jax.random.choice(key, N, (n,), p=p[b]) : p [B, N] (need not be normalised), out [B, n] */
+int fbs_random_choice_f32(fbs_stream_t s, const uint32_t* keys, const float* p, int64_t B, int64_t N, int64_t n,
+                          int32_t* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Resampling.  weights [B, N] normalised, idx_out [B, N].
+ * cond: (key, weights, i, j, conditional) of resamplings.py; i, j are [B] (may be NULL when
+ * conditional == 0).  Indices are bit-exact against the oracle on identical weights and keys;
+ * cumulative sums are sequential float32 (DESIGN.md "summation order").
+ * ---------------------------------------------------------------------------------------- */
+int fbs_cond_resample_f32(fbs_stream_t s, int scheme, const uint32_t* keys, const float* weights, const int32_t* i,
+                          const int32_t* j, int conditional, int64_t B, int64_t N, int32_t* idx_out);
+int fbs_resample_f32(fbs_stream_t s, int scheme, const uint32_t* keys, const float* weights, int64_t B, int64_t N,
+                     int32_t* idx_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Forward noising.
+ * ---------------------------------------------------------------------------------------- */
+/* make_linear_sde(...)[2] = simulate_cond_forward(key, x0, ts, keep_path=True), fbs/sdes/linear.py:190-221.
+ * F, sqrtQ: [K] exact-discretisation coefficients of the K intervals (linear.py:169-184).
+ * x0 [B, D] (or [1, D] broadcast when x0_batched == 0).
+ * Output layout: if rev == 0, path [B, K+1, D] in forward time.  If rev != 0 the path is
+ * written time-REVERSED and split the way gibbs_kernel consumes it (gibbs.py:128-130):
+ * out_u [B, K+1, du] = path[::-1][..., :du], out_v [B, K+1, D-du] = path[::-1][..., du:]
+ * (either may be NULL).  With rev == 0, out_u receives the full path and du must equal D. */
+int fbs_ou_forward_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0, int x0_batched, const float* F,
+                            const float* sqrtQ, int64_t B, int64_t K, int64_t D, int64_t du, int rev, float* out_u,
+                            float* out_v);
+
+/* euler_maruyama(key, x0, ts, drift, dispersion, integration_nsteps=m, return_path=True),
+ * fbs/sdes/simulators.py:53-106, for an affine drift  drift(x, t_{k,q}) = A_{k,q} x + a_{k,q}:
+ * AT [K*m, D, D] with AT[kq][j][i] = A_{k,q}[i][j];  a [K*m, D];  ddt [K] sub-step size;
+ * disp [K*m] = dispersion(t_{k,q}).  Output as in fbs_ou_forward_path_f32. */
+int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0, int x0_batched, const float* AT,
+                           const float* a, const float* ddt, const float* disp, int64_t B, int64_t K, int64_t m,
+                           int64_t D, int64_t du, int rev, float* out_u, float* out_v);
+
+/* ------------------------------------------------------------------------------------------
+ * Affine-Gaussian reverse-diffusion model: the closures transition_sampler / likelihood_logpdf
+ * of experiments/toy/gp_gibbs.py:94-135 and experiments/sb/gibbs.py:93-132 with the joint
+ * reverse drift written as  drift(uv, t_k) = M_k uv + m_k  for the K step times ts[:-1].
+ *   u' = u + dt_k * drift_u + sd_k * eps                       (gp_gibbs.py:120-122)
+ *   log w = sum_dv logN(v; v_prev + dt_k * drift_v, sd_k)      (gp_gibbs.py:132-135)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t K;        /* number of steps */
+  int32_t du;       /* dim of the unobserved part u */
+  int32_t dv;       /* dim of the observed part v   */
+  int32_t reserved;
+  const float* MT;  /* [K, D, D]  MT[k][j][i] = M_k[i][j]  (input-major, for coalesced reads) */
+  const float* m;   /* [K, D] */
+  const float* dt;  /* [K]   the step the closures multiply the drift by (reference: constant T/nsteps) */
+  const float* sd;  /* [K]   sqrt(dt) * dispersion(T - t_k) */
+  const float* lognorm; /* [K]  dv * log(2 pi sd_k^2), the Gaussian normaliser of the log-weight */
+} fbs_affine_model_t;
+
+/* One CSMC step (csmc.py:132-148 body) -- the per-timestep fused kernel, for large particle
+ * sets held in global memory.  us_prev [B, N, du], log_ws [B, N] (normalised) in;
+ * A_out [B, N], us_out [B, N, du], log_ws_out [B, N] out.  step_keys [B, 2] = keys[k] of csmc.py:157. */
+int fbs_csmc_step_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, int32_t k, int scheme,
+                             const uint32_t* step_keys, const float* us_prev, const float* log_ws,
+                             const float* v, const float* v_prev, const float* u_star, const int32_t* b_star_prev,
+                             const int32_t* b_star, int64_t B, int64_t N, int32_t* A_out, float* us_out,
+                             float* log_ws_out);
+
+/* The three closures of the reference drivers evaluated on their own, for callers that compose the
+ * samplers step by step (bootstrap filter / smoother, backward sampling):
+ *   us_out  [B,N,du] = transition_sampler(us_prev, v_prev, t_k, key)   gp_gibbs.py:120-122  (needs tr_keys [B,2])
+ *   lw_out  [B,N]    = likelihood_logpdf(v, us_prev, v_prev, t_k)      gp_gibbs.py:132-135  (needs v [B,dv])
+ *   tlp_out [B,N]    = transition_logpdf(u_eval, us_prev, v_prev, t_k) gp_gibbs.py:125-129  (needs u_eval [B,du])
+ * Any output may be NULL.  us_prev [B,N,du], v_prev [B,dv]. */
+int fbs_affine_eval_f32(fbs_stream_t s, const fbs_affine_model_t* model, int32_t k, const uint32_t* tr_keys,
+                        const float* us_prev, const float* v, const float* v_prev, const float* u_eval, int64_t B,
+                        int64_t N, float* us_out, float* lw_out, float* tlp_out);
+
+/* forward_pass(key, us_star, bs_star, vs, ts, init_sampler, init_likelihood_logpdf, transition_sampler,
+ *              likelihood_logpdf, cond_resampling, nsamples), csmc.py:80-164 -- the whole K-step sweep
+ * in one persistent kernel, particles resident on chip.
+ *   keys [B,2]; us_star [B,K+1,du]; bs_star [B,K+1]; vs [B,K+1,dv].
+ *   N = number of particles actually carried (nparticles for FBS_INIT_DEGENERATE, nparticles+1 for
+ *   FBS_INIT_NORMAL, finding 6d of SURVEY.md); init_log_w: the per-particle initial log-weight BEFORE
+ *   normalisation for FBS_INIT_DEGENERATE (reference: -log(nparticles), gibbs.py:144).
+ * History outputs (any may be NULL): As [B,K,N], log_wss [B,K+1,N], uss [B,K+1,N,du].
+ * Final-state outputs (any may be NULL): log_ws_last [B,N], us_last [B,N,du]. */
+int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* keys,
+                                const float* us_star, const int32_t* bs_star, const float* vs, int init_mode,
+                                float init_log_w, int scheme, int64_t B, int64_t N, int32_t* As, float* log_wss,
+                                float* uss, float* log_ws_last, float* us_last);
+
+/* backward_scanning_pass(key, As, xss, log_w_T), csmc.py:230-270: B_T ~ Cat(normalise(log_w_T)) (barker_move,
+ * :295-297), then ancestor tracing B_{t-1} = A_t[B_t].  keys [B,2] (key_bwd of csmc.py:65); As [B,K,N];
+ * uss [B,K+1,N,du]; log_w_T [B,N].  Out: xs_star [B,K+1,du], bs_star [B,K+1]. */
+int fbs_backward_scan_f32(fbs_stream_t s, const uint32_t* keys, const int32_t* As, const float* uss,
+                          const float* log_w_T, int64_t B, int64_t K, int64_t N, int64_t du, float* xs_star,
+                          int32_t* bs_star);
+
+/* pmcmc_filter_step(key, vs_bridge, u0s, ts, transition_sampler, likelihood_logpdf, resampling, nparticles),
+ * fbs/samplers/smc.py:115-158.  keys [B,2]; vs [B,K+1,dv]; u0s [B,N,du].
+ * Out: uT [B,N,du], log_ell [B].  Optional history (may be NULL): inds [B,K,N], log_ws_hist [B,K,N]
+ * (unnormalised log-weights of smc.py:144), us_hist [B,K,N,du]. */
+int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* keys,
+                                const float* vs, const float* u0s, int scheme, int64_t B, int64_t N, float* uT,
+                                float* log_ell, int32_t* inds, float* log_ws_hist, float* us_hist);
+
+/* force_move(key, weights, k), fbs/samplers/gibbs.py:171-214, fused with the selection
+ * x0 = uss[-1, idx] (gibbs.py:152-154).  log_ws_last [B,N]: normalised log-weights when weights_are_log != 0
+ * (the kernel exponentiates, as gibbs.py:152 does), else the weights themselves.
+ * us_last [B,N,du] (may be NULL when x0 is NULL); k [B].  Out: idx [B], alpha [B] (may be NULL), x0 [B,du] (may be NULL). */
+int fbs_force_move_f32(fbs_stream_t s, const uint32_t* keys, const float* log_ws_last, int weights_are_log,
+                       const float* us_last, const int32_t* k, int64_t B, int64_t N, int64_t du, int32_t* idx,
+                       float* alpha, float* x0);
+
+/* pcn_proposal(key, delta, x, mean, sampler) combination step, smc.py:161-168:
+ * out = beta * (x + sqrt(delta/2) (r0 - mean)) + (1 - beta) mean + sqrt(1 - beta) (r1 - mean),
+ * all [B, n] except mean [n] (shared).  */
+int fbs_pcn_combine_f32(fbs_stream_t s, double delta, const float* x, const float* mean, const float* r0,
+                        const float* r1, int64_t B, int64_t n, float* out);
+
+/* Metropolis--Hastings accept/select of pmcmc_kernel, smc.py:244-258.
+ * keys_mh [B,2]; in-place update of the chain state (uT [B,du], log_ell [B], ys [B,ny]) from the
+ * proposal (prop_uTs [B,N,du] -> particle which_u, prop_log_ell [B], prop_ys [B,ny]).
+ * Out: acceptance_prob [B], is_accepted [B] (uint8). */
+int fbs_mh_accept_f32(fbs_stream_t s, const uint32_t* keys_mh, const float* prop_uTs, const float* prop_log_ell,
+                      const float* prop_ys, int64_t B, int64_t N, int64_t du, int64_t ny, int32_t which_u, float* uT,
+                      float* log_ell, float* ys, float* acceptance_prob, uint8_t* is_accepted);
+
+/* ref_sampler(key, yT, n), experiments/toy/gp_gibbs.py:138-141: samples of the Gaussian conditional
+ * N(a + Bm (yT - c), L^T L):  out[b, n, :] = a + Bm (yT[b] - c) + eps[b, n, :] @ L,  eps = normal(key, (N, du)),
+ * with L = cholesky(cov) (lower, [du, du] row-major) exactly as gp_gibbs.py:141 multiplies it.
+ * a [du], Bm [du, dv] row-major, c [dv], yT [B, dv]. */
+int fbs_gaussian_ref_sample_f32(fbs_stream_t s, const uint32_t* keys, const float* yT, const float* a,
+                                const float* Bm, const float* c, const float* L, int64_t B, int64_t N, int64_t du,
+                                int64_t dv, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBS_B200_H_ */

@@ -1,0 +1,321 @@
+"""The fused sweep kernels vs the oracle.
+
+A particle system is chaotic: one ancestor index that differs changes everything downstream.  The
+sweep is therefore checked TEACHER-FORCED: the kernel returns its full history and every step k is
+re-derived by the oracle from the kernel's own state at k-1 (csmc.py:132-148 / smc.py:138-152), so
+each step is an independent parity check:
+  * ancestors: exact, except where the float32 weight the kernel exponentiated differs from
+    numpy's exp by an ULP (counted, must stay below 2e-4 of all draws);
+  * particles: rtol 1e-5 / atol 2e-5 against the float64 drift + the bit-pinned float32 noise;
+  * normalised log-weights: atol 2e-4.
+"""
+import numpy as np
+import pytest
+from oracle import jax_random as jr
+from oracle import cond_resampling as ocr
+from oracle import resampling as orx
+from oracle import csmc as ocsmc
+from oracle import gibbs as ogibbs
+from helpers import gp_problem, oracle_model, product_model
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL, LW_ATOL = 1e-5, 2e-5, 2e-4
+
+
+def _inputs(p, om, B, N, seed=0):
+    K, d = p['K'], p['d']
+    keys = jr.split(jr.PRNGKey(100 + seed), B)
+    us_star = np.zeros((B, K + 1, d), np.float32)
+    vs = np.zeros((B, K + 1, d), np.float32)
+    x0s = jr.normal(jr.PRNGKey(200 + seed), (B, d))
+    pk = jr.split(jr.PRNGKey(300 + seed), B)
+    for b in range(B):
+        path = om.fwd_sampler(pk[b], x0s[b], p['y0'])
+        us_star[b], vs[b] = path[::-1, :d], path[::-1, d:]
+    bs_star = np.stack([jr.randint(k, (K + 1,), 0, N) for k in jr.split(jr.PRNGKey(400 + seed), B)]).astype(np.int32)
+    return keys, us_star, bs_star, vs
+
+
+def _check_forward_history(p, om64, keys, us_star, bs_star, vs, As, log_wss, uss, scheme, init_normal):
+    K, d = p['K'], p['d']
+    B, N = As.shape[0], As.shape[2]
+    ts = om64.ts
+    resample = getattr(ocr, scheme)
+    mismatches = 0
+    for b in range(B):
+        key_init, key_scan = jr.split(keys[b], 2)
+        step_keys = jr.split(key_scan, K)
+        # initial particles / weights (csmc.py:150-155)
+        if init_normal:
+            u0 = jr.normal(key_init, (N, d))
+            u0[bs_star[b, 0]] = us_star[b, 0]
+            np.testing.assert_allclose(uss[b, 0], u0, rtol=0, atol=5e-7)
+            lw0 = ocsmc.normalise(om64.likelihood_logpdf(vs[b, 0].astype(np.float64), uss[b, 0].astype(np.float64),
+                                                         vs[b, 1].astype(np.float64), ts[0]), log_space=True)
+            np.testing.assert_allclose(log_wss[b, 0], lw0, atol=LW_ATOL)
+        else:
+            np.testing.assert_array_equal(uss[b, 0], np.broadcast_to(us_star[b, 0], (N, d)))
+            np.testing.assert_allclose(log_wss[b, 0], -np.log(N), atol=1e-6)
+        for k in range(K):
+            key_res, key_tr = jr.split(step_keys[k], 2)
+            w = np.exp(log_wss[b, k]).astype(np.float32)
+            A_or = resample(key_res, w, int(bs_star[b, k]), int(bs_star[b, k + 1]), True)
+            mismatches += int((A_or != As[b, k]).sum())
+            assert As[b, k, bs_star[b, k + 1]] == bs_star[b, k]                  # csmc.py:139 / resamplings.py:86
+            assert As[b, k].min() >= 0 and As[b, k].max() < N
+            parents = uss[b, k][As[b, k]].astype(np.float64)
+            mean = om64.transition_mean(parents, vs[b, k].astype(np.float64), ts[k])
+            want = mean + np.float64(om64.transition_sd(ts[k])) * jr.normal(key_tr, (N, d)).astype(np.float64)
+            want[bs_star[b, k + 1]] = us_star[b, k + 1]
+            np.testing.assert_allclose(uss[b, k + 1], want, rtol=RTOL, atol=ATOL, err_msg=f'particles b={b} k={k}')
+            np.testing.assert_array_equal(uss[b, k + 1, bs_star[b, k + 1]], us_star[b, k + 1])   # csmc.py:143
+            lw = ocsmc.normalise(om64.likelihood_logpdf(vs[b, k + 1].astype(np.float64), parents,
+                                                        vs[b, k].astype(np.float64), ts[k]), log_space=True)
+            np.testing.assert_allclose(log_wss[b, k + 1], lw, atol=LW_ATOL, err_msg=f'log-weights b={b} k={k}')
+    total = B * K * N
+    assert mismatches <= max(1, int(2e-4 * total)), f'{mismatches} ancestor mismatches out of {total}'
+    return mismatches
+
+
+@pytest.mark.parametrize('d,N,K,B', [(1, 10, 12, 5), (3, 7, 10, 9), (10, 10, 20, 14), (10, 100, 8, 3), (16, 33, 6, 2)])
+@pytest.mark.parametrize('scheme', ['killing', 'multinomial'])
+def test_forward_pass_teacher_forced(d, N, K, B, scheme):
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    p = gp_problem(d, K=K)
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N)
+    init = csmc.DegenerateInit(N)
+    As, log_wss, uss = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, getattr(R, scheme), N)
+    assert As.shape == (B, K, N) and log_wss.shape == (B, K + 1, N) and uss.shape == (B, K + 1, N, d)
+    _check_forward_history(p, om64, keys, us_star, bs_star, vs, As, log_wss, uss, scheme, False)
+    # normalised weights
+    np.testing.assert_allclose(np.log(np.exp(log_wss.astype(np.float64)).sum(-1)), 0., atol=1e-5)
+    # unbatched call == row of the batched call (vmap semantics)
+    A1, l1, u1 = csmc.forward_pass(keys[1], us_star[1], bs_star[1], vs[1], p['ts'], init.sampler,
+                                   init.likelihood_logpdf, pm.transition_sampler, pm.likelihood_logpdf,
+                                   getattr(R, scheme), N)
+    np.testing.assert_array_equal(A1, As[1]); np.testing.assert_array_equal(u1, uss[1]); np.testing.assert_array_equal(l1, log_wss[1])
+
+
+@pytest.mark.parametrize('d,N,K,B', [(2, 10, 10, 6), (10, 10, 12, 4)])
+def test_forward_pass_explicit_final(d, N, K, B):
+    """explicit_final=True: nparticles + 1 particles, N(0, I) start, likelihood weights with (v, v_prev) = (vs[0], vs[1])."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    p = gp_problem(d, K=K, sde_kind='lin')
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N + 1, seed=5)
+    init = csmc.NormalInit(pm)
+    As, log_wss, uss = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, R.killing, N)
+    assert As.shape == (B, K, N + 1)
+    _check_forward_history(p, om64, keys, us_star, bs_star, vs, As, log_wss, uss, 'killing', True)
+
+
+def test_forward_pass_vs_float32_reference_closures():
+    """Against the reference-faithful float32 closures (Cholesky solve per call, gp_gibbs.py:78-81) the
+    agreement is limited by THEIR float32 solve (cond(cov) ~ 1e3): rtol 2e-3 on the transition means."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    d, N, K, B = 10, 10, 10, 3
+    p = gp_problem(d, K=K)
+    om32 = oracle_model(p, np.float32)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N, seed=9)
+    init = csmc.DegenerateInit(N)
+    As, log_wss, uss = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, R.killing, N)
+    for b in range(B):
+        step_keys = jr.split(jr.split(keys[b], 2)[1], K)
+        for k in range(K):
+            _, key_tr = jr.split(step_keys[k], 2)
+            parents = uss[b, k][As[b, k]]
+            want = om32.transition_sampler(parents, vs[b, k], om32.ts[k], key_tr)
+            want[bs_star[b, k + 1]] = us_star[b, k + 1]
+            np.testing.assert_allclose(uss[b, k + 1], want, rtol=2e-3, atol=2e-3)
+
+
+def test_closures_match_oracle():
+    """The three closures on their own (gp_gibbs.py:120-135) against the float64 oracle."""
+    d, N = 10, 17
+    p = gp_problem(d, K=20)
+    om64 = oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    us = jr.normal(jr.PRNGKey(1), (N, d))
+    v, vp, u = jr.normal(jr.PRNGKey(2), (d,)), jr.normal(jr.PRNGKey(3), (d,)), jr.normal(jr.PRNGKey(4), (d,))
+    key = jr.PRNGKey(5)
+    for k in (0, 7, 19):
+        t = p['ts'][k]
+        got = pm.transition_sampler(us, vp, t, key)
+        want = om64.transition_mean(us.astype(np.float64), vp.astype(np.float64), om64.ts[k]) \
+            + np.float64(om64.transition_sd(om64.ts[k])) * jr.normal(key, (N, d))
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(pm.likelihood_logpdf(v, us, vp, t),
+                                   om64.likelihood_logpdf(v.astype(np.float64), us.astype(np.float64), vp.astype(np.float64), om64.ts[k]),
+                                   rtol=2e-5, atol=1e-3)
+        np.testing.assert_allclose(pm.transition_logpdf(u, us, vp, t),
+                                   om64.transition_logpdf(u.astype(np.float64), us.astype(np.float64), vp.astype(np.float64), om64.ts[k]),
+                                   rtol=2e-5, atol=1e-3)
+    with pytest.raises(ValueError):
+        pm.transition_sampler(us, vp, 0.123456, key)
+
+
+@pytest.mark.parametrize('d,N,K,B', [(1, 10, 10, 4), (10, 100, 10, 3), (10, 25, 16, 7)])
+@pytest.mark.parametrize('scheme', ['stratified', 'systematic', 'killing'])
+def test_pmcmc_filter_step_teacher_forced(d, N, K, B, scheme):
+    from fbs_b200.samplers import smc, resampling as R
+    p = gp_problem(d, K=K)
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, _, _, vs = _inputs(p, om32, B, N, seed=2)
+    u0s = np.stack([om32.ref_sampler(k, vs[b, 0], N) for b, k in enumerate(jr.split(jr.PRNGKey(55), B))])
+    uT, log_ell, inds, lwh, ush = smc.pmcmc_filter_step(keys, vs, u0s, p['ts'], pm.transition_sampler,
+                                                        pm.likelihood_logpdf, getattr(R, scheme), N,
+                                                        return_history=True)
+    ts = om64.ts
+    mism = 0
+    for b in range(B):
+        step_keys = jr.split(keys[b], K)
+        prev = u0s[b]
+        acc = np.float32(0.)
+        for k in range(K):
+            key_prop, key_res = jr.split(step_keys[k], 2)                         # smc.py:142
+            lw = om64.likelihood_logpdf(vs[b, k + 1].astype(np.float64), prev.astype(np.float64),
+                                        vs[b, k].astype(np.float64), ts[k])
+            np.testing.assert_allclose(lwh[b, k], lw, rtol=2e-5, atol=2e-3)
+            c = ocsmc.logsumexp(lwh[b, k])
+            acc = np.float32(np.float32(acc - np.float32(np.log(N))) + c)        # smc.py:146
+            w = np.exp(lwh[b, k] - c).astype(np.float32)
+            want_inds = getattr(orx, scheme)(w, key_res)
+            mism += int((want_inds != inds[b, k]).sum())
+            parents = prev[inds[b, k]].astype(np.float64)
+            want = om64.transition_mean(parents, vs[b, k].astype(np.float64), ts[k]) \
+                + np.float64(om64.transition_sd(ts[k])) * jr.normal(key_prop, (N, d))
+            np.testing.assert_allclose(ush[b, k], want, rtol=RTOL, atol=ATOL)
+            prev = ush[b, k]
+        np.testing.assert_allclose(log_ell[b], acc, rtol=1e-5, atol=1e-3)
+        np.testing.assert_array_equal(uT[b], ush[b, -1])
+    assert mism <= max(1, int(2e-4 * B * K * N)), mism
+
+
+def test_force_move_matches_oracle():
+    from fbs_b200.samplers import gibbs
+    rng = np.random.default_rng(3)
+    for N in (2, 10, 101):
+        B = 64
+        w = rng.random((B, N)).astype(np.float32) ** 2
+        w[0] = 0.; w[0, 1 % N] = 1.                      # degenerate: all mass on one particle
+        w = (w / w.sum(1, keepdims=True, dtype=np.float32)).astype(np.float32)
+        k = rng.integers(0, N, B).astype(np.int32)
+        k[0] = 1 % N                                       # w_k == 1 -> uniform fallback branch (gibbs.py:204-205)
+        keys = jr.split(jr.PRNGKey(N), B)
+        idx, alpha = gibbs.force_move(keys, w, k)
+        for b in range(B):
+            i_or, a_or = ogibbs.force_move(keys[b], w[b], int(k[b]))
+            assert idx[b] == i_or, (N, b)
+            np.testing.assert_allclose(alpha[b], a_or, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('explicit_final', [False, True])
+def test_gibbs_kernel_composition(explicit_final):
+    """gibbs_kernel (gibbs.py:68-168) piece by piece against the oracle under the same keys."""
+    from fbs_b200.samplers import gibbs_kernel
+    from fbs_b200.samplers.csmc import csmc
+    from fbs_b200.samplers.csmc.resamplings import killing
+    from fbs_b200 import random as fr
+    d, N, K, B = 4, 10, 15, 6
+    p = gp_problem(d, K=K)
+    om32 = oracle_model(p, np.float32)
+    pm, sde = product_model(p)
+    keys = jr.split(jr.PRNGKey(2024), B)
+    x0 = jr.normal(jr.PRNGKey(1), (B, d))
+    bs_star = np.stack([jr.randint(k, (K + 1,), 0, N) for k in jr.split(jr.PRNGKey(2), B)]).astype(np.int32)
+    x0n, usn, bsn, changed = gibbs_kernel(keys, x0, p['y0'], None, bs_star, p['ts'], pm.fwd_sampler, sde, pm.unpack, N,
+                                          pm.transition_sampler, pm.transition_logpdf, pm.likelihood_logpdf,
+                                          explicit_backward=True, explicit_final=explicit_final)
+    assert x0n.shape == (B, d) and usn.shape == (B, K + 1, d) and bsn.shape == (B, K + 1)
+    np.testing.assert_array_equal(x0n, usn[:, -1])                                # gibbs.py:167
+    np.testing.assert_array_equal(changed, bsn != bs_star)                        # gibbs.py:168
+    for b in range(B):
+        key_fwd, key_csmc, _ = jr.split(keys[b], 3)
+        k_fwd2, k_x0, k_us, k_bs = jr.split(key_csmc, 4)
+        np.testing.assert_array_equal(bsn[b], jr.randint(k_bs, (K + 1,), 0, N))  # gibbs.py:156
+        # forward noising + reversal (gibbs.py:127-130): the kernel's path is 1e-5-close to the oracle's ...
+        path = om32.fwd_sampler(key_fwd, x0[b], p['y0'])
+        us, vs = pm.fwd_sampler_reversed(key_fwd, x0[b], p['y0'])
+        np.testing.assert_allclose(us, path[::-1, :d], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(vs, path[::-1, d:], rtol=2e-5, atol=2e-6)
+        # ... and the sweep + forced move on that path reproduce x0 exactly (gibbs.py:148-154)
+        init = csmc.NormalInit(pm) if explicit_final else csmc.DegenerateInit(N)
+        r = csmc.forward_pass_device(k_fwd2, us, bs_star[b], vs, pm, init, killing.scheme, N, history=False)
+        lw_last, us_last = r['log_ws_last'][0].cpu().numpy(), r['us_last'][0].cpu().numpy()
+        idx, _ = ogibbs.force_move(k_x0, np.exp(lw_last).astype(np.float32), int(bs_star[b, -1]))   # gibbs.py:152
+        np.testing.assert_array_equal(x0n[b], us_last[idx])
+        want_us = om32.fwd_sampler(k_us, x0n[b], p['y0'])[::-1, :d]              # gibbs.py:155
+        np.testing.assert_allclose(usn[b], want_us, rtol=2e-5, atol=2e-6)
+
+
+def test_gibbs_kernel_generic_fwd_sampler_equals_fast_path():
+    """A user closure built from simulate_cond_forward + slicing gives the same sweep as the model's own sampler."""
+    from fbs_b200.samplers import gibbs_kernel
+    from fbs_b200 import sdes
+    import torch
+    d, N, K, B = 3, 10, 10, 5
+    p = gp_problem(d, K=K)
+    pm, sde = product_model(p)
+    _, _, sim = sdes.make_linear_sde(sde)
+    keys = jr.split(jr.PRNGKey(5), B)
+    x0 = jr.normal(jr.PRNGKey(6), (B, d))
+    bs = np.zeros((B, K + 1), np.int32)
+
+    def fwd_sampler(key_, x0_, y0_):
+        y = y0_.expand(x0_.shape[0], -1) if y0_.dim() == 2 and y0_.shape[0] == 1 else y0_
+        return sim(key_, torch.cat([x0_, y], dim=-1), p['ts'])
+
+    def unpack(xy):
+        return xy[..., :d], xy[..., d:]
+
+    a = gibbs_kernel(keys, x0, p['y0'], None, bs, p['ts'], fwd_sampler, sde, unpack, N, pm.transition_sampler,
+                     pm.transition_logpdf, pm.likelihood_logpdf)
+    b = gibbs_kernel(keys, x0, p['y0'], None, bs, p['ts'], pm.fwd_sampler, sde, pm.unpack, N, pm.transition_sampler,
+                     pm.transition_logpdf, pm.likelihood_logpdf)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+
+
+def test_opaque_closures_are_rejected():
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    p = gp_problem(2, K=4)
+    pm, _ = product_model(p)
+    init = csmc.DegenerateInit(4)
+    args = (jr.PRNGKey(0), np.zeros((5, 2), np.float32), np.zeros(5, np.int32), np.zeros((5, 2), np.float32), p['ts'],
+            init.sampler, init.likelihood_logpdf)
+    with pytest.raises(TypeError):
+        csmc.forward_pass(*args, lambda *a: None, pm.likelihood_logpdf, R.killing, 4)
+    with pytest.raises(TypeError):
+        csmc.forward_pass(*args, pm.transition_sampler, pm.likelihood_logpdf, lambda *a: None, 4)
+
+
+def test_csmc_kernel_backward_scanning():
+    """csmc_kernel(backward=False): ancestor tracing B_{t-1} = A_t[B_t] (csmc.py:260-264) against the oracle on
+    the kernel's own forward history."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    d, N, K, B = 3, 10, 12, 8
+    p = gp_problem(d, K=K)
+    om32 = oracle_model(p, np.float32)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N, seed=4)
+    init = csmc.DegenerateInit(N)
+    xs, bs = csmc.csmc_kernel(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                              pm.transition_sampler, pm.transition_logpdf, pm.likelihood_logpdf, R.killing, N,
+                              backward=False)
+    kf = np.stack([jr.split(k, 2)[0] for k in keys])
+    As, log_wss, uss = csmc.forward_pass(kf, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, R.killing, N)
+    for b in range(B):
+        key_bwd = jr.split(keys[b], 2)[1]
+        xs_or, bs_or = ocsmc.backward_scanning_pass(key_bwd, As[b], uss[b], log_wss[b, -1])
+        np.testing.assert_array_equal(bs[b], bs_or)
+        np.testing.assert_array_equal(xs[b], xs_or)
