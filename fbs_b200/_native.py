@@ -77,9 +77,23 @@ def lib():
     return _lib
 
 
+# name -> list of (start_event, end_event): filled when a caller asks for per-kernel device timing
+# (bench.py uses it to time the dominant kernel inside a whole step without a profiler).
+TIMED = {}
+
+
 def call(name, *args):
     handle = lib()
-    rc = getattr(handle, name)(*args)
+    rec = TIMED.get(name)
+    if rec is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(handle, name)(*args)
+        e1.record()
+        rec.append((e0, e1))
+    else:
+        rc = getattr(handle, name)(*args)
     if rc != 0:
         msg = handle.fbs_last_error().decode('utf-8', 'replace')
         cls = NotImplementedError if rc == 3 else (ValueError if rc == 1 else NativeError)

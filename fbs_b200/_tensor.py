@@ -28,7 +28,10 @@ def dev(x, dtype, device=None):
     if t.dtype != dtype:
         t = t.to(dtype)
     if not t.is_cuda:
-        t = t.pin_memory().to(device, non_blocking=True) if t.numel() > (1 << 16) else t.to(device)
+        if t.is_pinned():
+            t = t.to(device, non_blocking=True)
+        else:
+            t = t.to(device)
     return t.contiguous()
 
 
