@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Headline benchmark: CSMC particle-steps/s on BASELINE.json configs[1].
+
+Workload (config 2): the toy Gaussian pseudo-marginal MCMC of
+experiments/toy/gp_pmcmc.py scaled out -- d = du = dv = 100, K = 200 time steps, N = 100 particles,
+stratified resampling, pCN delta = 0.005, thousands of independent chains per GPU, chains partitioned
+over GPUs with no communication (weak scaling: chains per GPU fixed).
+
+One "step" = one pmcmc_kernel application to every chain (forward noising x2, pCN, reference draw, the
+K-step particle filter, MH accept).  particle-steps per step = chains * N * K.
+
+  value     device-resident: inputs live in HBM, CUDA-event timed, max over ranks
+  e2e       the same step through the public numpy-in/numpy-out API with pinned HOST buffers
+            (H2D of keys/state/paths and D2H of the results inside the timed region)
+  roofline  dominant kernel (sweep_affine_kernel) timed live with CUDA events around its launches
+  cpu_baseline / --impl reference: the oracle port of the same step on the host cores, bounded sample
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_TOY, K_STEPS, N_PART, DELTA = 100, 200, 100, 0.005
+ALG_BYTES_PER_PARTICLE_STEP = 8 * D_TOY + 16      # read parent + write child + weight + ancestor
+
+
+def gp_setup(d):
+    """experiments/toy/gp_pmcmc.py:28-54 (host, float64) + a synthetic observation y0."""
+    zs = np.linspace(0., 5., d)
+    cov = np.exp(-np.abs(zs[None, :] - zs[:, None]))
+    jm = np.zeros(2 * d)
+    jc = np.block([[cov, cov], [cov, cov + np.eye(d)]])
+    rng = np.random.default_rng(666)
+    y0 = (np.linalg.cholesky(cov) @ rng.standard_normal(d) + rng.standard_normal(d)).astype(np.float32)
+    return jm, jc, y0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def recorded_traffic():
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the same pMCMC step, one process per host core
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    seed, nchains, d, K, N = args
+    from oracle import jax_random as jr
+    from oracle import models as om, sdes as osd, smc as osmc, resampling as orx
+    jm, jc, y0 = gp_setup(d)
+    ts = np.linspace(0., 1., K + 1)
+    sde = osd.StationaryConstLinearSDE(a=-0.5, b=1.)
+    model = om.JointGaussianDiffusionModel(sde, jm, jc, d, ts, 1., dtype=np.float32)
+    key = jr.PRNGKey(seed)
+    t0 = time.perf_counter()
+    for c in range(nchains):
+        key, k_init, k_step = jr.split(key, 3)
+        ys = model.fwd_ys_sampler(k_init, y0)
+        osmc.pmcmc_kernel(k_step, np.zeros(d, np.float32), np.float32(0.), ys, y0, model.ts, model.fwd_ys_sampler, sde,
+                          model.ref_sampler, model.transition_sampler, model.likelihood_logpdf, orx.stratified, N,
+                          delta=DELTA)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(chains_per_core=1, d=D_TOY, K=K_STEPS, N=N_PART, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context('spawn')
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1000 + i, chains_per_core, d, K, N) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    nchains = cores * chains_per_core
+    return {'value': nchains * N * K / wall, 'unit': 'particle-steps/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{nchains} chains x 1 pMCMC step (d={d}, K={K}, N={N}) with the NumPy float32 oracle '
+                      f'(Cholesky-per-call closures as in gp_pmcmc.py), one process per core, {wall:.1f} s wall '
+                      f'incl. process start-up'}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_baseline(1)
+    base = None
+    for _ in range(min(steps, 3)):
+        base = cpu_baseline(2)
+        vals.append(base['value'])
+    v = float(np.mean(vals))
+    base['value'] = v
+    line = {'impl': 'reference', 'metric': 'CSMC particle-steps/sec (pMCMC step, toy Gaussian d=100)', 'value': v,
+            'unit': 'particle-steps/s', 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': 1,
+            'ms_per_step': 1e3 * (2 * base['cores'] * N_PART * K_STEPS) / v, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD_NAME, 'd': D_TOY, 'K': K_STEPS, 'N': N_PART, 'delta': DELTA,
+                       'note': 'JAX is not installable in this image: the reference arm is the oracle port on the host '
+                               'cores; each step is a bounded sample (two chains per core)'},
+            'cpu_baseline': base,
+            'e2e': {'value': v, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'wall_s': time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+WORKLOAD_NAME = ('configs[1]: toy Gaussian pseudo-marginal MCMC scaled out (experiments/toy/gp_pmcmc.py; d=100, K=200, '
+                 'N=100, stratified, pCN delta=0.005), independent chains partitioned over GPUs')
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import fbs_b200
+    from fbs_b200 import _native as nat, sdes, parallel
+    from fbs_b200 import random as fr
+    from fbs_b200.samplers import pmcmc_kernel, stratified
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    d, K, N, C = D_TOY, K_STEPS, N_PART, args.chains
+    jm, jc, y0 = gp_setup(d)
+    ts = np.linspace(0., 1., K + 1)
+    sde = sdes.StationaryConstLinearSDE(a=-0.5, b=1.)
+    model = fbs_b200.AffineGaussianModel.from_linear_sde(sde, jm, jc, d, ts, T=1.)
+    kw = dict(ts=ts, fwd_ys_sampler=model.fwd_ys_sampler, sde=sde, ref_sampler=model.ref_sampler,
+              transition_sampler=model.transition_sampler, likelihood_logpdf=model.likelihood_logpdf,
+              resampling=stratified, nparticles=N, delta=DELTA)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total_chains = world * C                      # weak scaling: C chains per GPU
+    master = fr.PRNGKey(2024)
+    k_init, k_run = parallel.threefry_split_host(master, 2)
+    init_keys = torch.from_numpy(parallel.chain_keys(k_init, total_chains, rank, world)).to(dev)
+    y0_d = torch.from_numpy(y0).to(dev)
+    # chain state resident in HBM: uT [C, du], log_ell [C], ys [C, K+1, dv]
+    ys = model.fwd_ys_sampler(init_keys, y0_d)
+    uT = torch.zeros((C, d), device=dev)
+    log_ell = torch.zeros((C,), device=dev)
+
+    run_keys = parallel.threefry_split_host(k_run, 1 << 14)
+
+    def step_keys(i):
+        return parallel.chain_keys(run_keys[i], total_chains, rank, world)
+
+    def one_step(i, state):
+        uT_, le_, ys_ = state
+        keys = torch.from_numpy(step_keys(i)).to(dev)
+        uT_, le_, ys_, st = pmcmc_kernel(keys, uT_, le_, ys_, y0_d, **kw)
+        return (uT_, le_, ys_), st
+
+    state = (uT, log_ell, ys)
+    for i in range(args.warmup):
+        state, st = one_step(i, state)
+    barrier()
+
+    # ---- device-resident timed region -------------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
+    nat.TIMED['fbs_pmcmc_filter_affine_f32'] = []
+    nat.reset_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        state, st = one_step(args.warmup + i, state)
+    ev1.record()
+    barrier()
+    launches = nat.launch_count()
+    ms_total = ev0.elapsed_time(ev1)
+    kern_ms = [a.elapsed_time(b) for a, b in nat.TIMED.pop('fbs_pmcmc_filter_affine_f32')]
+    clk = clocks.stop()
+    acc_rate = float(st.is_accepted.float().mean().item())
+
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    psteps_per_step = total_chains * N * K
+    value = psteps_per_step / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the host-buffer API ------------------------------------------------
+    h_state = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in state]
+    for h, x in zip(h_state, state):
+        h.copy_(x)
+    h_y0 = torch.from_numpy(y0).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+    h_keys = [torch.from_numpy(step_keys(10_000 + i)).pin_memory() for i in range(e2e_steps + 1)]
+    h2d = sum(x.numel() * x.element_size() for x in h_state) + h_keys[0].numel() * 4 + h_y0.numel() * 4
+
+    def e2e_step(i, hs):
+        o = pmcmc_kernel(h_keys[i], hs[0], hs[1], hs[2], h_y0, **kw)       # numpy out (D2H inside)
+        return o
+
+    o = e2e_step(e2e_steps, h_state)   # warm
+    d2h = sum(np.asarray(x).nbytes for x in o[:3]) + sum(np.asarray(x).nbytes for x in o[3])
+    barrier()
+    t0 = time.perf_counter()
+    hs = h_state
+    for i in range(e2e_steps):
+        o = e2e_step(i, hs)
+        hs = [torch.from_numpy(np.ascontiguousarray(x)) for x in o[:3]]
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = psteps_per_step / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k_ms = float(np.mean(kern_ms))
+        alg_bytes = C * N * K * ALG_BYTES_PER_PARTICLE_STEP            # per launch (this rank's chains)
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = recorded_traffic()
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(4)
+        line = {
+            'metric': 'CSMC particle-steps/sec (pMCMC step, toy Gaussian d=100)', 'value': value,
+            'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD_NAME, 'chains_per_gpu': C, 'total_chains': total_chains, 'd': d, 'K': K,
+                       'N': N, 'delta': DELTA, 'parallelism': f'chains x{world} (no collective on the data path)',
+                       'l2': 'inputs larger than L2: per-step chain state (ys, proposals) = '
+                             f'{3 * C * (K + 1) * d * 4 / 1e6:.0f} MB >> 126 MB',
+                       'mh_acceptance_rate_last_step': acc_rate},
+            'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms, 'steps': e2e_steps},
+            'gpu_launches': int(launches),
+            'clocks': clk,
+            'roofline': {'bound': 'hbm', 'kernel': 'sweep_affine_kernel (fbs_pmcmc_filter_affine_f32)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
+                         'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / ms_per_step,
+                         'algorithmic_bytes_per_particle_step': ALG_BYTES_PER_PARTICLE_STEP,
+                         'note': 'nominal HBM roofline of SURVEY 8(d); the persistent kernel keeps particles in shared '
+                                 'memory, so the binding resource is the FMA/ALU pipe (see DESIGN.md)'},
+            'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--chains', type=int, default=4096, help='chains per GPU (weak scaling)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()
