@@ -10,31 +10,14 @@
 //                pMCMC -> lw = LW; log_ell += logsumexp(lw) - log N; inds = resample(exp(lw - c))
 //   3. children: u'[n] = mean[A[n]] + sd * eps[n]   (in-kernel threefry normals), pin reference
 // Nothing but the optional history touches HBM inside the loop.
+#include <stdlib.h>
 #include "fbs_common.cuh"
 #include "fbs_resample.cuh"
+#include "fbs_sweep.cuh"
 
 namespace fbs {
 
-enum { MODE_CSMC = 0, MODE_PMCMC = 1 };
-
-struct SweepParams {
-  int K, du, dv;
-  const float *MT, *m, *dt, *sd, *lognorm;
-  const uint32_t* keys;
-  const float* us_star;
-  const int32_t* bs_star;
-  const float* vs;
-  const float* u0s;
-  int mode, init_mode, scheme;
-  float init_log_w;
-  int64_t B;
-  int N, G;
-  int32_t* As;
-  float *log_wss, *uss, *log_ws_last, *us_last;
-  float *uT, *log_ell;
-  int32_t* inds;
-  float *lw_hist, *us_hist;
-};
+// SweepParams, MODE_* : fbs_sweep.cuh
 
 constexpr int TI = 8;  // outputs per thread tile
 constexpr int TN = 4;  // particle rows per thread tile
@@ -456,6 +439,13 @@ __global__ void __launch_bounds__(1024, 1) sweep_affine_kernel(const SweepParams
 
 static int launch_sweep(fbs_stream_t s, SweepParams& p) {
   const int D = p.du + p.dv;
+  {
+    const char* impl = getenv("FBS_SWEEP_IMPL");
+    if (!(impl && impl[0] == 'v' && impl[1] == '1')) {
+      const int rc = launch_sweep_v2(s, p);
+      if (rc >= 0) return rc;  // ran (or failed loudly); -1 = shape not eligible -> general kernel below
+    }
+  }
   // chains per CTA: fill ~128 particle rows when N is small
   int G = 1;
   if (p.N < 64) G = (128 + p.N - 1) / p.N;
@@ -507,10 +497,16 @@ using namespace fbs;
 
 extern "C" {
 
+size_t fbs_sweep_workspace_bytes(const fbs_affine_model_t* model, int64_t B) {
+  if (!model || B <= 0) return 0;
+  return sweep_v2_workspace_bytes(B, model->K, model->du, model->dv);
+}
+
 int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* keys,
                                 const float* us_star, const int32_t* bs_star, const float* vs, int init_mode,
                                 float init_log_w, int scheme, int64_t B, int64_t N, int32_t* As, float* log_wss,
-                                float* uss, float* log_ws_last, float* us_last) {
+                                float* uss, float* log_ws_last, float* us_last, void* workspace,
+                                size_t workspace_bytes) {
   int rc = check_model(model);
   if (rc) return rc;
   FBS_REQUIRE(keys && us_star && bs_star && vs, "csmc_forward: null input");
@@ -526,12 +522,17 @@ int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
   p.mode = MODE_CSMC; p.init_mode = init_mode; p.scheme = scheme; p.init_log_w = init_log_w;
   p.B = B; p.N = (int)N;
   p.As = As; p.log_wss = log_wss; p.uss = uss; p.log_ws_last = log_ws_last; p.us_last = us_last;
+  if (model->MTp && workspace && workspace_bytes >= sweep_v2_workspace_bytes(B, p.K, p.du, p.dv)) {
+    p.MTp = model->MTp;
+    p.ws = static_cast<float*>(workspace);
+  }
   return launch_sweep(s, p);
 }
 
 int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* keys, const float* vs,
                                 const float* u0s, int scheme, int64_t B, int64_t N, float* uT, float* log_ell,
-                                int32_t* inds, float* log_ws_hist, float* us_hist) {
+                                int32_t* inds, float* log_ws_hist, float* us_hist, void* workspace,
+                                size_t workspace_bytes) {
   int rc = check_model(model);
   if (rc) return rc;
   FBS_REQUIRE(keys && vs && u0s, "pmcmc_filter: null input");
@@ -546,6 +547,10 @@ int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
   p.mode = MODE_PMCMC; p.scheme = scheme;
   p.B = B; p.N = (int)N;
   p.uT = uT; p.log_ell = log_ell; p.inds = inds; p.lw_hist = log_ws_hist; p.us_hist = us_hist;
+  if (model->MTp && workspace && workspace_bytes >= sweep_v2_workspace_bytes(B, p.K, p.du, p.dv)) {
+    p.MTp = model->MTp;
+    p.ws = static_cast<float*>(workspace);
+  }
   return launch_sweep(s, p);
 }
 

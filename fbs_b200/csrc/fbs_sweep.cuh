@@ -1,0 +1,38 @@
+// Parameters shared by the whole-sweep kernels (csmc_kernels.cu: general v1; sweep_v2.cu: tiled fast path).
+#pragma once
+#include <stdint.h>
+
+namespace fbs {
+
+enum { MODE_CSMC = 0, MODE_PMCMC = 1 };
+
+struct SweepParams {
+  int K, du, dv;
+  const float *MT, *m, *dt, *sd, *lognorm;
+  const uint32_t* keys;
+  const float* us_star;
+  const int32_t* bs_star;
+  const float* vs;
+  const float* u0s;
+  int mode, init_mode, scheme;
+  float init_log_w;
+  int64_t B;
+  int N, G;
+  int32_t* As;
+  float *log_wss, *uss, *log_ws_last, *us_last;
+  float *uT, *log_ell;
+  int32_t* inds;
+  float *lw_hist, *us_hist;
+  // v2 only: packed drift matrices [K][du][DP] (u-input rows; per row [u outputs dup | v outputs dvp], zero padded)
+  // and the per-chain step vectors precomputed into caller workspace [B][K+1][DP]
+  const float* MTp;
+  float* ws;
+  int dup, dvp;
+};
+
+
+// sweep_v2.cu.  Returns FBS_OK, an error, or -1 when the shape is not eligible for the fast path.
+int launch_sweep_v2(void* stream, SweepParams& p);
+size_t sweep_v2_workspace_bytes(int64_t B, int K, int du, int dv);
+
+}  // namespace fbs

@@ -1,0 +1,659 @@
+// Whole-sweep kernel, tiled fast path ("v2") for the affine-Gaussian model.
+//
+// Same algorithm and random streams as csmc_kernels.cu (csmc.py:80-164 / smc.py:115-158); what changes
+// is where the bytes live and who computes what:
+//   * the drift matrix of the step, M_k[:, :du] packed as [du][DP], is brought into shared memory by ONE
+//     elected thread with TMA bulk copies (cp.async.bulk + mbarrier), issued one step ahead, so the GEMM
+//     never waits on L2;
+//   * the per-chain step vectors (M_k[:, du:] v_prev + m_k and the v residual base) are precomputed for all
+//     K steps by a separate GEMM kernel into caller workspace -- they depend only on the inputs;
+//   * every thread owns a fixed 8-output x 8-particle register tile for the whole sweep (4 u + 4 v outputs;
+//     particles n..n+3 and n+N/2..n+N/2+3, the pairs that share threefry blocks), so there is no index
+//     arithmetic in the loop, the transition noise is generated in registers by the thread that consumes
+//     it, and both words of every threefry block are used;
+//   * the new particles overwrite the old in place (gather through registers), so one particle buffer.
+#include <stdlib.h>
+#include "fbs_common.cuh"
+#include "fbs_resample.cuh"
+#include "fbs_sweep.cuh"
+
+namespace fbs {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy (global -> shared)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+struct V2Layout {
+  int half, hp, RC, dup, dvp, DP, nti, rt_chain, ntr, ntiles;
+  size_t P, MTs, part, lw, w, cum, idx, tmp, keys, scal, bar, total;  // offsets in floats
+};
+
+__host__ __device__ inline V2Layout make_v2_layout(int G, int N, int du, int dv) {
+  V2Layout L;
+  L.half = N / 2;
+  L.hp = (L.half + 3) / 4 * 4;
+  L.RC = G * 2 * L.hp;
+  L.dup = (du + 3) / 4 * 4;
+  L.dvp = (dv + 3) / 4 * 4;
+  L.DP = L.dup + L.dvp;
+  L.nti = (L.dup > L.dvp ? L.dup : L.dvp) / 4;
+  L.rt_chain = L.hp / 4;
+  L.ntr = G * L.rt_chain;
+  L.ntiles = L.nti * L.ntr;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) {
+    size_t r = o;
+    o += (nfloats + 31) / 32 * 32;  // 128-byte granules
+    return r;
+  };
+  L.MTs = take((size_t)du * L.DP);
+  L.P = take((size_t)du * L.RC);
+  L.part = take((size_t)L.nti * L.RC);
+  L.lw = take((size_t)G * N);
+  L.w = take((size_t)G * N);
+  L.cum = take((size_t)G * (N + 1));
+  L.idx = take((size_t)G * N);
+  L.tmp = take((size_t)G * (N + 1));
+  L.keys = take((size_t)6 * G);
+  L.scal = take((size_t)G);
+  L.bar = take(4);
+  L.total = o;
+  return L;
+}
+
+size_t sweep_v2_workspace_bytes(int64_t B, int K, int du, int dv) {
+  const int DP = (du + 3) / 4 * 4 + (dv + 3) / 4 * 4;
+  return (size_t)B * (K + 1) * DP * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// step-vector precompute: ws[b][k][0:dup]   = m_k[:du] + M_k[:du, du:] v_prev            (drift offset of u)
+//                         ws[b][k][dup:DP]  = (v - v_prev) - dt_k (m_k[du:] + M_k[du:, du:] v_prev)   (residual base)
+// with (v, v_prev) = (vs[k+1], vs[k]) for k < K and the initial-weight slot k == K: coefficients of step 0,
+// (v, v_prev) = (vs[0], vs[1])  (gibbs.py:136-137 as called from csmc.py:154).
+// One CTA per (slot, 32 chains); thread i owns output i for the 32 chains.
+// ------------------------------------------------------------------------------------------------
+constexpr int CV_CH = 32;
+__global__ void __launch_bounds__(256) stepvec_kernel(const SweepParams p, int dup, int DP) {
+  extern __shared__ float sv[];  // [dv][CV_CH] v_prev ; [dv][CV_CH] v
+  const int du = p.du, dv = p.dv, D = du + dv, K = p.K;
+  const int slot = blockIdx.y;
+  const int k = slot < K ? slot : 0;
+  const int kv = slot < K ? slot + 1 : 0, kp = slot < K ? slot : 1;
+  const int64_t b0 = (int64_t)blockIdx.x * CV_CH;
+  const int nb = (int)min((int64_t)CV_CH, p.B - b0);
+  float* vp = sv;
+  float* vc = sv + (size_t)dv * CV_CH;
+  for (int t = threadIdx.x; t < dv * CV_CH; t += blockDim.x) {
+    const int c = t / dv, j = t - c * dv;
+    float a = 0.f, b = 0.f;
+    if (c < nb) {
+      a = p.vs[((size_t)(b0 + c) * (K + 1) + kp) * dv + j];
+      b = p.vs[((size_t)(b0 + c) * (K + 1) + kv) * dv + j];
+    }
+    vp[j * CV_CH + c] = a;
+    vc[j * CV_CH + c] = b;
+  }
+  __syncthreads();
+  const float* MTk = p.MT + (size_t)k * D * D + (size_t)du * D;  // rows du.. : inputs v
+  const float dt = p.dt[k];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float acc[CV_CH];
+#pragma unroll
+    for (int c = 0; c < CV_CH; ++c) acc[c] = 0.f;
+    for (int j = 0; j < dv; ++j) {
+      const float a = __ldg(MTk + (size_t)j * D + i);
+      const float4* v4 = reinterpret_cast<const float4*>(vp + j * CV_CH);
+#pragma unroll
+      for (int c4 = 0; c4 < CV_CH / 4; ++c4) {
+        const float4 x = v4[c4];
+        acc[4 * c4 + 0] = fmaf(a, x.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(a, x.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(a, x.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(a, x.w, acc[4 * c4 + 3]);
+      }
+    }
+    const float mi = p.m[(size_t)k * D + i];
+    const int col = i < du ? i : dup + (i - du);
+#pragma unroll
+    for (int c = 0; c < CV_CH; ++c) {
+      if (c < nb) {
+        float r = mi + acc[c];
+        if (i >= du) r = (vc[(i - du) * CV_CH + c] - vp[(i - du) * CV_CH + c]) - dt * r;
+        p.ws[((size_t)(b0 + c) * (K + 1) + slot) * DP + col] = r;
+      }
+    }
+  }
+  // zero the padding columns
+  for (int t = threadIdx.x; t < nb * (DP - D); t += blockDim.x) {
+    const int c = t / (DP - D), q = t - c * (DP - D);
+    const int col = q < dup - du ? du + q : dup + dv + (q - (dup - du));
+    p.ws[((size_t)(b0 + c) * (K + 1) + slot) * DP + col] = 0.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum_v2(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_normalise_v2(float* lw, int n, int lane) {
+  float m = -INFINITY;
+  for (int q = lane; q < n; q += 32) m = fmaxf(m, lw[q]);
+  m = warp_max(m);
+  if (!(fabsf(m) < INFINITY)) m = 0.f;
+  float s = 0.f;
+  for (int q = lane; q < n; q += 32) s += expf(lw[q] - m);
+  s = warp_sum_v2(s);
+  const float lse = logf(s) + m;
+  for (int q = lane; q < n; q += 32) lw[q] -= lse;
+  __syncwarp();
+  return lse;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) sweep_v2_kernel(const SweepParams p) {
+  extern __shared__ __align__(128) float sm[];
+  const V2Layout L = make_v2_layout(p.G, p.N, p.du, p.dv);
+  const int du = p.du, dv = p.dv, N = p.N, K = p.K, RC = L.RC, DP = L.DP, hp = L.hp, half = L.half, dup = L.dup;
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+  float* P = sm + L.P;
+  float* MTs = sm + L.MTs;
+  float* part = sm + L.part;
+  float* lw = sm + L.lw;
+  float* w = sm + L.w;
+  float* cum = sm + L.cum;
+  int* idx = reinterpret_cast<int*>(sm + L.idx);
+  int* tmp = reinterpret_cast<int*>(sm + L.tmp);
+  Key* kbase = reinterpret_cast<Key*>(sm + L.keys);
+  float* scal = sm + L.scal;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
+  const float logN = logf((float)N);
+  const uint32_t mt_bytes = (uint32_t)((size_t)du * DP * sizeof(float));
+
+  // ---- fixed tile ownership: row tile varies fastest across lanes (conflict-free P accesses, broadcast M) ----
+  const bool has_tile = tid < L.ntiles;
+  const int trg = has_tile ? tid % L.ntr : 0;
+  const int ti = has_tile ? tid / L.ntr : 0;
+  const int g = trg / L.rt_chain;
+  const int trl = trg - g * L.rt_chain;
+  const int col_lo = g * 2 * hp + 4 * trl;  // particles n0 .. n0+3
+  const int col_hi = col_lo + hp;           // particles half + n0 .. half + n0 + 3
+  const int n0 = 4 * trl;
+  const int uoff = min(4 * ti, dup - 4);
+  const int voff = dup + min(4 * ti, L.dvp - 4);
+  const bool u_tile = has_tile && 4 * ti < dup;
+  const bool v_tile = has_tile && 4 * ti < L.dvp;
+  const uint32_t nel = (uint32_t)N * du;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t mt_phase = 0;
+  auto wait_mt = [&]() {  // every issue_mt() opens one mbarrier phase; waits consume them in order
+    mbar_wait(bar, mt_phase);
+    mt_phase ^= 1u;
+  };
+
+  auto issue_mt = [&](int k) {  // one elected thread: TMA bulk copies of MTp[k] into shared memory
+    fence_proxy_async();
+    mbar_arrive_expect_tx(bar, mt_bytes);
+    const char* src = reinterpret_cast<const char*>(p.MTp + (size_t)k * du * DP);
+    char* dst = reinterpret_cast<char*>(MTs);
+    for (uint32_t off = 0; off < mt_bytes; off += 16384u) {
+      const uint32_t n = min(16384u, mt_bytes - off);
+      bulk_g2s(dst + off, src + off, n, bar);
+    }
+  };
+
+  for (int64_t chain0 = (int64_t)blockIdx.x * p.G; chain0 < p.B; chain0 += (int64_t)gridDim.x * p.G) {
+    const int nchains = (int)min((int64_t)p.G, p.B - chain0);
+    const bool live = has_tile && g < nchains;
+    const int64_t chain = chain0 + g;
+
+    // =============================== initialisation ===============================
+    if (tid == 0) issue_mt(0);
+    for (int t = tid; t < du * RC; t += NT) P[t] = 0.f;
+    if (tid < nchains) {
+      Key key{p.keys[2 * (chain0 + tid)], p.keys[2 * (chain0 + tid) + 1]};
+      if (p.mode == MODE_CSMC) {
+        Key key_init, key_scan;
+        split2(key, key_init, key_scan);  // csmc.py:150
+        kbase[tid] = key_scan;
+        kbase[2 * p.G + tid] = key_init;
+      } else {
+        kbase[tid] = key;
+      }
+      scal[tid] = 0.f;
+    }
+    __syncthreads();
+
+    // own-element I/O helpers -------------------------------------------------------------------
+    // particle index of tile row r (0..7): r < 4 -> n0 + r ; else half + n0 + r - 4 ; valid iff n0 + (r & 3) < half
+    auto load_own = [&](const float* src /* [N][du] of this chain */) {
+      if (!(live && u_tile)) return;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int nl = n0 + (r & 3);
+        if (nl >= half) continue;
+        const int n = r < 4 ? nl : half + nl;
+        const int col = (r < 4 ? col_lo : col_hi) + (r & 3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * ti + q < du) P[(size_t)(4 * ti + q) * RC + col] = src[(size_t)n * du + 4 * ti + q];
+      }
+    };
+    auto store_own = [&](float* dst /* [N][du] of this chain */) {
+      if (!(live && u_tile)) return;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int nl = n0 + (r & 3);
+        if (nl >= half) continue;
+        const int n = r < 4 ? nl : half + nl;
+        const int col = (r < 4 ? col_lo : col_hi) + (r & 3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * ti + q < du) dst[(size_t)n * du + 4 * ti + q] = P[(size_t)(4 * ti + q) * RC + col];
+      }
+    };
+
+    // the tile GEMM + epilogue:  P <- P + dt (M_uu P + cu)   (in place, own elements);  part <- partial residual sums
+    auto parents = [&](int k, int slot) {
+      float cu[4] = {0.f, 0.f, 0.f, 0.f}, cv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live) {  // issued before the GEMM, consumed after it: the L2 latency hides behind the FMAs
+        const float* wsrow = p.ws + ((size_t)chain * (K + 1) + slot) * DP;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(wsrow + uoff));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(wsrow + voff));
+        cu[0] = a.x; cu[1] = a.y; cu[2] = a.z; cu[3] = a.w;
+        cv[0] = b.x; cv[1] = b.y; cv[2] = b.z; cv[3] = b.w;
+      }
+      const float dt = p.dt[k];
+      float au[4][8], av[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) au[q][r] = av[q][r] = 0.f;
+      if (has_tile) {
+        const float* pl = P + col_lo;
+        const float* ph = P + col_hi;
+        const float* mu = MTs + uoff;
+        const float* mv = MTs + voff;
+#pragma unroll 2
+        for (int j = 0; j < du; ++j) {
+          const float4 xl = *reinterpret_cast<const float4*>(pl + (size_t)j * RC);
+          const float4 xh = *reinterpret_cast<const float4*>(ph + (size_t)j * RC);
+          const float4 a4 = *reinterpret_cast<const float4*>(mu + (size_t)j * DP);
+          const float4 b4 = *reinterpret_cast<const float4*>(mv + (size_t)j * DP);
+          const float x[8] = {xl.x, xl.y, xl.z, xl.w, xh.x, xh.y, xh.z, xh.w};
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              au[q][r] = fmaf(a[q], x[r], au[q][r]);
+              av[q][r] = fmaf(b[q], x[r], av[q][r]);
+            }
+        }
+      }
+      __syncthreads();  // every read of P and MTs by the GEMM is done
+      if (tid == 0 && k + 1 < K && slot < K) issue_mt(k + 1);  // next step's matrix lands during phases 2-3
+      if (has_tile) {
+        if (u_tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (4 * ti + q >= du) continue;
+            float* row = P + (size_t)(4 * ti + q) * RC;
+            float4 ol = *reinterpret_cast<float4*>(row + col_lo);
+            float4 oh = *reinterpret_cast<float4*>(row + col_hi);
+            ol.x += dt * (au[q][0] + cu[q]); ol.y += dt * (au[q][1] + cu[q]);
+            ol.z += dt * (au[q][2] + cu[q]); ol.w += dt * (au[q][3] + cu[q]);
+            oh.x += dt * (au[q][4] + cu[q]); oh.y += dt * (au[q][5] + cu[q]);
+            oh.z += dt * (au[q][6] + cu[q]); oh.w += dt * (au[q][7] + cu[q]);
+            *reinterpret_cast<float4*>(row + col_lo) = ol;
+            *reinterpret_cast<float4*>(row + col_hi) = oh;
+          }
+        }
+        float ss[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (v_tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (4 * ti + q >= dv) continue;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const float resid = cv[q] - dt * av[q][r];
+              ss[r] = fmaf(resid, resid, ss[r]);
+            }
+          }
+        }
+        float* prow = part + (size_t)ti * RC;
+        *reinterpret_cast<float4*>(prow + col_lo) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+        *reinterpret_cast<float4*>(prow + col_hi) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+      }
+      __syncthreads();
+    };
+
+    // LW[n] of chain gg into dst[n] (one warp)
+    auto reduce_lw = [&](int gg, int k, float* dst) {
+      const float sd = p.sd[k];
+      const float inv_s2 = 1.0f / (sd * sd), lognorm = p.lognorm[k];
+      for (int n = lane; n < N; n += 32) {
+        const int col = gg * 2 * hp + (n < half ? n : hp + (n - half));
+        float s = 0.f;
+        for (int t = 0; t < L.nti; ++t) s += part[(size_t)t * RC + col];
+        dst[n] = -0.5f * (s * inv_s2 + lognorm);
+      }
+      __syncwarp();
+    };
+
+    // transition noise of the tile in registers: element (n, i), n < half shares its threefry block with (n + half, i)
+    float nz[4][8];
+    auto make_noise = [&](Key ktr, float scale) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int n = n0 + s;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = 4 * ti + q;
+          uint32_t y0 = 0u, y1 = 0u;
+          if (n < half && i < du) random_bits_block(ktr, nel, (uint32_t)n * du + i, y0, y1);
+          nz[q][s] = scale * bits_to_normal(y0);
+          nz[q][4 + s] = scale * bits_to_normal(y1);
+        }
+      }
+    };
+
+    if (p.mode == MODE_PMCMC) {
+      load_own(p.u0s + (size_t)chain * N * du);
+    } else if (p.init_mode == FBS_INIT_DEGENERATE) {  // gibbs.py:140-144
+      if (live && u_tile) {
+        const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (4 * ti + q >= du) continue;
+          const float x = u0[4 * ti + q];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (n0 + (r & 3) < half) P[(size_t)(4 * ti + q) * RC + (r < 4 ? col_lo : col_hi) + (r & 3)] = x;
+        }
+      }
+      for (int t = tid; t < nchains * N; t += NT) lw[t] = p.init_log_w;
+    } else {  // gibbs.py:133-137
+      if (live && u_tile) {
+        make_noise(kbase[2 * p.G + g], 1.0f);
+        const int b0 = p.bs_star[(size_t)chain * (K + 1)];
+        const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (4 * ti + q >= du) continue;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int nl = n0 + (r & 3);
+            if (nl >= half) continue;
+            const int n = r < 4 ? nl : half + nl;
+            P[(size_t)(4 * ti + q) * RC + (r < 4 ? col_lo : col_hi) + (r & 3)] = (n == b0) ? u0[4 * ti + q] : nz[q][r];  // csmc.py:152
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (p.mode == MODE_CSMC) {
+      if (p.uss) store_own(p.uss + (size_t)chain * (K + 1) * N * du);
+      if (p.init_mode == FBS_INIT_NORMAL) {
+        // initial weights: likelihood with the step-0 coefficients and (v, v_prev) = (vs[0], vs[1])  -> workspace slot K.
+        // The in-place mean update of `parents` must not touch the particles here, so save and restore them.
+        float keep[4][8];
+        if (live && u_tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              keep[q][r] = P[(size_t)min(4 * ti + q, du - 1) * RC + (r < 4 ? col_lo : col_hi) + (r & 3)];
+        }
+        wait_mt();  // MT_0 landed (kept for step 0: slot K does not re-issue)
+        parents(0, K);
+        if (live && u_tile) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * ti + q < du)
+#pragma unroll
+              for (int r = 0; r < 8; ++r) P[(size_t)(4 * ti + q) * RC + (r < 4 ? col_lo : col_hi) + (r & 3)] = keep[q][r];
+        }
+        for (int gg = warp; gg < nchains; gg += nwarps) reduce_lw(gg, 0, lw + gg * N);
+        __syncthreads();
+      }
+      for (int gg = warp; gg < nchains; gg += nwarps) warp_normalise_v2(lw + gg * N, N, lane);  // csmc.py:155
+      __syncthreads();
+      if (p.log_wss)
+        for (int t = tid; t < nchains * N; t += NT) {
+          const int gg = t / N, n = t - gg * N;
+          p.log_wss[(size_t)(chain0 + gg) * (K + 1) * N + n] = lw[t];
+        }
+    }
+    const bool mt0_consumed = (p.mode == MODE_CSMC && p.init_mode == FBS_INIT_NORMAL);
+
+    // =============================== the K-step sweep ===============================
+    for (int k = 0; k < K; ++k) {
+      if (tid < nchains) {
+        const Key key_k = split_key(kbase[tid], (uint32_t)K, (uint32_t)k);  // csmc.py:157 / smc.py:154
+        Key a, b;
+        split2(key_k, a, b);
+        if (p.mode == MODE_CSMC) {  // csmc.py:136: (key_resampling, key_transition)
+          kbase[p.G + tid] = a;
+          kbase[2 * p.G + tid] = b;
+        } else {  // smc.py:142: (key_proposal, key_resampling)
+          kbase[2 * p.G + tid] = a;
+          kbase[p.G + tid] = b;
+        }
+      }
+      // 1. parents: wait for M_k (TMA), GEMM, in-place means, residual partial sums
+      if (!(k == 0 && mt0_consumed)) wait_mt();
+      parents(k, k);
+
+      // 2. weights + ancestors (one warp per chain) overlapped with the noise generation of the other warps
+      for (int gg = warp; gg < nchains; gg += nwarps) {
+        float* lwg = lw + gg * N;
+        float* wg = w + gg * N;
+        float* cumg = cum + gg * (N + 1);
+        int* idxg = idx + gg * N;
+        int* tmpg = tmp + gg * (N + 1);
+        const Key kres = kbase[p.G + gg];
+        if (p.mode == MODE_CSMC) {
+          for (int q = lane; q < N; q += 32) wg[q] = expf(lwg[q]);  // csmc.py:139
+          __syncwarp();
+          const int32_t* bs = p.bs_star + (size_t)(chain0 + gg) * (K + 1);
+          const int bi = bs[k], bj = bs[k + 1];
+          if (p.scheme == FBS_RESAMPLE_KILLING)
+            warp_cond_killing(kres, wg, N, bi, bj, true, cumg, tmpg, idxg, lane);
+          else
+            warp_cond_multinomial(kres, wg, N, bi, bj, true, cumg, idxg, lane);
+          reduce_lw(gg, k, wg);                                         // LW of every parent ...
+          for (int q = lane; q < N; q += 32) lwg[q] = wg[idxg[q]];      // ... gathered: csmc.py:145
+          __syncwarp();
+          warp_normalise_v2(lwg, N, lane);                              // csmc.py:146
+        } else {
+          reduce_lw(gg, k, lwg);                                        // smc.py:144
+          if (p.lw_hist)
+            for (int q = lane; q < N; q += 32) p.lw_hist[((size_t)(chain0 + gg) * K + k) * N + q] = lwg[q];
+          const float c = warp_normalise_v2(lwg, N, lane);              // smc.py:145,147
+          if (lane == 0) scal[gg] = (scal[gg] - logN) + c;              // smc.py:146
+          for (int q = lane; q < N; q += 32) wg[q] = expf(lwg[q]);
+          __syncwarp();
+          if (p.scheme == FBS_RESAMPLE_KILLING)
+            warp_cond_killing(kres, wg, N, 0, 0, false, cumg, tmpg, idxg, lane);
+          else if (p.scheme == FBS_RESAMPLE_MULTINOMIAL)
+            warp_sorted_multinomial(kres, wg, N, cumg, reinterpret_cast<float*>(tmpg), idxg, lane);
+          else
+            warp_systematic_or_stratified(kres, wg, N, p.scheme == FBS_RESAMPLE_SYSTEMATIC, true, cumg, idxg, lane);
+        }
+      }
+      if (live && u_tile) make_noise(kbase[2 * p.G + g], p.sd[k]);
+      __syncthreads();
+
+      // 3. children: gather the parent means through registers, add the noise, write in place, pin the reference
+      float val[4][8];
+      if (live && u_tile) {
+        int pc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int nl = n0 + (r & 3);
+          const int n = r < 4 ? nl : half + nl;
+          const int a = nl < half ? idx[g * N + n] : 0;
+          pc[r] = g * 2 * hp + (a < half ? a : hp + (a - half));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* row = P + (size_t)min(4 * ti + q, du - 1) * RC;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) val[q][r] = row[pc[r]] + nz[q][r];
+        }
+      }
+      __syncthreads();
+      if (live && u_tile) {
+        int bj = -1;
+        const float* ustar = nullptr;
+        if (p.mode == MODE_CSMC) {
+          bj = p.bs_star[(size_t)chain * (K + 1) + k + 1];
+          ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (4 * ti + q >= du) continue;
+          float* row = P + (size_t)(4 * ti + q) * RC;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int nl = n0 + (r & 3);
+            if (nl >= half) continue;
+            const int n = r < 4 ? nl : half + nl;
+            row[(r < 4 ? col_lo : col_hi) + (r & 3)] = (n == bj) ? ustar[4 * ti + q] : val[q][r];  // csmc.py:143
+          }
+        }
+      }
+      __syncthreads();
+
+      // optional history
+      if (p.mode == MODE_CSMC) {
+        if (p.As)
+          for (int t = tid; t < nchains * N; t += NT) {
+            const int gg = t / N, n = t - gg * N;
+            p.As[((size_t)(chain0 + gg) * K + k) * N + n] = idx[t];
+          }
+        if (p.log_wss)
+          for (int t = tid; t < nchains * N; t += NT) {
+            const int gg = t / N, n = t - gg * N;
+            p.log_wss[((size_t)(chain0 + gg) * (K + 1) + k + 1) * N + n] = lw[t];
+          }
+        if (p.uss) store_own(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du);
+      } else {
+        if (p.inds)
+          for (int t = tid; t < nchains * N; t += NT) {
+            const int gg = t / N, n = t - gg * N;
+            p.inds[((size_t)(chain0 + gg) * K + k) * N + n] = idx[t];
+          }
+        if (p.us_hist) store_own(p.us_hist + ((size_t)chain * K + k) * N * du);
+      }
+    }
+
+    // =============================== final state ===============================
+    if (p.mode == MODE_CSMC) {
+      if (p.us_last) store_own(p.us_last + (size_t)chain * N * du);
+      if (p.log_ws_last)
+        for (int t = tid; t < nchains * N; t += NT) p.log_ws_last[(size_t)chain0 * N + t] = lw[t];
+    } else {
+      if (p.uT) store_own(p.uT + (size_t)chain * N * du);
+      if (p.log_ell && tid < nchains) p.log_ell[chain0 + tid] = scal[tid];
+    }
+    __syncthreads();
+  }
+}
+
+template <int MAXT>
+static int launch_variant(cudaStream_t st, SweepParams& p, int grid, int threads, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_v2_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("sweep_v2: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+    return FBS_ERR_CUDA;
+  }
+  sweep_v2_kernel<MAXT><<<grid, threads, smem, st>>>(p);
+  return check_launch("sweep_v2_kernel");
+}
+
+int launch_sweep_v2(void* stream, SweepParams& p) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.MTp == nullptr || p.ws == nullptr) return -1;
+  if (p.N < 2 || (p.N & 1)) return -1;  // the threefry pairing needs an even particle count
+  const char* gforce = getenv("FBS_SWEEP_G");
+  // chains per CTA: as many as fit 384 threads (one 8x8 register tile each, <= 168 registers) and shared memory;
+  // FBS_SWEEP_G overrides (up to 704 threads) for experiments
+  const int max_tiles = gforce ? 704 : 384;
+  int bestG = 0;
+  V2Layout L{};
+  for (int G = 1; G <= 64; ++G) {
+    V2Layout c = make_v2_layout(G, p.N, p.du, p.dv);
+    if (c.ntiles > max_tiles || c.total * sizeof(float) > 225 * 1024) break;
+    if ((int64_t)G > p.B && bestG > 0) break;
+    bestG = G;
+    L = c;
+    if (gforce && G == atoi(gforce)) break;
+  }
+  if (bestG == 0) return -1;
+  p.G = bestG;
+  const size_t smem = L.total * sizeof(float);
+  int threads = (L.ntiles + 31) / 32 * 32;
+  if (threads < 64) threads = 64;
+  // step vectors for all slots
+  {
+    dim3 grid((unsigned)((p.B + CV_CH - 1) / CV_CH), (unsigned)(p.K + 1));
+    const size_t sm = (size_t)2 * p.dv * CV_CH * sizeof(float);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(stepvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    stepvec_kernel<<<grid, 256, sm, st>>>(p, L.dup, L.DP);
+    int rc = check_launch("stepvec_kernel");
+    if (rc) return rc;
+  }
+  p.dup = L.dup;
+  p.dvp = L.dvp;
+  int64_t groups = (p.B + p.G - 1) / p.G;
+  int64_t grid = groups < sm_count() ? groups : sm_count();
+  if (threads <= 384) return launch_variant<384>(st, p, (int)grid, threads, smem);
+  return launch_variant<704>(st, p, (int)grid, threads, smem);
+}
+
+}  // namespace fbs

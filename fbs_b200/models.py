@@ -55,8 +55,15 @@ class AffineGaussianModel:
             dt=np.full((self.K,), self.dt, dtype=np.float32),
             sd=sd32,
             lognorm=(self.dv * np.log(2. * np.pi * sd32.astype(np.float64) ** 2)).astype(np.float32))
+        # u-input rows re-packed for the tiled sweep kernel: [K][du][dup | dvp], zero padded (fbs_b200.h: MTp)
+        dup, dvp = (self.du + 3) // 4 * 4, (self.dv + 3) // 4 * 4
+        MTp = np.zeros((self.K, self.du, dup + dvp), dtype=np.float32)
+        MTp[:, :, :self.du] = self.host['MT'][:, :self.du, :self.du]
+        MTp[:, :, dup:dup + self.dv] = self.host['MT'][:, :self.du, self.du:]
+        self.host['MTp'] = MTp
         self._dev = None
         self._struct = None
+        self._ws = None
 
     # ---------------------------------------------------------------- construction helpers
     @classmethod
@@ -123,7 +130,7 @@ class AffineGaussianModel:
             self._dev = {k: dev(v, torch.float32) for k, v in self.host.items()}
             st = nat.AffineModelStruct()
             st.K, st.du, st.dv, st.reserved = self.K, self.du, self.dv, 0
-            for name in ('MT', 'm', 'dt', 'sd', 'lognorm'):
+            for name in ('MT', 'm', 'dt', 'sd', 'lognorm', 'MTp'):
                 setattr(st, name, self._dev[name].data_ptr())
             self._struct = st
         return self._dev
@@ -131,6 +138,14 @@ class AffineGaussianModel:
     def struct(self):
         self.device_arrays()
         return ctypes.byref(self._struct)
+
+    def workspace(self, B: int):
+        """(tensor, nbytes) scratch for the tiled sweep kernel: per-chain step vectors of all K steps."""
+        self.device_arrays()
+        nbytes = int(nat.lib().fbs_sweep_workspace_bytes(ctypes.byref(self._struct), int(B)))
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self._dev['MT'].device)
+        return self._ws, nbytes
 
     def step_index(self, t_prev) -> int:
         t = float(t_prev.item() if isinstance(t_prev, torch.Tensor) else t_prev)

@@ -87,8 +87,9 @@ def forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples
         uss = empty((B, K + 1, N, du), torch.float32)
     lw_last = empty((B, N), torch.float32)
     us_last = empty((B, N, du), torch.float32)
+    ws, ws_bytes = model.workspace(B)
     nat.call('fbs_csmc_forward_affine_f32', stream(), model.struct(), ptr(k), ptr(us), ptr(bs), ptr(v), init_mode,
-             init_log_w, scheme, B, N, ptr(As), ptr(log_wss), ptr(uss), ptr(lw_last), ptr(us_last))
+             init_log_w, scheme, B, N, ptr(As), ptr(log_wss), ptr(uss), ptr(lw_last), ptr(us_last), ptr(ws), ws_bytes)
     res.update(As=As, log_wss=log_wss, uss=uss, log_ws_last=lw_last, us_last=us_last)
     return res
 

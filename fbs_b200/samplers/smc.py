@@ -36,8 +36,9 @@ def pmcmc_filter_step(key, vs_bridge, u0s, ts, transition_sampler, likelihood_lo
         inds = empty((B, K, N), torch.int32)
         lwh = empty((B, K, N), torch.float32)
         ush = empty((B, K, N, model.du), torch.float32)
+    ws, ws_bytes = model.workspace(B)
     nat.call('fbs_pmcmc_filter_affine_f32', stream(), model.struct(), ptr(k), ptr(v), ptr(u0), scheme, B, N, ptr(uT),
-             ptr(log_ell), ptr(inds), ptr(lwh), ptr(ush))
+             ptr(log_ell), ptr(inds), ptr(lwh), ptr(ush), ptr(ws), ws_bytes)
     res = (uT, log_ell) + ((inds, lwh, ush) if return_history else ())
     if single:
         res = tuple(t[0] for t in res)

@@ -125,7 +125,15 @@ typedef struct {
   const float* dt;  /* [K]   the step the closures multiply the drift by (reference: constant T/nsteps) */
   const float* sd;  /* [K]   sqrt(dt) * dispersion(T - t_k) */
   const float* lognorm; /* [K]  dv * log(2 pi sd_k^2), the Gaussian normaliser of the log-weight */
+  const float* MTp; /* optional (may be NULL): [K, du, DP] the u-input rows of MT re-packed for the tiled sweep kernel:
+                       row j = [M_k[0:du, j] zero-padded to dup | M_k[du:D, j] zero-padded to dvp], dup/dvp = du/dv
+                       rounded up to 4, DP = dup + dvp.  Without it the sweeps use the general kernel. */
 } fbs_affine_model_t;
+
+/* Scratch the tiled sweep kernel needs for B chains (per-chain step vectors of all K steps); pass a device
+ * buffer of at least this many bytes as `workspace` to fbs_csmc_forward_affine_f32 / fbs_pmcmc_filter_affine_f32.
+ * With workspace == NULL (or too small) the general kernel runs instead. */
+size_t fbs_sweep_workspace_bytes(const fbs_affine_model_t* model, int64_t B);
 
 /* One CSMC step (csmc.py:132-148 body) -- the per-timestep fused kernel, for large particle
  * sets held in global memory.  us_prev [B, N, du], log_ws [B, N] (normalised) in;
@@ -158,7 +166,8 @@ int fbs_affine_eval_f32(fbs_stream_t s, const fbs_affine_model_t* model, int32_t
 int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* keys,
                                 const float* us_star, const int32_t* bs_star, const float* vs, int init_mode,
                                 float init_log_w, int scheme, int64_t B, int64_t N, int32_t* As, float* log_wss,
-                                float* uss, float* log_ws_last, float* us_last);
+                                float* uss, float* log_ws_last, float* us_last, void* workspace,
+                                size_t workspace_bytes);
 
 /* backward_scanning_pass(key, As, xss, log_w_T), csmc.py:230-270: B_T ~ Cat(normalise(log_w_T)) (barker_move,
  * :295-297), then ancestor tracing B_{t-1} = A_t[B_t].  keys [B,2] (key_bwd of csmc.py:65); As [B,K,N];
@@ -173,7 +182,8 @@ int fbs_backward_scan_f32(fbs_stream_t s, const uint32_t* keys, const int32_t* A
  * (unnormalised log-weights of smc.py:144), us_hist [B,K,N,du]. */
 int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* keys,
                                 const float* vs, const float* u0s, int scheme, int64_t B, int64_t N, float* uT,
-                                float* log_ell, int32_t* inds, float* log_ws_hist, float* us_hist);
+                                float* log_ell, int32_t* inds, float* log_ws_hist, float* us_hist, void* workspace,
+                                size_t workspace_bytes);
 
 /* force_move(key, weights, k), fbs/samplers/gibbs.py:171-214, fused with the selection
  * x0 = uss[-1, idx] (gibbs.py:152-154).  log_ws_last [B,N]: normalised log-weights when weights_are_log != 0
