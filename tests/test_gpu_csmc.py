@@ -343,3 +343,49 @@ def test_general_and_tiled_sweep_kernels_agree(d, N, K, B, monkeypatch):
     np.testing.assert_allclose(u1[:, 1], u2[:, 1], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(l1[:, 1], l2[:, 1], atol=1e-4)
     assert (A1 == A2).mean() > 0.99
+
+
+@pytest.mark.parametrize('delta', [None, 0.3])
+def test_pmcmc_kernel_composition(delta):
+    """pmcmc_kernel (smc.py:171-258) piece by piece against the oracle under the same keys: proposal path (fresh or
+    pCN), reference draw, filter, Metropolis--Hastings decision and state selection."""
+    from fbs_b200.samplers import pmcmc_kernel, pmcmc_filter_step, stratified
+    from oracle import smc as osmc
+    d, N, K, B = 3, 16, 12, 24
+    p = gp_problem(d, K=K)
+    om32 = oracle_model(p, np.float32)
+    pm, sde = product_model(p)
+    keys = jr.split(jr.PRNGKey(77), B)
+    uT = jr.normal(jr.PRNGKey(1), (B, d))
+    ys = np.stack([om32.fwd_ys_sampler(k, p['y0']) for k in jr.split(jr.PRNGKey(2), B)])
+    # half the chains start from a huge log_ell (always reject), half from a tiny one (always accept), rest in between
+    log_ell = np.concatenate([np.full(B // 3, 1e30), np.full(B // 3, -1e30), np.zeros(B - 2 * (B // 3))]).astype(np.float32)
+    uT2, le2, ys2, st = pmcmc_kernel(keys, uT, log_ell, ys, p['y0'], p['ts'], pm.fwd_ys_sampler, sde, pm.ref_sampler,
+                                     pm.transition_sampler, pm.likelihood_logpdf, stratified, N, delta=delta)
+    for b in range(B):
+        key_prop, key_u0, key_filter, key_mh = jr.split(keys[b], 4)
+        if delta is None:
+            prop_ys = om32.fwd_ys_sampler(key_prop, p['y0'])
+        else:
+            mean = np.stack([om32.sde.mean(t, om32.ts[0], p['y0']) for t in om32.ts]).astype(np.float32)
+            prop_ys = osmc.pcn_proposal(key_prop, delta, ys[b], mean, lambda k_: om32.fwd_ys_sampler(k_, p['y0']))
+        vs = prop_ys[::-1]
+        u0s = om32.ref_sampler(key_u0, vs[0], N)
+        # the filter is chaotic w.r.t. 1e-6 input differences, so run OUR filter on the oracle's inputs for the evidence
+        puT, ple = pmcmc_filter_step(key_filter, vs.copy(), u0s, p['ts'], pm.transition_sampler, pm.likelihood_logpdf,
+                                     stratified, N)
+        np.testing.assert_allclose(st.prop_log_ell[b], ple, rtol=2e-4, atol=2e-2)
+        z = jr.uniform(key_mh, ())
+        log_acc = min(0., float(st.prop_log_ell[b]) - float(log_ell[b]))
+        acc = bool(np.log(z) < log_acc)
+        assert bool(st.is_accepted[b]) == acc
+        np.testing.assert_allclose(st.acceptance_prob[b], np.exp(log_acc), rtol=1e-5, atol=1e-30)
+        assert st.log_ell[b] == log_ell[b]
+        if acc:
+            np.testing.assert_allclose(ys2[b], prop_ys, rtol=2e-5, atol=2e-5)
+            assert le2[b] == st.prop_log_ell[b]
+        else:
+            np.testing.assert_array_equal(ys2[b], ys[b])
+            np.testing.assert_array_equal(uT2[b], uT[b])
+            assert le2[b] == log_ell[b]
+    assert 0 < st.is_accepted.sum() < B
