@@ -22,7 +22,7 @@ _int = C.c_int
 
 class AffineModelStruct(C.Structure):
     _fields_ = [('K', _i32), ('du', _i32), ('dv', _i32), ('reserved', _i32),
-                ('MT', _p), ('m', _p), ('dt', _p), ('sd', _p), ('lognorm', _p), ('MTp', _p)]
+                ('MT', _p), ('m', _p), ('dt', _p), ('sd', _p), ('lognorm', _p), ('MTp', _p), ('MTc', _p)]
 
 
 _M = C.POINTER(AffineModelStruct)
@@ -45,6 +45,7 @@ SIGNATURES = {
     'fbs_em_affine_path_f32': ([_p, _p, _p, _int, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p, _p], _int),
     'fbs_csmc_step_affine_f32': ([_p, _M, _i32, _int, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p], _int),
     'fbs_affine_eval_f32': ([_p, _M, _i32, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p], _int),
+    'fbs_debug_umma_gemm': ([_p, _p, _p, _i32, _i32, _p], _int),
     'fbs_sweep_workspace_bytes': ([_M, _i64], C.c_size_t),
     'fbs_csmc_forward_affine_f32': ([_p, _M, _p, _p, _p, _p, _int, _f32, _int, _i64, _i64, _p, _p, _p, _p, _p, _p,
                                      C.c_size_t], _int),

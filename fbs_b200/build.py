@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_DIR = os.path.join(_HERE, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libfbs_b200.so')
-SOURCES = ['random_kernels.cu', 'resample_kernels.cu', 'sde_kernels.cu', 'csmc_kernels.cu', 'sweep_v2.cu', 'step_kernels.cu']
+SOURCES = ['random_kernels.cu', 'resample_kernels.cu', 'sde_kernels.cu', 'csmc_kernels.cu', 'sweep_v2.cu', 'sweep_v3.cu', 'step_kernels.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -441,9 +441,16 @@ static int launch_sweep(fbs_stream_t s, SweepParams& p) {
   const int D = p.du + p.dv;
   {
     const char* impl = getenv("FBS_SWEEP_IMPL");
-    if (!(impl && impl[0] == 'v' && impl[1] == '1')) {
+    // preference: tcgen05 kernel (v3) -> tiled CUDA-core kernel (v2) -> general kernel (v1); each returns -1 when the
+    // shape is not eligible.  FBS_SWEEP_IMPL = v1 | v2 | v3 pins the choice (tests / A-B measurements).
+    const bool only1 = impl && impl[1] == '1', only2 = impl && impl[1] == '2';
+    if (!only1 && !only2) {
+      const int rc = launch_sweep_v3(s, p);
+      if (rc >= 0) return rc;
+    }
+    if (!only1) {
       const int rc = launch_sweep_v2(s, p);
-      if (rc >= 0) return rc;  // ran (or failed loudly); -1 = shape not eligible -> general kernel below
+      if (rc >= 0) return rc;
     }
   }
   // chains per CTA: fill ~128 particle rows when N is small
@@ -497,6 +504,10 @@ using namespace fbs;
 
 extern "C" {
 
+int fbs_debug_umma_gemm(fbs_stream_t s, const float* A, const float* Bimg, int32_t K8, int32_t nout, float* D) {
+  return launch_umma_selftest(s, A, Bimg, K8, nout, D);
+}
+
 size_t fbs_sweep_workspace_bytes(const fbs_affine_model_t* model, int64_t B) {
   if (!model || B <= 0) return 0;
   return sweep_v2_workspace_bytes(B, model->K, model->du, model->dv);
@@ -524,6 +535,7 @@ int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
   p.As = As; p.log_wss = log_wss; p.uss = uss; p.log_ws_last = log_ws_last; p.us_last = us_last;
   if (model->MTp && workspace && workspace_bytes >= sweep_v2_workspace_bytes(B, p.K, p.du, p.dv)) {
     p.MTp = model->MTp;
+    p.MTc = model->MTc;
     p.ws = static_cast<float*>(workspace);
   }
   return launch_sweep(s, p);
@@ -549,6 +561,7 @@ int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
   p.uT = uT; p.log_ell = log_ell; p.inds = inds; p.lw_hist = log_ws_hist; p.us_hist = us_hist;
   if (model->MTp && workspace && workspace_bytes >= sweep_v2_workspace_bytes(B, p.K, p.du, p.dv)) {
     p.MTp = model->MTp;
+    p.MTc = model->MTc;
     p.ws = static_cast<float*>(workspace);
   }
   return launch_sweep(s, p);

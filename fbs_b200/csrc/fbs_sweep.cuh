@@ -28,11 +28,18 @@ struct SweepParams {
   const float* MTp;
   float* ws;
   int dup, dvp;
+  // v3 only: tensor-core image of the step matrices (fbs_b200.h: MTc)
+  const float* MTc;
 };
 
 
 // sweep_v2.cu.  Returns FBS_OK, an error, or -1 when the shape is not eligible for the fast path.
 int launch_sweep_v2(void* stream, SweepParams& p);
+// sweep_v3.cu (tcgen05).  Same return convention.
+int launch_sweep_v3(void* stream, SweepParams& p);
+int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8, int nout, float* D);
+// fills p.ws with the per-chain step vectors of all K + 1 slots (sweep_v2.cu)
+int launch_stepvec(void* stream, SweepParams& p);
 size_t sweep_v2_workspace_bytes(int64_t B, int K, int du, int dv);
 
 }  // namespace fbs

@@ -616,6 +616,16 @@ static int launch_variant(cudaStream_t st, SweepParams& p, int grid, int threads
   return check_launch("sweep_v2_kernel");
 }
 
+int launch_stepvec(void* stream, SweepParams& p) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int dup = (p.du + 3) / 4 * 4, DP = dup + (p.dv + 3) / 4 * 4;
+  dim3 grid((unsigned)((p.B + CV_CH - 1) / CV_CH), (unsigned)(p.K + 1));
+  const size_t sm = (size_t)2 * p.dv * CV_CH * sizeof(float);
+  if (sm > 48 * 1024) cudaFuncSetAttribute(stepvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  stepvec_kernel<<<grid, 256, sm, st>>>(p, dup, DP);
+  return check_launch("stepvec_kernel");
+}
+
 int launch_sweep_v2(void* stream, SweepParams& p) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p.MTp == nullptr || p.ws == nullptr) return -1;
@@ -639,13 +649,8 @@ int launch_sweep_v2(void* stream, SweepParams& p) {
   const size_t smem = L.total * sizeof(float);
   int threads = (L.ntiles + 31) / 32 * 32;
   if (threads < 64) threads = 64;
-  // step vectors for all slots
   {
-    dim3 grid((unsigned)((p.B + CV_CH - 1) / CV_CH), (unsigned)(p.K + 1));
-    const size_t sm = (size_t)2 * p.dv * CV_CH * sizeof(float);
-    if (sm > 48 * 1024) cudaFuncSetAttribute(stepvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    stepvec_kernel<<<grid, 256, sm, st>>>(p, L.dup, L.DP);
-    int rc = check_launch("stepvec_kernel");
+    const int rc = launch_stepvec(stream, p);
     if (rc) return rc;
   }
   p.dup = L.dup;

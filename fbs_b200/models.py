@@ -21,6 +21,37 @@ from .sdes.linear import LinearSDE, step_coefficients, forward_path
 from .sdes.simulators import em_tables, em_path
 
 
+def tf32_round(x):
+    """float32 -> nearest tf32 (10-bit mantissa), ties away from zero: what ``cvt.rna.tf32.f32`` computes."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def pack_umma_image(Mu, du, dv):
+    """Tensor-core image of the step matrices (include/fbs_b200.h: ``MTc``).
+
+    ``Mu [K, D, du]``: rows = outputs (u then v), columns = u inputs.  Returns float32
+    ``[K, nkb, 2, 2, nout // 8, 8, 4]`` -- per step and 8-input K-block: (hi | lo) x 2 k-chunks x 8-row x 16-byte core
+    matrices, the no-swizzle K-major layout a UMMA shared-memory descriptor with LBO = nout/8 * 128, SBO = 128 reads.
+    """
+    K = Mu.shape[0]
+    du8, dv8 = (du + 7) // 8 * 8, (dv + 7) // 8 * 8
+    nout = du8 + dv8
+    if nout % 16:
+        nout += 8
+    B = np.zeros((K, nout, du8), dtype=np.float32)
+    B[:, :du, :du] = Mu[:, :du, :]
+    B[:, du8:du8 + dv, :du] = Mu[:, du:, :]
+    hi = tf32_round(B)
+    lo = (B - hi).astype(np.float32)
+    nkb = du8 // 8
+    img = np.empty((K, nkb, 2, 2, nout // 8, 8, 4), dtype=np.float32)
+    for part, X in enumerate((hi, lo)):
+        # X[k, o, j] with o = rg * 8 + r8, j = kb * 8 + c * 4 + kk  ->  img[k, kb, part, c, rg, r8, kk]
+        img[:, :, part] = X.reshape(K, nout // 8, 8, nkb, 2, 4).transpose(0, 3, 4, 1, 2, 5)
+    return img
+
+
 def _host64(x):
     if isinstance(x, torch.Tensor):
         x = x.detach().cpu().numpy()
@@ -61,6 +92,10 @@ class AffineGaussianModel:
         MTp[:, :, :self.du] = self.host['MT'][:, :self.du, :self.du]
         MTp[:, :, dup:dup + self.dv] = self.host['MT'][:, :self.du, self.du:]
         self.host['MTp'] = MTp
+        # tensor-core image for the tcgen05 sweep kernel (only when the GEMM fits one UMMA tile: nout <= 256)
+        du8, dv8 = (self.du + 7) // 8 * 8, (self.dv + 7) // 8 * 8
+        if du8 + dv8 + 8 <= 256 + 8 and self.du % 4 == 0:
+            self.host['MTc'] = pack_umma_image(np.ascontiguousarray(M[:, :, :self.du]).astype(np.float32), self.du, self.dv)
         self._dev = None
         self._struct = None
         self._ws = None
@@ -132,6 +167,7 @@ class AffineGaussianModel:
             st.K, st.du, st.dv, st.reserved = self.K, self.du, self.dv, 0
             for name in ('MT', 'm', 'dt', 'sd', 'lognorm', 'MTp'):
                 setattr(st, name, self._dev[name].data_ptr())
+            st.MTc = self._dev['MTc'].data_ptr() if 'MTc' in self._dev else None
             self._struct = st
         return self._dev
 

@@ -128,7 +128,16 @@ typedef struct {
   const float* MTp; /* optional (may be NULL): [K, du, DP] the u-input rows of MT re-packed for the tiled sweep kernel:
                        row j = [M_k[0:du, j] zero-padded to dup | M_k[du:D, j] zero-padded to dvp], dup/dvp = du/dv
                        rounded up to 4, DP = dup + dvp.  Without it the sweeps use the general kernel. */
+  const float* MTc; /* optional (may be NULL): tensor-core image of the same rows for the tcgen05 sweep kernel,
+                       [K, nkb, 2 (hi, lo), 2 (k-chunks), nout/8, 8, 4] float32: for step k and K-block kb (8 inputs j),
+                       the UMMA K-major core-matrix layout of B[o][j] = M_k[row(o)][j], o < du8: u output o,
+                       o >= du8: v output o - du8 (du8/dv8 = du/dv rounded up to 8, nout = du8 + dv8 rounded up to 16),
+                       split into hi = tf32-rounded value and lo = float32 remainder. */
 } fbs_affine_model_t;
+
+/* Test hook for the tcgen05 plumbing: D [128, nout] = A [128, K8] * B^T with the split-TF32 scheme of the sweep
+ * kernel; Bimg is ONE step of the MTc image (nkb = K8 / 8 blocks). */
+int fbs_debug_umma_gemm(fbs_stream_t s, const float* A, const float* Bimg, int32_t K8, int32_t nout, float* D);
 
 /* Scratch the tiled sweep kernel needs for B chains (per-chain step vectors of all K steps); pass a device
  * buffer of at least this many bytes as `workspace` to fbs_csmc_forward_affine_f32 / fbs_pmcmc_filter_affine_f32.
