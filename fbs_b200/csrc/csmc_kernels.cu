@@ -444,14 +444,18 @@ static int launch_sweep(fbs_stream_t s, SweepParams& p) {
     // preference: tcgen05 kernel (v3) -> tiled CUDA-core kernel (v2) -> general kernel (v1); each returns -1 when the
     // shape is not eligible.  FBS_SWEEP_IMPL = v1 | v2 | v3 pins the choice (tests / A-B measurements).
     const bool only1 = impl && impl[1] == '1', only2 = impl && impl[1] == '2';
+    const bool verbose = getenv("FBS_SWEEP_VERBOSE") != nullptr;
     if (!only1 && !only2) {
       const int rc = launch_sweep_v3(s, p);
+      if (verbose) fprintf(stderr, "[fbs] sweep v3 (tcgen05) -> %d\n", rc);
       if (rc >= 0) return rc;
     }
     if (!only1) {
       const int rc = launch_sweep_v2(s, p);
+      if (verbose) fprintf(stderr, "[fbs] sweep v2 (tiled) -> %d\n", rc);
       if (rc >= 0) return rc;
     }
+    if (verbose) fprintf(stderr, "[fbs] sweep v1 (general)\n");
   }
   // chains per CTA: fill ~128 particle rows when N is small
   int G = 1;

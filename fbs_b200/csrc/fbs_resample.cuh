@@ -21,7 +21,21 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float warp_seq_cumsum(const float* w, float* cum, int n, int lane) {
   float acc = 0.f;
   if (lane == 0) {
-    for (int i = 0; i < n; ++i) {
+    // batches of 8: independent loads first, then the dependent FADD chain (the only serial part), then stores
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+      float x[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) x[q] = w[i + q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        acc = __fadd_rn(acc, x[q]);
+        x[q] = acc;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cum[i + q] = x[q];
+    }
+    for (; i < n; ++i) {
       acc = __fadd_rn(acc, w[i]);
       cum[i] = acc;
     }
@@ -79,20 +93,23 @@ __device__ __forceinline__ void warp_cond_killing(Key key, const float* w, int n
   // J_prob = (1 - w / w_max) / N, J_prob[i] = max(1 - sum(J_prob with J_prob[i] = 0), 0)   (:79-82)
   const float fn = (float)n;
   float acc = 0.f;
+  // J_prob computed in parallel into cum[], then two sequential passes by lane 0 (sum, cumulative sum)
+  for (int q = lane; q < n; q += 32) cum[q] = (q == i) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(w[q], w_max)), fn);
+  __syncwarp();
   if (lane == 0) {
-    for (int q = 0; q < n; ++q) {
-      float jp = (q == i) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(w[q], w_max)), fn);
-      acc = __fadd_rn(acc, jp);
+    int q = 0;
+    for (; q + 8 <= n; q += 8) {
+      float x[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) x[t] = cum[q + t];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, x[t]);
     }
-    const float jp_i = fmaxf(__fsub_rn(1.0f, acc), 0.f);
-    acc = 0.f;
-    for (int q = 0; q < n; ++q) {
-      float jp = (q == i) ? jp_i : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(w[q], w_max)), fn);
-      acc = __fadd_rn(acc, jp);
-      cum[q] = acc;
-    }
+    for (; q < n; ++q) acc = __fadd_rn(acc, cum[q]);
+    cum[i] = fmaxf(__fsub_rn(1.0f, acc), 0.f);
   }
   __syncwarp();
+  warp_seq_cumsum(cum, cum, n, lane);
   // J ~ Cat(J_prob): choice(key_3, N, (), p=J_prob)   (:84) -- random_bits(key_3, 1) = block (0, 0), word 0
   uint32_t x0 = 0u, x1 = 0u;
   threefry2x32(key_3.k0, key_3.k1, x0, x1);

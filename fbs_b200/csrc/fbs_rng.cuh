@@ -97,8 +97,18 @@ __device__ __forceinline__ float bits_to_uniform(uint32_t bits, float lo, float 
 }
 
 // XLA's float32 erf_inv (Giles' single-precision polynomial), |x| < 1.
+// w = -log1p(-x^2) = -ln2 * lg2(a), a = 1 - fl(x^2) in [2^-23, 1] (the subtraction is exact or 2^-24-accurate).  a is split as m * 2^e with
+// m in [0.75, 1.5) so that the hardware lg2 (MUFU.LG2: absolute error 2^-22 on [0.5, 2]) is only used where it is
+// accurate; w then carries ~1e-7 absolute error + its own float32 rounding, i.e. the normal stays within an ULP or
+// two of the log1pf evaluation (tests/test_gpu_random.py) at a third of its instruction count.
 __device__ __forceinline__ float erfinv_f32(float x) {
-  float w = -log1pf(-x * x);
+  const int ia = __float_as_int(__fsub_rn(1.0f, __fmul_rn(x, x)));  // x * x rounded first, as log1p(-x * x) sees it
+  const int eb = (ia - 0x3F400000) & 0xFF800000;            // e << 23
+  const float m = __int_as_float(ia - eb);                  // [0.75, 1.5)
+  const float fe = __int_as_float((eb >> 23) + 0x4B400000) - 12582912.0f;  // (float)e without the XU-pipe I2F
+  float l2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(m));
+  float w = fmaf(fe, -0.693147182f, -0.693147182f * l2);
   float p;
   if (w < 5.0f) {
     w -= 2.5f;
@@ -112,6 +122,7 @@ __device__ __forceinline__ float erfinv_f32(float x) {
     p = fmaf(p, w, 0.246640727f);
     p = fmaf(p, w, 1.50140941f);
   } else {
+    asm volatile("");  // keep the tail (0.3 % of the draws) a real branch: if-converted it costs every draw ~15 instructions
     w = sqrtf(w) - 3.0f;
     p = -0.000200214257f;
     p = fmaf(p, w, 0.000100950558f);

@@ -1,22 +1,30 @@
-// Whole-sweep kernel on the 5th-generation tensor cores ("v3"): tcgen05.mma + TMEM + TMA.
+// Whole-sweep kernel on the 5th-generation tensor cores ("v3"): tcgen05.mma + TMEM + TMA, two chains per CTA.
 //
 // Per chain-step the joint drift of all particles is ONE GEMM  D[128 x Nout] = U[128 x du] * Mu_k^T  with
 // Nout = du8 + dv8 outputs (u-drift | v-drift).  float32 parity is kept by a split-TF32 product
 //   U M = Uhi Mhi + Ulo Mhi + Uhi Mlo        (hi = round-to-nearest tf32, lo = exact float32 remainder)
-// accumulated in float32 in TENSOR MEMORY.  While the tensor core runs, the CUDA cores generate the step's
-// transition noise (threefry2x32) in registers -- the two pipes overlap.
+// accumulated in float32 in TENSOR MEMORY.
 //
-//   warp 0        : control.  One elected thread streams the packed (hi, lo) K-blocks of M_k through a ring of
-//                   shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier), issues the
-//                   tcgen05.mma's, frees stages with tcgen05.commit, and signals the accumulator barrier.
-//   warps 1..16   : workers.  During the GEMM: noise.  After it: warps 1..8 read the accumulators from TMEM
-//                   (tcgen05.ld, one particle row per thread: u-half / v-half), write the transition means and
-//                   the per-row Gaussian log-likelihood; one warp resamples; all workers gather + add noise and
-//                   write the new particles (hi / lo split) in the UMMA K-major core-matrix layout.
+// A CSMC step is a strictly serial chain of phases (GEMM -> weights -> ancestors -> gather), one of which
+// (resampling) keeps a single warp busy.  So one CTA runs TWO independent chains, one per group of 8 warps, each
+// with its own particle operands, accumulator (256 TMEM columns) and named barrier; the groups drift half a step
+// apart and fill each other's bubbles ("ping-pong"):
+//
+//   warp 0          : control.  One elected thread streams the packed (hi, lo) K-blocks of M_k through a ring of
+//                     shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier) and issues the
+//                     tcgen05.mma's of both groups in a fixed alternating order (GEMM t of group 0, GEMM t of
+//                     group 1, ...), each when that group has signalled "particles ready".
+//   warps 1+8g..8+8g: group g.  During its GEMM: the step's transition noise (threefry2x32) in registers.  After it:
+//                     4 warps read the u-half of the accumulator from TMEM (tcgen05.ld, one particle row per
+//                     thread) and write the transition means, 4 warps the v-half and the per-row Gaussian
+//                     log-likelihood; one warp resamples; all gather the parents' means + noise and write the new
+//                     particles (hi / lo split) in the UMMA K-major core-matrix layout.
 //
 // Shared-memory operand layout (no swizzle, K-major "interleave"): element (row r, k) of an operand lives at
-//   (k / 4) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 4) * 4  bytes,   LBO = (#rows / 8) * 128,
-// i.e. 8-row x 16-byte core matrices; one MMA consumes K = 8 (two k-chunks, LBO apart), SBO = 128.
+//   (k / 4) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 4) * 4  bytes,
+// i.e. 8-row x 16-byte core matrices; one MMA consumes K = 8 (two k-chunks, LBO apart), SBO = 128.  For the particle
+// operand LBO = ceil(N / 8) * 128: the MMA always reads M = 128 rows, rows >= N alias the next k-chunk (finite
+// garbage) and only produce accumulator rows >= N, which are never read.
 //
 // Reference: fbs/samplers/csmc/csmc.py:80-164, fbs/samplers/smc.py:115-158 (same algorithm and random streams
 // as csmc_kernels.cu / sweep_v2.cu).
@@ -30,11 +38,13 @@ namespace fbs {
 namespace v3 {
 
 constexpr int ROWS = 128;            // MMA M: particle rows per chain (N <= 128)
-constexpr int NWORK = 16;            // worker warps
-constexpr int NTHREADS = 32 * (1 + NWORK);
-constexpr int STAGES = 6;            // ring of K-blocks of the step matrix
-constexpr int GPC_MAX = 4;           // k-groups (of 4 columns) per worker in the children phase
-constexpr uint32_t A_LBO = (ROWS / 8) * 128;  // 2048 bytes between k-chunks of the particle operand
+constexpr int GROUPS = 2;            // chains in flight per CTA
+constexpr int GWARPS = 8;            // warps per group
+constexpr int GTHREADS = 32 * GWARPS;
+constexpr int NTHREADS = 32 * (1 + GROUPS * GWARPS);
+constexpr int MAX_STAGES = 4;        // ring of K-blocks of the step matrix (2..4, chosen by the host to fit)
+constexpr int TMEM_COLS_PER_GROUP = 256;
+constexpr uint32_t SELFTEST_LBO = (ROWS / 8) * 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -132,40 +142,54 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
-// byte offset of particle element (row r, column k) in the A operands
-__device__ __forceinline__ uint32_t a_off(int r, int k) {
-  return (uint32_t)(k >> 2) * A_LBO + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 3) * 4u;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier of one group (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GTHREADS) : "memory"); }
+
+// byte offset of the 4 consecutive columns 4 cg .. 4 cg + 3 of particle row r in an A operand
+__device__ __forceinline__ uint32_t a_off(uint32_t lbo, int r, int cg) {
+  return (uint32_t)cg * lbo + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
 }
 
 struct Layout {
-  int du8, dv8, nout, nkb, dup4;
-  uint32_t b_lbo, blk_bytes, stage_bytes;  // one K-block image of M (hi or lo), one ring stage (hi + lo)
-  uint32_t a_bytes;
-  size_t Ahi, Alo, ring, cvs, lwraw, lw, w, cum, idx, tmp, keys, scal, bars, tmem, total;  // byte offsets
+  int du8, dv8, nout, nkb, ncg, stages;
+  uint32_t a_lbo, b_lbo, blk_bytes, stage_bytes, a_bytes;
+  // byte offsets.  Group g: A operands at A + g * 2 * a_bytes (hi, then lo), small arrays at grp + g * grp_bytes + <field>
+  uint32_t A, ring, coef, bars, tmem, grp, grp_bytes;
+  uint32_t cvs, lwraw, lw, w, cum, idx, tmp, keys, scal, skeys, pin;
+  uint32_t total;
 };
 
-__host__ __device__ inline Layout make_layout(int N, int du, int dv) {
+__host__ __device__ inline Layout make_layout(int N, int du, int dv, int K, int stages) {
   Layout L;
   L.du8 = (du + 7) / 8 * 8;
   L.dv8 = (dv + 7) / 8 * 8;
   L.nout = L.du8 + L.dv8;
   if (L.nout % 16) L.nout += 8;
   L.nkb = L.du8 / 8;
-  L.dup4 = (du + 3) / 4 * 4;
+  L.ncg = du / 4;
+  L.stages = stages;
+  L.a_lbo = (uint32_t)((N + 7) / 8) * 128u;
   L.b_lbo = (uint32_t)(L.nout / 8) * 128u;
   L.blk_bytes = 2u * L.b_lbo;
   L.stage_bytes = 2u * L.blk_bytes;
-  L.a_bytes = (uint32_t)(L.du8 / 4) * A_LBO;
-  size_t o = 0;
-  auto take = [&](size_t bytes) {
-    size_t r = o;
-    o += (bytes + 127) / 128 * 128;
+  L.a_bytes = (uint32_t)(L.du8 / 4) * L.a_lbo;
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes) {
+    uint32_t r = o;
+    o += (bytes + 127u) / 128u * 128u;
     return r;
   };
-  L.Ahi = take(L.a_bytes);
-  L.Alo = take(L.a_bytes);
-  L.ring = take((size_t)STAGES * L.stage_bytes);
-  L.cvs = take((size_t)(L.du8 + L.dv8) * 4);
+  L.A = take(2u * GROUPS * L.a_bytes);
+  L.ring = take((uint32_t)stages * L.stage_bytes);  // also absorbs the M = 128 over-read of the last k-chunk
+  L.coef = take((uint32_t)K * 16u);                 // per step: dt, sd, lognorm, 1 / sd^2
+  L.bars = take((2 * MAX_STAGES + 2 * GROUPS) * 8);
+  L.tmem = take(16);
+  L.grp = o;
+  o = 0;
+  L.cvs = take((uint32_t)(L.du8 + L.dv8) * 4u);
   L.lwraw = take(ROWS * 4);
   L.lw = take(ROWS * 4);
   L.w = take(ROWS * 4);
@@ -174,9 +198,10 @@ __host__ __device__ inline Layout make_layout(int N, int du, int dv) {
   L.tmp = take((ROWS + 1) * 4);
   L.keys = take(64);
   L.scal = take(16);
-  L.bars = take((2 * STAGES + 1) * 8);
-  L.tmem = take(16);
-  L.total = o;
+  L.skeys = take((uint32_t)K * 16u);        // per step: (resampling key, transition key)
+  L.pin = take((uint32_t)(du + 4) * 4u);    // pinned reference particle of the step + its slot
+  L.grp_bytes = o;
+  L.total = L.grp + GROUPS * L.grp_bytes;
   return L;
 }
 
@@ -203,394 +228,472 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
   return lse;
 }
 
-__global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p) {
+template <int NT>
+__global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const Layout L = make_layout(p.N, p.du, p.dv);
+  const Layout L = make_layout(p.N, p.du, p.dv, p.K, stages);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned char* Ahi = smem + L.Ahi;
-  unsigned char* Alo = smem + L.Alo;  // doubles as the transition-mean buffer between the GEMM and the gather
   unsigned char* ring = smem + L.ring;
-  float* cvs = reinterpret_cast<float*>(smem + L.cvs);  // [0, du8): cu, [du8, du8 + dv8): cv of this step
-  float* lwraw = reinterpret_cast<float*>(smem + L.lwraw);
-  float* lw = reinterpret_cast<float*>(smem + L.lw);
-  float* w = reinterpret_cast<float*>(smem + L.w);
-  float* cum = reinterpret_cast<float*>(smem + L.cum);
-  int* idx = reinterpret_cast<int*>(smem + L.idx);
-  int* tmp = reinterpret_cast<int*>(smem + L.tmp);
-  Key* kbase = reinterpret_cast<Key*>(smem + L.keys);  // [0]: sweep key, [1]: resampling, [2]: transition
-  float* scal = reinterpret_cast<float*>(smem + L.scal);
+  float4* coef = reinterpret_cast<float4*>(smem + L.coef);  // (dt, sd, lognorm, 1/sd^2) of step k
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* empty = full + STAGES;
-  uint64_t* accum = empty + STAGES;
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* accum = empty + MAX_STAGES;  // [g]: accumulator of group g complete
+  uint64_t* ready = accum + GROUPS;      // [g]: particles of group g written, accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem);
-  const float logN = logf((float)N);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nout >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, GROUPS * TMEM_COLS_PER_GROUP);
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < MAX_STAGES; ++s) {
         mbar_init(full + s, 1);
         mbar_init(empty + s, 1);
       }
-      mbar_init(accum, 1);
+      for (int g = 0; g < GROUPS; ++g) {
+        mbar_init(accum + g, 1);
+        mbar_init(ready + g, 1);
+      }
       fence_barrier_init();
     }
+  }
+  for (int k = tid; k < K; k += NTHREADS) {
+    const float sd = p.sd[k];
+    coef[k] = make_float4(p.dt[k], sd, p.lognorm[k], 1.0f / (sd * sd));
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- worker ownership for noise + children: row pair (n, n + half) x a chunk of k-groups ------------
-  const int wt = tid - 32;  // worker thread index, < 0 for the control warp
-  const int ngroups = L.dup4 / 4;
-  const int per_pair = max(1, (NWORK * 32) / max(half, 1));
-  const int gpc = (ngroups + per_pair - 1) / per_pair;  // <= GPC_MAX (checked on the host)
-  const int nchunk = (ngroups + gpc - 1) / gpc;
-  const int own_pair = wt >= 0 ? wt / nchunk : -1;
-  const int own_chunk = wt >= 0 ? wt - own_pair * nchunk : 0;
-  const bool owner = wt >= 0 && own_pair < half;
-  const int g0 = own_chunk * gpc;  // first k-group
-  const uint32_t nel = (uint32_t)N * du;
-
-  // ring bookkeeping (control thread): global K-block counter over the whole launch
-  uint32_t prod_blk = 0, cons_blk = 0;  // blocks issued to TMA / consumed by MMA
-  uint32_t accum_phase = 0;
-
-  for (int64_t chain = blockIdx.x; chain < p.B; chain += gridDim.x) {
-    const float* vs0 = p.vs + (size_t)chain * (K + 1) * dv;
-    (void)vs0;
-    // total K-blocks this chain consumes: one GEMM for the initial weights (explicit_final) + K steps
-    const bool init_gemm = (p.mode == MODE_CSMC && p.init_mode == FBS_INIT_NORMAL);
-    const uint32_t chain_blocks = (uint32_t)(K + (init_gemm ? 1 : 0)) * L.nkb;
-    uint32_t chain_prod = 0;  // blocks of this chain already requested
-    auto block_src = [&](uint32_t b) {  // b-th block of this chain -> step matrix index, K-block
-      uint32_t step = b / L.nkb;
-      const uint32_t kb = b - step * L.nkb;
-      if (init_gemm) step = step == 0 ? 0 : step - 1;  // initial weights use the step-0 matrix
-      return reinterpret_cast<const unsigned char*>(p.MTc) + ((size_t)step * L.nkb + kb) * L.stage_bytes;
-    };
-    auto produce = [&]() {  // control thread: fill the next ring stage if this chain still has blocks to fetch
-      if (chain_prod >= chain_blocks) return;
-      const uint32_t s = prod_blk % STAGES;
-      if (prod_blk >= STAGES) mbar_wait(empty + s, ((prod_blk / STAGES) - 1) & 1);
-      mbar_expect_tx(full + s, L.stage_bytes);
-      bulk_g2s(ring + (size_t)s * L.stage_bytes, block_src(chain_prod), L.stage_bytes, full + s);
-      ++prod_blk;
-      ++chain_prod;
-    };
-
-    // =============================== initialisation ===============================
-    if (tid == 0) {
-      fence_proxy_async();
-      for (int s = 0; s < STAGES - 1; ++s) produce();
-      Key key{p.keys[2 * chain], p.keys[2 * chain + 1]};
-      if (p.mode == MODE_CSMC) {
-        Key key_init, key_scan;
-        split2(key, key_init, key_scan);  // csmc.py:150
-        kbase[0] = key_scan;
-        kbase[2] = key_init;
-      } else {
-        kbase[0] = key;
-      }
-      scal[0] = 0.f;
-    }
-    for (int t = tid; t < (int)(L.a_bytes / 4); t += NTHREADS) {
-      reinterpret_cast<float*>(Ahi)[t] = 0.f;
-      reinterpret_cast<float*>(Alo)[t] = 0.f;
-    }
-    __syncthreads();
-
-    // write particle value x of (row, column) as the hi / lo pair
-    auto put = [&](int r, int k, float x) {
-      const float hi = tf32_rn(x);
-      const uint32_t off = a_off(r, k);
-      *reinterpret_cast<float*>(Ahi + off) = hi;
-      *reinterpret_cast<float*>(Alo + off) = x - hi;
-    };
-    auto get = [&](int r, int k) {
-      const uint32_t off = a_off(r, k);
-      return *reinterpret_cast<const float*>(Ahi + off) + *reinterpret_cast<const float*>(Alo + off);
-    };
-
-    float nz[2][4 * GPC_MAX];  // noise of (n, n + half) x the owned columns
-    auto make_noise = [&](Key ktr, float scale) {
+  // chains of this CTA: pair P = blockIdx.x + i * gridDim.x, group g runs chain 2 P + g
+  const bool init_gemm = (p.mode == MODE_CSMC && p.init_mode == FBS_INIT_NORMAL);
+  const uint32_t GP = (uint32_t)K + (init_gemm ? 1u : 0u);  // GEMMs per chain
+  uint32_t nch[GROUPS];
 #pragma unroll
-      for (int q = 0; q < 4 * GPC_MAX; ++q) {
-        const int k = 4 * g0 + q;
-        uint32_t y0 = 0u, y1 = 0u;
-        if (owner && q < 4 * gpc && k < du) random_bits_block(ktr, nel, (uint32_t)own_pair * du + k, y0, y1);
-        nz[0][q] = scale * bits_to_normal(y0);
-        nz[1][q] = scale * bits_to_normal(y1);
-      }
-    };
+  for (int g = 0; g < GROUPS; ++g) {
+    const int64_t lim = (p.B - g + 1) / 2;  // pairs P with 2 P + g < B
+    nch[g] = lim > (int64_t)blockIdx.x ? (uint32_t)((lim - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  }
 
-    if (p.mode == MODE_PMCMC) {
-      const float* src = p.u0s + (size_t)chain * N * du;
-      for (int t = tid; t < N * du; t += NTHREADS) put(t / du, t % du, src[t]);
-    } else if (p.init_mode == FBS_INIT_DEGENERATE) {  // gibbs.py:140-144
-      const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
-      for (int t = tid; t < N * du; t += NTHREADS) put(t / du, t % du, u0[t % du]);
-      for (int t = tid; t < N; t += NTHREADS) lw[t] = p.init_log_w;
-    } else {  // gibbs.py:133-137
-      make_noise(kbase[2], 1.0f);
-      if (owner) {
-        const int b0 = p.bs_star[(size_t)chain * (K + 1)];
-        const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
-#pragma unroll
-        for (int q = 0; q < 4 * GPC_MAX; ++q) {
-          const int k = 4 * g0 + q;
-          if (q < 4 * gpc && k < du) {
-            put(own_pair, k, own_pair == b0 ? u0[k] : nz[0][q]);                  // csmc.py:152
-            put(own_pair + half, k, own_pair + half == b0 ? u0[k] : nz[1][q]);
+  if (warp == 0) {
+    // =============================== control warp ===============================
+    if (lane == 0) {
+      const uint32_t G0 = nch[0] * GP, G1 = nch[1] * GP;  // G0 >= G1; GEMM order: (0,0) (1,0) (0,1) (1,1) ...
+      uint32_t prod = 0, cons = 0;                         // K-blocks requested from TMA / consumed by the MMA
+      uint32_t pt = 0, pg = 0, pkb = 0;                    // producer cursor: GEMM (pg, pt), K-block pkb
+      bool pvalid = G0 > 0;
+      auto produce = [&]() {
+        if (!pvalid) return;
+        const uint32_t s = prod % (uint32_t)stages;
+        if (prod >= (uint32_t)stages) mbar_wait(empty + s, ((prod / (uint32_t)stages) - 1u) & 1u);
+        uint32_t step = pt % GP;
+        if (init_gemm) step = step == 0 ? 0 : step - 1;  // the initial weights use the step-0 matrix
+        mbar_expect_tx(full + s, L.stage_bytes);
+        bulk_g2s(ring + (size_t)s * L.stage_bytes,
+                 reinterpret_cast<const unsigned char*>(p.MTc) + ((size_t)step * L.nkb + pkb) * L.stage_bytes, L.stage_bytes,
+                 full + s);
+        ++prod;
+        if (++pkb == (uint32_t)L.nkb) {
+          pkb = 0;
+          if (pg == 0 && pt < G1) {
+            pg = 1;
+          } else {
+            pg = 0;
+            ++pt;
+            pvalid = pt < G0;
           }
         }
-      }
-    }
-    fence_proxy_async();
-    __syncthreads();
-
-    // history helper: particles of this chain -> dst [N][du]
-    auto store_particles = [&](float* dst) {
-      for (int t = tid; t < N * du; t += NTHREADS) dst[t] = get(t / du, t % du);
-    };
-
-    // ---- one GEMM + epilogue: Alo <- transition means, lwraw <- per-row Gaussian log-likelihood -------
-    //      k: coefficient step, slot: workspace slot of the per-chain step vectors, restore: keep the particles
-    auto gemm_and_epilogue = [&](int k, int slot, bool with_noise, bool restore) {
-      if (warp == 0) {
-        if (lane == 0) {
+      };
+      fence_proxy_async();
+      for (int s = 0; s < stages - 1; ++s) produce();
+      for (uint32_t t = 0; t < G0; ++t) {
+        for (int g = 0; g < GROUPS; ++g) {
+          if (g == 1 && t >= G1) break;
+          mbar_wait(ready + g, t & 1u);
           tc_fence_after();
+          const uint32_t a_hi0 = smem_u32(smem + L.A) + (uint32_t)g * 2u * L.a_bytes;
+          const uint32_t d_tmem = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
           for (int kb = 0; kb < L.nkb; ++kb) {
-            produce();  // refill the stage freed by the PREVIOUS K-block's MMAs (keeps two batches in flight)
-            const uint32_t s = cons_blk % STAGES;
-            mbar_wait(full + s, (cons_blk / STAGES) & 1);
+            produce();  // refill the stage freed by the previous K-block's MMAs
+            const uint32_t s = cons % (uint32_t)stages;
+            mbar_wait(full + s, (cons / (uint32_t)stages) & 1u);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(Ahi) + (uint32_t)kb * 2u * A_LBO;
-            const uint32_t a_lo = smem_u32(Alo) + (uint32_t)kb * 2u * A_LBO;
+            const uint32_t a_hi = a_hi0 + (uint32_t)kb * 2u * L.a_lbo;
+            const uint32_t a_lo = a_hi + L.a_bytes;
             const uint32_t b_hi = smem_u32(ring + (size_t)s * L.stage_bytes);
             const uint32_t b_lo = b_hi + L.blk_bytes;
-            const uint64_t dAh = make_desc(a_hi, A_LBO, 128), dAl = make_desc(a_lo, A_LBO, 128);
+            const uint64_t dAh = make_desc(a_hi, L.a_lbo, 128), dAl = make_desc(a_lo, L.a_lbo, 128);
             const uint64_t dBh = make_desc(b_hi, L.b_lbo, 128), dBl = make_desc(b_lo, L.b_lbo, 128);
-            umma_tf32(tmem_base, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
-            umma_tf32(tmem_base, dAl, dBh, idesc, 1u);
-            umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+            umma_tf32(d_tmem, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
+            umma_tf32(d_tmem, dAl, dBh, idesc, 1u);
+            umma_tf32(d_tmem, dAh, dBl, idesc, 1u);
             umma_commit(empty + s);  // stage free once these MMAs have read it
-            ++cons_blk;
+            ++cons;
           }
-          umma_commit(accum);  // accumulator complete
+          umma_commit(accum + g);  // accumulator of group g complete
         }
-        __syncwarp();
-      } else {
-        // stage the per-chain step vectors, then noise while the tensor core works
-        const float* wsrow = p.ws + ((size_t)chain * (K + 1) + slot) * (size_t)(L.dup4 + (dv + 3) / 4 * 4);
-        for (int t = wt; t < L.du8 + L.dv8; t += NWORK * 32) {
-          float x = 0.f;
-          if (t < L.du8) {
-            if (t < du) x = wsrow[t];
-          } else if (t - L.du8 < dv) {
-            x = wsrow[L.dup4 + (t - L.du8)];
-          }
-          cvs[t] = x;
-        }
-        if (with_noise) make_noise(kbase[2], p.sd[k]);
       }
-      mbar_wait(accum, accum_phase);
-      accum_phase ^= 1u;
-      tc_fence_after();
-      __syncthreads();  // cvs visible; every thread past the accumulator barrier
-      if (warp >= 1 && warp <= 8) {
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        const int r = 32 * q + lane;
-        const bool vhalf = warp > 4;
-        const float dt = p.dt[k];
-        const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
-        float acc[32];
-        if (!vhalf) {
-          for (int c0 = 0; c0 < L.du8; c0 += 32) {
-            const int nc = min(32, L.du8 - c0);
-            if (nc == 32) {
-              tmem_ld32(trow + c0, acc);
-            } else {
-              for (int c = 0; c < nc; c += 8) tmem_ld8(trow + c0 + c, acc + c);
-            }
-            if (r < N) {
-#pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                if (c < nc && c0 + c < du) {
-                  const uint32_t off = a_off(r, c0 + c);
-                  const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
-                  float4 lo = *reinterpret_cast<const float4*>(Alo + off);
-                  const float4 cu = *reinterpret_cast<const float4*>(cvs + c0 + c);
-                  // mean = x + dt (drift + offset); when restoring, the particles stay untouched
-                  if (!restore) {
-                    lo.x = (hi.x + lo.x) + dt * (acc[c + 0] + cu.x);
-                    lo.y = (hi.y + lo.y) + dt * (acc[c + 1] + cu.y);
-                    lo.z = (hi.z + lo.z) + dt * (acc[c + 2] + cu.z);
-                    lo.w = (hi.w + lo.w) + dt * (acc[c + 3] + cu.w);
-                    *reinterpret_cast<float4*>(Alo + off) = lo;
-                  }
-                }
-              }
-            }
-          }
-        } else {
-          float ss = 0.f;
-          for (int c0 = 0; c0 < L.dv8; c0 += 32) {
-            const int nc = min(32, L.dv8 - c0);
-            if (nc == 32) {
-              tmem_ld32(trow + L.du8 + c0, acc);
-            } else {
-              for (int c = 0; c < nc; c += 8) tmem_ld8(trow + L.du8 + c0 + c, acc + c);
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (c < nc && c0 + c < dv) {
-                const float resid = cvs[L.du8 + c0 + c] - dt * acc[c];
-                ss = fmaf(resid, resid, ss);
-              }
-            }
-          }
-          const float sd = p.sd[k];
-          if (r < N) lwraw[r] = -0.5f * (ss / (sd * sd) + p.lognorm[k]);
-        }
-        tc_fence_before();
-      }
-      __syncthreads();
-    };
-
-    if (p.mode == MODE_CSMC) {
-      if (p.uss) store_particles(p.uss + (size_t)chain * (K + 1) * N * du);
-      if (p.init_mode == FBS_INIT_NORMAL) {
-        gemm_and_epilogue(0, K, false, true);  // gibbs.py:136-137: (v, v_prev) = (vs[0], vs[1]) -> workspace slot K
-        for (int t = tid; t < N; t += NTHREADS) lw[t] = lwraw[t];
-        __syncthreads();
-      }
-      if (warp == 1) warp_normalise_v3(lw, N, lane);  // csmc.py:155
-      __syncthreads();
-      if (p.log_wss)
-        for (int t = tid; t < N; t += NTHREADS) p.log_wss[(size_t)chain * (K + 1) * N + t] = lw[t];
     }
+    __syncwarp();
+  } else {
+    // =============================== worker group g ===============================
+    const int g = (warp - 1) / GWARPS;
+    const int gt = tid - 32 - g * GTHREADS, gw = gt >> 5;
+    unsigned char* Ahi = smem + L.A + (size_t)g * 2u * L.a_bytes;
+    unsigned char* Alo = Ahi + L.a_bytes;  // doubles as the transition-mean buffer between the GEMM and the gather
+    unsigned char* gb = smem + L.grp + (size_t)g * L.grp_bytes;
+    float* cvs = reinterpret_cast<float*>(gb + L.cvs);  // [0, du8): cu, [du8, du8 + dv8): cv of this step
+    float* lwraw = reinterpret_cast<float*>(gb + L.lwraw);
+    float* lw = reinterpret_cast<float*>(gb + L.lw);
+    float* w = reinterpret_cast<float*>(gb + L.w);
+    float* cum = reinterpret_cast<float*>(gb + L.cum);
+    int* idx = reinterpret_cast<int*>(gb + L.idx);
+    int* tmp = reinterpret_cast<int*>(gb + L.tmp);
+    Key* kbase = reinterpret_cast<Key*>(gb + L.keys);  // [0]: sweep key, [2]: init key
+    float* scal = reinterpret_cast<float*>(gb + L.scal);
+    Key* skeys = reinterpret_cast<Key*>(gb + L.skeys);  // [2k]: resampling key, [2k+1]: transition key of step k
+    float* pin = reinterpret_cast<float*>(gb + L.pin);  // [0, du): u*_{k+1}, [du]: its slot b*_{k+1} (as int bits)
+    const float logN = logf((float)N);
+    const uint32_t tmem_g = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
+    const uint32_t lbo = L.a_lbo;
+    const int ncg = L.ncg;
+    const uint32_t nel = (uint32_t)N * du;
 
-    // =============================== the K-step sweep ===============================
-    for (int k = 0; k < K; ++k) {
-      if (tid == 32) {
+    // tasks of this thread: (row pair (n, n + half), column group cg), pairs fastest so that a warp touches
+    // consecutive rows of one core-matrix column (conflict-free 16-byte accesses)
+    const int ntasks = half * ncg;
+    uint32_t task[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int t = gt + GTHREADS * i;
+      task[i] = t < ntasks ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
+    }
+    float nz[2][4 * NT];  // noise, then the children, of the owned (rows, columns)
+
+    uint32_t gcount = 0;  // GEMMs of this group so far (phase of accum[g] / ready[g])
+
+    for (uint32_t ci = 0; ci < nch[g]; ++ci) {
+      const int64_t chain = 2 * ((int64_t)blockIdx.x + (int64_t)ci * gridDim.x) + g;
+
+      // =============================== initialisation ===============================
+      if (gt == 0) {
+        Key key{p.keys[2 * chain], p.keys[2 * chain + 1]};
+        if (p.mode == MODE_CSMC) {
+          Key key_init, key_scan;
+          split2(key, key_init, key_scan);  // csmc.py:150
+          kbase[0] = key_scan;
+          kbase[2] = key_init;
+        } else {
+          kbase[0] = key;
+        }
+        scal[0] = 0.f;
+      }
+      for (uint32_t t = gt; t < L.a_bytes / 4; t += GTHREADS) {
+        reinterpret_cast<float*>(Ahi)[t] = 0.f;
+        reinterpret_cast<float*>(Alo)[t] = 0.f;
+      }
+      group_sync(g);
+      // all step keys of the sweep up front, in parallel (they depend only on the chain key)
+      for (int k = gt; k < K; k += GTHREADS) {
         const Key key_k = split_key(kbase[0], (uint32_t)K, (uint32_t)k);  // csmc.py:157 / smc.py:154
         Key a, b;
         split2(key_k, a, b);
         if (p.mode == MODE_CSMC) {  // csmc.py:136: (key_resampling, key_transition)
-          kbase[1] = a;
-          kbase[2] = b;
+          skeys[2 * k] = a;
+          skeys[2 * k + 1] = b;
         } else {  // smc.py:142: (key_proposal, key_resampling)
-          kbase[2] = a;
-          kbase[1] = b;
+          skeys[2 * k + 1] = a;
+          skeys[2 * k] = b;
         }
       }
-      __syncthreads();
-      // 1. GEMM on the tensor core || noise on the CUDA cores; epilogue: means -> Alo, log-likelihood -> lwraw
-      gemm_and_epilogue(k, k, true, false);
 
-      // 2. weights + ancestors
-      if (warp == 1) {
-        const Key kres = kbase[1];
-        if (p.mode == MODE_CSMC) {
-          for (int q = lane; q < N; q += 32) w[q] = expf(lw[q]);  // csmc.py:139
-          __syncwarp();
-          const int32_t* bs = p.bs_star + (size_t)chain * (K + 1);
-          if (p.scheme == FBS_RESAMPLE_KILLING)
-            warp_cond_killing(kres, w, N, bs[k], bs[k + 1], true, cum, tmp, idx, lane);
-          else
-            warp_cond_multinomial(kres, w, N, bs[k], bs[k + 1], true, cum, idx, lane);
-          for (int q = lane; q < N; q += 32) lw[q] = lwraw[idx[q]];  // csmc.py:145 on the resampled parents
-          __syncwarp();
-          warp_normalise_v3(lw, N, lane);  // csmc.py:146
-        } else {
-          for (int q = lane; q < N; q += 32) lw[q] = lwraw[q];  // smc.py:144
-          __syncwarp();
-          if (p.lw_hist)
-            for (int q = lane; q < N; q += 32) p.lw_hist[((size_t)chain * K + k) * N + q] = lw[q];
-          const float c = warp_normalise_v3(lw, N, lane);  // smc.py:145,147
-          if (lane == 0) scal[0] = (scal[0] - logN) + c;   // smc.py:146
-          for (int q = lane; q < N; q += 32) w[q] = expf(lw[q]);
-          __syncwarp();
-          if (p.scheme == FBS_RESAMPLE_KILLING)
-            warp_cond_killing(kres, w, N, 0, 0, false, cum, tmp, idx, lane);
-          else if (p.scheme == FBS_RESAMPLE_MULTINOMIAL)
-            warp_sorted_multinomial(kres, w, N, cum, reinterpret_cast<float*>(tmp), idx, lane);
-          else
-            warp_systematic_or_stratified(kres, w, N, p.scheme == FBS_RESAMPLE_SYSTEMATIC, true, cum, idx, lane);
+      // write 4 consecutive particle values as the hi / lo pair
+      auto put4 = [&](uint32_t off, float4 x) {
+        float4 hi;
+        hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
+        *reinterpret_cast<float4*>(Ahi + off) = hi;
+        *reinterpret_cast<float4*>(Alo + off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+      };
+      auto get4 = [&](uint32_t off) {
+        const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
+        const float4 lo = *reinterpret_cast<const float4*>(Alo + off);
+        return make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+      };
+      // global [N][du] <-> operands, row-major linear over the group's threads (coalesced on the global side)
+      auto load_particles = [&](const float* src, int row_stride) {  // row_stride = 0: every row is src[0..du)
+        for (int t = gt; t < N * ncg; t += GTHREADS) {
+          const int r = t / ncg, cg = t - r * ncg;
+          put4(a_off(lbo, r, cg), *reinterpret_cast<const float4*>(src + (size_t)r * row_stride + 4 * cg));
         }
-      }
-      __syncthreads();
+      };
+      auto store_particles = [&](float* dst) {
+        for (int t = gt; t < N * ncg; t += GTHREADS) {
+          const int r = t / ncg, cg = t - r * ncg;
+          *reinterpret_cast<float4*>(dst + (size_t)r * du + 4 * cg) = get4(a_off(lbo, r, cg));
+        }
+      };
 
-      // 3. children: gather the parents' means (through registers), add the noise, write hi / lo, pin the reference
-      float val[2][4 * GPC_MAX];
-      if (owner) {
-        const int a0 = idx[own_pair], a1 = idx[own_pair + half];
+      auto make_noise = [&](Key ktr, float scale) {
 #pragma unroll
-        for (int gq = 0; gq < GPC_MAX; ++gq) {
-          const int kk = 4 * (g0 + gq);
-          if (gq < gpc && kk < du) {
-            const float4 m0 = *reinterpret_cast<const float4*>(Alo + a_off(a0, kk));
-            const float4 m1 = *reinterpret_cast<const float4*>(Alo + a_off(a1, kk));
-            val[0][4 * gq + 0] = m0.x + nz[0][4 * gq + 0]; val[0][4 * gq + 1] = m0.y + nz[0][4 * gq + 1];
-            val[0][4 * gq + 2] = m0.z + nz[0][4 * gq + 2]; val[0][4 * gq + 3] = m0.w + nz[0][4 * gq + 3];
-            val[1][4 * gq + 0] = m1.x + nz[1][4 * gq + 0]; val[1][4 * gq + 1] = m1.y + nz[1][4 * gq + 1];
-            val[1][4 * gq + 2] = m1.z + nz[1][4 * gq + 2]; val[1][4 * gq + 3] = m1.w + nz[1][4 * gq + 3];
+        for (int i = 0; i < NT; ++i) {
+          const uint32_t pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
+          if (task[i] != 0xFFFFFFFFu) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t y0, y1;
+              random_bits_block(ktr, nel, pr * du + 4u * cg + c, y0, y1);
+              nz[0][4 * i + c] = scale * bits_to_normal(y0);
+              nz[1][4 * i + c] = scale * bits_to_normal(y1);
+            }
+          }
+        }
+      };
+
+      if (p.mode == MODE_PMCMC) {
+        load_particles(p.u0s + (size_t)chain * N * du, du);
+      } else if (p.init_mode == FBS_INIT_DEGENERATE) {  // gibbs.py:140-144
+        load_particles(p.us_star + (size_t)chain * (K + 1) * du, 0);
+        for (int t = gt; t < N; t += GTHREADS) lw[t] = p.init_log_w;
+      } else {  // gibbs.py:133-137
+        make_noise(kbase[2], 1.0f);
+        const int b0 = p.bs_star[(size_t)chain * (K + 1)];
+        const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          if (task[i] != 0xFFFFFFFFu) {
+            const int pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
+            const float4 ref = *reinterpret_cast<const float4*>(u0 + 4 * cg);
+            put4(a_off(lbo, pr, cg), pr == b0 ? ref : make_float4(nz[0][4 * i], nz[0][4 * i + 1], nz[0][4 * i + 2], nz[0][4 * i + 3]));  // csmc.py:152
+            put4(a_off(lbo, pr + half, cg),
+                 pr + half == b0 ? ref : make_float4(nz[1][4 * i], nz[1][4 * i + 1], nz[1][4 * i + 2], nz[1][4 * i + 3]));
           }
         }
       }
-      __syncthreads();
-      if (owner) {
-        int bj = -1;
-        const float* ustar = nullptr;
-        if (p.mode == MODE_CSMC) {
-          bj = p.bs_star[(size_t)chain * (K + 1) + k + 1];
-          ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
-        }
-#pragma unroll
-        for (int q = 0; q < 4 * GPC_MAX; ++q) {
-          const int kk = 4 * g0 + q;
-          if (q < 4 * gpc && kk < du) {
-            put(own_pair, kk, own_pair == bj ? ustar[kk] : val[0][q]);  // csmc.py:143
-            put(own_pair + half, kk, own_pair + half == bj ? ustar[kk] : val[1][q]);
-          }
-        }
-      }
-      fence_proxy_async();  // the new particles are read by the tensor core (async proxy) next step
-      __syncthreads();
+      fence_proxy_async();  // the particles are read by the tensor core (async proxy)
+      group_sync(g);
+      if (gt == 0) mbar_arrive(ready + g);
 
-      // optional history
+      // ---- one GEMM + epilogue: Alo <- transition means, lwraw <- per-row Gaussian log-likelihood -------
+      //      k: coefficient step, slot: workspace slot of the per-chain step vectors, restore: keep the particles
+      auto gemm_and_epilogue = [&](int k, int slot, bool with_noise, bool restore) {
+        // stage the per-chain step vectors, then noise while the tensor core works
+        const float* wsrow = p.ws + ((size_t)chain * (K + 1) + slot) * (size_t)(du + (dv + 3) / 4 * 4);
+        for (int t = gt; t < L.du8 + L.dv8; t += GTHREADS) {
+          float x = 0.f;
+          if (t < L.du8) {
+            if (t < du) x = wsrow[t];
+          } else if (t - L.du8 < dv) {
+            x = wsrow[du + (t - L.du8)];
+          }
+          cvs[t] = x;
+        }
+        if (with_noise) {
+          // the pinned reference particle of this step (CSMC)
+          if (p.mode == MODE_CSMC) {
+            const float* ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
+            for (int t = gt; t < du; t += GTHREADS) pin[t] = ustar[t];
+            if (gt == 0) reinterpret_cast<int*>(pin)[du] = p.bs_star[(size_t)chain * (K + 1) + k + 1];
+          }
+          make_noise(skeys[2 * k + 1], coef[k].y);
+        }
+        mbar_wait(accum + g, gcount & 1u);
+        ++gcount;
+        tc_fence_after();
+        group_sync(g);  // cvs / pin visible; every thread of the group past the accumulator barrier
+        {
+          const int q = warp & 3;  // TMEM lane quadrant this warp may access
+          const int r = 32 * q + lane;
+          const bool vhalf = gw >= 4;
+          const float4 cf = coef[k];
+          const float dt = cf.x;
+          const uint32_t trow = tmem_g + ((uint32_t)(32 * q) << 16);
+          if (!vhalf) {
+            // mean = x + dt (drift + offset) written over the lo operand (in place, own row)
+            auto u_chunk = [&](const float* acc, int c0, int nc) {
+              if (r >= N) return;
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                if (c < nc && c0 + c < du) {
+                  const uint32_t off = a_off(lbo, r, (c0 + c) >> 2);
+                  const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
+                  float4 lo = *reinterpret_cast<const float4*>(Alo + off);
+                  const float4 cu = *reinterpret_cast<const float4*>(cvs + c0 + c);
+                  lo.x = (hi.x + lo.x) + dt * (acc[c + 0] + cu.x);
+                  lo.y = (hi.y + lo.y) + dt * (acc[c + 1] + cu.y);
+                  lo.z = (hi.z + lo.z) + dt * (acc[c + 2] + cu.z);
+                  lo.w = (hi.w + lo.w) + dt * (acc[c + 3] + cu.w);
+                  *reinterpret_cast<float4*>(Alo + off) = lo;
+                }
+              }
+            };
+            if (!restore) {
+              int c0 = 0;
+              for (; c0 + 32 <= L.du8; c0 += 32) {
+                float acc[32];
+                tmem_ld32(trow + c0, acc);
+                u_chunk(acc, c0, 32);
+              }
+              for (; c0 < L.du8; c0 += 8) {
+                float acc[32];
+                tmem_ld8(trow + c0, acc);
+                u_chunk(acc, c0, 8);
+              }
+            }
+          } else {
+            float ss = 0.f;
+            const float* cv = cvs + L.du8;
+            auto v_chunk = [&](const float* acc, int c0, int nc) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                if (c < nc) {
+                  const float4 cc = *reinterpret_cast<const float4*>(cv + c0 + c);
+                  // columns >= dv: cv = 0 and the accumulator column is exactly 0 (zero rows of M)
+                  const float r0 = cc.x - dt * acc[c + 0], r1 = cc.y - dt * acc[c + 1];
+                  const float r2 = cc.z - dt * acc[c + 2], r3 = cc.w - dt * acc[c + 3];
+                  ss = fmaf(r0, r0, ss);
+                  ss = fmaf(r1, r1, ss);
+                  ss = fmaf(r2, r2, ss);
+                  ss = fmaf(r3, r3, ss);
+                }
+              }
+            };
+            int c0 = 0;
+            for (; c0 + 32 <= L.dv8; c0 += 32) {
+              float acc[32];
+              tmem_ld32(trow + L.du8 + c0, acc);
+              v_chunk(acc, c0, 32);
+            }
+            for (; c0 < L.dv8; c0 += 8) {
+              float acc[32];
+              tmem_ld8(trow + L.du8 + c0, acc);
+              v_chunk(acc, c0, 8);
+            }
+            if (r < N) lwraw[r] = -0.5f * (ss * cf.w + cf.z);
+          }
+          tc_fence_before();
+        }
+        group_sync(g);
+      };
+
       if (p.mode == MODE_CSMC) {
-        if (p.As)
-          for (int t = tid; t < N; t += NTHREADS) p.As[((size_t)chain * K + k) * N + t] = idx[t];
+        if (p.uss) store_particles(p.uss + (size_t)chain * (K + 1) * N * du);
+        if (init_gemm) {
+          gemm_and_epilogue(0, K, false, true);  // gibbs.py:136-137: (v, v_prev) = (vs[0], vs[1]) -> workspace slot K
+          for (int t = gt; t < N; t += GTHREADS) lw[t] = lwraw[t];
+          group_sync(g);
+          if (gt == 0) mbar_arrive(ready + g);  // particles unchanged, accumulator drained
+        }
+        if (gw == 0) warp_normalise_v3(lw, N, lane);  // csmc.py:155
+        group_sync(g);
         if (p.log_wss)
-          for (int t = tid; t < N; t += NTHREADS) p.log_wss[((size_t)chain * (K + 1) + k + 1) * N + t] = lw[t];
-        if (p.uss) store_particles(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du);
-      } else {
-        if (p.inds)
-          for (int t = tid; t < N; t += NTHREADS) p.inds[((size_t)chain * K + k) * N + t] = idx[t];
-        if (p.us_hist) store_particles(p.us_hist + ((size_t)chain * K + k) * N * du);
+          for (int t = gt; t < N; t += GTHREADS) p.log_wss[(size_t)chain * (K + 1) * N + t] = lw[t];
       }
-    }
 
-    // =============================== final state ===============================
-    if (p.mode == MODE_CSMC) {
-      if (p.us_last) store_particles(p.us_last + (size_t)chain * N * du);
-      if (p.log_ws_last)
-        for (int t = tid; t < N; t += NTHREADS) p.log_ws_last[(size_t)chain * N + t] = lw[t];
-    } else {
-      if (p.uT) store_particles(p.uT + (size_t)chain * N * du);
-      if (p.log_ell && tid == 0) p.log_ell[chain] = scal[0];
+      // =============================== the K-step sweep ===============================
+      for (int k = 0; k < K; ++k) {
+        // 1. GEMM on the tensor core || noise on the CUDA cores; epilogue: means -> Alo, log-likelihood -> lwraw
+        gemm_and_epilogue(k, k, true, false);
+
+        // 2. weights + ancestors
+        if (gw == 0) {
+          const Key kres = skeys[2 * k];
+          if (p.mode == MODE_CSMC) {
+            for (int q = lane; q < N; q += 32) w[q] = expf(lw[q]);  // csmc.py:139
+            __syncwarp();
+            const int32_t* bs = p.bs_star + (size_t)chain * (K + 1);
+            if (p.scheme == FBS_RESAMPLE_KILLING)
+              warp_cond_killing(kres, w, N, bs[k], bs[k + 1], true, cum, tmp, idx, lane);
+            else
+              warp_cond_multinomial(kres, w, N, bs[k], bs[k + 1], true, cum, idx, lane);
+            for (int q = lane; q < N; q += 32) lw[q] = lwraw[idx[q]];  // csmc.py:145 on the resampled parents
+            __syncwarp();
+            warp_normalise_v3(lw, N, lane);  // csmc.py:146
+          } else {
+            for (int q = lane; q < N; q += 32) lw[q] = lwraw[q];  // smc.py:144
+            __syncwarp();
+            if (p.lw_hist)
+              for (int q = lane; q < N; q += 32) p.lw_hist[((size_t)chain * K + k) * N + q] = lw[q];
+            const float c = warp_normalise_v3(lw, N, lane);  // smc.py:145,147
+            if (lane == 0) scal[0] = (scal[0] - logN) + c;   // smc.py:146
+            for (int q = lane; q < N; q += 32) w[q] = expf(lw[q]);
+            __syncwarp();
+            if (p.scheme == FBS_RESAMPLE_KILLING)
+              warp_cond_killing(kres, w, N, 0, 0, false, cum, tmp, idx, lane);
+            else if (p.scheme == FBS_RESAMPLE_MULTINOMIAL)
+              warp_sorted_multinomial(kres, w, N, cum, reinterpret_cast<float*>(tmp), idx, lane);
+            else
+              warp_systematic_or_stratified(kres, w, N, p.scheme == FBS_RESAMPLE_SYSTEMATIC, true, cum, idx, lane);
+          }
+        }
+        group_sync(g);
+
+        // 3. children: gather the parents' means, add the noise (in the noise registers)
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          if (task[i] != 0xFFFFFFFFu) {
+            const int pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
+            const float4 m0 = *reinterpret_cast<const float4*>(Alo + a_off(lbo, idx[pr], cg));
+            const float4 m1 = *reinterpret_cast<const float4*>(Alo + a_off(lbo, idx[pr + half], cg));
+            nz[0][4 * i + 0] += m0.x; nz[0][4 * i + 1] += m0.y; nz[0][4 * i + 2] += m0.z; nz[0][4 * i + 3] += m0.w;
+            nz[1][4 * i + 0] += m1.x; nz[1][4 * i + 1] += m1.y; nz[1][4 * i + 2] += m1.z; nz[1][4 * i + 3] += m1.w;
+          }
+        }
+        group_sync(g);  // every mean read before the operands are overwritten
+        {
+          const int bj = p.mode == MODE_CSMC ? reinterpret_cast<const int*>(pin)[du] : -1;
+#pragma unroll
+          for (int i = 0; i < NT; ++i) {
+            if (task[i] != 0xFFFFFFFFu) {
+              const int pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
+              float4 x0 = make_float4(nz[0][4 * i], nz[0][4 * i + 1], nz[0][4 * i + 2], nz[0][4 * i + 3]);
+              float4 x1 = make_float4(nz[1][4 * i], nz[1][4 * i + 1], nz[1][4 * i + 2], nz[1][4 * i + 3]);
+              if (pr == bj) x0 = *reinterpret_cast<const float4*>(pin + 4 * cg);  // csmc.py:143
+              if (pr + half == bj) x1 = *reinterpret_cast<const float4*>(pin + 4 * cg);
+              put4(a_off(lbo, pr, cg), x0);
+              put4(a_off(lbo, pr + half, cg), x1);
+            }
+          }
+        }
+        fence_proxy_async();  // the new particles are read by the tensor core (async proxy) next step
+        group_sync(g);
+        if (gt == 0 && (k + 1 < K)) mbar_arrive(ready + g);
+
+        // optional history
+        if (p.mode == MODE_CSMC) {
+          if (p.As)
+            for (int t = gt; t < N; t += GTHREADS) p.As[((size_t)chain * K + k) * N + t] = idx[t];
+          if (p.log_wss)
+            for (int t = gt; t < N; t += GTHREADS) p.log_wss[((size_t)chain * (K + 1) + k + 1) * N + t] = lw[t];
+          if (p.uss) store_particles(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du);
+        } else {
+          if (p.inds)
+            for (int t = gt; t < N; t += GTHREADS) p.inds[((size_t)chain * K + k) * N + t] = idx[t];
+          if (p.us_hist) store_particles(p.us_hist + ((size_t)chain * K + k) * N * du);
+        }
+      }
+
+      // =============================== final state ===============================
+      if (p.mode == MODE_CSMC) {
+        if (p.us_last) store_particles(p.us_last + (size_t)chain * N * du);
+        if (p.log_ws_last)
+          for (int t = gt; t < N; t += GTHREADS) p.log_ws_last[(size_t)chain * N + t] = lw[t];
+      } else {
+        if (p.uT) store_particles(p.uT + (size_t)chain * N * du);
+        if (p.log_ell && gt == 0) p.log_ell[chain] = scal[0];
+      }
+      group_sync(g);
     }
-    __syncthreads();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, GROUPS * TMEM_COLS_PER_GROUP);
+}
+
+// selftest operand layout: element (row r, column k), LBO = SELFTEST_LBO
+__device__ __forceinline__ uint32_t st_off(int r, int k) {
+  return (uint32_t)(k >> 2) * SELFTEST_LBO + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 3) * 4u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -601,7 +704,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
                                                                int K8, int nout, float* __restrict__ D) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int nkb = K8 / 8;
-  const uint32_t a_bytes = (uint32_t)(K8 / 4) * A_LBO;
+  const uint32_t a_bytes = (uint32_t)(K8 / 4) * SELFTEST_LBO;
   const uint32_t b_lbo = (uint32_t)(nout / 8) * 128u, blk = 2u * b_lbo, stage = 2u * blk;
   unsigned char* Ahi = smem;
   unsigned char* Alo = smem + a_bytes;
@@ -619,8 +722,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   for (int t = tid; t < ROWS * K8; t += 128) {
     const int r = t / K8, k = t - r * K8;
     const float x = A[t], hi = tf32_rn(x);
-    *reinterpret_cast<float*>(Ahi + a_off(r, k)) = hi;
-    *reinterpret_cast<float*>(Alo + a_off(r, k)) = x - hi;
+    *reinterpret_cast<float*>(Ahi + st_off(r, k)) = hi;
+    *reinterpret_cast<float*>(Alo + st_off(r, k)) = x - hi;
   }
   tc_fence_before();
   __syncthreads();
@@ -635,11 +738,11 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a_hi = smem_u32(Ahi) + (uint32_t)kb * 2u * A_LBO, a_lo = smem_u32(Alo) + (uint32_t)kb * 2u * A_LBO;
+      const uint32_t a_hi = smem_u32(Ahi) + (uint32_t)kb * 2u * SELFTEST_LBO, a_lo = smem_u32(Alo) + (uint32_t)kb * 2u * SELFTEST_LBO;
       const uint32_t b_hi = smem_u32(Bst), b_lo = b_hi + blk;
-      umma_tf32(tbase, make_desc(a_hi, A_LBO, 128), make_desc(b_hi, b_lbo, 128), idesc, kb > 0 ? 1u : 0u);
-      umma_tf32(tbase, make_desc(a_lo, A_LBO, 128), make_desc(b_hi, b_lbo, 128), idesc, 1u);
-      umma_tf32(tbase, make_desc(a_hi, A_LBO, 128), make_desc(b_lo, b_lbo, 128), idesc, 1u);
+      umma_tf32(tbase, make_desc(a_hi, SELFTEST_LBO, 128), make_desc(b_hi, b_lbo, 128), idesc, kb > 0 ? 1u : 0u);
+      umma_tf32(tbase, make_desc(a_lo, SELFTEST_LBO, 128), make_desc(b_hi, b_lbo, 128), idesc, 1u);
+      umma_tf32(tbase, make_desc(a_hi, SELFTEST_LBO, 128), make_desc(b_lo, b_lbo, 128), idesc, 1u);
       umma_commit(bar);
     }
     mbar_wait(bar, phase);
@@ -664,7 +767,7 @@ int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8
     set_error("umma_selftest: need K8 %% 8 == 0, nout %% 16 == 0, nout <= 256");
     return FBS_ERR_INVALID_ARGUMENT;
   }
-  const size_t smem = (size_t)2 * (K8 / 4) * A_LBO + (size_t)4 * (nout / 8) * 128 + 64;
+  const size_t smem = (size_t)2 * (K8 / 4) * SELFTEST_LBO + (size_t)4 * (nout / 8) * 128 + 64;
   if (smem > 227 * 1024) {
     set_error("umma_selftest: K8=%d too large", K8);
     return FBS_ERR_UNSUPPORTED;
@@ -675,30 +778,41 @@ int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8
 }
 
 // Host: eligibility + launch.  p.MTc is the tensor-core image of the step matrices; p.ws the step-vector workspace.
+template <int NT>
+static cudaError_t launch_v3_nt(cudaStream_t st, int grid, size_t smem, const SweepParams& p, int stages) {
+  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  sweep_v3_kernel<NT><<<grid, NTHREADS, smem, st>>>(p, stages);
+  return cudaSuccess;
+}
+
 int launch_sweep_v3(void* stream, SweepParams& p) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p.MTc == nullptr || p.ws == nullptr) return -1;
   if (p.N < 2 || (p.N & 1) || p.N > ROWS) return -1;
-  if (p.du % 4 != 0) return -1;
-  const Layout L = make_layout(p.N, p.du, p.dv);
-  if (L.nout > 256 || L.nkb < 1) return -1;
-  const int half = p.N / 2, ngroups = L.dup4 / 4;
-  const int per_pair = (NWORK * 32) / half;
-  if (per_pair < 1) return -1;
-  const int gpc = (ngroups + per_pair - 1) / per_pair;
-  if (gpc > GPC_MAX) return -1;
+  if (p.du % 4 != 0 || p.du < 4) return -1;
+  int stages = MAX_STAGES;
+  Layout L = make_layout(p.N, p.du, p.dv, p.K, stages);
+  while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, p.K, --stages);
   if (L.total > 227 * 1024) return -1;
-  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-  if (e != cudaSuccess) {
-    set_error("sweep_v3: cudaFuncSetAttribute(%zu B) failed: %s", L.total, cudaGetErrorString(e));
-    return FBS_ERR_CUDA;
-  }
+  if (L.nout > TMEM_COLS_PER_GROUP || L.nkb < 1) return -1;
+  const int ntasks = (p.N / 2) * L.ncg;
+  const int need = (ntasks + GTHREADS - 1) / GTHREADS;
+  if (need > 8) return -1;
   {
     const int rc = launch_stepvec(stream, p);
     if (rc) return rc;
   }
-  const int64_t grid = p.B < sm_count() ? p.B : sm_count();
-  sweep_v3_kernel<<<(int)grid, NTHREADS, L.total, st>>>(p);
+  const int64_t pairs = (p.B + 1) / 2;
+  const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+  cudaError_t e;
+  if (need <= 2) e = launch_v3_nt<2>(st, grid, L.total, p, stages);
+  else if (need <= 5) e = launch_v3_nt<5>(st, grid, L.total, p, stages);
+  else e = launch_v3_nt<8>(st, grid, L.total, p, stages);
+  if (e != cudaSuccess) {
+    set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
+    return FBS_ERR_CUDA;
+  }
   return check_launch("sweep_v3_kernel");
 }
 
