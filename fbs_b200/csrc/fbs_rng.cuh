@@ -41,6 +41,35 @@ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t&
 #undef FBS_TF_ROUND
 }
 
+// Four blocks in lockstep (independent dependency chains interleaved: the rounds are latency bound one at a time).
+__device__ __forceinline__ void threefry2x32_x4(uint32_t k0, uint32_t k1, uint32_t (&x0)[4], uint32_t (&x1)[4]) {
+  const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+#define FBS_TF_INJ(a, b)            \
+  _Pragma("unroll") for (int j = 0; j < 4; ++j) { \
+    x0[j] += (a);                   \
+    x1[j] += (b);                   \
+  }
+#define FBS_TF_ROUND4(r)            \
+  _Pragma("unroll") for (int j = 0; j < 4; ++j) { \
+    x0[j] += x1[j];                 \
+    x1[j] = rotl32(x1[j], r);       \
+    x1[j] ^= x0[j];                 \
+  }
+  FBS_TF_INJ(k0, k1)
+  FBS_TF_ROUND4(13) FBS_TF_ROUND4(15) FBS_TF_ROUND4(26) FBS_TF_ROUND4(6)
+  FBS_TF_INJ(k1, k2 + 1u)
+  FBS_TF_ROUND4(17) FBS_TF_ROUND4(29) FBS_TF_ROUND4(16) FBS_TF_ROUND4(24)
+  FBS_TF_INJ(k2, k0 + 2u)
+  FBS_TF_ROUND4(13) FBS_TF_ROUND4(15) FBS_TF_ROUND4(26) FBS_TF_ROUND4(6)
+  FBS_TF_INJ(k0, k1 + 3u)
+  FBS_TF_ROUND4(17) FBS_TF_ROUND4(29) FBS_TF_ROUND4(16) FBS_TF_ROUND4(24)
+  FBS_TF_INJ(k1, k2 + 4u)
+  FBS_TF_ROUND4(13) FBS_TF_ROUND4(15) FBS_TF_ROUND4(26) FBS_TF_ROUND4(6)
+  FBS_TF_INJ(k2, k0 + 5u)
+#undef FBS_TF_INJ
+#undef FBS_TF_ROUND4
+}
+
 // Block b (0 <= b < h) of random_bits(key, n): y0 is element b, y1 is element b + h (valid iff b + h < n).
 __device__ __forceinline__ void random_bits_block(Key key, uint32_t n, uint32_t b, uint32_t& y0, uint32_t& y1) {
   const uint32_t h = (n + 1u) >> 1;

@@ -29,6 +29,7 @@
 // Reference: fbs/samplers/csmc/csmc.py:80-164, fbs/samplers/smc.py:115-158 (same algorithm and random streams
 // as csmc_kernels.cu / sweep_v2.cu).
 #include <stdlib.h>
+#include <type_traits>
 #include "fbs_common.cuh"
 #include "fbs_resample.cuh"
 #include "fbs_sweep.cuh"
@@ -39,8 +40,9 @@ namespace v3 {
 
 constexpr int ROWS = 128;            // MMA M: particle rows per chain (N <= 128)
 constexpr int GROUPS = 2;            // chains in flight per CTA
-constexpr int GWARPS = 8;            // warps per group
+constexpr int GWARPS = 7;            // warps per group: 4 epilogue + noise, 1 resampling, 2 noise only
 constexpr int GTHREADS = 32 * GWARPS;
+constexpr int NOISE_THREADS = 32 * (GWARPS - 1);
 constexpr int NTHREADS = 32 * (1 + GROUPS * GWARPS);
 constexpr int MAX_STAGES = 4;        // ring of K-blocks of the step matrix (2..4, chosen by the host to fit)
 constexpr int TMEM_COLS_PER_GROUP = 256;
@@ -145,12 +147,29 @@ __device__ __forceinline__ float tf32_rn(float x) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// named barrier of one group (ids 1, 2; id 0 is __syncthreads)
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GTHREADS) : "memory"); }
 
 // byte offset of the 4 consecutive columns 4 cg .. 4 cg + 3 of particle row r in an A operand
 __device__ __forceinline__ uint32_t a_off(uint32_t lbo, int r, int cg) {
   return (uint32_t)cg * lbo + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+}
+
+// Four threefry blocks -> 8 scaled normals: elements b .. b + 3 (lo) and b + hblk .. b + hblk + 3 (hi) of
+// normal(key, (2 * hblk,)).  Deliberately NOT inlined: the sweep's hot loop has to stay inside the 32 KB instruction
+// cache while two warp groups in different phases execute it; inlined per task it is > 60 KB of straight-line code.
+struct Noise8 {
+  float lo[4], hi[4];
+};
+__device__ __noinline__ Noise8 noise_task(uint32_t k0, uint32_t k1, uint32_t b, uint32_t hblk, float scale) {
+  uint32_t x0[4] = {b, b + 1u, b + 2u, b + 3u};
+  uint32_t x1[4] = {b + hblk, b + hblk + 1u, b + hblk + 2u, b + hblk + 3u};
+  threefry2x32_x4(k0, k1, x0, x1);
+  Noise8 r;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    r.lo[c] = scale * bits_to_normal(x0[c]);
+    r.hi[c] = scale * bits_to_normal(x1[c]);
+  }
+  return r;
 }
 
 struct Layout {
@@ -231,6 +250,7 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
 template <int NT>
 __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int NT1 = (NT + 1) / 2;  // noise tasks generated in the shadow of the GEMM; the rest overlap the resampling
   const Layout L = make_layout(p.N, p.du, p.dv, p.K, stages);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -338,8 +358,11 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     __syncwarp();
   } else {
     // =============================== worker group g ===============================
+    // roles inside a group (gw = warp of the group): 0..3 "E" epilogue + noise, 4 "R" resampling only, 5.. "X" noise only
     const int g = (warp - 1) / GWARPS;
     const int gt = tid - 32 - g * GTHREADS, gw = gt >> 5;
+    const bool is_E = gw < 4, is_R = gw == 4, is_noise = !is_R;
+    const int nt = gw < 4 ? gt : gt - 32;  // index among the NOISE_THREADS noise threads
     unsigned char* Ahi = smem + L.A + (size_t)g * 2u * L.a_bytes;
     unsigned char* Alo = Ahi + L.a_bytes;  // doubles as the transition-mean buffer between the GEMM and the gather
     unsigned char* gb = smem + L.grp + (size_t)g * L.grp_bytes;
@@ -358,16 +381,23 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     const uint32_t tmem_g = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
     const uint32_t lbo = L.a_lbo;
     const int ncg = L.ncg;
-    const uint32_t nel = (uint32_t)N * du;
+    const uint32_t hblk = (uint32_t)half * du;  // random_bits(key, N * du): element e and e + hblk share a block
 
-    // tasks of this thread: (row pair (n, n + half), column group cg), pairs fastest so that a warp touches
+    // named barriers of this group
+    auto bar_all = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GTHREADS) : "memory"); };
+    auto bar_noise = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "n"(NOISE_THREADS) : "memory"); };
+    auto bar_E = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(5 + g), "n"(128) : "memory"); };
+    auto bar_ER_arrive = [&]() { asm volatile("bar.arrive %0, %1;" ::"r"(7 + g), "n"(160) : "memory"); };
+    auto bar_ER_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(7 + g), "n"(160) : "memory"); };
+
+    // noise tasks of this thread: (row pair (n, n + half), column group cg), pairs fastest so that a warp touches
     // consecutive rows of one core-matrix column (conflict-free 16-byte accesses)
     const int ntasks = half * ncg;
     uint32_t task[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      const int t = gt + GTHREADS * i;
-      task[i] = t < ntasks ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
+      const int t = nt + NOISE_THREADS * i;
+      task[i] = (is_noise && t < ntasks) ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
     }
     float nz[2][4 * NT];  // noise, then the children, of the owned (rows, columns)
 
@@ -375,6 +405,132 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
 
     for (uint32_t ci = 0; ci < nch[g]; ++ci) {
       const int64_t chain = 2 * ((int64_t)blockIdx.x + (int64_t)ci * gridDim.x) + g;
+
+      // write 4 consecutive particle values as the hi / lo pair
+      auto put4 = [&](uint32_t off, float4 x) {
+        float4 hi;
+        hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
+        *reinterpret_cast<float4*>(Ahi + off) = hi;
+        *reinterpret_cast<float4*>(Alo + off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+      };
+      auto get4 = [&](uint32_t off) {
+        const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
+        const float4 lo = *reinterpret_cast<const float4*>(Alo + off);
+        return make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+      };
+      // global [N][du] <-> operands, row-major linear over `nthr` threads (coalesced on the global side)
+      auto load_particles = [&](const float* src, int row_stride, int t0, int nthr) {  // row_stride = 0: every row is src[0..du)
+        for (int t = t0; t < N * ncg; t += nthr) {
+          const int r = t / ncg, cg = t - r * ncg;
+          put4(a_off(lbo, r, cg), *reinterpret_cast<const float4*>(src + (size_t)r * row_stride + 4 * cg));
+        }
+      };
+      auto store_particles = [&](float* dst, int t0, int nthr) {
+        for (int t = t0; t < N * ncg; t += nthr) {
+          const int r = t / ncg, cg = t - r * ncg;
+          *reinterpret_cast<float4*>(dst + (size_t)r * du + 4 * cg) = get4(a_off(lbo, r, cg));
+        }
+      };
+      // transition noise of tasks [I0, I1): element (row, column) of normal(key, (N, du)) scaled
+      auto make_noise = [&](Key ktr, float scale, auto I0, auto I1) {
+#pragma unroll
+        for (int i = decltype(I0)::value; i < decltype(I1)::value; ++i) {
+          if (task[i] != 0xFFFFFFFFu) {
+            const uint32_t b = (task[i] & 0xFFFFu) * du + 4u * (task[i] >> 16);
+            const Noise8 r = noise_task(ktr.k0, ktr.k1, b, hblk, scale);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              nz[0][4 * i + c] = r.lo[c];
+              nz[1][4 * i + c] = r.hi[c];
+            }
+          }
+        }
+      };
+      using I_0 = std::integral_constant<int, 0>;
+      using I_1 = std::integral_constant<int, NT1>;
+      using I_2 = std::integral_constant<int, NT>;
+
+      // E warps: stage the per-chain step vectors of workspace slot `slot`
+      auto stage_cvs = [&](int slot) {
+        const float* wsrow = p.ws + ((size_t)chain * (K + 1) + slot) * (size_t)(du + (dv + 3) / 4 * 4);
+        for (int t = gt; t < L.du8 + L.dv8; t += 128) {
+          float x = 0.f;
+          if (t < L.du8) {
+            if (t < du) x = wsrow[t];
+          } else if (t - L.du8 < dv) {
+            x = wsrow[du + (t - L.du8)];
+          }
+          cvs[t] = x;
+        }
+      };
+      // E warps, one particle row per thread.  v-half of the accumulator -> lwraw (per-row Gaussian log-likelihood)
+      const int erow = 32 * (warp & 3) + lane;  // TMEM lane quadrant this warp may access
+      const uint32_t trow = tmem_g + ((uint32_t)(32 * (warp & 3)) << 16);
+      auto epilogue_v = [&](int k) {
+        const float4 cf = coef[k];
+        const float dt = cf.x;
+        float ss = 0.f;
+        const float* cv = cvs + L.du8;
+        auto v_chunk = [&](const float* acc, int c0, int nc) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            if (c < nc) {
+              const float4 cc = *reinterpret_cast<const float4*>(cv + c0 + c);
+              // columns >= dv: cv = 0 and the accumulator column is exactly 0 (zero rows of M)
+              const float r0 = cc.x - dt * acc[c + 0], r1 = cc.y - dt * acc[c + 1];
+              const float r2 = cc.z - dt * acc[c + 2], r3 = cc.w - dt * acc[c + 3];
+              ss = fmaf(r0, r0, ss);
+              ss = fmaf(r1, r1, ss);
+              ss = fmaf(r2, r2, ss);
+              ss = fmaf(r3, r3, ss);
+            }
+          }
+        };
+        int c0 = 0;
+        for (; c0 + 32 <= L.dv8; c0 += 32) {
+          float acc[32];
+          tmem_ld32(trow + L.du8 + c0, acc);
+          v_chunk(acc, c0, 32);
+        }
+        for (; c0 < L.dv8; c0 += 8) {
+          float acc[32];
+          tmem_ld8(trow + L.du8 + c0, acc);
+          v_chunk(acc, c0, 8);
+        }
+        if (erow < N) lwraw[erow] = -0.5f * (ss * cf.w + cf.z);
+      };
+      // u-half: mean = x + dt (drift + offset) written over the lo operand (in place, own row)
+      auto epilogue_u = [&](int k) {
+        const float dt = coef[k].x;
+        auto u_chunk = [&](const float* acc, int c0, int nc) {
+          if (erow >= N) return;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            if (c < nc && c0 + c < du) {
+              const uint32_t off = a_off(lbo, erow, (c0 + c) >> 2);
+              const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
+              float4 lo = *reinterpret_cast<const float4*>(Alo + off);
+              const float4 cu = *reinterpret_cast<const float4*>(cvs + c0 + c);
+              lo.x = (hi.x + lo.x) + dt * (acc[c + 0] + cu.x);
+              lo.y = (hi.y + lo.y) + dt * (acc[c + 1] + cu.y);
+              lo.z = (hi.z + lo.z) + dt * (acc[c + 2] + cu.z);
+              lo.w = (hi.w + lo.w) + dt * (acc[c + 3] + cu.w);
+              *reinterpret_cast<float4*>(Alo + off) = lo;
+            }
+          }
+        };
+        int c0 = 0;
+        for (; c0 + 32 <= L.du8; c0 += 32) {
+          float acc[32];
+          tmem_ld32(trow + c0, acc);
+          u_chunk(acc, c0, 32);
+        }
+        for (; c0 < L.du8; c0 += 8) {
+          float acc[32];
+          tmem_ld8(trow + c0, acc);
+          u_chunk(acc, c0, 8);
+        }
+      };
 
       // =============================== initialisation ===============================
       if (gt == 0) {
@@ -393,7 +549,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         reinterpret_cast<float*>(Ahi)[t] = 0.f;
         reinterpret_cast<float*>(Alo)[t] = 0.f;
       }
-      group_sync(g);
+      bar_all();
       // all step keys of the sweep up front, in parallel (they depend only on the chain key)
       for (int k = gt; k < K; k += GTHREADS) {
         const Key key_k = split_key(kbase[0], (uint32_t)K, (uint32_t)k);  // csmc.py:157 / smc.py:154
@@ -407,56 +563,13 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           skeys[2 * k] = b;
         }
       }
-
-      // write 4 consecutive particle values as the hi / lo pair
-      auto put4 = [&](uint32_t off, float4 x) {
-        float4 hi;
-        hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
-        *reinterpret_cast<float4*>(Ahi + off) = hi;
-        *reinterpret_cast<float4*>(Alo + off) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-      };
-      auto get4 = [&](uint32_t off) {
-        const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
-        const float4 lo = *reinterpret_cast<const float4*>(Alo + off);
-        return make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
-      };
-      // global [N][du] <-> operands, row-major linear over the group's threads (coalesced on the global side)
-      auto load_particles = [&](const float* src, int row_stride) {  // row_stride = 0: every row is src[0..du)
-        for (int t = gt; t < N * ncg; t += GTHREADS) {
-          const int r = t / ncg, cg = t - r * ncg;
-          put4(a_off(lbo, r, cg), *reinterpret_cast<const float4*>(src + (size_t)r * row_stride + 4 * cg));
-        }
-      };
-      auto store_particles = [&](float* dst) {
-        for (int t = gt; t < N * ncg; t += GTHREADS) {
-          const int r = t / ncg, cg = t - r * ncg;
-          *reinterpret_cast<float4*>(dst + (size_t)r * du + 4 * cg) = get4(a_off(lbo, r, cg));
-        }
-      };
-
-      auto make_noise = [&](Key ktr, float scale) {
-#pragma unroll
-        for (int i = 0; i < NT; ++i) {
-          const uint32_t pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
-          if (task[i] != 0xFFFFFFFFu) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t y0, y1;
-              random_bits_block(ktr, nel, pr * du + 4u * cg + c, y0, y1);
-              nz[0][4 * i + c] = scale * bits_to_normal(y0);
-              nz[1][4 * i + c] = scale * bits_to_normal(y1);
-            }
-          }
-        }
-      };
-
       if (p.mode == MODE_PMCMC) {
-        load_particles(p.u0s + (size_t)chain * N * du, du);
+        load_particles(p.u0s + (size_t)chain * N * du, du, gt, GTHREADS);
       } else if (p.init_mode == FBS_INIT_DEGENERATE) {  // gibbs.py:140-144
-        load_particles(p.us_star + (size_t)chain * (K + 1) * du, 0);
+        load_particles(p.us_star + (size_t)chain * (K + 1) * du, 0, gt, GTHREADS);
         for (int t = gt; t < N; t += GTHREADS) lw[t] = p.init_log_w;
       } else {  // gibbs.py:133-137
-        make_noise(kbase[2], 1.0f);
+        make_noise(kbase[2], 1.0f, I_0{}, I_2{});
         const int b0 = p.bs_star[(size_t)chain * (K + 1)];
         const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
 #pragma unroll
@@ -471,132 +584,59 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         }
       }
       fence_proxy_async();  // the particles are read by the tensor core (async proxy)
-      group_sync(g);
+      bar_all();
       if (gt == 0) mbar_arrive(ready + g);
 
-      // ---- one GEMM + epilogue: Alo <- transition means, lwraw <- per-row Gaussian log-likelihood -------
-      //      k: coefficient step, slot: workspace slot of the per-chain step vectors, restore: keep the particles
-      auto gemm_and_epilogue = [&](int k, int slot, bool with_noise, bool restore) {
-        // stage the per-chain step vectors, then noise while the tensor core works
-        const float* wsrow = p.ws + ((size_t)chain * (K + 1) + slot) * (size_t)(du + (dv + 3) / 4 * 4);
-        for (int t = gt; t < L.du8 + L.dv8; t += GTHREADS) {
-          float x = 0.f;
-          if (t < L.du8) {
-            if (t < du) x = wsrow[t];
-          } else if (t - L.du8 < dv) {
-            x = wsrow[du + (t - L.du8)];
-          }
-          cvs[t] = x;
-        }
-        if (with_noise) {
-          // the pinned reference particle of this step (CSMC)
-          if (p.mode == MODE_CSMC) {
-            const float* ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
-            for (int t = gt; t < du; t += GTHREADS) pin[t] = ustar[t];
-            if (gt == 0) reinterpret_cast<int*>(pin)[du] = p.bs_star[(size_t)chain * (K + 1) + k + 1];
-          }
-          make_noise(skeys[2 * k + 1], coef[k].y);
-        }
-        mbar_wait(accum + g, gcount & 1u);
-        ++gcount;
-        tc_fence_after();
-        group_sync(g);  // cvs / pin visible; every thread of the group past the accumulator barrier
-        {
-          const int q = warp & 3;  // TMEM lane quadrant this warp may access
-          const int r = 32 * q + lane;
-          const bool vhalf = gw >= 4;
-          const float4 cf = coef[k];
-          const float dt = cf.x;
-          const uint32_t trow = tmem_g + ((uint32_t)(32 * q) << 16);
-          if (!vhalf) {
-            // mean = x + dt (drift + offset) written over the lo operand (in place, own row)
-            auto u_chunk = [&](const float* acc, int c0, int nc) {
-              if (r >= N) return;
-#pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                if (c < nc && c0 + c < du) {
-                  const uint32_t off = a_off(lbo, r, (c0 + c) >> 2);
-                  const float4 hi = *reinterpret_cast<const float4*>(Ahi + off);
-                  float4 lo = *reinterpret_cast<const float4*>(Alo + off);
-                  const float4 cu = *reinterpret_cast<const float4*>(cvs + c0 + c);
-                  lo.x = (hi.x + lo.x) + dt * (acc[c + 0] + cu.x);
-                  lo.y = (hi.y + lo.y) + dt * (acc[c + 1] + cu.y);
-                  lo.z = (hi.z + lo.z) + dt * (acc[c + 2] + cu.z);
-                  lo.w = (hi.w + lo.w) + dt * (acc[c + 3] + cu.w);
-                  *reinterpret_cast<float4*>(Alo + off) = lo;
-                }
-              }
-            };
-            if (!restore) {
-              int c0 = 0;
-              for (; c0 + 32 <= L.du8; c0 += 32) {
-                float acc[32];
-                tmem_ld32(trow + c0, acc);
-                u_chunk(acc, c0, 32);
-              }
-              for (; c0 < L.du8; c0 += 8) {
-                float acc[32];
-                tmem_ld8(trow + c0, acc);
-                u_chunk(acc, c0, 8);
-              }
-            }
-          } else {
-            float ss = 0.f;
-            const float* cv = cvs + L.du8;
-            auto v_chunk = [&](const float* acc, int c0, int nc) {
-#pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                if (c < nc) {
-                  const float4 cc = *reinterpret_cast<const float4*>(cv + c0 + c);
-                  // columns >= dv: cv = 0 and the accumulator column is exactly 0 (zero rows of M)
-                  const float r0 = cc.x - dt * acc[c + 0], r1 = cc.y - dt * acc[c + 1];
-                  const float r2 = cc.z - dt * acc[c + 2], r3 = cc.w - dt * acc[c + 3];
-                  ss = fmaf(r0, r0, ss);
-                  ss = fmaf(r1, r1, ss);
-                  ss = fmaf(r2, r2, ss);
-                  ss = fmaf(r3, r3, ss);
-                }
-              }
-            };
-            int c0 = 0;
-            for (; c0 + 32 <= L.dv8; c0 += 32) {
-              float acc[32];
-              tmem_ld32(trow + L.du8 + c0, acc);
-              v_chunk(acc, c0, 32);
-            }
-            for (; c0 < L.dv8; c0 += 8) {
-              float acc[32];
-              tmem_ld8(trow + L.du8 + c0, acc);
-              v_chunk(acc, c0, 8);
-            }
-            if (r < N) lwraw[r] = -0.5f * (ss * cf.w + cf.z);
-          }
-          tc_fence_before();
-        }
-        group_sync(g);
-      };
-
       if (p.mode == MODE_CSMC) {
-        if (p.uss) store_particles(p.uss + (size_t)chain * (K + 1) * N * du);
+        if (p.uss) store_particles(p.uss + (size_t)chain * (K + 1) * N * du, gt, GTHREADS);
         if (init_gemm) {
-          gemm_and_epilogue(0, K, false, true);  // gibbs.py:136-137: (v, v_prev) = (vs[0], vs[1]) -> workspace slot K
+          // gibbs.py:136-137: weights of the initial particles, (v, v_prev) = (vs[0], vs[1]) -> workspace slot K
+          if (is_E) {
+            stage_cvs(K);
+            mbar_wait(accum + g, gcount & 1u);
+            tc_fence_after();
+            bar_E();
+            epilogue_v(0);
+            tc_fence_before();
+          }
+          ++gcount;
+          bar_all();
           for (int t = gt; t < N; t += GTHREADS) lw[t] = lwraw[t];
-          group_sync(g);
+          bar_all();
           if (gt == 0) mbar_arrive(ready + g);  // particles unchanged, accumulator drained
         }
-        if (gw == 0) warp_normalise_v3(lw, N, lane);  // csmc.py:155
-        group_sync(g);
+        if (is_R) warp_normalise_v3(lw, N, lane);  // csmc.py:155
+        bar_all();
         if (p.log_wss)
           for (int t = gt; t < N; t += GTHREADS) p.log_wss[(size_t)chain * (K + 1) * N + t] = lw[t];
       }
 
       // =============================== the K-step sweep ===============================
       for (int k = 0; k < K; ++k) {
-        // 1. GEMM on the tensor core || noise on the CUDA cores; epilogue: means -> Alo, log-likelihood -> lwraw
-        gemm_and_epilogue(k, k, true, false);
-
-        // 2. weights + ancestors
-        if (gw == 0) {
+        if (is_noise) {
+          // ---- noise on the CUDA cores || GEMM on the tensor core (first part) and || resampling (second part) ----
+          if (is_E) stage_cvs(k);
+          if (p.mode == MODE_CSMC) {  // the pinned reference particle of this step
+            const float* ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
+            for (int t = nt; t < du; t += NOISE_THREADS) pin[t] = ustar[t];
+            if (nt == 0) reinterpret_cast<int*>(pin)[du] = p.bs_star[(size_t)chain * (K + 1) + k + 1];
+          }
+          const Key ktr = skeys[2 * k + 1];
+          const float sd = coef[k].y;
+          make_noise(ktr, sd, I_0{}, I_1{});
+          if (is_E) {
+            mbar_wait(accum + g, gcount & 1u);
+            tc_fence_after();
+            bar_E();         // cvs visible to the four E warps
+            epilogue_v(k);   // log-likelihood -> lwraw
+            bar_ER_arrive(); // ... releases the resampling warp
+            epilogue_u(k);   // means -> Alo
+            tc_fence_before();
+          }
+          make_noise(ktr, sd, I_1{}, I_2{});
+        } else {
+          // ---- weights + ancestors (one warp) ----
+          bar_ER_sync();
           const Key kres = skeys[2 * k];
           if (p.mode == MODE_CSMC) {
             for (int q = lane; q < N; q += 32) w[q] = expf(lw[q]);  // csmc.py:139
@@ -609,6 +649,10 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             for (int q = lane; q < N; q += 32) lw[q] = lwraw[idx[q]];  // csmc.py:145 on the resampled parents
             __syncwarp();
             warp_normalise_v3(lw, N, lane);  // csmc.py:146
+            if (p.As)
+              for (int q = lane; q < N; q += 32) p.As[((size_t)chain * K + k) * N + q] = idx[q];
+            if (p.log_wss)
+              for (int q = lane; q < N; q += 32) p.log_wss[((size_t)chain * (K + 1) + k + 1) * N + q] = lw[q];
           } else {
             for (int q = lane; q < N; q += 32) lw[q] = lwraw[q];  // smc.py:144
             __syncwarp();
@@ -624,65 +668,66 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
               warp_sorted_multinomial(kres, w, N, cum, reinterpret_cast<float*>(tmp), idx, lane);
             else
               warp_systematic_or_stratified(kres, w, N, p.scheme == FBS_RESAMPLE_SYSTEMATIC, true, cum, idx, lane);
+            if (p.inds)
+              for (int q = lane; q < N; q += 32) p.inds[((size_t)chain * K + k) * N + q] = idx[q];
           }
         }
-        group_sync(g);
+        ++gcount;
+        bar_all();  // ancestors, means and noise complete
 
-        // 3. children: gather the parents' means, add the noise (in the noise registers)
-#pragma unroll
-        for (int i = 0; i < NT; ++i) {
-          if (task[i] != 0xFFFFFFFFu) {
-            const int pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
-            const float4 m0 = *reinterpret_cast<const float4*>(Alo + a_off(lbo, idx[pr], cg));
-            const float4 m1 = *reinterpret_cast<const float4*>(Alo + a_off(lbo, idx[pr + half], cg));
-            nz[0][4 * i + 0] += m0.x; nz[0][4 * i + 1] += m0.y; nz[0][4 * i + 2] += m0.z; nz[0][4 * i + 3] += m0.w;
-            nz[1][4 * i + 0] += m1.x; nz[1][4 * i + 1] += m1.y; nz[1][4 * i + 2] += m1.z; nz[1][4 * i + 3] += m1.w;
-          }
-        }
-        group_sync(g);  // every mean read before the operands are overwritten
-        {
-          const int bj = p.mode == MODE_CSMC ? reinterpret_cast<const int*>(pin)[du] : -1;
+        if (is_noise) {
+          // ---- children: gather the parents' means, add the noise (in the noise registers) ----
 #pragma unroll
           for (int i = 0; i < NT; ++i) {
             if (task[i] != 0xFFFFFFFFu) {
               const int pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
-              float4 x0 = make_float4(nz[0][4 * i], nz[0][4 * i + 1], nz[0][4 * i + 2], nz[0][4 * i + 3]);
-              float4 x1 = make_float4(nz[1][4 * i], nz[1][4 * i + 1], nz[1][4 * i + 2], nz[1][4 * i + 3]);
-              if (pr == bj) x0 = *reinterpret_cast<const float4*>(pin + 4 * cg);  // csmc.py:143
-              if (pr + half == bj) x1 = *reinterpret_cast<const float4*>(pin + 4 * cg);
-              put4(a_off(lbo, pr, cg), x0);
-              put4(a_off(lbo, pr + half, cg), x1);
+              const float4 m0 = *reinterpret_cast<const float4*>(Alo + a_off(lbo, idx[pr], cg));
+              const float4 m1 = *reinterpret_cast<const float4*>(Alo + a_off(lbo, idx[pr + half], cg));
+              nz[0][4 * i + 0] += m0.x; nz[0][4 * i + 1] += m0.y; nz[0][4 * i + 2] += m0.z; nz[0][4 * i + 3] += m0.w;
+              nz[1][4 * i + 0] += m1.x; nz[1][4 * i + 1] += m1.y; nz[1][4 * i + 2] += m1.z; nz[1][4 * i + 3] += m1.w;
             }
           }
-        }
-        fence_proxy_async();  // the new particles are read by the tensor core (async proxy) next step
-        group_sync(g);
-        if (gt == 0 && (k + 1 < K)) mbar_arrive(ready + g);
-
-        // optional history
-        if (p.mode == MODE_CSMC) {
-          if (p.As)
-            for (int t = gt; t < N; t += GTHREADS) p.As[((size_t)chain * K + k) * N + t] = idx[t];
-          if (p.log_wss)
-            for (int t = gt; t < N; t += GTHREADS) p.log_wss[((size_t)chain * (K + 1) + k + 1) * N + t] = lw[t];
-          if (p.uss) store_particles(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du);
-        } else {
-          if (p.inds)
-            for (int t = gt; t < N; t += GTHREADS) p.inds[((size_t)chain * K + k) * N + t] = idx[t];
-          if (p.us_hist) store_particles(p.us_hist + ((size_t)chain * K + k) * N * du);
+          bar_noise();  // every mean read before the operands are overwritten
+          {
+            const int bj = p.mode == MODE_CSMC ? reinterpret_cast<const int*>(pin)[du] : -1;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+              if (task[i] != 0xFFFFFFFFu) {
+                const int pr = task[i] & 0xFFFFu, cg = task[i] >> 16;
+                float4 x0 = make_float4(nz[0][4 * i], nz[0][4 * i + 1], nz[0][4 * i + 2], nz[0][4 * i + 3]);
+                float4 x1 = make_float4(nz[1][4 * i], nz[1][4 * i + 1], nz[1][4 * i + 2], nz[1][4 * i + 3]);
+                if (pr == bj) x0 = *reinterpret_cast<const float4*>(pin + 4 * cg);  // csmc.py:143
+                if (pr + half == bj) x1 = *reinterpret_cast<const float4*>(pin + 4 * cg);
+                put4(a_off(lbo, pr, cg), x0);
+                put4(a_off(lbo, pr + half, cg), x1);
+              }
+            }
+          }
+          fence_proxy_async();  // the new particles are read by the tensor core (async proxy) next step
+          bar_noise();
+          if (nt == 0 && (k + 1 < K)) mbar_arrive(ready + g);
+          // optional history
+          if (p.mode == MODE_CSMC) {
+            if (p.uss) store_particles(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du, nt, NOISE_THREADS);
+          } else {
+            if (p.us_hist) store_particles(p.us_hist + ((size_t)chain * K + k) * N * du, nt, NOISE_THREADS);
+          }
         }
       }
 
       // =============================== final state ===============================
-      if (p.mode == MODE_CSMC) {
-        if (p.us_last) store_particles(p.us_last + (size_t)chain * N * du);
-        if (p.log_ws_last)
-          for (int t = gt; t < N; t += GTHREADS) p.log_ws_last[(size_t)chain * N + t] = lw[t];
+      if (is_noise) {
+        float* dst = p.mode == MODE_CSMC ? p.us_last : p.uT;
+        if (dst) store_particles(dst + (size_t)chain * N * du, nt, NOISE_THREADS);
       } else {
-        if (p.uT) store_particles(p.uT + (size_t)chain * N * du);
-        if (p.log_ell && gt == 0) p.log_ell[chain] = scal[0];
+        if (p.mode == MODE_CSMC) {
+          if (p.log_ws_last)
+            for (int t = lane; t < N; t += 32) p.log_ws_last[(size_t)chain * N + t] = lw[t];
+        } else {
+          if (p.log_ell && lane == 0) p.log_ell[chain] = scal[0];
+        }
       }
-      group_sync(g);
+      bar_all();
     }
   }
 
@@ -797,8 +842,8 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   if (L.total > 227 * 1024) return -1;
   if (L.nout > TMEM_COLS_PER_GROUP || L.nkb < 1) return -1;
   const int ntasks = (p.N / 2) * L.ncg;
-  const int need = (ntasks + GTHREADS - 1) / GTHREADS;
-  if (need > 8) return -1;
+  const int need = (ntasks + NOISE_THREADS - 1) / NOISE_THREADS;
+  if (need > 7) return -1;
   {
     const int rc = launch_stepvec(stream, p);
     if (rc) return rc;
@@ -806,9 +851,8 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int64_t pairs = (p.B + 1) / 2;
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   cudaError_t e;
-  if (need <= 2) e = launch_v3_nt<2>(st, grid, L.total, p, stages);
-  else if (need <= 5) e = launch_v3_nt<5>(st, grid, L.total, p, stages);
-  else e = launch_v3_nt<8>(st, grid, L.total, p, stages);
+  if (need <= 3) e = launch_v3_nt<3>(st, grid, L.total, p, stages);
+  else e = launch_v3_nt<7>(st, grid, L.total, p, stages);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
