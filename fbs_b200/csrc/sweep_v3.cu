@@ -144,6 +144,22 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
+// polling wait that backs off: the waiting warps must not steal issue slots from the other group's noise
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done) __nanosleep(200);
+  } while (!done);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -176,12 +192,12 @@ struct Layout {
   int du8, dv8, nout, nkb, ncg, stages;
   uint32_t a_lbo, b_lbo, blk_bytes, stage_bytes, a_bytes;
   // byte offsets.  Group g: A operands at A + g * 2 * a_bytes (hi, then lo), small arrays at grp + g * grp_bytes + <field>
-  uint32_t A, ring, coef, bars, tmem, grp, grp_bytes;
+  uint32_t A, ring, bars, tmem, grp, grp_bytes;
   uint32_t cvs, lwraw, lw, w, cum, idx, tmp, keys, scal, skeys, pin;
   uint32_t total;
 };
 
-__host__ __device__ inline Layout make_layout(int N, int du, int dv, int K, int stages) {
+__host__ __device__ inline Layout make_layout(int N, int du, int dv, int stages) {
   Layout L;
   L.du8 = (du + 7) / 8 * 8;
   L.dv8 = (dv + 7) / 8 * 8;
@@ -203,7 +219,6 @@ __host__ __device__ inline Layout make_layout(int N, int du, int dv, int K, int 
   };
   L.A = take(2u * GROUPS * L.a_bytes);
   L.ring = take((uint32_t)stages * L.stage_bytes);  // also absorbs the M = 128 over-read of the last k-chunk
-  L.coef = take((uint32_t)K * 16u);                 // per step: dt, sd, lognorm, 1 / sd^2
   L.bars = take((2 * MAX_STAGES + 2 * GROUPS) * 8);
   L.tmem = take(16);
   L.grp = o;
@@ -217,7 +232,7 @@ __host__ __device__ inline Layout make_layout(int N, int du, int dv, int K, int 
   L.tmp = take((ROWS + 1) * 4);
   L.keys = take(64);
   L.scal = take(16);
-  L.skeys = take((uint32_t)K * 16u);        // per step: (resampling key, transition key)
+  L.skeys = take(64);                       // 2 slots (step parity) x (resampling key, transition key)
   L.pin = take((uint32_t)(du + 4) * 4u);    // pinned reference particle of the step + its slot
   L.grp_bytes = o;
   L.total = L.grp + GROUPS * L.grp_bytes;
@@ -250,12 +265,13 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
 template <int NT>
 __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int NT1 = (NT + 1) / 2;  // noise tasks generated in the shadow of the GEMM; the rest overlap the resampling
-  const Layout L = make_layout(p.N, p.du, p.dv, p.K, stages);
+  // noise tasks per thread: X (noise only) warps NT, E (epilogue + noise) warps NE = NT - 2 (the epilogue costs about two
+  // tasks); an E warp generates NE1 of them in the shadow of its GEMM and the rest while the resampling warp works
+  constexpr int NE = NT - 2, NE1 = NE > 2 ? NE - 2 : 0;
+  const Layout L = make_layout(p.N, p.du, p.dv, stages);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* ring = smem + L.ring;
-  float4* coef = reinterpret_cast<float4*>(smem + L.coef);  // (dt, sd, lognorm, 1/sd^2) of step k
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* accum = empty + MAX_STAGES;  // [g]: accumulator of group g complete
@@ -276,10 +292,6 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
       }
       fence_barrier_init();
     }
-  }
-  for (int k = tid; k < K; k += NTHREADS) {
-    const float sd = p.sd[k];
-    coef[k] = make_float4(p.dt[k], sd, p.lognorm[k], 1.0f / (sd * sd));
   }
   tc_fence_before();
   __syncthreads();
@@ -363,6 +375,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     const int gt = tid - 32 - g * GTHREADS, gw = gt >> 5;
     const bool is_E = gw < 4, is_R = gw == 4, is_noise = !is_R;
     const int nt = gw < 4 ? gt : gt - 32;  // index among the NOISE_THREADS noise threads
+    const int xt = gt - 160;               // index among the 64 X threads
     unsigned char* Ahi = smem + L.A + (size_t)g * 2u * L.a_bytes;
     unsigned char* Alo = Ahi + L.a_bytes;  // doubles as the transition-mean buffer between the GEMM and the gather
     unsigned char* gb = smem + L.grp + (size_t)g * L.grp_bytes;
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     int* tmp = reinterpret_cast<int*>(gb + L.tmp);
     Key* kbase = reinterpret_cast<Key*>(gb + L.keys);  // [0]: sweep key, [2]: init key
     float* scal = reinterpret_cast<float*>(gb + L.scal);
-    Key* skeys = reinterpret_cast<Key*>(gb + L.skeys);  // [2k]: resampling key, [2k+1]: transition key of step k
+    Key* skeys = reinterpret_cast<Key*>(gb + L.skeys);  // slot k & 1: [0] resampling key, [1] transition key of step k
     float* pin = reinterpret_cast<float*>(gb + L.pin);  // [0, du): u*_{k+1}, [du]: its slot b*_{k+1} (as int bits)
     const float logN = logf((float)N);
     const uint32_t tmem_g = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
@@ -396,8 +409,10 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     uint32_t task[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-      const int t = nt + NOISE_THREADS * i;
-      task[i] = (is_noise && t < ntasks) ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
+      int t = ntasks;
+      if (is_E && i < NE) t = gt + 128 * i;
+      if (gw > 4) t = 128 * NE + xt + 64 * i;
+      task[i] = t < ntasks ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
     }
     float nz[2][4 * NT];  // noise, then the children, of the owned (rows, columns)
 
@@ -447,28 +462,37 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         }
       };
       using I_0 = std::integral_constant<int, 0>;
-      using I_1 = std::integral_constant<int, NT1>;
+      using I_1 = std::integral_constant<int, NE1>;
       using I_2 = std::integral_constant<int, NT>;
 
-      // E warps: stage the per-chain step vectors of workspace slot `slot`
-      auto stage_cvs = [&](int slot) {
+      // E warps: stage the per-chain step vectors of workspace slot `slot` (global loads first, shared stores later so
+      // that the load latency hides behind the noise)
+      float cv_reg[2];
+      auto load_cvs = [&](int slot) {
         const float* wsrow = p.ws + ((size_t)chain * (K + 1) + slot) * (size_t)(du + (dv + 3) / 4 * 4);
-        for (int t = gt; t < L.du8 + L.dv8; t += 128) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int t = gt + 128 * j;
           float x = 0.f;
           if (t < L.du8) {
-            if (t < du) x = wsrow[t];
+            if (t < du) x = __ldg(wsrow + t);
           } else if (t - L.du8 < dv) {
-            x = wsrow[du + (t - L.du8)];
+            x = __ldg(wsrow + du + (t - L.du8));
           }
-          cvs[t] = x;
+          cv_reg[j] = x;
         }
+      };
+      auto store_cvs = [&]() {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (gt + 128 * j < L.du8 + L.dv8) cvs[gt + 128 * j] = cv_reg[j];
       };
       // E warps, one particle row per thread.  v-half of the accumulator -> lwraw (per-row Gaussian log-likelihood)
       const int erow = 32 * (warp & 3) + lane;  // TMEM lane quadrant this warp may access
       const uint32_t trow = tmem_g + ((uint32_t)(32 * (warp & 3)) << 16);
       auto epilogue_v = [&](int k) {
-        const float4 cf = coef[k];
-        const float dt = cf.x;
+        const float dt = __ldg(p.dt + k), sdk = __ldg(p.sd + k), lognorm = __ldg(p.lognorm + k);
+        const float inv_var = 1.0f / (sdk * sdk);
         float ss = 0.f;
         const float* cv = cvs + L.du8;
         auto v_chunk = [&](const float* acc, int c0, int nc) {
@@ -497,11 +521,11 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           tmem_ld8(trow + L.du8 + c0, acc);
           v_chunk(acc, c0, 8);
         }
-        if (erow < N) lwraw[erow] = -0.5f * (ss * cf.w + cf.z);
+        if (erow < N) lwraw[erow] = -0.5f * (ss * inv_var + lognorm);
       };
       // u-half: mean = x + dt (drift + offset) written over the lo operand (in place, own row)
       auto epilogue_u = [&](int k) {
-        const float dt = coef[k].x;
+        const float dt = __ldg(p.dt + k);
         auto u_chunk = [&](const float* acc, int c0, int nc) {
           if (erow >= N) return;
 #pragma unroll
@@ -550,19 +574,21 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         reinterpret_cast<float*>(Alo)[t] = 0.f;
       }
       bar_all();
-      // all step keys of the sweep up front, in parallel (they depend only on the chain key)
-      for (int k = gt; k < K; k += GTHREADS) {
+      // keys of step k -> slot k & 1.  Step 0 here; step k + 1 by the resampling warp while it waits in step k.
+      auto step_keys = [&](int k) {
         const Key key_k = split_key(kbase[0], (uint32_t)K, (uint32_t)k);  // csmc.py:157 / smc.py:154
         Key a, b;
         split2(key_k, a, b);
+        Key* dst = skeys + 2 * (k & 1);
         if (p.mode == MODE_CSMC) {  // csmc.py:136: (key_resampling, key_transition)
-          skeys[2 * k] = a;
-          skeys[2 * k + 1] = b;
+          dst[0] = a;
+          dst[1] = b;
         } else {  // smc.py:142: (key_proposal, key_resampling)
-          skeys[2 * k + 1] = a;
-          skeys[2 * k] = b;
+          dst[1] = a;
+          dst[0] = b;
         }
-      }
+      };
+      if (gt == GTHREADS - 1) step_keys(0);
       if (p.mode == MODE_PMCMC) {
         load_particles(p.u0s + (size_t)chain * N * du, du, gt, GTHREADS);
       } else if (p.init_mode == FBS_INIT_DEGENERATE) {  // gibbs.py:140-144
@@ -592,8 +618,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         if (init_gemm) {
           // gibbs.py:136-137: weights of the initial particles, (v, v_prev) = (vs[0], vs[1]) -> workspace slot K
           if (is_E) {
-            stage_cvs(K);
-            mbar_wait(accum + g, gcount & 1u);
+            load_cvs(K);
+            store_cvs();
+            mbar_wait_sleep(accum + g, gcount & 1u);
             tc_fence_after();
             bar_E();
             epilogue_v(0);
@@ -615,17 +642,18 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
       for (int k = 0; k < K; ++k) {
         if (is_noise) {
           // ---- noise on the CUDA cores || GEMM on the tensor core (first part) and || resampling (second part) ----
-          if (is_E) stage_cvs(k);
+          if (is_E) load_cvs(k);
           if (p.mode == MODE_CSMC) {  // the pinned reference particle of this step
             const float* ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
             for (int t = nt; t < du; t += NOISE_THREADS) pin[t] = ustar[t];
             if (nt == 0) reinterpret_cast<int*>(pin)[du] = p.bs_star[(size_t)chain * (K + 1) + k + 1];
           }
-          const Key ktr = skeys[2 * k + 1];
-          const float sd = coef[k].y;
+          const Key ktr = skeys[2 * (k & 1) + 1];
+          const float sd = __ldg(p.sd + k);
           make_noise(ktr, sd, I_0{}, I_1{});
           if (is_E) {
-            mbar_wait(accum + g, gcount & 1u);
+            store_cvs();
+            mbar_wait_sleep(accum + g, gcount & 1u);
             tc_fence_after();
             bar_E();         // cvs visible to the four E warps
             epilogue_v(k);   // log-likelihood -> lwraw
@@ -636,8 +664,99 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           make_noise(ktr, sd, I_1{}, I_2{});
         } else {
           // ---- weights + ancestors (one warp) ----
+          const bool fast = p.mode == MODE_PMCMC && (p.scheme == FBS_RESAMPLE_STRATIFIED || p.scheme == FBS_RESAMPLE_SYSTEMATIC);
+          float* ubuf = reinterpret_cast<float*>(tmp);
+          // everything that does not depend on the weights happens BEFORE the barrier, off the step's critical path:
+          // the keys of the next step and (fast path) this step's resampling uniforms
+          if (lane == 0 && k + 1 < K) step_keys(k + 1);
+          if (fast) {
+            const Key kr = skeys[2 * (k & 1)];
+            if (p.scheme == FBS_RESAMPLE_SYSTEMATIC) {  // uniform(key, ()) = random_bits(key, 1) word 0
+              uint32_t x0 = 0u, x1 = 0u;
+              threefry2x32(kr.k0, kr.k1, x0, x1);
+              if (lane == 0) ubuf[0] = bits_to_unit(x0);
+            } else {
+              const uint32_t h = ((uint32_t)N + 1u) >> 1;
+              for (uint32_t b = lane; b < h; b += 32) {
+                uint32_t c0, c1;
+                random_bits_block(kr, N, b, c0, c1);
+                ubuf[b] = bits_to_unit(c0);
+                if (b + h < (uint32_t)N) ubuf[b + h] = bits_to_unit(c1);
+              }
+            }
+            __syncwarp();
+          }
           bar_ER_sync();
-          const Key kres = skeys[2 * k];
+          const Key kres = skeys[2 * (k & 1)];
+          if (fast) {
+            // pmcmc_filter_step (smc.py:144-148) with the warp's 4 elements per lane (q = lane + 32 j) in registers;
+            // same operation order as warp_normalise_v3 / warp_systematic_or_stratified, hence the same bits
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              v[j] = q < N ? lwraw[q] : -INFINITY;  // smc.py:144
+            }
+            if (p.lw_hist) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (lane + 32 * j < N) p.lw_hist[((size_t)chain * K + k) * N + lane + 32 * j] = v[j];
+            }
+            float m = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+            m = warp_max(m);
+            if (!(fabsf(m) < INFINITY)) m = 0.f;
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (lane + 32 * j < N) sacc += expf(v[j] - m);
+            sacc = warp_sum_v3(sacc);
+            const float lse = logf(sacc) + m;  // smc.py:145,147
+            if (lane == 0) scal[0] = (scal[0] - logN) + lse;  // smc.py:146
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              if (q < N) {
+                v[j] -= lse;
+                lw[q] = v[j];
+                w[q] = expf(v[j]);
+              }
+            }
+            __syncwarp();
+            warp_seq_cumsum(w, cum, N, lane);
+            // ancestors: clip(searchsorted(cumsum(w), (arange(n) + u) / n), 0, n - 1)   (resampling.py:43-59), the four
+            // binary searches of a lane interleaved
+            const float fn = (float)N;
+            const bool sys = p.scheme == FBS_RESAMPLE_SYSTEMATIC;
+            float r[4];
+            int lo[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              const float u = ubuf[sys ? 0 : (q < N ? q : 0)];
+              r[j] = __fdiv_rn(__fadd_rn((float)q, u), fn);
+              lo[j] = 0;
+              hi[j] = q < N ? N : 0;
+            }
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (lo[j] < hi[j]) {
+                  const int mid = (lo[j] + hi[j]) >> 1;
+                  if (cum[mid] < r[j]) lo[j] = mid + 1; else hi[j] = mid;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              if (q < N) {
+                const int id = min(max(lo[j], 0), N - 1);
+                idx[q] = id;
+                if (p.inds) p.inds[((size_t)chain * K + k) * N + q] = id;
+              }
+            }
+          } else
           if (p.mode == MODE_CSMC) {
             for (int q = lane; q < N; q += 32) w[q] = expf(lw[q]);  // csmc.py:139
             __syncwarp();
@@ -837,13 +956,14 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   if (p.N < 2 || (p.N & 1) || p.N > ROWS) return -1;
   if (p.du % 4 != 0 || p.du < 4) return -1;
   int stages = MAX_STAGES;
-  Layout L = make_layout(p.N, p.du, p.dv, p.K, stages);
-  while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, p.K, --stages);
+  Layout L = make_layout(p.N, p.du, p.dv, stages);
+  while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, --stages);
   if (L.total > 227 * 1024) return -1;
   if (L.nout > TMEM_COLS_PER_GROUP || L.nkb < 1) return -1;
   const int ntasks = (p.N / 2) * L.ncg;
-  const int need = (ntasks + NOISE_THREADS - 1) / NOISE_THREADS;
-  if (need > 7) return -1;
+  if (((p.du + 7) / 8 * 8 + (p.dv + 7) / 8 * 8) > 2 * 128) return -1;  // cv_reg: 2 values per E thread
+  const int need = (ntasks + 256 + NOISE_THREADS - 1) / NOISE_THREADS;  // 128 (NT - 2) + 64 NT >= ntasks
+  if (need > 8) return -1;
   {
     const int rc = launch_stepvec(stream, p);
     if (rc) return rc;
@@ -851,8 +971,8 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int64_t pairs = (p.B + 1) / 2;
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   cudaError_t e;
-  if (need <= 3) e = launch_v3_nt<3>(st, grid, L.total, p, stages);
-  else e = launch_v3_nt<7>(st, grid, L.total, p, stages);
+  if (need <= 4) e = launch_v3_nt<4>(st, grid, L.total, p, stages);
+  else e = launch_v3_nt<8>(st, grid, L.total, p, stages);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
