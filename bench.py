@@ -317,7 +317,7 @@ def run_gpu(args):
                     'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms, 'steps': e2e_steps},
             'gpu_launches': int(launches),
             'clocks': clk,
-            'roofline': {'bound': 'hbm', 'kernel': 'sweep_affine_kernel (fbs_pmcmc_filter_affine_f32)',
+            'roofline': {'bound': 'hbm', 'kernel': 'sweep_v3_kernel (fbs_pmcmc_filter_affine_f32; tcgen05 split-TF32 GEMM + in-kernel threefry + resampling)',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
                          'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / ms_per_step,

@@ -48,7 +48,17 @@ def stream():
 
 
 def out(t, host: bool):
-    """Return a device tensor as-is, or as a numpy array when the caller passed host buffers."""
+    """Return a device tensor as-is, or as a numpy array when the caller passed host buffers.
+
+    The D2H copy lands in page-locked memory from torch's caching host allocator (a pageable destination makes the
+    driver stage the copy through a bounce buffer at a fraction of the PCIe rate); the numpy array returned is a view
+    of that block and keeps it alive, and feeding it back as an input is again a pinned H2D copy.
+    """
     if t is None or not host:
         return t
-    return t.cpu().numpy()
+    if t.dtype == torch.uint32 or t.numel() < 4096:
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()

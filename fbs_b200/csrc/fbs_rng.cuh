@@ -42,6 +42,7 @@ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t&
 }
 
 // Four blocks in lockstep (independent dependency chains interleaved: the rounds are latency bound one at a time).
+// ptxas splits the additions between the ALU pipe (IADD3 / VIADD) and the FMA pipe (IMAD.IADD) by itself.
 __device__ __forceinline__ void threefry2x32_x4(uint32_t k0, uint32_t k1, uint32_t (&x0)[4], uint32_t (&x1)[4]) {
   const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
 #define FBS_TF_INJ(a, b)            \

@@ -5,20 +5,24 @@
 //   U M = Uhi Mhi + Ulo Mhi + Uhi Mlo        (hi = round-to-nearest tf32, lo = exact float32 remainder)
 // accumulated in float32 in TENSOR MEMORY.
 //
-// A CSMC step is a strictly serial chain of phases (GEMM -> weights -> ancestors -> gather), one of which
-// (resampling) keeps a single warp busy.  So one CTA runs TWO independent chains, one per group of 8 warps, each
-// with its own particle operands, accumulator (256 TMEM columns) and named barrier; the groups drift half a step
-// apart and fill each other's bubbles ("ping-pong"):
+// A CSMC step is a strictly serial chain of phases (GEMM -> weights -> ancestors -> gather), so one CTA runs TWO
+// independent chains, one per group of 7 warps, each with its own particle operands, accumulator (256 TMEM columns)
+// and named barriers; the groups drift half a step apart and fill each other's bubbles.  16 warps = 512 threads is
+// the largest CTA that still gets 128 registers per thread.
 //
-//   warp 0          : control.  One elected thread streams the packed (hi, lo) K-blocks of M_k through a ring of
-//                     shared-memory stages with TMA bulk copies (cp.async.bulk + mbarrier) and issues the
-//                     tcgen05.mma's of both groups in a fixed alternating order (GEMM t of group 0, GEMM t of
-//                     group 1, ...), each when that group has signalled "particles ready".
-//   warps 1+8g..8+8g: group g.  During its GEMM: the step's transition noise (threefry2x32) in registers.  After it:
-//                     4 warps read the u-half of the accumulator from TMEM (tcgen05.ld, one particle row per
-//                     thread) and write the transition means, 4 warps the v-half and the per-row Gaussian
-//                     log-likelihood; one warp resamples; all gather the parents' means + noise and write the new
-//                     particles (hi / lo split) in the UMMA K-major core-matrix layout.
+//   warp 0   : MMA.  One elected thread issues the tcgen05.mma's of both groups in a fixed alternating order (GEMM t of
+//              group 0, GEMM t of group 1, ...), each when that group has signalled "particles ready" (mbarrier).
+//   warp 15  : TMA producer.  One elected thread streams the packed (hi, lo) K-blocks of M_k through a ring of
+//              shared-memory slots with bulk copies (cp.async.bulk + mbarrier), in the order the MMA warp consumes them.
+//   group g (warps 1 + 7g .. 7 + 7g), by role:
+//     E x4   : epilogue + noise.  Noise tasks (threefry2x32 -> normals, kept in registers) in the shadow of the GEMM;
+//              then tcgen05.ld of the accumulator, one particle row per thread: v-half -> Gaussian log-likelihood
+//              (releases R), u-half -> transition means; then the rest of their noise.
+//     R x1   : resampling only (normalise, sequential cumsum, searches), register resident; the step keys of the next
+//              step and this step's uniforms are computed before the weights arrive, off the critical path.
+//     X x2   : noise only (two tasks more than an E warp: what the epilogue costs).
+//   After the group barrier all noise warps gather the parents' means + their noise and write the new particles
+//   (hi / lo split) in the UMMA K-major core-matrix layout.
 //
 // Shared-memory operand layout (no swizzle, K-major "interleave"): element (row r, k) of an operand lives at
 //   (k / 4) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 4) * 4  bytes,
@@ -43,8 +47,9 @@ constexpr int GROUPS = 2;            // chains in flight per CTA
 constexpr int GWARPS = 7;            // warps per group: 4 epilogue + noise, 1 resampling, 2 noise only
 constexpr int GTHREADS = 32 * GWARPS;
 constexpr int NOISE_THREADS = 32 * (GWARPS - 1);
-constexpr int NTHREADS = 32 * (1 + GROUPS * GWARPS);
-constexpr int MAX_STAGES = 4;        // ring of K-blocks of the step matrix (2..4, chosen by the host to fit)
+constexpr int NWARPS = 2 + GROUPS * GWARPS;  // MMA warp, two groups, TMA producer warp
+constexpr int NTHREADS = 32 * NWARPS;
+constexpr int MAX_STAGES = 8;        // ring of K-blocks of the step matrix (2..4, chosen by the host to fit)
 constexpr int TMEM_COLS_PER_GROUP = 256;
 constexpr uint32_t SELFTEST_LBO = (ROWS / 8) * 128;
 
@@ -190,14 +195,17 @@ __device__ __noinline__ Noise8 noise_task(uint32_t k0, uint32_t k1, uint32_t b, 
 
 struct Layout {
   int du8, dv8, nout, nkb, ncg, stages;
-  uint32_t a_lbo, b_lbo, blk_bytes, stage_bytes, a_bytes;
+  int nu_pass, nv_pass;  // output rows of the second (u) and first (v + the last u rows) GEMM pass, multiples of 16
+  uint32_t a_lbo, b_lbo, blk_bytes, img_bytes, stage_bytes, a_bytes;
   // byte offsets.  Group g: A operands at A + g * 2 * a_bytes (hi, then lo), small arrays at grp + g * grp_bytes + <field>
   uint32_t A, ring, bars, tmem, grp, grp_bytes;
   uint32_t cvs, lwraw, lw, w, cum, idx, tmp, keys, scal, skeys, pin;
   uint32_t total;
 };
 
-__host__ __device__ inline Layout make_layout(int N, int du, int dv, int stages) {
+__host__ __device__ inline Layout make_layout(int N, int du, int dv, int stages_flags) {
+  const int stages = stages_flags & 0xFF;
+  const bool twopass = (stages_flags >> 8) & 1;
   Layout L;
   L.du8 = (du + 7) / 8 * 8;
   L.dv8 = (dv + 7) / 8 * 8;
@@ -209,7 +217,10 @@ __host__ __device__ inline Layout make_layout(int N, int du, int dv, int stages)
   L.a_lbo = (uint32_t)((N + 7) / 8) * 128u;
   L.b_lbo = (uint32_t)(L.nout / 8) * 128u;
   L.blk_bytes = 2u * L.b_lbo;
-  L.stage_bytes = 2u * L.blk_bytes;
+  L.img_bytes = 2u * L.blk_bytes;           // one K-block of the image in global memory: (hi | lo) x 2 k-chunks x nout rows
+  L.nu_pass = twopass ? (L.du8 / 16) * 16 : 0;
+  L.nv_pass = L.nout - L.nu_pass;
+  L.stage_bytes = 4u * (uint32_t)(L.nv_pass / 8) * 128u;  // ring slot: the rows of ONE pass, (hi | lo) x 2 k-chunks, compact
   L.a_bytes = (uint32_t)(L.du8 / 4) * L.a_lbo;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes) {
@@ -219,7 +230,7 @@ __host__ __device__ inline Layout make_layout(int N, int du, int dv, int stages)
   };
   L.A = take(2u * GROUPS * L.a_bytes);
   L.ring = take((uint32_t)stages * L.stage_bytes);  // also absorbs the M = 128 over-read of the last k-chunk
-  L.bars = take((2 * MAX_STAGES + 2 * GROUPS) * 8);
+  L.bars = take((2 * MAX_STAGES + 3 * GROUPS) * 8);
   L.tmem = take(16);
   L.grp = o;
   o = 0;
@@ -263,22 +274,23 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages) {
+__global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages_flags) {
+  const int stages = stages_flags & 0xFF;
   extern __shared__ __align__(1024) unsigned char smem[];
   // noise tasks per thread: X (noise only) warps NT, E (epilogue + noise) warps NE = NT - 2 (the epilogue costs about two
-  // tasks); an E warp generates NE1 of them in the shadow of its GEMM and the rest while the resampling warp works
-  constexpr int NE = NT - 2, NE1 = NE > 2 ? NE - 2 : 0;
-  const Layout L = make_layout(p.N, p.du, p.dv, stages);
+  // tasks); an E warp generates NE1 of them in the shadow of the first GEMM pass, up to NE2 in the shadow of the second
+  // pass (while the resampling warp works), the rest after its u-epilogue
+  constexpr int NE = NT - 2, NE1 = NE / 2, NE2 = NE > 0 ? NE - 1 : 0;
+  const Layout L = make_layout(p.N, p.du, p.dv, stages_flags);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* ring = smem + L.ring;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + MAX_STAGES;
-  uint64_t* accum = empty + MAX_STAGES;  // [g]: accumulator of group g complete
-  uint64_t* ready = accum + GROUPS;      // [g]: particles of group g written, accumulator drained
+  uint64_t* accum = empty + MAX_STAGES;  // [g]: first pass (v columns) of group g's accumulator complete
+  uint64_t* accum_u = accum + GROUPS;    // [g]: second pass (u columns) complete
+  uint64_t* ready = accum_u + GROUPS;    // [g]: particles of group g written, accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem);
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nout >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-
   if (warp == 0) {
     tmem_alloc(tmem_slot, GROUPS * TMEM_COLS_PER_GROUP);
     if (lane == 0) {
@@ -288,6 +300,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
       }
       for (int g = 0; g < GROUPS; ++g) {
         mbar_init(accum + g, 1);
+        mbar_init(accum_u + g, 1);
         mbar_init(ready + g, 1);
       }
       fence_barrier_init();
@@ -308,37 +321,51 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     nch[g] = lim > (int64_t)blockIdx.x ? (uint32_t)((lim - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
   }
 
-  if (warp == 0) {
-    // =============================== control warp ===============================
+  const uint32_t G0 = nch[0] * GP, G1 = nch[1] * GP;  // G0 >= G1; GEMM order: (0,0) (1,0) (0,1) (1,1) ...
+  // Each GEMM runs as two passes over the K-blocks: first the output rows [nu_pass, nout) -- every v row, what the
+  // weights need -- then the rows [0, nu_pass), so that the resampling overlaps the second pass.
+  const int npass = L.nu_pass > 0 ? 2 : 1;
+
+  if (warp == NWARPS - 1) {
+    // =============================== TMA producer warp ===============================
+    // streams the K-blocks of the step matrices, in the order the MMA warp consumes them, through the ring
     if (lane == 0) {
-      const uint32_t G0 = nch[0] * GP, G1 = nch[1] * GP;  // G0 >= G1; GEMM order: (0,0) (1,0) (0,1) (1,1) ...
-      uint32_t prod = 0, cons = 0;                         // K-blocks requested from TMA / consumed by the MMA
-      uint32_t pt = 0, pg = 0, pkb = 0;                    // producer cursor: GEMM (pg, pt), K-block pkb
-      bool pvalid = G0 > 0;
-      auto produce = [&]() {
-        if (!pvalid) return;
-        const uint32_t s = prod % (uint32_t)stages;
-        if (prod >= (uint32_t)stages) mbar_wait(empty + s, ((prod / (uint32_t)stages) - 1u) & 1u);
-        uint32_t step = pt % GP;
+      uint32_t ps = 0, pph = 1;  // slot, parity of its "empty" barrier (1: passes on a fresh barrier)
+      fence_proxy_async();
+      for (uint32_t t = 0; t < G0; ++t) {
+        uint32_t step = t % GP;
         if (init_gemm) step = step == 0 ? 0 : step - 1;  // the initial weights use the step-0 matrix
-        mbar_expect_tx(full + s, L.stage_bytes);
-        bulk_g2s(ring + (size_t)s * L.stage_bytes,
-                 reinterpret_cast<const unsigned char*>(p.MTc) + ((size_t)step * L.nkb + pkb) * L.stage_bytes, L.stage_bytes,
-                 full + s);
-        ++prod;
-        if (++pkb == (uint32_t)L.nkb) {
-          pkb = 0;
-          if (pg == 0 && pt < G1) {
-            pg = 1;
-          } else {
-            pg = 0;
-            ++pt;
-            pvalid = pt < G0;
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(p.MTc) + (size_t)step * L.nkb * L.img_bytes;
+        for (int g = 0; g < GROUPS; ++g) {
+          if (g == 1 && t >= G1) break;
+          for (int pass = 0; pass < npass; ++pass) {
+            const uint32_t r0 = pass == 0 ? (uint32_t)L.nu_pass : 0u;
+            const uint32_t np = pass == 0 ? (uint32_t)L.nv_pass : (uint32_t)L.nu_pass;
+            const uint32_t run = (np / 8u) * 128u;  // bytes of this pass's rows inside one (part, k-chunk) of the image
+            const unsigned char* src = img + (size_t)(r0 / 8u) * 128u;
+            for (int kb = 0; kb < L.nkb; ++kb, src += L.img_bytes) {
+              mbar_wait(empty + ps, pph);
+              unsigned char* dst = ring + (size_t)ps * L.stage_bytes;
+              mbar_expect_tx(full + ps, 4u * run);
+#pragma unroll
+              for (uint32_t c = 0; c < 4; ++c)  // (hi, chunk 0) (hi, chunk 1) (lo, chunk 0) (lo, chunk 1)
+                bulk_g2s(dst + c * run, src + (size_t)c * L.b_lbo, run, full + ps);
+              if (++ps == (uint32_t)stages) {
+                ps = 0;
+                pph ^= 1u;
+              }
+            }
           }
         }
-      };
-      fence_proxy_async();
-      for (int s = 0; s < stages - 1; ++s) produce();
+      }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
+    // =============================== MMA warp ===============================
+    if (lane == 0) {
+      uint32_t cs = 0, cph = 0;  // slot, parity of its "full" barrier
+      const uint32_t ring16 = smem_u32(ring) >> 4, stage16 = L.stage_bytes >> 4;
+      const uint64_t desc_hi_A = ((uint64_t)((L.a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
       for (uint32_t t = 0; t < G0; ++t) {
         for (int g = 0; g < GROUPS; ++g) {
           if (g == 1 && t >= G1) break;
@@ -346,24 +373,35 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           tc_fence_after();
           const uint32_t a_hi0 = smem_u32(smem + L.A) + (uint32_t)g * 2u * L.a_bytes;
           const uint32_t d_tmem = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
-          for (int kb = 0; kb < L.nkb; ++kb) {
-            produce();  // refill the stage freed by the previous K-block's MMAs
-            const uint32_t s = cons % (uint32_t)stages;
-            mbar_wait(full + s, (cons / (uint32_t)stages) & 1u);
-            tc_fence_after();
-            const uint32_t a_hi = a_hi0 + (uint32_t)kb * 2u * L.a_lbo;
-            const uint32_t a_lo = a_hi + L.a_bytes;
-            const uint32_t b_hi = smem_u32(ring + (size_t)s * L.stage_bytes);
-            const uint32_t b_lo = b_hi + L.blk_bytes;
-            const uint64_t dAh = make_desc(a_hi, L.a_lbo, 128), dAl = make_desc(a_lo, L.a_lbo, 128);
-            const uint64_t dBh = make_desc(b_hi, L.b_lbo, 128), dBl = make_desc(b_lo, L.b_lbo, 128);
-            umma_tf32(d_tmem, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
-            umma_tf32(d_tmem, dAl, dBh, idesc, 1u);
-            umma_tf32(d_tmem, dAh, dBl, idesc, 1u);
-            umma_commit(empty + s);  // stage free once these MMAs have read it
-            ++cons;
+          for (int pass = 0; pass < npass; ++pass) {
+            const uint32_t r0 = pass == 0 ? (uint32_t)L.nu_pass : 0u;
+            const uint32_t np = pass == 0 ? (uint32_t)L.nv_pass : (uint32_t)L.nu_pass;
+            const uint32_t run = (np / 8u) * 128u;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((np >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+            const uint64_t desc_hi_B = ((uint64_t)((run >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+            const uint32_t dt = d_tmem + r0;
+            // descriptors advance by plain adds on the (address >> 4) field; all operands sit below 256 KB, no carry
+            uint64_t dAh = desc_hi_A | (uint64_t)((a_hi0 >> 4) & 0x3FFFu);
+            uint64_t dAl = desc_hi_A | (uint64_t)(((a_hi0 + L.a_bytes) >> 4) & 0x3FFFu);
+            const uint64_t a_inc = (uint64_t)((2u * L.a_lbo) >> 4), b_lo_off = (uint64_t)((2u * run) >> 4);
+            for (int kb = 0; kb < L.nkb; ++kb) {
+              mbar_wait(full + cs, cph);
+              tc_fence_after();
+              const uint64_t dBh = desc_hi_B | (uint64_t)((ring16 + cs * stage16) & 0x3FFFu);
+              const uint64_t dBl = dBh + b_lo_off;
+              umma_tf32(dt, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
+              umma_tf32(dt, dAl, dBh, idesc, 1u);
+              umma_tf32(dt, dAh, dBl, idesc, 1u);
+              umma_commit(empty + cs);  // slot free once these MMAs have read it
+              dAh += a_inc;
+              dAl += a_inc;
+              if (++cs == (uint32_t)stages) {
+                cs = 0;
+                cph ^= 1u;
+              }
+            }
+            umma_commit((pass == 0 ? accum : accum_u) + g);  // accumulator columns of this pass complete
           }
-          umma_commit(accum + g);  // accumulator of group g complete
         }
       }
     }
@@ -463,7 +501,8 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
       };
       using I_0 = std::integral_constant<int, 0>;
       using I_1 = std::integral_constant<int, NE1>;
-      using I_2 = std::integral_constant<int, NT>;
+      using I_2 = std::integral_constant<int, NE2>;
+      using I_3 = std::integral_constant<int, NT>;
 
       // E warps: stage the per-chain step vectors of workspace slot `slot` (global loads first, shared stores later so
       // that the load latency hides behind the noise)
@@ -595,7 +634,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         load_particles(p.us_star + (size_t)chain * (K + 1) * du, 0, gt, GTHREADS);
         for (int t = gt; t < N; t += GTHREADS) lw[t] = p.init_log_w;
       } else {  // gibbs.py:133-137
-        make_noise(kbase[2], 1.0f, I_0{}, I_2{});
+        make_noise(kbase[2], 1.0f, I_0{}, I_3{});
         const int b0 = p.bs_star[(size_t)chain * (K + 1)];
         const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
 #pragma unroll
@@ -653,15 +692,20 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           make_noise(ktr, sd, I_0{}, I_1{});
           if (is_E) {
             store_cvs();
-            mbar_wait_sleep(accum + g, gcount & 1u);
+            mbar_wait_sleep(accum + g, gcount & 1u);  // first pass: every v column
             tc_fence_after();
             bar_E();         // cvs visible to the four E warps
             epilogue_v(k);   // log-likelihood -> lwraw
             bar_ER_arrive(); // ... releases the resampling warp
+          }
+          make_noise(ktr, sd, I_1{}, I_2{});
+          if (is_E) {
+            if (L.nu_pass > 0) mbar_wait_sleep(accum_u + g, gcount & 1u);  // second pass: the u columns
+            tc_fence_after();
             epilogue_u(k);   // means -> Alo
             tc_fence_before();
           }
-          make_noise(ktr, sd, I_1{}, I_2{});
+          make_noise(ktr, sd, I_2{}, I_3{});
         } else {
           // ---- weights + ancestors (one warp) ----
           const bool fast = p.mode == MODE_PMCMC && (p.scheme == FBS_RESAMPLE_STRATIFIED || p.scheme == FBS_RESAMPLE_SYSTEMATIC);
@@ -956,8 +1000,10 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   if (p.N < 2 || (p.N & 1) || p.N > ROWS) return -1;
   if (p.du % 4 != 0 || p.du < 4) return -1;
   int stages = MAX_STAGES;
-  Layout L = make_layout(p.N, p.du, p.dv, stages);
-  while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, --stages);
+  const char* tp = getenv("FBS_V3_TWOPASS");
+  const int flags = (tp != nullptr && tp[0] == '1') ? 0x100 : 0;  // two-pass GEMM (v columns first): slower, the small-N MMAs are bound by operand fetch
+  Layout L = make_layout(p.N, p.du, p.dv, stages | flags);
+  while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, --stages | flags);
   if (L.total > 227 * 1024) return -1;
   if (L.nout > TMEM_COLS_PER_GROUP || L.nkb < 1) return -1;
   const int ntasks = (p.N / 2) * L.ncg;
@@ -971,8 +1017,8 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int64_t pairs = (p.B + 1) / 2;
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   cudaError_t e;
-  if (need <= 4) e = launch_v3_nt<4>(st, grid, L.total, p, stages);
-  else e = launch_v3_nt<8>(st, grid, L.total, p, stages);
+  if (need <= 4) e = launch_v3_nt<4>(st, grid, L.total, p, stages | flags);
+  else e = launch_v3_nt<8>(st, grid, L.total, p, stages | flags);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
