@@ -27,6 +27,15 @@ class AffineModelStruct(C.Structure):
 
 _M = C.POINTER(AffineModelStruct)
 
+
+class NNConvStruct(C.Structure):
+    _fields_ = [('B', _i32), ('H', _i32), ('W', _i32), ('Hin', _i32), ('Win', _i32), ('C0', _i32), ('C1', _i32), ('Cout', _i32),
+                ('kh', _i32), ('kw', _i32), ('off_h', _i32), ('off_w', _i32), ('pixel_shuffle', _i32), ('reserved', _i32),
+                ('in0', _p), ('in1', _p), ('weight', _p), ('bias', _p), ('residual', _p), ('out_f32', _p), ('out_bf16', _p)]
+
+
+_CV = C.POINTER(NNConvStruct)
+
 # name -> (argtypes, restype); every symbol include/fbs_b200.h declares (checked by tests/test_abi.py)
 SIGNATURES = {
     'fbs_version': ([], _int),
@@ -55,6 +64,19 @@ SIGNATURES = {
     'fbs_pcn_combine_f32': ([_p, _f64, _p, _p, _p, _p, _i64, _i64, _p], _int),
     'fbs_mh_accept_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p], _int),
     'fbs_gaussian_ref_sample_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p], _int),
+    'fbs_nn_conv_bf16': ([_p, _CV], _int),
+    'fbs_nn_groupnorm_swish_f32': ([_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p], _int),
+    'fbs_nn_layernorm_f32': ([_p, _p, _i64, _i32, _p, _p, _f32, _p, _p], _int),
+    'fbs_nn_linear_attention_f32': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),
+    'fbs_nn_attention_f32': ([_p, _p, _i64, _i32, _i32, _i32, _f32, _p], _int),
+    'fbs_nn_time_mlp_f32': ([_p, _p, _f32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p], _int),
+    'fbs_nn_stem_conv_f32': ([_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p], _int),
+    'fbs_nn_head_conv_f32': ([_p, _p, _i64, _i32, _i32, _p, _p, _p], _int),
+    'fbs_nn_space_to_depth_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),
+    'fbs_nn_assemble_image_f32': ([_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p], _int),
+    'fbs_nn_em_step_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _p], _int),
+    'fbs_gather_rows_f32': ([_p, _p, _p, _i64, _i64, _p], _int),
+    'fbs_nn_f32_to_bf16': ([_p, _p, _i64, _p], _int),
 }
 
 _lib = None

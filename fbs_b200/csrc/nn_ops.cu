@@ -1,0 +1,572 @@
+// Non-GEMM pieces of the score network (fbs/nn/unet.py) and the closures around it (experiments/imgs/inpainting.py:
+// 94-147): normalisations fused with their activations / residuals, the two attention flavours, the time-embedding
+// MLP, the tiny first / last convolutions, the space-to-depth copy in front of the stride-2 convolutions, and the
+// image assembly + Euler--Maruyama / log-weight step.  All activations are NHWC; "P" = H * W pixels.
+#include <cuda_bf16.h>
+#include <math.h>
+#include "fbs_common.cuh"
+#include "fbs_rng.cuh"
+
+namespace fbs {
+namespace nnops {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_maxf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum (blockDim.x <= 1024, multiple of 32); red: shared float[32]
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm (+ time-embedding scale / shift) + swish (+ residual): unet.py:144-155,159-160,172.
+// One CTA per (sample, group); the slice (P x C / groups values, L2 / L1 resident) is read three times.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int P, int C, int groups,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ tss, const float* __restrict__ residual,
+                                                       float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, float eps) {
+  __shared__ float red[32];
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = C / groups, q4 = cpg / 4;  // float4 per pixel of this group
+  const size_t base = (size_t)b * P * C + (size_t)g * cpg;
+  const int n4 = P * q4;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < n4; e += blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + base + (size_t)(e / q4) * C + 4 * (e % q4));
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = block_sum(s, red) / (float)(P * cpg);
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < n4; e += blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + base + (size_t)(e / q4) * C + 4 * (e % q4));
+    const float a = v.x - mean, bq = v.y - mean, c = v.z - mean, d = v.w - mean;
+    ss += (a * a + bq * bq) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / (float)(P * cpg) + eps);
+  for (int e = threadIdx.x; e < n4; e += blockDim.x) {
+    const int c0 = g * cpg + 4 * (e % q4);
+    const size_t off = (size_t)b * P * C + (size_t)(e / q4) * C + c0;
+    const float4 v = *reinterpret_cast<const float4*>(x + off);
+    float y[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = (y[j] - mean) * rstd * __ldg(gamma + c0 + j) + __ldg(beta + c0 + j);
+      if (tss) t = t * (1.0f + __ldg(tss + c0 + j)) + __ldg(tss + C + c0 + j);  // h * (1 + scale) + shift
+      y[j] = swishf(t);
+    }
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + off);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_bf16) {
+      __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y[0], y[1]), __floats2bfloat162_rn(y[2], y[3])};
+      *reinterpret_cast<uint2*>(out_bf16 + off) = *reinterpret_cast<const uint2*>(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm over channels, scale only (+ residual): unet.py:243,258,264.  One warp per pixel.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t R, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ residual,
+                                                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* xr = x + row * C;
+  float v[16];  // C <= 512
+  const int per = C / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < per) {
+      v[j] = xr[lane + 32 * j];
+      s += v[j];
+    }
+  const float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < per) {
+      const float d = v[j] - mean;
+      ss += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < per) {
+      const int c = lane + 32 * j;
+      float y = (v[j] - mean) * rstd * __ldg(gamma + c);
+      if (residual) y += residual[row * C + c];
+      if (out_f32) out_f32[row * C + c] = y;
+      if (out_bf16) out_bf16[row * C + c] = __float2bfloat16_rn(y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LinearAttention core (unet.py:227-239): q softmax over the head dimension, k softmax over the pixels,
+// context = k^T (v / P), out = context^T (q / sqrt(d)).  One CTA per (sample, head); dim_head = 32.
+// qkv: fp32 [B, P, 3 * heads * 32] (q | k | v, each (head, d));  out: bf16 [B, P, heads * 32].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_attention_kernel(const float* __restrict__ qkv, int P, int heads,
+                                                               __nv_bfloat16* __restrict__ out) {
+  __shared__ float ctx[32][33];
+  __shared__ float kmax[32], ksum[32];
+  __shared__ float part[8][32];
+  const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
+  const int HD = heads * 32, ld = 3 * HD;
+  const float* q = qkv + (size_t)b * P * ld + hd * 32;
+  const float* k = q + HD;
+  const float* v = k + HD;
+  const int d = threadIdx.x & 31, sl = threadIdx.x >> 5;  // 8 warps
+  // column max of k over the pixels
+  float m = -INFINITY;
+  for (int n = sl; n < P; n += 8) m = fmaxf(m, k[(size_t)n * ld + d]);
+  part[sl][d] = m;
+  __syncthreads();
+  if (sl == 0) {
+    float t = part[0][d];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) t = fmaxf(t, part[j][d]);
+    kmax[d] = t;
+  }
+  __syncthreads();
+  // context[d][e] = sum_n exp(k[n,d] - kmax[d]) v[n,e]; thread (d, e-block of 4): sl selects e in [4 sl, 4 sl + 4)
+  {
+    const float km = kmax[d];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ks = 0.f;
+    for (int n = 0; n < P; ++n) {
+      const float ek = __expf(k[(size_t)n * ld + d] - km);
+      const float4 vv = *reinterpret_cast<const float4*>(v + (size_t)n * ld + 4 * sl);
+      a0 = fmaf(ek, vv.x, a0); a1 = fmaf(ek, vv.y, a1); a2 = fmaf(ek, vv.z, a2); a3 = fmaf(ek, vv.w, a3);
+      ks += ek;
+    }
+    if (sl == 0) ksum[d] = ks;
+    __syncthreads();
+    const float sc = 1.0f / (ksum[d] * (float)P);  // softmax denominator and v / (H W)
+    ctx[d][4 * sl + 0] = a0 * sc; ctx[d][4 * sl + 1] = a1 * sc; ctx[d][4 * sl + 2] = a2 * sc; ctx[d][4 * sl + 3] = a3 * sc;
+  }
+  __syncthreads();
+  // out[n][e] = sum_d ctx[d][e] softmax_d(q[n,:])[d] / sqrt(32); one warp per pixel, lane = d then e
+  const float inv_sqrt_d = 0.17677669529663687f;
+  for (int n = sl; n < P; n += 8) {
+    const float qv = q[(size_t)n * ld + d];
+    const float qm = warp_maxf(qv);
+    const float qe = __expf(qv - qm);
+    const float qs = qe / warp_sum(qe) * inv_sqrt_d;
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o = fmaf(ctx[j][d], __shfl_sync(0xffffffffu, qs, j), o);
+    out[((size_t)b * P + n) * HD + hd * 32 + d] = __float2bfloat16_rn(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Attention core of the middle block (unet.py:192-199): q, k l2-normalised ALONG THE TOKEN AXIS (axis=1 of
+// 'b (x y) h d', as written upstream), sim = 10 q k^T, softmax over keys, out = attn v.  One CTA per
+// (sample, head, 128-query block); keys / values streamed through shared memory in blocks of 128, online softmax.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int P, int heads, float scale,
+                                                        __nv_bfloat16* __restrict__ out) {
+  __shared__ float ks[128][33], vs[128][33];
+  __shared__ float qn[32], kn[32];
+  __shared__ float part[4][32];
+  const int qblocks = (P + 127) / 128;
+  const int b = blockIdx.x / (heads * qblocks), rem = blockIdx.x % (heads * qblocks);
+  const int hd = rem / qblocks, qb = rem % qblocks;
+  const int HD = heads * 32, ld = 3 * HD;
+  const float* q = qkv + (size_t)b * P * ld + hd * 32;
+  const float* k = q + HD;
+  const float* v = k + HD;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // column norms over the tokens
+  {
+    float sq = 0.f, sk = 0.f;
+    for (int n = w; n < P; n += 4) {
+      const float a = q[(size_t)n * ld + lane], c = k[(size_t)n * ld + lane];
+      sq = fmaf(a, a, sq);
+      sk = fmaf(c, c, sk);
+    }
+    part[w][lane] = sq;
+    __syncthreads();
+    if (w == 0) qn[lane] = 1.0f / fmaxf(sqrtf(part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]), 1e-12f);
+    __syncthreads();
+    part[w][lane] = sk;
+    __syncthreads();
+    if (w == 0) kn[lane] = 1.0f / fmaxf(sqrtf(part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]), 1e-12f);
+    __syncthreads();
+  }
+  const int i = qb * 128 + threadIdx.x;  // this thread's query
+  float qi[32], acc[32];
+#pragma unroll
+  for (int dd = 0; dd < 32; ++dd) {
+    qi[dd] = i < P ? q[(size_t)i * ld + dd] * qn[dd] * scale : 0.f;
+    acc[dd] = 0.f;
+  }
+  float mx = -INFINITY, den = 0.f;
+  for (int j0 = 0; j0 < P; j0 += 128) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 128 * 32; t += 128) {
+      const int j = t >> 5, dd = t & 31;
+      const bool ok = j0 + j < P;
+      ks[j][dd] = ok ? k[(size_t)(j0 + j) * ld + dd] * kn[dd] : 0.f;
+      vs[j][dd] = ok ? v[(size_t)(j0 + j) * ld + dd] : 0.f;
+    }
+    __syncthreads();
+    const int jn = min(128, P - j0);
+    for (int j = 0; j < jn; ++j) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < 32; ++dd) sdot = fmaf(qi[dd], ks[j][dd], sdot);
+      const float nm = fmaxf(mx, sdot);
+      const float corr = __expf(mx - nm), pj = __expf(sdot - nm);
+      den = den * corr + pj;
+#pragma unroll
+      for (int dd = 0; dd < 32; ++dd) acc[dd] = fmaf(acc[dd], corr, pj * vs[j][dd]);
+      mx = nm;
+    }
+  }
+  if (i < P) {
+    const float inv = 1.0f / den;
+#pragma unroll
+    for (int dd = 0; dd < 32; ++dd) out[((size_t)b * P + i) * HD + hd * 32 + dd] = __float2bfloat16_rn(acc[dd] * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Time embedding (unet.py:293-300, base.py:44-77) and every ResnetBlock's Dense(2 dim)(swish(time_emb))
+// (:148-149) in one launch: table[j] = sum_i swish(temb)[i] Wcat[i][j] + bcat[j].  Each CTA recomputes the
+// shared 64 -> 4 dim -> 4 dim trunk (dim = 64) and produces 64 outputs.  `tval` holds the network time.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) time_mlp_kernel(const float* __restrict__ tval, float inv_dt, int dim,
+                                                       const float* __restrict__ W0, const float* __restrict__ b0,
+                                                       const float* __restrict__ W1, const float* __restrict__ b1,
+                                                       const float* __restrict__ Wcat, const float* __restrict__ bcat, int nout,
+                                                       float* __restrict__ table) {
+  __shared__ float emb[256], h1[1024], h2[1024];
+  const int D4 = 4 * dim, half = dim / 2;
+  const float t = tval[0] * inv_dt;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const int j = i < half ? i : i - half;
+    const float f = expf(-logf(10000.0f) * (float)j / (float)(half - 1));
+    emb[i] = i < half ? sinf(t * f) : cosf(t * f);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < D4; o += blockDim.x) {
+    float a = b0[o];
+    for (int i = 0; i < dim; ++i) a = fmaf(emb[i], W0[(size_t)i * D4 + o], a);
+    // flax nn.gelu: tanh approximation
+    h1[o] = 0.5f * a * (1.0f + tanhf(0.7978845608028654f * (a + 0.044715f * a * a * a)));
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < D4; o += blockDim.x) {
+    float a = b1[o];
+    for (int i = 0; i < D4; ++i) a = fmaf(h1[i], W1[(size_t)i * D4 + o], a);
+    h2[o] = a / (1.0f + expf(-a));  // swish(time_emb), the input of every block's time MLP
+  }
+  __syncthreads();
+  // 64 outputs per CTA, 4 threads per output
+  const int o = blockIdx.x * 64 + (threadIdx.x >> 2), part = threadIdx.x & 3;
+  float a = 0.f;
+  if (o < nout)
+    for (int i = part; i < D4; i += 4) a = fmaf(h2[i], Wcat[(size_t)i * nout + o], a);
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  if (o < nout && part == 0) table[o] = a + bcat[o];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// First convolution: 7x7, padding 3, Cin in {1..4} -> 64 (unet.py:286-291).  CUDA cores: K = 49 Cin is tiny.
+// thread = (pixel, 4 output channels); weights [7][7][Cin][Cout] in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, int B, int H, int W, int Cin, int Cout,
+                                                        const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  extern __shared__ float ws[];
+  const int nw = 49 * Cin * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wgt[i];
+  __syncthreads();
+  const int cgs = Cout / 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * W * cgs) return;
+  const int cg = (int)(idx % cgs);
+  const int64_t pix = idx / cgs;
+  const int w = (int)(pix % W), h = (int)((pix / W) % H);
+  const int64_t b = pix / ((int64_t)W * H);
+  float a0 = bias[4 * cg], a1 = bias[4 * cg + 1], a2 = bias[4 * cg + 2], a3 = bias[4 * cg + 3];
+  for (int ty = 0; ty < 7; ++ty) {
+    const int hh = h + ty - 3;
+    if (hh < 0 || hh >= H) continue;
+    for (int tx = 0; tx < 7; ++tx) {
+      const int ww = w + tx - 3;
+      if (ww < 0 || ww >= W) continue;
+      const float* xp = x + ((b * H + hh) * W + ww) * Cin;
+      const float* wp = ws + ((ty * 7 + tx) * Cin) * Cout + 4 * cg;
+      for (int c = 0; c < Cin; ++c) {
+        const float xv = xp[c];
+        const float4 wv = *reinterpret_cast<const float4*>(wp + c * Cout);
+        a0 = fmaf(xv, wv.x, a0); a1 = fmaf(xv, wv.y, a1); a2 = fmaf(xv, wv.z, a2); a3 = fmaf(xv, wv.w, a3);
+      }
+    }
+  }
+  const size_t off = (size_t)pix * Cout + 4 * cg;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(a0, a1, a2, a3);
+  if (out_bf16) {
+    __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(a0, a1), __floats2bfloat162_rn(a2, a3)};
+    *reinterpret_cast<uint2*>(out_bf16 + off) = *reinterpret_cast<const uint2*>(o);
+  }
+}
+
+// Last convolution: 1x1, 64 -> Cimg (unet.py:363).  One warp per pixel.
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int64_t R, int C, int Cimg,
+                                                        const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                        float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  for (int o = 0; o < Cimg; ++o) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(x[row * C + c], __ldg(wgt + (size_t)c * Cimg + o), a);
+    a = warp_sum(a);
+    if (lane == 0) out[row * Cimg + o] = a + bias[o];
+  }
+}
+
+// Space-to-depth in front of the 4x4 stride-2 convolution (unet.py:50): out[b, i, j, (r, s, c)] =
+// in[b, 2 i - 1 + r, 2 j - 1 + s, c] (zero outside), i in [0, H/2], j in [0, W/2]; the convolution then is 2x2, stride 1.
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int C,
+                                                             __nv_bfloat16* __restrict__ out) {
+  const int Ho = H / 2 + 1, Wo = W / 2 + 1, c8 = C / 8;
+  const int64_t total = (int64_t)B * Ho * Wo * 4 * c8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(idx % c8);
+    int64_t t = idx / c8;
+    const int rs = (int)(t % 4);
+    t /= 4;
+    const int j = (int)(t % Wo);
+    t /= Wo;
+    const int i = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    const int hh = 2 * i - 1 + (rs >> 1), ww = 2 * j - 1 + (rs & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = *reinterpret_cast<const uint4*>(in + ((b * H + hh) * W + ww) * C + 8 * cc);
+    *reinterpret_cast<uint4*>(out + (((b * Ho + i) * Wo + j) * 4 + rs) * C + 8 * cc) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Closures (experiments/imgs/inpainting.py:94-147).
+// assemble: image[b] = concat(us[b], v) = scatter by the mask's index lists (fbs/data/images.py:352-363).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__ us, const float* __restrict__ v,
+                                                       const int32_t* __restrict__ unobs, const int32_t* __restrict__ obs, int64_t B,
+                                                       int p, int q, int c, float* __restrict__ img) {
+  const int P = p + q;
+  const int64_t total = B * (int64_t)P * c;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % c);
+    const int e = (int)((idx / c) % P);
+    const int64_t b = idx / ((int64_t)c * P);
+    if (e < p)
+      img[(b * P + unobs[e]) * c + ch] = us[(b * p + e) * c + ch];
+    else
+      img[(b * P + obs[e - p]) * c + ch] = v[(int64_t)(e - p) * c + ch];
+  }
+}
+
+// One Euler--Maruyama step of the reverse SDE for every particle + the Gaussian log-weight of the next observation:
+//   rd = -a x + g2 score                                  (inpainting.py:102-103; linear SDE drift a x)
+//   u' = u + rd_u dt + sd normal(key, (B, p, c))            (:122-128)      [skipped when us_new == nullptr]
+//   lw[b] = sum logN(v_next; v_prev + rd_v dt, sd)           (:141-147)      [skipped when lw == nullptr]
+// One CTA per particle.
+__global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ img, const float* __restrict__ score,
+                                                      const int32_t* __restrict__ unobs, const int32_t* __restrict__ obs,
+                                                      const float* __restrict__ v_next, const uint32_t* __restrict__ key, int64_t B,
+                                                      int p, int q, int c, float a, float g2, float dt, float sd,
+                                                      float* __restrict__ us_new, float* __restrict__ mean_out, float* __restrict__ lw) {
+  __shared__ float red[32];
+  const int64_t b = blockIdx.x;
+  const int P = p + q;
+  const float* xi = img + b * (int64_t)P * c;
+  const float* si = score + b * (int64_t)P * c;
+  if (us_new || mean_out) {
+    const uint32_t nel = (uint32_t)(B * p * c);
+    Key k{0u, 0u};
+    if (key) k = Key{key[0], key[1]};
+    for (int e = threadIdx.x; e < p * c; e += blockDim.x) {
+      const int pix = unobs[e / c], ch = e % c;
+      const float x = xi[pix * c + ch];
+      const float rd = -a * x + g2 * si[pix * c + ch];
+      const float mean = x + rd * dt;
+      if (mean_out) mean_out[b * (int64_t)p * c + e] = mean;
+      if (us_new) {
+        const uint32_t el = (uint32_t)(b * p * c + e);
+        us_new[b * (int64_t)p * c + e] = mean + sd * bits_to_normal(random_bits_elem(k, nel, el));
+      }
+    }
+  }
+  if (lw) {
+    float acc = 0.f;
+    const float inv = 1.0f / sd, lognorm = -logf(sd) - 0.9189385332046727f;
+    for (int e = threadIdx.x; e < q * c; e += blockDim.x) {
+      const int pix = obs[e / c], ch = e % c;
+      const float x = xi[pix * c + ch];
+      const float rd = -a * x + g2 * si[pix * c + ch];
+      const float z = (v_next[e] - (x + rd * dt)) * inv;
+      acc += -0.5f * z * z + lognorm;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) lw[b] = acc;
+  }
+}
+
+// rows of src gathered by an index list: dst[b, :] = src[idx[b], :]  (csmc.py:140, the ancestor gather)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int64_t B,
+                                                          int64_t row, float* __restrict__ dst) {
+  const int64_t total = B * row;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / row;
+    dst[t] = src[(int64_t)idx[b] * row + (t - b * row)];
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    y[t] = __float2bfloat16_rn(x[t]);
+}
+
+static inline int grid_for(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace nnops
+}  // namespace fbs
+
+using namespace fbs;
+using namespace fbs::nnops;
+
+extern "C" {
+
+int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma,
+                               const float* beta, const float* time_scale_shift, const float* residual, float eps,
+                               float* out_f32, void* out_bf16) {
+  FBS_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), "groupnorm: null argument");
+  FBS_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0, "groupnorm: channels per group must be a multiple of 4");
+  gn_apply_kernel<<<(unsigned)(B * groups), 256, 0, as_stream(s)>>>(x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  return check_launch("gn_apply_kernel");
+}
+
+int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, const float* gamma, const float* residual,
+                         float eps, float* out_f32, void* out_bf16) {
+  FBS_REQUIRE(x && gamma && (out_f32 || out_bf16), "layernorm: null argument");
+  FBS_REQUIRE(C % 32 == 0 && C <= 512, "layernorm: C must be a multiple of 32, <= 512");
+  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(s)>>>(x, rows, C, gamma, residual, out_f32,
+                                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  return check_launch("layernorm_kernel");
+}
+
+int fbs_nn_linear_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head,
+                                void* out_bf16) {
+  FBS_REQUIRE(qkv && out_bf16, "linear_attention: null argument");
+  FBS_REQUIRE(dim_head == 32 && heads >= 1 && heads <= 8, "linear_attention: dim_head must be 32");
+  linear_attention_kernel<<<(unsigned)(B * heads), 256, 0, as_stream(s)>>>(qkv, P, heads, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return check_launch("linear_attention_kernel");
+}
+
+int fbs_nn_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head, float scale,
+                         void* out_bf16) {
+  FBS_REQUIRE(qkv && out_bf16, "attention: null argument");
+  FBS_REQUIRE(dim_head == 32 && heads >= 1, "attention: dim_head must be 32");
+  const int qblocks = (P + 127) / 128;
+  attention_kernel<<<(unsigned)(B * heads * qblocks), 128, 0, as_stream(s)>>>(qkv, P, heads, scale,
+                                                                             reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return check_launch("attention_kernel");
+}
+
+int fbs_nn_time_mlp_f32(fbs_stream_t s, const float* tval, float dt, int32_t dim, const float* W0, const float* b0, const float* W1,
+                        const float* b1, const float* Wcat, const float* bcat, int32_t nout, float* table) {
+  FBS_REQUIRE(tval && W0 && b0 && W1 && b1 && Wcat && bcat && table, "time_mlp: null argument");
+  FBS_REQUIRE(dim >= 4 && dim <= 256 && dim % 2 == 0, "time_mlp: 4 <= dim <= 256");
+  time_mlp_kernel<<<(unsigned)((nout + 63) / 64), 256, 0, as_stream(s)>>>(tval, 1.0f / dt, dim, W0, b0, W1, b1, Wcat, bcat, nout, table);
+  return check_launch("time_mlp_kernel");
+}
+
+int fbs_nn_stem_conv_f32(fbs_stream_t s, const float* x, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                         const float* weight, const float* bias, float* out_f32, void* out_bf16) {
+  FBS_REQUIRE(x && weight && bias && (out_f32 || out_bf16), "stem_conv: null argument");
+  FBS_REQUIRE(Cout % 4 == 0 && (size_t)49 * Cin * Cout * 4 <= 96 * 1024, "stem_conv: weights must fit shared memory");
+  const size_t smem = (size_t)49 * Cin * Cout * 4;
+  cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t n = B * H * W * (Cout / 4);
+  stem_conv_kernel<<<(unsigned)((n + 255) / 256), 256, smem, as_stream(s)>>>(x, (int)B, H, W, Cin, Cout, weight, bias, out_f32,
+                                                                             reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return check_launch("stem_conv_kernel");
+}
+
+int fbs_nn_head_conv_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, int32_t Cimg, const float* weight,
+                         const float* bias, float* out) {
+  FBS_REQUIRE(x && weight && bias && out, "head_conv: null argument");
+  head_conv_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(s)>>>(x, rows, C, Cimg, weight, bias, out);
+  return check_launch("head_conv_kernel");
+}
+
+int fbs_nn_space_to_depth_bf16(fbs_stream_t s, const void* in, int64_t B, int32_t H, int32_t W, int32_t C, void* out) {
+  FBS_REQUIRE(in && out, "space_to_depth: null argument");
+  FBS_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "space_to_depth: need C % 8 == 0 and even H, W");
+  const int64_t n = B * (H / 2 + 1) * (W / 2 + 1) * 4 * (C / 8);
+  space_to_depth_kernel<<<grid_for(n), 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(in), (int)B, H, W, C,
+                                                               reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("space_to_depth_kernel");
+}
+
+int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, const int32_t* unobs_idx, const int32_t* obs_idx,
+                              int64_t B, int32_t p, int32_t q, int32_t c, float* img) {
+  FBS_REQUIRE(us && v && unobs_idx && obs_idx && img, "assemble_image: null argument");
+  assemble_kernel<<<grid_for(B * (int64_t)(p + q) * c), 256, 0, as_stream(s)>>>(us, v, unobs_idx, obs_idx, B, p, q, c, img);
+  return check_launch("assemble_kernel");
+}
+
+int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
+                       const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
+                       float dt, float sd, float* us_new, float* mean_out, float* lw) {
+  FBS_REQUIRE(img && score && unobs_idx && obs_idx, "em_step: null argument");
+  FBS_REQUIRE(lw == nullptr || v_next != nullptr, "em_step: v_next missing");
+  FBS_REQUIRE(us_new == nullptr || key != nullptr, "em_step: key missing");
+  em_step_kernel<<<(unsigned)B, 256, 0, as_stream(s)>>>(img, score, unobs_idx, obs_idx, v_next, key, B, p, q, c, a, g2, dt, sd, us_new,
+                                                        mean_out, lw);
+  return check_launch("em_step_kernel");
+}
+
+int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, float* dst) {
+  FBS_REQUIRE(src && idx && dst, "gather_rows: null argument");
+  gather_rows_kernel<<<grid_for(B * row), 256, 0, as_stream(s)>>>(src, idx, B, row, dst);
+  return check_launch("gather_rows_kernel");
+}
+
+int fbs_nn_f32_to_bf16(fbs_stream_t s, const float* x, int64_t n, void* y) {
+  FBS_REQUIRE(x && y, "f32_to_bf16: null argument");
+  f32_to_bf16_kernel<<<grid_for(n), 256, 0, as_stream(s)>>>(x, n, reinterpret_cast<__nv_bfloat16*>(y));
+  return check_launch("f32_to_bf16_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+"""The score U-Net of ``fbs/nn/unet.py`` (``UNet(dt, dim=64, upsampling='pixel_shuffle')``, the configuration of every
+image experiment: experiments/imgs/inpainting.py:85, experiments/sb_imgs/supr.py:67) as a fixed schedule of sm_100a
+kernels, and the NN-score closures built on it (experiments/imgs/inpainting.py:94-147).
+
+* every 3x3 / 1x1 / stride-2 convolution with >= 64 input channels is an implicit GEMM on the tcgen05 tensor cores
+  (bf16 operands, fp32 accumulation in tensor memory): ``fbs_nn_conv_bf16``; skip concatenations are never
+  materialised (two-source K loop), pixel-shuffle is an epilogue addressing mode;
+* weight standardisation (unet.py:110-118, recomputed on every call upstream) is a one-time transform here: the
+  weights are constants at sampling time;
+* GroupNorm + time scale/shift + swish (+ residual), LayerNorm (+ residual), both attention cores and the time MLP are
+  one fused kernel each (nn_ops.cu);
+* the whole evaluation is captured in a CUDA graph per batch size and replayed (the network time lives in a device
+  scalar), so one score evaluation costs one graph launch from the host.
+
+Parameters: a flat dict ``name -> float32 array`` with flax's HWIO kernels, the naming of oracle/unet.py's
+``unet_param_shapes`` (this module does not import the oracle; the names are the interface).
+"""
+import math
+import numpy as np
+import torch
+from . import ops
+from .._tensor import cuda_device, dev
+from .. import random as frandom
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _standardize(w, eps=1e-5):
+    """unet.py:110-118 in float32: per output filter over (kh, kw, Cin)."""
+    w = np.asarray(w, dtype=np.float32)
+    mean = w.mean(axis=(0, 1, 2), keepdims=True, dtype=np.float32)
+    var = w.var(axis=(0, 1, 2), keepdims=True, dtype=np.float32)
+    return ((w - mean) / np.sqrt(var + np.float32(eps))).astype(np.float32)
+
+
+def _pack(w):
+    """flax HWIO kernel [kh, kw, Cin, Cout] -> bf16 [Cout, kh * kw * Cin], K ordered (ty, tx, channel)."""
+    kh, kw, cin, cout = w.shape
+    return np.ascontiguousarray(w.reshape(kh * kw * cin, cout).T)
+
+
+def _pack_stride2(w):
+    """4x4 stride-2 kernel -> the 2x2 kernel over the space-to-depth copy: k2[ty, tx, (r, s, c), o] = w[2 ty + r, 2 tx + s, c, o]."""
+    _, _, cin, cout = w.shape
+    k2 = w.reshape(2, 2, 2, 2, cin, cout).transpose(0, 2, 1, 3, 4, 5)  # [ty, r, tx, s, c, o] -> [ty, tx, r, s, c, o]
+    return _pack(np.ascontiguousarray(k2).reshape(2, 2, 4 * cin, cout))
+
+
+class ScoreUNet:
+    def __init__(self, params, image_shape, dt, dim=64, dim_mults=(1, 2, 4), groups=8, heads=4, dim_head=32, device=None):
+        self.H, self.W, self.Cimg = (int(s) for s in image_shape)
+        self.dt, self.dim, self.dim_mults, self.groups = float(dt), int(dim), tuple(dim_mults), int(groups)
+        self.heads, self.dim_head = heads, dim_head
+        self.device = device or cuda_device()
+        if dim % 64:
+            raise NotImplementedError('ScoreUNet: dim must be a multiple of 64 (tensor-core K blocks of 64 channels)')
+        nres = len(self.dim_mults)
+        if self.H % (1 << (nres - 1)) or self.W % (1 << (nres - 1)) or self.W > 128:
+            raise NotImplementedError('ScoreUNet: H, W must be divisible by 2^(levels-1) and W <= 128')
+        self._w = {}
+        self._bufs = {}
+        self._graphs = {}
+        self._time_blocks = []       # resnet block name -> offset into the time table
+        self._prepare(params)
+        self.tval = torch.zeros((1,), dtype=F32, device=self.device)
+
+    # ------------------------------------------------------------------ weights
+    def _put(self, name, arr, dtype=F32):
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
+        self._w[name] = t.to(dtype).contiguous()
+
+    def _prepare(self, P):
+        off = 0
+        wcat, bcat = [], []
+        for name in sorted(P):
+            if name.endswith('.kernel'):
+                base = name[:-len('.kernel')]
+                w = np.asarray(P[name], dtype=np.float32)
+                if base == 'init.conv_0' or base == 'final.conv_0':
+                    self._put(base + '.w', w if base == 'init.conv_0' else w.reshape(w.shape[2], w.shape[3]))
+                elif base.startswith('time.'):
+                    self._put(base + '.w', w)
+                elif base.endswith('time_mlp.dense_0'):
+                    pass  # concatenated below, in execution order
+                elif base.endswith('.conv_0') and '.resblock' in base or base.endswith('.conv_1') and '.resblock' in base:
+                    self._put(base + '.w', _pack(_standardize(w)), BF16)
+                elif 'downsample_0' in base:
+                    self._put(base + '.w', _pack_stride2(w), BF16)
+                else:
+                    self._put(base + '.w', _pack(w), BF16)
+            elif name.endswith('.bias') or name.endswith('.scale'):
+                if not name.endswith('time_mlp.dense_0.bias'):
+                    self._put(name, P[name])
+        for blk in self._resblock_order():
+            k = np.asarray(P[blk + '.time_mlp.dense_0.kernel'], dtype=np.float32)
+            wcat.append(k)
+            bcat.append(np.asarray(P[blk + '.time_mlp.dense_0.bias'], dtype=np.float32))
+            self._time_blocks.append((blk, off, k.shape[1] // 2))
+            off += k.shape[1]
+        self._put('time.Wcat', np.concatenate(wcat, axis=1))
+        self._put('time.bcat', np.concatenate(bcat))
+        self._toff = {blk: (o, d) for blk, o, d in self._time_blocks}
+        self.table = torch.empty((off,), dtype=F32, device=self.device)
+
+    def _resblock_order(self):
+        nres = len(self.dim_mults)
+        names = []
+        for ind in range(nres):
+            names += [f'down_{ind}.resblock_0', f'down_{ind}.resblock_1']
+        names += ['mid.resblock_0', 'mid.resblock_1']
+        for ind in reversed(range(nres)):
+            names += [f'up_{ind}.resblock_0', f'up_{ind}.resblock_1']
+        names.append('final.resblock_0')
+        return names
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, B, name, shape, dtype):
+        key = (B, name)
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    # ------------------------------------------------------------------ blocks
+    def _resblock(self, B, name, srcs, x_f32, H, W, d, tag):
+        """ResnetBlock (unet.py:127-172).  srcs: bf16 tensors whose channel concatenation is the block input."""
+        w = self._w
+        in0, in1 = srcs[0], (srcs[1] if len(srcs) > 1 else None)
+        cin = sum(s.shape[-1] for s in srcs)
+        t_f32 = self._buf(B, f'tmp_f32_{H}x{d}', (B, H, W, d), F32)
+        t_bf = self._buf(B, f'tmp_bf16_{H}x{d}', (B, H, W, d), BF16)
+        ops.conv(in0, w[name + '.conv_0.w'], d, 3, 3, -1, H, W, in1=in1, bias=w[name + '.conv_0.bias'], out_f32=t_f32)
+        o, dd = self._toff[name]
+        ops.groupnorm_swish(t_f32, w[name + '.norm_0.scale'], w[name + '.norm_0.bias'], self.groups, tss=self.table[o:o + 2 * dd],
+                            out_bf16=t_bf)
+        ops.conv(t_bf, w[name + '.conv_1.w'], d, 3, 3, -1, H, W, bias=w[name + '.conv_1.bias'], out_f32=t_f32)
+        if cin != d:
+            res = self._buf(B, f'res_f32_{H}x{d}', (B, H, W, d), F32)
+            ops.conv(in0, w[name + '.res_conv_0.w'], d, 1, 1, 0, H, W, in1=in1, bias=w[name + '.res_conv_0.bias'], out_f32=res)
+        else:
+            res = x_f32
+        out_f32 = self._buf(B, tag + '_f32', (B, H, W, d), F32)
+        out_bf = self._buf(B, tag + '_bf16', (B, H, W, d), BF16)
+        ops.groupnorm_swish(t_f32, w[name + '.norm_1.scale'], w[name + '.norm_1.bias'], self.groups, residual=res, out_f32=out_f32,
+                            out_bf16=out_bf)
+        return out_f32, out_bf
+
+    def _attnblock(self, B, name, x_f32, H, W, C, tag, linear=True):
+        """AttnBlock (unet.py:248-264) around LinearAttention (:209-245) or Attention (:175-206)."""
+        w = self._w
+        hd = self.heads * self.dim_head
+        n_bf = self._buf(B, f'attn_norm_{H}x{C}', (B, H, W, C), BF16)
+        qkv = self._buf(B, f'attn_qkv_{H}', (B, H, W, 3 * hd), F32)
+        ao = self._buf(B, f'attn_out_{H}', (B, H, W, hd), BF16)
+        out_f32 = self._buf(B, tag + '_f32', (B, H, W, C), F32)
+        out_bf = self._buf(B, tag + '_bf16', (B, H, W, C), BF16)
+        ops.layernorm(x_f32, w[name + '.norm.scale'], out_bf16=n_bf)
+        ops.conv(n_bf, w[name + '.attn.to_qkv.conv_0.w'], 3 * hd, 1, 1, 0, H, W, out_f32=qkv)
+        if linear:
+            ops.linear_attention(qkv, ao, self.heads, self.dim_head)
+            proj = self._buf(B, f'attn_proj_{H}x{C}', (B, H, W, C), F32)
+            ops.conv(ao, w[name + '.attn.to_out.conv_0.w'], C, 1, 1, 0, H, W, bias=w[name + '.attn.to_out.conv_0.bias'], out_f32=proj)
+            ops.layernorm(proj, w[name + '.attn.to_out.norm_0.scale'], residual=x_f32, out_f32=out_f32, out_bf16=out_bf)
+        else:
+            ops.attention(qkv, ao, self.heads, self.dim_head, 10.0)
+            ops.conv(ao, w[name + '.attn.to_out.conv_0.w'], C, 1, 1, 0, H, W, bias=w[name + '.attn.to_out.conv_0.bias'],
+                     residual=x_f32, out_f32=out_f32, out_bf16=out_bf)
+        return out_f32, out_bf
+
+    # ------------------------------------------------------------------ forward
+    def _forward(self, x, B):
+        """x: fp32 [B, H, W, Cimg] (device); self.tval holds the network time.  Returns fp32 [B, H, W, Cimg]."""
+        w, dim = self._w, self.dim
+        H, W = self.H, self.W
+        nres = len(self.dim_mults)
+        ops.time_mlp(self.tval, self.dt, dim, w['time.dense_0.w'], w['time.dense_0.bias'], w['time.dense_1.w'],
+                     w['time.dense_1.bias'], w['time.Wcat'], w['time.bcat'], self.table)
+        h_f32 = self._buf(B, 'h0_f32', (B, H, W, dim), F32)
+        h_bf = self._buf(B, 'h0_bf16', (B, H, W, dim), BF16)
+        ops.stem_conv(x, w['init.conv_0.w'], w['init.conv_0.bias'], out_f32=h_f32, out_bf16=h_bf)
+        skips = [h_bf]
+        c = dim
+        for ind in range(nres):
+            h_f32, h_bf = self._resblock(B, f'down_{ind}.resblock_0', [h_bf], h_f32, H, W, c, f'd{ind}r0')
+            skips.append(h_bf)
+            h_f32, h_bf = self._resblock(B, f'down_{ind}.resblock_1', [h_bf], h_f32, H, W, c, f'd{ind}r1')
+            h_f32, h_bf = self._attnblock(B, f'down_{ind}.attnblock_0', h_f32, H, W, c, f'd{ind}a')
+            skips.append(h_bf)
+            if ind < nres - 1:
+                cout = dim * self.dim_mults[ind]
+                s2d = self._buf(B, f's2d_{ind}', (B, H // 2 + 1, W // 2 + 1, 4 * c), BF16)
+                ops.space_to_depth(h_bf, s2d)
+                H, W = H // 2, W // 2
+                h_f32 = self._buf(B, f'd{ind}ds_f32', (B, H, W, cout), F32)
+                h_bf = self._buf(B, f'd{ind}ds_bf16', (B, H, W, cout), BF16)
+                ops.conv(s2d, w[f'down_{ind}.downsample_0.w'], cout, 2, 2, 0, H, W, bias=w[f'down_{ind}.downsample_0.bias'],
+                         out_f32=h_f32, out_bf16=h_bf)
+                c = cout
+        mid = dim * self.dim_mults[-1]
+        m_f32 = self._buf(B, 'midin_f32', (B, H, W, mid), F32)
+        m_bf = self._buf(B, 'midin_bf16', (B, H, W, mid), BF16)
+        ops.conv(h_bf, w[f'down_{nres - 1}.conv_0.w'], mid, 3, 3, -1, H, W, bias=w[f'down_{nres - 1}.conv_0.bias'], out_f32=m_f32,
+                 out_bf16=m_bf)
+        h_f32, h_bf = self._resblock(B, 'mid.resblock_0', [m_bf], m_f32, H, W, mid, 'm0')
+        h_f32, h_bf = self._attnblock(B, 'mid.attenblock_0', h_f32, H, W, mid, 'ma', linear=False)
+        h_f32, h_bf = self._resblock(B, 'mid.resblock_1', [h_bf], h_f32, H, W, mid, 'm1')
+        for ind in reversed(range(nres)):
+            dim_in = dim * self.dim_mults[ind]
+            dim_out = dim * self.dim_mults[ind - 1] if ind > 0 else dim
+            h_f32, h_bf = self._resblock(B, f'up_{ind}.resblock_0', [h_bf, skips.pop()], None, H, W, dim_in, f'u{ind}r0')
+            h_f32, h_bf = self._resblock(B, f'up_{ind}.resblock_1', [h_bf, skips.pop()], None, H, W, dim_in, f'u{ind}r1')
+            h_f32, h_bf = self._attnblock(B, f'up_{ind}.attnblock_0', h_f32, H, W, dim_in, f'u{ind}a')
+            if ind > 0:
+                ps = self._buf(B, f'u{ind}ps_bf16', (B, 2 * H, 2 * W, dim_in), BF16)
+                ops.conv(h_bf, w[f'up_{ind}.upsample_0.conv_0.w'], 4 * dim_in, 3, 3, -1, H, W,
+                         bias=w[f'up_{ind}.upsample_0.conv_0.bias'], out_bf16=ps, pixel_shuffle=True)
+                H, W = 2 * H, 2 * W
+                h_f32 = self._buf(B, f'u{ind}us_f32', (B, H, W, dim_out), F32)
+                h_bf = self._buf(B, f'u{ind}us_bf16', (B, H, W, dim_out), BF16)
+                ops.conv(ps, w[f'up_{ind}.upsample_0.conv_1.w'], dim_out, 3, 3, -1, H, W,
+                         bias=w[f'up_{ind}.upsample_0.conv_1.bias'], out_f32=h_f32, out_bf16=h_bf)
+        last_bf = self._buf(B, 'u0c_bf16', (B, H, W, dim), BF16)
+        ops.conv(h_bf, w['up_0.conv_0.w'], dim, 3, 3, -1, H, W, bias=w['up_0.conv_0.bias'], out_bf16=last_bf)
+        f_f32, _ = self._resblock(B, 'final.resblock_0', [last_bf, skips.pop()], None, H, W, dim, 'fin')
+        out = self._buf(B, 'score', (B, H, W, self.Cimg), F32)
+        ops.head_conv(f_f32, w['final.conv_0.w'], w['final.conv_0.bias'], out)
+        return out
+
+    def __call__(self, x, time, use_graph=True):
+        """Score network at ``x`` fp32 [B, H, W, Cimg] (CUDA) and scalar ``time`` -> fp32 [B, H, W, Cimg] (a buffer owned
+        by the network, overwritten by the next call)."""
+        B = x.shape[0]
+        if isinstance(time, torch.Tensor):
+            self.tval.copy_(time.reshape(1).to(F32))
+        else:
+            self.tval.fill_(float(time))
+        xin = self._buf(B, 'x_in', (B, self.H, self.W, self.Cimg), F32)
+        xin.copy_(x.reshape(xin.shape))
+        if not use_graph:
+            return self._forward(xin, B)
+        g = self._graphs.get(B)
+        if g is None:
+            self._forward(xin, B)      # allocates every buffer outside the capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward(xin, B)
+            g = self._graphs[B] = (graph, out)
+        g[0].replay()
+        return g[1]
+
+
+class ScoreNetModel:
+    """The closures of experiments/imgs/inpainting.py:94-147 (identical in supr.py) over a :class:`ScoreUNet`.
+
+    ``unobs_idx`` / ``obs_idx`` are the mask's ravelled pixel index lists (fbs/data/images.py:258-303); the SDE is a
+    scalar linear SDE (``drift(x, t) = a(t) x``).  One network evaluation serves both the transition and the weight
+    (:meth:`step`); the bound methods keep the reference's closure signatures.
+    """
+
+    def __init__(self, unet: ScoreUNet, sde, ts, T, unobs_idx, obs_idx):
+        self.unet, self.sde, self.T = unet, sde, float(T)
+        self.ts = np.asarray(ts, dtype=np.float64)
+        self.K = self.ts.shape[0] - 1
+        self.dt = self.T / self.K                                   # inpainting.py:58
+        d = unet.device
+        self.unobs = torch.as_tensor(np.asarray(unobs_idx), dtype=torch.int32, device=d).contiguous()
+        self.obs = torch.as_tensor(np.asarray(obs_idx), dtype=torch.int32, device=d).contiguous()
+        self.p, self.q, self.c = int(self.unobs.numel()), int(self.obs.numel()), unet.Cimg
+        if self.p + self.q != unet.H * unet.W:
+            raise ValueError('mask index lists must partition the image')
+
+    def _coef(self, t_prev):
+        s = self.T - float(t_prev)
+        a = float(self.sde.drift_coef(s))
+        g = float(self.sde.dispersion(s))
+        return s, a, g * g, float(np.float32(math.sqrt(self.dt)) * np.float32(g))
+
+    def _score(self, us_prev, v_prev, t_prev):
+        B = us_prev.shape[0]
+        img = self.unet._buf(B, 'closure_img', (B, self.unet.H, self.unet.W, self.c), F32)
+        ops.assemble_image(us_prev, v_prev, self.unobs, self.obs, img)
+        s, a, g2, sd = self._coef(t_prev)
+        return img, self.unet(img, s), a, g2, sd
+
+    def step(self, us_prev, v_prev, v_next, t_prev, key):
+        """(us_new [N, p, c], log_w [N]) from ONE score evaluation (transition_sampler + likelihood_logpdf)."""
+        us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
+        v_prev = dev(v_prev, F32).reshape(self.q, self.c)
+        v_next = dev(v_next, F32).reshape(self.q, self.c)
+        key = dev(key, torch.uint32).reshape(2)
+        B = us_prev.shape[0]
+        img, score, a, g2, sd = self._score(us_prev, v_prev, t_prev)
+        us_new = torch.empty_like(us_prev)
+        lw = torch.empty((B,), dtype=F32, device=us_prev.device)
+        ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, v_next=v_next, key=key,
+                    us_new=us_new, lw=lw)
+        return us_new, lw
+
+    def transition_sampler(self, us_prev, v_prev, t_prev, key, **kwargs):
+        """inpainting.py:122-128."""
+        us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
+        v_prev = dev(v_prev, F32).reshape(self.q, self.c)
+        key = dev(key, torch.uint32).reshape(2)
+        B = us_prev.shape[0]
+        img, score, a, g2, sd = self._score(us_prev, v_prev, t_prev)
+        us_new = torch.empty_like(us_prev)
+        ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, key=key, us_new=us_new)
+        return us_new
+
+    def likelihood_logpdf(self, v, us_prev, v_prev, t_prev, **kwargs):
+        """inpainting.py:141-147."""
+        us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
+        v_prev = dev(v_prev, F32).reshape(self.q, self.c)
+        v = dev(v, F32).reshape(self.q, self.c)
+        B = us_prev.shape[0]
+        img, score, a, g2, sd = self._score(us_prev, v_prev, t_prev)
+        lw = torch.empty((B,), dtype=F32, device=us_prev.device)
+        ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, v_next=v, lw=lw)
+        return lw
+
+    def transition_logpdf(self, u, us_prev, v_prev, t_prev, **kwargs):
+        """inpainting.py:131-138: sum logN(u; mean(us_prev), sd) per particle."""
+        us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
+        v_prev = dev(v_prev, F32).reshape(self.q, self.c)
+        u = dev(u, F32).reshape(1, self.p * self.c)
+        B = us_prev.shape[0]
+        img, score, a, g2, sd = self._score(us_prev, v_prev, t_prev)
+        mean = torch.empty_like(us_prev)
+        ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, mean_out=mean)
+        z = (u - mean.reshape(B, -1)) / sd
+        return (-0.5 * z * z - math.log(sd) - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
+
+    def unpack(self, xy, **kwargs):
+        """dataset.unpack (fbs/data/images.py:333-350)."""
+        xy = dev(xy, F32)
+        flat = xy.reshape(*xy.shape[:-3], self.unet.H * self.unet.W, self.c)
+        return flat[..., self.unobs.long(), :], flat[..., self.obs.long(), :]

@@ -224,6 +224,72 @@ int fbs_gaussian_ref_sample_f32(fbs_stream_t s, const uint32_t* keys, const floa
                                 const float* Bm, const float* c, const float* L, int64_t B, int64_t N, int64_t du,
                                 int64_t dv, float* out);
 
+/* ------------------------------------------------------------------------------------------
+ * Score network (fbs/nn/unet.py) on the tensor cores, and the NN-score closures
+ * (experiments/imgs/inpainting.py:94-147, supr.py, experiments/sb_imgs/supr.py:84-129).
+ * Activations are NHWC; "bf16" pointers are __nv_bfloat16 (passed as void*); P = H * W.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Implicit-GEMM convolution, stride 1 (flax.linen.Conv call sites of unet.py: 3x3 pad 1 -> kh = kw = 3, off = -1;
+ * 1x1 -> kh = kw = 1, off = 0; the 4x4 stride-2 Downsample (unet.py:50) as kh = kw = 2, off = 0 on the
+ * fbs_nn_space_to_depth_bf16 copy).  The channel axis of the input may be split over two tensors (the U-Net's
+ * skip concatenations, unet.py:335,340,355).  weight: bf16 [Cout][kh * kw * (C0 + C1)], K ordered (ty, tx, channel) --
+ * the flax HWIO kernel reshaped to [K, Cout] and transposed.  out = conv + bias (+ residual), written as fp32
+ * and / or bf16; pixel_shuffle != 0 writes 'b h w (h2 w2 c) -> b (h h2) (w w2) c' (fbs/nn/utils.py:53-57). */
+typedef struct {
+  int32_t B, H, W;      /* output pixels per sample */
+  int32_t Hin, Win;     /* input pixels per sample (0: same as the output) */
+  int32_t C0, C1, Cout; /* source channels (multiples of 64; C1 = 0: one source), output channels (multiple of 16) */
+  int32_t kh, kw, off_h, off_w;
+  int32_t pixel_shuffle, reserved;
+  const void* in0;      /* bf16 [B, Hin, Win, C0] */
+  const void* in1;      /* bf16 [B, Hin, Win, C1] or NULL */
+  const void* weight;
+  const float* bias;     /* [Cout] or NULL */
+  const float* residual; /* fp32, same layout as the output, or NULL */
+  float* out_f32;        /* either output may be NULL */
+  void* out_bf16;
+} fbs_nn_conv_t;
+int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* args);
+
+/* swish(GroupNorm(x) * gamma + beta [* (1 + scale) + shift]) [+ residual]   (unet.py:144-155,159-160,172).
+ * x fp32 [B, P, C]; time_scale_shift: [2 C] = (scale | shift) shared by the batch, or NULL. */
+int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma,
+                               const float* beta, const float* time_scale_shift, const float* residual, float eps,
+                               float* out_f32, void* out_bf16);
+/* LayerNorm over channels, scale only (unet.py:243,258) [+ residual (unet.py:264)].  x fp32 [rows, C]. */
+int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, const float* gamma, const float* residual,
+                         float eps, float* out_f32, void* out_bf16);
+/* LinearAttention core (unet.py:227-239) and Attention core (unet.py:192-199): qkv fp32 [B, P, 3 heads dim_head]
+ * -> bf16 [B, P, heads dim_head]. */
+int fbs_nn_linear_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head,
+                                void* out_bf16);
+int fbs_nn_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head, float scale,
+                         void* out_bf16);
+/* Time embedding (unet.py:293-300, base.py:44-77) + every ResnetBlock's Dense(2 dim)(swish(time_emb)) (:148-149):
+ * table[nout] = swish(temb) @ Wcat + bcat; tval: device scalar with the network time. */
+int fbs_nn_time_mlp_f32(fbs_stream_t s, const float* tval, float dt, int32_t dim, const float* W0, const float* b0, const float* W1,
+                        const float* b1, const float* Wcat, const float* bcat, int32_t nout, float* table);
+/* First (7x7, unet.py:286-291) and last (1x1, unet.py:363) convolutions, fp32 on the CUDA cores. */
+int fbs_nn_stem_conv_f32(fbs_stream_t s, const float* x, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                         const float* weight, const float* bias, float* out_f32, void* out_bf16);
+int fbs_nn_head_conv_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, int32_t Cimg, const float* weight,
+                         const float* bias, float* out);
+/* out[b, i, j, (r, s, c)] = in[b, 2 i - 1 + r, 2 j - 1 + s, c] (zero outside): bf16 [B, H, W, C] -> [B, H/2 + 1, W/2 + 1, 4 C]. */
+int fbs_nn_space_to_depth_bf16(fbs_stream_t s, const void* in, int64_t B, int32_t H, int32_t W, int32_t C, void* out);
+/* dataset.concat (fbs/data/images.py:352-363): img[b] = scatter(us[b] -> unobs_idx, v -> obs_idx). */
+int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, const int32_t* unobs_idx, const int32_t* obs_idx,
+                              int64_t B, int32_t p, int32_t q, int32_t c, float* img);
+/* transition_sampler + likelihood_logpdf (inpainting.py:122-147) from ONE score evaluation: rd = -a x + g2 score;
+ * us_new = u + rd_u dt + sd normal(key, (B, p, c)) (NULL: skip), mean_out = u + rd_u dt (NULL: skip),
+ * lw[b] = sum logN(v_next; v_prev + rd_v dt, sd) (NULL: skip). */
+int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
+                       const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
+                       float dt, float sd, float* us_new, float* mean_out, float* lw);
+/* dst[b, :] = src[idx[b], :]  (the ancestor gather, csmc.py:140). */
+int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, float* dst);
+int fbs_nn_f32_to_bf16(fbs_stream_t s, const float* x, int64_t n, void* y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,213 @@
+"""Score network on the tensor cores (fbs_b200/nn, nn_conv.cu, nn_ops.cu) against plain float32 torch references:
+each kernel against the same op in torch (bf16-rounded operands where the kernel takes bf16), the whole U-Net and
+the NN-score closures against the oracle restatement of fbs/nn/unet.py + experiments/imgs/inpainting.py:94-147.
+
+Tolerances: the kernels multiply bf16 operands and accumulate in fp32.  Single ops given identical bf16 inputs:
+rtol 2e-3 (summation order).  Whole network vs the fp32 oracle: bf16 rounding of every activation and weight,
+|err| <= 4e-2 * max|ref| (measured ~1e-2), log-weights atol 2e-2 * sqrt(q c) relative scale (see the closure test).
+"""
+import math
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import unet as ou          # noqa: E402
+from oracle import jax_random as jr    # noqa: E402
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _conv_ref(x, w, bias, pad, stride=1):
+    """fp32 CPU conv on NHWC input / HWIO kernel."""
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, stride=stride, padding=pad)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize('B,H,W,C0,C1,Cout,k', [
+    (3, 28, 28, 64, 0, 64, 3),       # the most common layer
+    (5, 14, 14, 128, 64, 128, 3),    # two sources (skip concatenation), tile rows cross the image end
+    (4, 7, 7, 256, 128, 256, 3),     # two samples per M tile
+    (2, 7, 7, 256, 0, 1024, 3),      # N tiles of 256
+    (3, 28, 28, 64, 0, 384, 1),      # qkv projection: N tile 192, no bias
+    (2, 16, 16, 64, 64, 64, 1),      # res_conv over a concatenation
+    (1, 64, 64, 64, 0, 64, 3),       # CelebA-64 width: two full rows per tile
+])
+def test_conv_matches_torch(B, H, W, C0, C1, Cout, k):
+    from fbs_b200.nn import ops
+    g = torch.Generator().manual_seed(1)
+    x0 = _bf(torch.randn(B, H, W, C0, generator=g))
+    x1 = _bf(torch.randn(B, H, W, C1, generator=g)) if C1 else None
+    w = _bf(torch.randn(k, k, C0 + C1, Cout, generator=g) / math.sqrt(k * k * (C0 + C1)))
+    bias = torch.randn(Cout, generator=g) if k == 3 else None
+    res = torch.randn(B, H, W, Cout, generator=g)
+    xin = torch.cat([x0, x1], dim=-1) if C1 else x0
+    want = _conv_ref(xin.float(), w.float(), bias, k // 2) + res
+    wp = w.float().reshape(k * k * (C0 + C1), Cout).t().contiguous().to(torch.bfloat16).cuda()
+    out32 = torch.empty(B, H, W, Cout, device='cuda')
+    out16 = torch.empty(B, H, W, Cout, device='cuda', dtype=torch.bfloat16)
+    ops.conv(x0.cuda(), wp, Cout, k, k, -(k // 2), H, W, in1=None if x1 is None else x1.cuda(),
+             bias=None if bias is None else bias.cuda(), residual=res.cuda(), out_f32=out32, out_bf16=out16)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out32.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-2)
+
+
+def test_conv_pixel_shuffle_and_stride2():
+    from fbs_b200.nn import ops
+    from fbs_b200.nn.unet import _pack, _pack_stride2
+    g = torch.Generator().manual_seed(2)
+    # Upsample conv_0 + PixelShuffle (unet.py:68-69)
+    B, H, W, C = 3, 7, 7, 128
+    x = _bf(torch.randn(B, H, W, C, generator=g))
+    w = _bf(torch.randn(3, 3, C, 4 * C, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(4 * C, generator=g)
+    want = ou.pixel_shuffle(_conv_ref(x.float(), w.float(), bias, 1), 2)
+    out = torch.empty(B, 2 * H, 2 * W, C, device='cuda', dtype=torch.bfloat16)
+    ops.conv(x.cuda(), torch.from_numpy(_pack(w.float().numpy())).to(torch.bfloat16).cuda(), 4 * C, 3, 3, -1, H, W, bias=bias.cuda(),
+             out_bf16=out, pixel_shuffle=True)
+    np.testing.assert_allclose(out.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-2)
+    # Downsample: 4x4 stride 2 padding 1 (unet.py:50) as space-to-depth + 2x2
+    B, H, W, C, Cout = 3, 28, 28, 64, 128
+    x = _bf(torch.randn(B, H, W, C, generator=g))
+    w = _bf(torch.randn(4, 4, C, Cout, generator=g) / math.sqrt(16 * C))
+    bias = torch.randn(Cout, generator=g)
+    want = _conv_ref(x.float(), w.float(), bias, 1, stride=2)
+    s2d = torch.empty(B, H // 2 + 1, W // 2 + 1, 4 * C, device='cuda', dtype=torch.bfloat16)
+    ops.space_to_depth(x.cuda(), s2d)
+    out = torch.empty(B, H // 2, W // 2, Cout, device='cuda')
+    ops.conv(s2d, torch.from_numpy(_pack_stride2(w.float().numpy())).to(torch.bfloat16).cuda(), Cout, 2, 2, 0, H // 2, W // 2,
+             bias=bias.cuda(), out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
+
+
+def test_norms_and_attention_match_oracle_pieces():
+    from fbs_b200.nn import ops
+    g = torch.Generator().manual_seed(3)
+    B, H, W, C = 3, 14, 14, 128
+    x = torch.randn(B, H, W, C, generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    tss = torch.randn(2 * C, generator=g) * 0.3
+    res = torch.randn(B, H, W, C, generator=g)
+    P = ou._P({'n.scale': gamma.numpy(), 'n.bias': beta.numpy()})
+    want = ou._swish(ou._group_norm(P, 'n', x) * (1 + tss[:C]) + tss[C:]) + res
+    out = torch.empty_like(x, device='cuda')
+    ops.groupnorm_swish(x.cuda(), gamma.cuda(), beta.cuda(), 8, tss=tss.cuda(), residual=res.cuda(), out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
+    want = ou._layer_norm(P, 'n', x) + res
+    ops.layernorm(x.cuda(), gamma.cuda(), residual=res.cuda(), out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
+    # attention cores on a given qkv
+    for P_, linear in ((196, True), (49, False), (300, False)):
+        qkv = torch.randn(B, P_, 1, 384, generator=g)
+        q, k, v = ou._split_heads(qkv, 4)
+        if linear:
+            qs, ks = torch.softmax(q, dim=-1) / math.sqrt(32), torch.softmax(k, dim=-3)
+            ctx = torch.einsum('bnhd,bnhe->bhde', ks, v / P_)
+            want = torch.einsum('bhde,bnhd->bhen', ctx, qs).permute(0, 3, 1, 2).reshape(B, P_, 128)
+        else:
+            l2 = lambda t: t / torch.clamp(torch.linalg.norm(t, dim=1, keepdim=True), min=1e-12)
+            sim = torch.einsum('bihd,bjhd->bhij', l2(q), l2(k)) * 10
+            want = torch.einsum('bhij,bjhd->bhid', torch.softmax(sim, dim=-1), v).permute(0, 2, 1, 3).reshape(B, P_, 128)
+        o = torch.empty(B, P_, 128, device='cuda', dtype=torch.bfloat16)
+        (ops.linear_attention if linear else ops.attention)(qkv.cuda().contiguous(), o)
+        np.testing.assert_allclose(o.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-3 * float(want.abs().max()))
+
+
+def _mnist_setup(seed=0, B=3):
+    params = ou.init_unet_params(seed, 1)
+    rng = np.random.default_rng(seed + 1)
+    x = rng.standard_normal((B, 28, 28, 1)).astype(np.float32)
+    return params, x
+
+
+def test_time_mlp_and_stem_match_oracle():
+    from fbs_b200.nn import ScoreUNet
+    params, x = _mnist_setup()
+    net = ScoreUNet(params, (28, 28, 1), dt=2. / 200)
+    net(torch.from_numpy(x).cuda(), 0.731, use_graph=False)
+    torch.cuda.synchronize()
+    P = ou._P(params)
+    temb = ou.sinusoidal_embedding(torch.tensor(0.731 / (2. / 200)), 64)[None]
+    temb = ou._dense(P, 'time.dense_1', F.gelu(ou._dense(P, 'time.dense_0', temb), approximate='tanh'))
+    for blk, off, d in net._time_blocks:
+        want = ou._dense(P, blk + '.time_mlp.dense_0', ou._swish(temb))[0]
+        np.testing.assert_allclose(net.table[off:off + 2 * d].cpu().numpy(), want.numpy(), rtol=2e-4, atol=2e-4)
+    want = ou._conv(P, 'init.conv_0', torch.from_numpy(x), padding=3)
+    np.testing.assert_allclose(net._bufs[(3, 'h0_f32')].cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('shape', [(28, 28, 1), (32, 32, 3)])
+def test_unet_matches_oracle(shape):
+    from fbs_b200.nn import ScoreUNet
+    H, W, C = shape
+    params = ou.init_unet_params(5, C)
+    rng = np.random.default_rng(6)
+    B = 5
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    net = ScoreUNet(params, shape, dt=2. / 200)
+    for t in (0.02, 1.3):
+        want = ou.unet_forward(params, x, t, 2. / 200)
+        got_eager = net(torch.from_numpy(x).cuda(), t, use_graph=False).cpu().numpy().copy()
+        got_graph = net(torch.from_numpy(x).cuda(), t).cpu().numpy().copy()
+        np.testing.assert_array_equal(got_eager, got_graph)      # the CUDA graph replays the same kernels
+        scale = float(np.abs(want).max())
+        err = np.abs(got_graph - want)
+        assert err.max() <= 4e-2 * scale, (err.max(), scale)
+        assert err.mean() <= 6e-3 * scale, (err.mean(), scale)
+    # batch-size independence: one sample alone gives the same result as inside the batch (bitwise: same tiles' math)
+    one = net(torch.from_numpy(x[:1]).cuda(), 1.3).cpu().numpy()
+    np.testing.assert_allclose(one[0], got_graph[0], rtol=1e-3, atol=1e-3 * scale)
+
+
+def test_score_closures_match_oracle():
+    """ScoreNetModel.step == transition_sampler + likelihood_logpdf of experiments/imgs/inpainting.py:122-147 restated
+    with the fp32 oracle network: noise bit-pinned by the key, means / log-weights within the bf16 network tolerance."""
+    from fbs_b200.nn import ScoreUNet, ScoreNetModel
+    from fbs_b200 import sdes
+    params, _ = _mnist_setup(7)
+    H = W = 28
+    T, K, N = 2.0, 200, 6
+    ts = np.linspace(0., T, K + 1)
+    sde = sdes.StationaryLinLinearSDE(beta_min=0.02, beta_max=5., t0=0., T=T)
+    # inpaint-15 style mask: a 15x15 square unobserved
+    rect = np.array([(i + 4) * W + (j + 4) for i in range(15) for j in range(15)], dtype=np.int32)
+    obs = np.setdiff1d(np.arange(H * W, dtype=np.int32), rect)
+    net = ScoreUNet(params, (H, W, 1), dt=T / 200)
+    model = ScoreNetModel(net, sde, ts, T, rect, obs)
+    rng = np.random.default_rng(8)
+    us = rng.standard_normal((N, rect.size, 1)).astype(np.float32)
+    v_prev = rng.standard_normal((obs.size, 1)).astype(np.float32)
+    v_next = (v_prev + 0.05 * rng.standard_normal((obs.size, 1))).astype(np.float32)
+    key = jr.PRNGKey(99)
+    k = 120
+    t_prev = ts[k]
+    us_new, lw = model.step(us, v_prev, v_next, t_prev, key)
+    us_new, lw = us_new.cpu().numpy(), lw.cpu().numpy()
+    # oracle restatement
+    dt = T / K
+    s = T - t_prev
+    img = np.zeros((N, H * W, 1), np.float32)
+    img[:, rect] = us
+    img[:, obs] = v_prev
+    score = ou.unet_forward(params, img.reshape(N, H, W, 1), s, T / 200).reshape(N, H * W, 1)
+    a, g = sde.drift_coef(s), sde.dispersion(s)
+    rd = -a * img + g ** 2 * score
+    sd = math.sqrt(dt) * g
+    mean_u = us + rd[:, rect] * dt
+    want_us = mean_u + np.float32(sd) * jr.normal(key, us.shape)
+    z = (v_next[None] - (v_prev[None] + rd[:, obs] * dt)) / sd
+    want_lw = (-0.5 * z ** 2 - math.log(sd) - 0.5 * math.log(2 * math.pi)).sum(axis=(1, 2))
+    np.testing.assert_allclose(us_new, want_us, rtol=0, atol=4e-2 * dt * g ** 2 * float(np.abs(score).max()) + 1e-5)
+    # log-weights: differences between particles are what the sampler uses
+    np.testing.assert_allclose(lw - lw.mean(), want_lw - want_lw.mean(), rtol=0, atol=5e-2 * max(1.0, float(np.ptp(want_lw))))
+    np.testing.assert_allclose(lw, want_lw, rtol=2e-3, atol=0.5)
+    # the separate closures agree with the fused step
+    us2 = model.transition_sampler(us, v_prev, t_prev, key).cpu().numpy()
+    lw2 = model.likelihood_logpdf(v_next, us, v_prev, t_prev).cpu().numpy()
+    np.testing.assert_array_equal(us2, us_new)
+    np.testing.assert_array_equal(lw2, lw)
