@@ -332,6 +332,38 @@ class ScoreNetModel:
         z = (u - mean.reshape(B, -1)) / sd
         return (-0.5 * z * z - math.log(sd) - 0.5 * math.log(2 * math.pi)).sum(dim=-1)
 
+    @property
+    def du(self):
+        return self.p * self.c
+
+    @property
+    def dv(self):
+        return self.q * self.c
+
+    def concat(self, x, y, **kwargs):
+        """dataset.concat (fbs/data/images.py:352-363) for one image: x [p, c], y [q, c] -> [H, W, c]."""
+        x = dev(x, F32).reshape(1, self.p, self.c)
+        y = dev(y, F32).reshape(self.q, self.c)
+        img = torch.empty((1, self.unet.H, self.unet.W, self.c), dtype=F32, device=x.device)
+        ops.assemble_image(x, y, self.unobs, self.obs, img)
+        return img[0]
+
+    def fwd_sampler(self, key, x0, y0, **kwargs):
+        """inpainting.py:150-152: simulate_cond_forward(key, concat(x0, y0), ts) -> path [K + 1, H, W, c]."""
+        from ..sdes.linear import step_coefficients, forward_path
+        if not hasattr(self, '_fwd_coef'):
+            self._fwd_coef = step_coefficients(self.sde, self.ts)
+        xy0 = self.concat(x0, y0)
+        path = forward_path(dev(key, torch.uint32).reshape(2), xy0.reshape(-1), *self._fwd_coef)
+        return path.reshape(self.K + 1, self.unet.H, self.unet.W, self.c)
+
+    def fwd_sampler_reversed(self, key, x0, y0):
+        """(us, vs) = (path_x[::-1], path_y[::-1]) of one forward-noising draw (gibbs.py:127-130), flattened per step."""
+        path = self.fwd_sampler(key, dev(x0, F32).reshape(self.p, self.c), dev(y0, F32).reshape(self.q, self.c))
+        px, py = self.unpack(path)
+        return (torch.flip(px, dims=[0]).reshape(1, self.K + 1, self.du).contiguous(),
+                torch.flip(py, dims=[0]).reshape(1, self.K + 1, self.dv).contiguous())
+
     def unpack(self, xy, **kwargs):
         """dataset.unpack (fbs/data/images.py:333-350)."""
         xy = dev(xy, F32)

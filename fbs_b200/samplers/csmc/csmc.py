@@ -15,6 +15,8 @@ import torch
 from ... import _native as nat
 from ..._tensor import dev, empty, ptr, stream, out, is_host
 from ...models import AffineGaussianModel
+from ...nn.unet import ScoreNetModel
+from ...nn import ops as nnops
 from ... import random as frandom
 
 
@@ -53,9 +55,9 @@ def _model_of(*fns):
     if len(models) != 1:
         raise TypeError('transition_sampler / likelihood_logpdf must be bound methods of ONE model object')
     model = next(iter(models.values()))
-    if not isinstance(model, AffineGaussianModel):
+    if not isinstance(model, (AffineGaussianModel, ScoreNetModel)):
         raise TypeError('fbs_b200 fuses the sweep into a CUDA kernel and cannot call opaque Python closures: pass '
-                        'bound methods of an fbs_b200.AffineGaussianModel (no interpreted fallback exists)')
+                        'bound methods of an fbs_b200.AffineGaussianModel or fbs_b200.nn.ScoreNetModel (no interpreted fallback exists)')
     return model
 
 
@@ -65,8 +67,63 @@ def _scheme_of(resampling, family):
     return resampling.scheme
 
 
+def forward_pass_nn(key, us_star, bs_star, vs, model, init, scheme, nsamples, history=True):
+    """csmc.py:132-164 for ONE chain with a :class:`ScoreNetModel`: a host loop over the K steps, each step = conditional
+    resampling kernel, ancestor gather, ONE score-network evaluation (CUDA-graph replay) feeding both the transition
+    and the weight (the reference evaluates the network twice, SURVEY finding 6c), pinning and normalisation.
+    Shapes: us_star [K + 1, p, c], vs [K + 1, q, c], bs_star [K + 1]."""
+    k = dev(key, torch.uint32).reshape(2)
+    K, p, q, c = model.K, model.p, model.q, model.c
+    us_star = dev(us_star, torch.float32).reshape(K + 1, p, c)
+    v = dev(vs, torch.float32).reshape(K + 1, q, c)
+    bs = dev(bs_star, torch.int32).reshape(K + 1)
+    bsl = bs.long()
+    ks = frandom.split(k, 2)                                                       # csmc.py:150
+    key_init, key_scan = ks[0].contiguous(), ks[1].contiguous()
+    sk = frandom.split(frandom.split(key_scan, K), 2).contiguous()                 # csmc.py:157,136: [K, (resampling, transition), 2]
+    ts = model.ts
+    if isinstance(init, NormalInit):
+        N = int(nsamples) + 1                                                      # csmc.py:151
+        us = frandom.normal(key_init, (N, p, c)).contiguous()
+        us.index_copy_(0, bsl[0:1], us_star[0:1])                                  # csmc.py:152
+        lw = model.likelihood_logpdf(v[0], us, v[1], ts[0])                        # gibbs.py:136-137
+    elif isinstance(init, DegenerateInit):
+        N = init.nparticles
+        us = us_star[0:1].expand(N, p, c).contiguous()
+        lw = torch.full((N,), init.init_log_w, dtype=torch.float32, device=us.device)
+    else:
+        raise TypeError('init_sampler / init_likelihood_logpdf must come from DegenerateInit or NormalInit')
+    log_w = lw - torch.logsumexp(lw, dim=0)                                        # csmc.py:155
+    As = log_wss = uss = None
+    if history:
+        As = empty((K, N), torch.int32)
+        log_wss = empty((K + 1, N), torch.float32)
+        uss = empty((K + 1, N, p, c), torch.float32)
+        log_wss[0].copy_(log_w)
+        uss[0].copy_(us)
+    A = empty((1, N), torch.int32)
+    us_prev = torch.empty_like(us)
+    for kk in range(K):
+        w = torch.exp(log_w).contiguous()
+        nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(sk[kk, 0]), ptr(w), ptr(bs[kk:kk + 1]), ptr(bs[kk + 1:kk + 2]), 1,
+                 1, N, ptr(A))                                                     # csmc.py:139
+        nnops.gather_rows(us, A.reshape(N), us_prev)                               # csmc.py:140
+        us, lw = model.step(us_prev, v[kk], v[kk + 1], ts[kk], sk[kk, 1])          # csmc.py:142,145
+        us.index_copy_(0, bsl[kk + 1:kk + 2], us_star[kk + 1:kk + 2])              # csmc.py:143
+        log_w = lw - torch.logsumexp(lw, dim=0)                                    # csmc.py:146
+        if history:
+            As[kk].copy_(A[0])
+            log_wss[kk + 1].copy_(log_w)
+            uss[kk + 1].copy_(us)
+    ex = (lambda t: None if t is None else t.unsqueeze(0))
+    return dict(N=N, As=ex(As), log_wss=ex(log_wss), uss=None if uss is None else uss.reshape(1, K + 1, N, p * c),
+                log_ws_last=log_w.unsqueeze(0).contiguous(), us_last=us.reshape(1, N, p * c).contiguous())
+
+
 def forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples, history=True):
     """Device-level forward pass on batched device tensors.  Returns a dict of device tensors."""
+    if isinstance(model, ScoreNetModel):
+        return forward_pass_nn(key, us_star, bs_star, vs, model, init, scheme, nsamples, history)
     k = dev(key, torch.uint32).reshape(-1, 2)
     B = k.shape[0]
     K, du, dv = model.K, model.du, model.dv

@@ -12,6 +12,7 @@ from .. import _native as nat
 from .._tensor import dev, empty, ptr, stream, out, is_host
 from .. import random as frandom
 from ..models import AffineGaussianModel
+from ..nn.unet import ScoreNetModel
 from .csmc.csmc import (DegenerateInit, NormalInit, forward_pass_device, backward_scanning_pass, _model_of)
 from .csmc.resamplings import killing
 from .resampling import stratified
@@ -65,6 +66,8 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
     single = k.dim() == 1
     k = k.reshape(-1, 2)
     B, K, N = k.shape[0], model.K, int(nparticles)
+    if isinstance(model, ScoreNetModel) and B != 1:
+        raise NotImplementedError('image chains run one at a time (the reference loops over test images, inpainting.py:205-210)')
     x0_d = dev(x0, torch.float32).reshape(B, model.du)
     y0_d = dev(y0, torch.float32).reshape(-1, model.dv)
     bs = dev(bs_star, torch.int32).reshape(B, K + 1)

@@ -211,3 +211,97 @@ def test_score_closures_match_oracle():
     lw2 = model.likelihood_logpdf(v_next, us, v_prev, t_prev).cpu().numpy()
     np.testing.assert_array_equal(us2, us_new)
     np.testing.assert_array_equal(lw2, lw)
+
+
+def _inpaint_problem(K=5, N=7, seed=11):
+    from fbs_b200.nn import ScoreUNet, ScoreNetModel
+    from fbs_b200 import sdes
+    params = ou.init_unet_params(seed, 1)
+    H = W = 28
+    T = 2.0
+    ts = np.linspace(0., T, K + 1)
+    sde = sdes.StationaryLinLinearSDE(beta_min=0.02, beta_max=5., t0=0., T=T)
+    rect = np.array([(i + 6) * W + (j + 6) for i in range(15) for j in range(15)], dtype=np.int32)
+    obs = np.setdiff1d(np.arange(H * W, dtype=np.int32), rect)
+    net = ScoreUNet(params, (H, W, 1), dt=T / 200)
+    model = ScoreNetModel(net, sde, ts, T, rect, obs)
+    return params, model, sde, ts, T, rect, obs
+
+
+def _oracle_step(params, sde, T, dt, rect, obs, us, v_prev, v_next, t_prev, key):
+    """transition_sampler + likelihood_logpdf of inpainting.py:122-147 with the fp32 oracle network."""
+    N = us.shape[0]
+    s = T - t_prev
+    img = np.zeros((N, 784, 1), np.float32)
+    img[:, rect] = us
+    img[:, obs] = v_prev
+    score = ou.unet_forward(params, img.reshape(N, 28, 28, 1), s, T / 200).reshape(N, 784, 1)
+    a, g = sde.drift_coef(s), sde.dispersion(s)
+    rd = -a * img + g ** 2 * score
+    sd = math.sqrt(dt) * g
+    new = us + rd[:, rect] * dt + np.float32(sd) * jr.normal(key, us.shape)
+    z = (v_next[None] - (v_prev[None] + rd[:, obs] * dt)) / sd
+    return new.astype(np.float32), (-0.5 * z ** 2 - math.log(sd) - 0.5 * math.log(2 * math.pi)).sum(axis=(1, 2))
+
+
+@pytest.mark.parametrize('explicit_final', [False, True])
+def test_nn_forward_pass_teacher_forced(explicit_final):
+    """csmc.py:132-164 with the score-network closures, step by step from the kernel's own history: ancestors bit-exact
+    on identical weights, children / log-weights within the bf16 network tolerance, the reference slot pinned exactly."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    from oracle import cond_resampling as ocr, csmc as ocsmc
+    K, N = 5, 7
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(3)
+    us_star = rng.standard_normal((K + 1, rect.size, 1)).astype(np.float32)
+    vs = np.cumsum(0.05 * rng.standard_normal((K + 1, obs.size, 1)), axis=0).astype(np.float32)
+    key = jr.PRNGKey(5)
+    init = csmc.NormalInit(model) if explicit_final else csmc.DegenerateInit(N)
+    Np = N + 1 if explicit_final else N
+    bs_star = jr.randint(jr.PRNGKey(6), (K + 1,), 0, N).astype(np.int32)
+    As, log_wss, uss = csmc.forward_pass(key, us_star, bs_star, vs, ts, init.sampler, init.likelihood_logpdf,
+                                         model.transition_sampler, model.likelihood_logpdf, R.killing, N)
+    uss = uss.reshape(K + 1, Np, rect.size, 1)
+    assert As.shape == (K, Np) and log_wss.shape == (K + 1, Np)
+    key_init, key_scan = jr.split(key, 2)
+    if explicit_final:
+        u0 = jr.normal(key_init, (Np, rect.size, 1))
+        u0[bs_star[0]] = us_star[0]
+        np.testing.assert_allclose(uss[0], u0, rtol=0, atol=5e-7)
+    else:
+        np.testing.assert_array_equal(uss[0], np.broadcast_to(us_star[0], uss[0].shape))
+        np.testing.assert_allclose(log_wss[0], -np.log(N), atol=1e-6)
+    dt = T / K
+    for k, step_key in enumerate(jr.split(key_scan, K)):
+        key_res, key_tr = jr.split(step_key, 2)
+        A = ocr.killing(key_res, np.exp(log_wss[k]).astype(np.float32), bs_star[k], bs_star[k + 1], True)
+        np.testing.assert_array_equal(As[k], A)
+        want_us, want_lw = _oracle_step(params, sde, T, dt, rect, obs, uss[k][As[k]], vs[k], vs[k + 1], ts[k], key_tr)
+        want_us[bs_star[k + 1]] = us_star[k + 1]
+        np.testing.assert_array_equal(uss[k + 1][bs_star[k + 1]], us_star[k + 1])
+        # dt = T / K = 0.4 here: the bf16 network error (<= 4e-2 of the score scale) is multiplied by g^2 dt ~ 1
+        np.testing.assert_allclose(uss[k + 1], want_us, rtol=0, atol=3e-2 * max(1.0, float(np.abs(want_us).max())))
+        want = ocsmc.normalise(want_lw, log_space=True)
+        np.testing.assert_allclose(log_wss[k + 1], want, rtol=0, atol=5e-2 * max(1.0, float(np.ptp(want))))
+
+
+def test_nn_gibbs_kernel_runs():
+    """gibbs_kernel (gibbs.py:68-168, method 'gibbs-eb-ef' of experiments/bashes/imgs_gibbs.sh) over the score network."""
+    from fbs_b200.samplers import gibbs_kernel
+    K, N = 4, 5
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(4)
+    x0 = rng.standard_normal((rect.size, 1)).astype(np.float32)
+    y0 = rng.uniform(size=(obs.size, 1)).astype(np.float32)
+    bs_star = np.zeros((K + 1,), np.int32)
+    key = jr.PRNGKey(21)
+    x0n, us_star, bs_next, changed = gibbs_kernel(key, x0, y0, None, bs_star, ts, model.fwd_sampler, sde, model.unpack, N,
+                                                  model.transition_sampler, model.transition_logpdf, model.likelihood_logpdf,
+                                                  explicit_backward=True, explicit_final=True)
+    assert x0n.shape == (rect.size,) and us_star.shape == (K + 1, rect.size)
+    assert np.isfinite(x0n).all() and np.isfinite(us_star).all()
+    assert bs_next.shape == (K + 1,) and (bs_next >= 0).all() and (bs_next < N).all()
+    np.testing.assert_array_equal(us_star[-1], x0n)
+    # bs_star_next is randint(key_csmc_bwd_bs, (K + 1,), 0, nparticles)   (gibbs.py:156)
+    kc = jr.split(jr.split(key, 3)[1], 4)
+    np.testing.assert_array_equal(bs_next, jr.randint(kc[3], (K + 1,), 0, N))
