@@ -67,8 +67,8 @@ SIGNATURES = {
     'fbs_nn_conv_bf16': ([_p, _CV], _int),
     'fbs_nn_groupnorm_swish_f32': ([_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p], _int),
     'fbs_nn_layernorm_f32': ([_p, _p, _i64, _i32, _p, _p, _f32, _p, _p], _int),
-    'fbs_nn_linear_attention_f32': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),
-    'fbs_nn_attention_f32': ([_p, _p, _i64, _i32, _i32, _i32, _f32, _p], _int),
+    'fbs_nn_linear_attention_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),
+    'fbs_nn_attention_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _f32, _p], _int),
     'fbs_nn_time_mlp_f32': ([_p, _p, _f32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p], _int),
     'fbs_nn_stem_conv_f32': ([_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _p, _p], _int),
     'fbs_nn_head_conv_f32': ([_p, _p, _i64, _i32, _i32, _p, _p, _p], _int),

@@ -352,8 +352,9 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   p.h_tiles = (a->H + p.BH - 1) / p.BH;
   const int n_tiles = (a->B + p.BNb - 1) / p.BNb;
   const size_t stage = (size_t)A_STAGE_BYTES + (size_t)ntile * 128;
-  int stages = (int)((200 * 1024) / stage);
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  // short K loops (9..54 blocks) and small tiles: prologue / epilogue latency matters more than ring depth, so keep the
+  // ring shallow enough for 2-3 CTAs to share an SM and overlap one CTA's epilogue with another's main loop
+  int stages = ntile <= 128 ? 3 : 4;
   if (stages < 2) {
     set_error("nn_conv: tile does not fit shared memory");
     return FBS_ERR_UNSUPPORTED;

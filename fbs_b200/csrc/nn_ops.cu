@@ -36,10 +36,12 @@ __device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)
 // GroupNorm (+ time-embedding scale / shift) + swish (+ residual): unet.py:144-155,159-160,172.
 // One CTA per (sample, group); the slice (P x C / groups values, L2 / L1 resident) is read three times.
 // ---------------------------------------------------------------------------------------------------------
+template <bool STAGED>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, int P, int C, int groups,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ tss, const float* __restrict__ residual,
                                                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, float eps) {
+  extern __shared__ float4 slice[];  // STAGED: the (sample, group) slice, read from global memory exactly once
   __shared__ float red[32];
   const int b = blockIdx.x / groups, g = blockIdx.x % groups;
   const int cpg = C / groups, q4 = cpg / 4;  // float4 per pixel of this group
@@ -48,12 +50,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   float s = 0.f;
   for (int e = threadIdx.x; e < n4; e += blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(x + base + (size_t)(e / q4) * C + 4 * (e % q4));
+    if (STAGED) slice[e] = v;
     s += (v.x + v.y) + (v.z + v.w);
   }
   const float mean = block_sum(s, red) / (float)(P * cpg);
   float ss = 0.f;
   for (int e = threadIdx.x; e < n4; e += blockDim.x) {
-    const float4 v = *reinterpret_cast<const float4*>(x + base + (size_t)(e / q4) * C + 4 * (e % q4));
+    const float4 v = STAGED ? slice[e] : *reinterpret_cast<const float4*>(x + base + (size_t)(e / q4) * C + 4 * (e % q4));
     const float a = v.x - mean, bq = v.y - mean, c = v.z - mean, d = v.w - mean;
     ss += (a * a + bq * bq) + (c * c + d * d);
   }
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   for (int e = threadIdx.x; e < n4; e += blockDim.x) {
     const int c0 = g * cpg + 4 * (e % q4);
     const size_t off = (size_t)b * P * C + (size_t)(e / q4) * C + c0;
-    const float4 v = *reinterpret_cast<const float4*>(x + off);
+    const float4 v = STAGED ? slice[e] : *reinterpret_cast<const float4*>(x + off);
     float y[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -123,22 +126,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------
 // LinearAttention core (unet.py:227-239): q softmax over the head dimension, k softmax over the pixels,
 // context = k^T (v / P), out = context^T (q / sqrt(d)).  One CTA per (sample, head); dim_head = 32.
-// qkv: fp32 [B, P, 3 * heads * 32] (q | k | v, each (head, d));  out: bf16 [B, P, heads * 32].
+// qkv: bf16 [B, P, 3 * heads * 32] (q | k | v, each (head, d));  out: bf16 [B, P, heads * 32].
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) linear_attention_kernel(const float* __restrict__ qkv, int P, int heads,
+__global__ void __launch_bounds__(256) linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int P, int heads,
                                                                __nv_bfloat16* __restrict__ out) {
+  constexpr int TN = 128;  // pixels per shared-memory tile
+  __shared__ float ek[TN][33], vt[TN][32];
   __shared__ float ctx[32][33];
   __shared__ float kmax[32], ksum[32];
   __shared__ float part[8][32];
   const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
   const int HD = heads * 32, ld = 3 * HD;
-  const float* q = qkv + (size_t)b * P * ld + hd * 32;
-  const float* k = q + HD;
-  const float* v = k + HD;
+  const __nv_bfloat16* q = qkv + (size_t)b * P * ld + hd * 32;
+  const __nv_bfloat16* k = q + HD;
+  const __nv_bfloat16* v = k + HD;
   const int d = threadIdx.x & 31, sl = threadIdx.x >> 5;  // 8 warps
   // column max of k over the pixels
   float m = -INFINITY;
-  for (int n = sl; n < P; n += 8) m = fmaxf(m, k[(size_t)n * ld + d]);
+  for (int n = sl; n < P; n += 8) m = fmaxf(m, __bfloat162float(k[(size_t)n * ld + d]));
   part[sl][d] = m;
   __syncthreads();
   if (sl == 0) {
@@ -148,33 +153,74 @@ __global__ void __launch_bounds__(256) linear_attention_kernel(const float* __re
     kmax[d] = t;
   }
   __syncthreads();
-  // context[d][e] = sum_n exp(k[n,d] - kmax[d]) v[n,e]; thread (d, e-block of 4): sl selects e in [4 sl, 4 sl + 4)
-  {
-    const float km = kmax[d];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ks = 0.f;
-    for (int n = 0; n < P; ++n) {
-      const float ek = __expf(k[(size_t)n * ld + d] - km);
-      const float4 vv = *reinterpret_cast<const float4*>(v + (size_t)n * ld + 4 * sl);
-      a0 = fmaf(ek, vv.x, a0); a1 = fmaf(ek, vv.y, a1); a2 = fmaf(ek, vv.z, a2); a3 = fmaf(ek, vv.w, a3);
-      ks += ek;
-    }
-    if (sl == 0) ksum[d] = ks;
+  // context[d][e] = sum_n exp(k[n,d] - kmax[d]) v[n,e]: tiles of TN pixels staged (exp applied) in shared memory;
+  // thread (d, e-block of 4: e in [4 sl, 4 sl + 4)) accumulates over the tile
+  const float km = kmax[d];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ks = 0.f;
+  for (int n0 = 0; n0 < P; n0 += TN) {
     __syncthreads();
+    for (int n = sl; n < TN; n += 8) {
+      const bool ok = n0 + n < P;
+      ek[n][d] = ok ? __expf(__bfloat162float(k[(size_t)(n0 + n) * ld + d]) - km) : 0.f;
+      vt[n][d] = ok ? __bfloat162float(v[(size_t)(n0 + n) * ld + d]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int n = 0; n < TN; ++n) {
+      const float e = ek[n][d];
+      const float4 vv = *reinterpret_cast<const float4*>(&vt[n][4 * sl]);
+      a0 = fmaf(e, vv.x, a0); a1 = fmaf(e, vv.y, a1); a2 = fmaf(e, vv.z, a2); a3 = fmaf(e, vv.w, a3);
+      ks += e;
+    }
+  }
+  if (sl == 0) ksum[d] = ks;
+  __syncthreads();
+  {
     const float sc = 1.0f / (ksum[d] * (float)P);  // softmax denominator and v / (H W)
     ctx[d][4 * sl + 0] = a0 * sc; ctx[d][4 * sl + 1] = a1 * sc; ctx[d][4 * sl + 2] = a2 * sc; ctx[d][4 * sl + 3] = a3 * sc;
   }
   __syncthreads();
-  // out[n][e] = sum_d ctx[d][e] softmax_d(q[n,:])[d] / sqrt(32); one warp per pixel, lane = d then e
+  // out[n][e] = sum_d ctx[d][e] softmax_d(q[n,:])[d] / sqrt(32): per tile of TN pixels the softmaxed q goes to shared
+  // memory TRANSPOSED (reusing the k tile), then every thread computes a 4 pixel x 4 channel block from 16-byte reads
   const float inv_sqrt_d = 0.17677669529663687f;
-  for (int n = sl; n < P; n += 8) {
-    const float qv = q[(size_t)n * ld + d];
-    const float qm = warp_maxf(qv);
-    const float qe = __expf(qv - qm);
-    const float qs = qe / warp_sum(qe) * inv_sqrt_d;
-    float o = 0.f;
+  float (*qsT)[TN + 4] = reinterpret_cast<float (*)[TN + 4]>(&ek[0][0]);  // [32][TN + 4] fills the ek tile exactly; +4: 4-way instead of 32-way store conflicts
+  float (*ctx4)[32] = reinterpret_cast<float (*)[32]>(&vt[0][0]);  // aligned copy of the context inside the v tile
+  __syncthreads();
+  for (int t = threadIdx.x; t < 32 * 32; t += 256) ctx4[t >> 5][t & 31] = ctx[t >> 5][t & 31];
+  const int eb = threadIdx.x & 7, nb = threadIdx.x >> 3;  // channels 4 eb .. 4 eb + 3, pixels 4 nb .. 4 nb + 3 of the tile
+  for (int n0 = 0; n0 < P; n0 += TN) {
+    __syncthreads();
+    for (int n = sl; n < TN; n += 8) {
+      const bool ok = n0 + n < P;
+      const float qv = ok ? __bfloat162float(q[(size_t)(n0 + n) * ld + d]) : 0.f;
+      const float qm = warp_maxf(qv);
+      const float qe = __expf(qv - qm);
+      qsT[d][n] = qe / warp_sum(qe) * inv_sqrt_d;
+    }
+    __syncthreads();
+    float o[4][4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o = fmaf(ctx[j][d], __shfl_sync(0xffffffffu, qs, j), o);
-    out[((size_t)b * P + n) * HD + hd * 32 + d] = __float2bfloat16_rn(o);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+#pragma unroll 8
+    for (int dd = 0; dd < 32; ++dd) {
+      const float4 q4 = *reinterpret_cast<const float4*>(&qsT[dd][4 * nb]);
+      const float4 c4 = *reinterpret_cast<const float4*>(&ctx4[dd][4 * eb]);
+      const float qa[4] = {q4.x, q4.y, q4.z, q4.w}, ca[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(qa[i], ca[j], o[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + 4 * nb + i;
+      if (n < P) {
+        __align__(8) __nv_bfloat162 w2[2] = {__floats2bfloat162_rn(o[i][0], o[i][1]), __floats2bfloat162_rn(o[i][2], o[i][3])};
+        *reinterpret_cast<uint2*>(out + ((size_t)b * P + n) * HD + hd * 32 + 4 * eb) = *reinterpret_cast<const uint2*>(w2);
+      }
+    }
   }
 }
 
@@ -183,7 +229,7 @@ __global__ void __launch_bounds__(256) linear_attention_kernel(const float* __re
 // 'b (x y) h d', as written upstream), sim = 10 q k^T, softmax over keys, out = attn v.  One CTA per
 // (sample, head, 128-query block); keys / values streamed through shared memory in blocks of 128, online softmax.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int P, int heads, float scale,
+__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int P, int heads, float scale,
                                                         __nv_bfloat16* __restrict__ out) {
   __shared__ float ks[128][33], vs[128][33];
   __shared__ float qn[32], kn[32];
@@ -192,15 +238,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   const int b = blockIdx.x / (heads * qblocks), rem = blockIdx.x % (heads * qblocks);
   const int hd = rem / qblocks, qb = rem % qblocks;
   const int HD = heads * 32, ld = 3 * HD;
-  const float* q = qkv + (size_t)b * P * ld + hd * 32;
-  const float* k = q + HD;
-  const float* v = k + HD;
+  const __nv_bfloat16* q = qkv + (size_t)b * P * ld + hd * 32;
+  const __nv_bfloat16* k = q + HD;
+  const __nv_bfloat16* v = k + HD;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // column norms over the tokens
   {
     float sq = 0.f, sk = 0.f;
     for (int n = w; n < P; n += 4) {
-      const float a = q[(size_t)n * ld + lane], c = k[(size_t)n * ld + lane];
+      const float a = __bfloat162float(q[(size_t)n * ld + lane]), c = __bfloat162float(k[(size_t)n * ld + lane]);
       sq = fmaf(a, a, sq);
       sk = fmaf(c, c, sk);
     }
@@ -217,7 +263,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   float qi[32], acc[32];
 #pragma unroll
   for (int dd = 0; dd < 32; ++dd) {
-    qi[dd] = i < P ? q[(size_t)i * ld + dd] * qn[dd] * scale : 0.f;
+    qi[dd] = i < P ? __bfloat162float(q[(size_t)i * ld + dd]) * qn[dd] * scale : 0.f;
     acc[dd] = 0.f;
   }
   float mx = -INFINITY, den = 0.f;
@@ -226,8 +272,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     for (int t = threadIdx.x; t < 128 * 32; t += 128) {
       const int j = t >> 5, dd = t & 31;
       const bool ok = j0 + j < P;
-      ks[j][dd] = ok ? k[(size_t)(j0 + j) * ld + dd] * kn[dd] : 0.f;
-      vs[j][dd] = ok ? v[(size_t)(j0 + j) * ld + dd] : 0.f;
+      ks[j][dd] = ok ? __bfloat162float(k[(size_t)(j0 + j) * ld + dd]) * kn[dd] : 0.f;
+      vs[j][dd] = ok ? __bfloat162float(v[(size_t)(j0 + j) * ld + dd]) : 0.f;
     }
     __syncthreads();
     const int jn = min(128, P - j0);
@@ -303,14 +349,16 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
   const int nw = 49 * Cin * Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wgt[i];
   __syncthreads();
-  const int cgs = Cout / 4;
+  const int cgs = Cout / 16;  // thread = (pixel, 16 output channels)
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * H * W * cgs) return;
   const int cg = (int)(idx % cgs);
   const int64_t pix = idx / cgs;
   const int w = (int)(pix % W), h = (int)((pix / W) % H);
   const int64_t b = pix / ((int64_t)W * H);
-  float a0 = bias[4 * cg], a1 = bias[4 * cg + 1], a2 = bias[4 * cg + 2], a3 = bias[4 * cg + 3];
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = bias[16 * cg + j];
   for (int ty = 0; ty < 7; ++ty) {
     const int hh = h + ty - 3;
     if (hh < 0 || hh >= H) continue;
@@ -318,19 +366,31 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
       const int ww = w + tx - 3;
       if (ww < 0 || ww >= W) continue;
       const float* xp = x + ((b * H + hh) * W + ww) * Cin;
-      const float* wp = ws + ((ty * 7 + tx) * Cin) * Cout + 4 * cg;
+      const float* wp = ws + ((ty * 7 + tx) * Cin) * Cout + 16 * cg;
       for (int c = 0; c < Cin; ++c) {
         const float xv = xp[c];
-        const float4 wv = *reinterpret_cast<const float4*>(wp + c * Cout);
-        a0 = fmaf(xv, wv.x, a0); a1 = fmaf(xv, wv.y, a1); a2 = fmaf(xv, wv.z, a2); a3 = fmaf(xv, wv.w, a3);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp + c * Cout + j);
+          acc[j] = fmaf(xv, wv.x, acc[j]); acc[j + 1] = fmaf(xv, wv.y, acc[j + 1]);
+          acc[j + 2] = fmaf(xv, wv.z, acc[j + 2]); acc[j + 3] = fmaf(xv, wv.w, acc[j + 3]);
+        }
       }
     }
   }
-  const size_t off = (size_t)pix * Cout + 4 * cg;
-  if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(a0, a1, a2, a3);
+  const size_t off = (size_t)pix * Cout + 16 * cg;
+  if (out_f32) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(out_f32 + off + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  }
   if (out_bf16) {
-    __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(a0, a1), __floats2bfloat162_rn(a2, a3)};
-    *reinterpret_cast<uint2*>(out_bf16 + off) = *reinterpret_cast<const uint2*>(o);
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) o[t] = __floats2bfloat162_rn(acc[j + 2 * t], acc[j + 2 * t + 1]);
+      *reinterpret_cast<uint4*>(out_bf16 + off + j) = *reinterpret_cast<const uint4*>(o);
+    }
   }
 }
 
@@ -471,8 +531,16 @@ int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_
                                float* out_f32, void* out_bf16) {
   FBS_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), "groupnorm: null argument");
   FBS_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0, "groupnorm: channels per group must be a multiple of 4");
-  gn_apply_kernel<<<(unsigned)(B * groups), 256, 0, as_stream(s)>>>(x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32,
-                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  const size_t slice_bytes = (size_t)P * (C / groups) * sizeof(float);
+  if (slice_bytes <= 160 * 1024) {
+    if (slice_bytes > 48 * 1024)
+      cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes);
+    gn_apply_kernel<true><<<(unsigned)(B * groups), 256, slice_bytes, as_stream(s)>>>(
+        x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  } else {
+    gn_apply_kernel<false><<<(unsigned)(B * groups), 256, 0, as_stream(s)>>>(
+        x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  }
   return check_launch("gn_apply_kernel");
 }
 
@@ -485,20 +553,21 @@ int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C
   return check_launch("layernorm_kernel");
 }
 
-int fbs_nn_linear_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head,
-                                void* out_bf16) {
+int fbs_nn_linear_attention_bf16(fbs_stream_t s, const void* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head,
+                                 void* out_bf16) {
   FBS_REQUIRE(qkv && out_bf16, "linear_attention: null argument");
   FBS_REQUIRE(dim_head == 32 && heads >= 1 && heads <= 8, "linear_attention: dim_head must be 32");
-  linear_attention_kernel<<<(unsigned)(B * heads), 256, 0, as_stream(s)>>>(qkv, P, heads, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  linear_attention_kernel<<<(unsigned)(B * heads), 256, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), P, heads,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return check_launch("linear_attention_kernel");
 }
 
-int fbs_nn_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head, float scale,
-                         void* out_bf16) {
+int fbs_nn_attention_bf16(fbs_stream_t s, const void* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head, float scale,
+                          void* out_bf16) {
   FBS_REQUIRE(qkv && out_bf16, "attention: null argument");
   FBS_REQUIRE(dim_head == 32 && heads >= 1, "attention: dim_head must be 32");
   const int qblocks = (P + 127) / 128;
-  attention_kernel<<<(unsigned)(B * heads * qblocks), 128, 0, as_stream(s)>>>(qkv, P, heads, scale,
+  attention_kernel<<<(unsigned)(B * heads * qblocks), 128, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), P, heads, scale,
                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return check_launch("attention_kernel");
 }
@@ -514,10 +583,10 @@ int fbs_nn_time_mlp_f32(fbs_stream_t s, const float* tval, float dt, int32_t dim
 int fbs_nn_stem_conv_f32(fbs_stream_t s, const float* x, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                          const float* weight, const float* bias, float* out_f32, void* out_bf16) {
   FBS_REQUIRE(x && weight && bias && (out_f32 || out_bf16), "stem_conv: null argument");
-  FBS_REQUIRE(Cout % 4 == 0 && (size_t)49 * Cin * Cout * 4 <= 96 * 1024, "stem_conv: weights must fit shared memory");
+  FBS_REQUIRE(Cout % 16 == 0 && (size_t)49 * Cin * Cout * 4 <= 96 * 1024, "stem_conv: weights must fit shared memory");
   const size_t smem = (size_t)49 * Cin * Cout * 4;
   cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int64_t n = B * H * W * (Cout / 4);
+  const int64_t n = B * H * W * (Cout / 16);
   stem_conv_kernel<<<(unsigned)((n + 255) / 256), 256, smem, as_stream(s)>>>(x, (int)B, H, W, Cin, Cout, weight, bias, out_f32,
                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return check_launch("stem_conv_kernel");

@@ -39,13 +39,13 @@ def layernorm(x, gamma, residual=None, out_f32=None, out_bf16=None, eps=1e-5):
 def linear_attention(qkv, out_bf16, heads=4, dim_head=32):
     B = qkv.shape[0]
     P = qkv.numel() // (B * qkv.shape[-1])
-    nat.call('fbs_nn_linear_attention_f32', stream(), ptr(qkv), B, P, heads, dim_head, ptr(out_bf16))
+    nat.call('fbs_nn_linear_attention_bf16', stream(), ptr(qkv), B, P, heads, dim_head, ptr(out_bf16))
 
 
 def attention(qkv, out_bf16, heads=4, dim_head=32, scale=10.0):
     B = qkv.shape[0]
     P = qkv.numel() // (B * qkv.shape[-1])
-    nat.call('fbs_nn_attention_f32', stream(), ptr(qkv), B, P, heads, dim_head, float(scale), ptr(out_bf16))
+    nat.call('fbs_nn_attention_bf16', stream(), ptr(qkv), B, P, heads, dim_head, float(scale), ptr(out_bf16))
 
 
 def time_mlp(tval, dt, dim, W0, b0, W1, b1, Wcat, bcat, table):

@@ -151,12 +151,12 @@ class ScoreUNet:
         w = self._w
         hd = self.heads * self.dim_head
         n_bf = self._buf(B, f'attn_norm_{H}x{C}', (B, H, W, C), BF16)
-        qkv = self._buf(B, f'attn_qkv_{H}', (B, H, W, 3 * hd), F32)
+        qkv = self._buf(B, f'attn_qkv_{H}', (B, H, W, 3 * hd), BF16)
         ao = self._buf(B, f'attn_out_{H}', (B, H, W, hd), BF16)
         out_f32 = self._buf(B, tag + '_f32', (B, H, W, C), F32)
         out_bf = self._buf(B, tag + '_bf16', (B, H, W, C), BF16)
         ops.layernorm(x_f32, w[name + '.norm.scale'], out_bf16=n_bf)
-        ops.conv(n_bf, w[name + '.attn.to_qkv.conv_0.w'], 3 * hd, 1, 1, 0, H, W, out_f32=qkv)
+        ops.conv(n_bf, w[name + '.attn.to_qkv.conv_0.w'], 3 * hd, 1, 1, 0, H, W, out_bf16=qkv)
         if linear:
             ops.linear_attention(qkv, ao, self.heads, self.dim_head)
             proj = self._buf(B, f'attn_proj_{H}x{C}', (B, H, W, C), F32)

@@ -260,12 +260,12 @@ int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_
 /* LayerNorm over channels, scale only (unet.py:243,258) [+ residual (unet.py:264)].  x fp32 [rows, C]. */
 int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, const float* gamma, const float* residual,
                          float eps, float* out_f32, void* out_bf16);
-/* LinearAttention core (unet.py:227-239) and Attention core (unet.py:192-199): qkv fp32 [B, P, 3 heads dim_head]
- * -> bf16 [B, P, heads dim_head]. */
-int fbs_nn_linear_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head,
-                                void* out_bf16);
-int fbs_nn_attention_f32(fbs_stream_t s, const float* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head, float scale,
-                         void* out_bf16);
+/* LinearAttention core (unet.py:227-239) and Attention core (unet.py:192-199): qkv bf16 [B, P, 3 heads dim_head]
+ * -> bf16 [B, P, heads dim_head] (bf16 so that the projection stays L2 resident between the two kernels). */
+int fbs_nn_linear_attention_bf16(fbs_stream_t s, const void* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head,
+                                 void* out_bf16);
+int fbs_nn_attention_bf16(fbs_stream_t s, const void* qkv, int64_t B, int32_t P, int32_t heads, int32_t dim_head, float scale,
+                          void* out_bf16);
 /* Time embedding (unet.py:293-300, base.py:44-77) + every ResnetBlock's Dense(2 dim)(swish(time_emb)) (:148-149):
  * table[nout] = swish(temb) @ Wcat + bcat; tval: device scalar with the network time. */
 int fbs_nn_time_mlp_f32(fbs_stream_t s, const float* tval, float dt, int32_t dim, const float* W0, const float* b0, const float* W1,

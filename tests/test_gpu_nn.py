@@ -103,7 +103,7 @@ def test_norms_and_attention_match_oracle_pieces():
     np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
     # attention cores on a given qkv
     for P_, linear in ((196, True), (49, False), (300, False)):
-        qkv = torch.randn(B, P_, 1, 384, generator=g)
+        qkv = _bf(torch.randn(B, P_, 1, 384, generator=g)).float()
         q, k, v = ou._split_heads(qkv, 4)
         if linear:
             qs, ks = torch.softmax(q, dim=-1) / math.sqrt(32), torch.softmax(k, dim=-3)
@@ -114,7 +114,7 @@ def test_norms_and_attention_match_oracle_pieces():
             sim = torch.einsum('bihd,bjhd->bhij', l2(q), l2(k)) * 10
             want = torch.einsum('bhij,bjhd->bhid', torch.softmax(sim, dim=-1), v).permute(0, 2, 1, 3).reshape(B, P_, 128)
         o = torch.empty(B, P_, 128, device='cuda', dtype=torch.bfloat16)
-        (ops.linear_attention if linear else ops.attention)(qkv.cuda().contiguous(), o)
+        (ops.linear_attention if linear else ops.attention)(qkv.to(torch.bfloat16).cuda().contiguous(), o)
         np.testing.assert_allclose(o.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-3 * float(want.abs().max()))
 
 
