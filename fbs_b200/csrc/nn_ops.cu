@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
                                                       const int32_t* __restrict__ unobs, const int32_t* __restrict__ obs,
                                                       const float* __restrict__ v_next, const uint32_t* __restrict__ key, int64_t B,
                                                       int p, int q, int c, float a, float g2, float dt, float sd,
+                                                      int64_t row_offset, int64_t rows_total,
                                                       float* __restrict__ us_new, float* __restrict__ mean_out, float* __restrict__ lw) {
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
   const float* xi = img + b * (int64_t)P * c;
   const float* si = score + b * (int64_t)P * c;
   if (us_new || mean_out) {
-    const uint32_t nel = (uint32_t)(B * p * c);
+    const uint32_t nel = (uint32_t)(rows_total * p * c);  // the noise is normal(key, (rows_total, p, c)); this launch owns rows row_offset ..
     Key k{0u, 0u};
     if (key) k = Key{key[0], key[1]};
     for (int e = threadIdx.x; e < p * c; e += blockDim.x) {
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
       const float mean = x + rd * dt;
       if (mean_out) mean_out[b * (int64_t)p * c + e] = mean;
       if (us_new) {
-        const uint32_t el = (uint32_t)(b * p * c + e);
+        const uint32_t el = (uint32_t)((row_offset + b) * p * c + e);
         us_new[b * (int64_t)p * c + e] = mean + sd * bits_to_normal(random_bits_elem(k, nel, el));
       }
     }
@@ -617,12 +618,13 @@ int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, c
 
 int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
                        const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
-                       float dt, float sd, float* us_new, float* mean_out, float* lw) {
+                       float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw) {
   FBS_REQUIRE(img && score && unobs_idx && obs_idx, "em_step: null argument");
   FBS_REQUIRE(lw == nullptr || v_next != nullptr, "em_step: v_next missing");
   FBS_REQUIRE(us_new == nullptr || key != nullptr, "em_step: key missing");
-  em_step_kernel<<<(unsigned)B, 256, 0, as_stream(s)>>>(img, score, unobs_idx, obs_idx, v_next, key, B, p, q, c, a, g2, dt, sd, us_new,
-                                                        mean_out, lw);
+  FBS_REQUIRE(row_offset >= 0 && row_offset + B <= rows_total, "em_step: rows [row_offset, row_offset + B) must lie inside rows_total");
+  em_step_kernel<<<(unsigned)B, 256, 0, as_stream(s)>>>(img, score, unobs_idx, obs_idx, v_next, key, B, p, q, c, a, g2, dt, sd,
+                                                        row_offset, rows_total, us_new, mean_out, lw);
   return check_launch("em_step_kernel");
 }
 

@@ -74,9 +74,11 @@ def assemble_image(us, v, unobs, obs, img):
     nat.call('fbs_nn_assemble_image_f32', stream(), ptr(us), ptr(v), ptr(unobs), ptr(obs), B, p, v.shape[0], c, ptr(img))
 
 
-def em_step(img, score, unobs, obs, B, p, q, c, a, g2, dt, sd, v_next=None, key=None, us_new=None, mean_out=None, lw=None):
+def em_step(img, score, unobs, obs, B, p, q, c, a, g2, dt, sd, v_next=None, key=None, us_new=None, mean_out=None, lw=None,
+            row_offset=0, rows_total=None):
     nat.call('fbs_nn_em_step_f32', stream(), ptr(img), ptr(score), ptr(unobs), ptr(obs), ptr(v_next), ptr(key), B, p, q, c,
-             float(a), float(g2), float(dt), float(sd), ptr(us_new), ptr(mean_out), ptr(lw))
+             float(a), float(g2), float(dt), float(sd), int(row_offset), int(B if rows_total is None else rows_total),
+             ptr(us_new), ptr(mean_out), ptr(lw))
 
 
 def gather_rows(src, idx, dst):

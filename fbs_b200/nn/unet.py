@@ -284,8 +284,11 @@ class ScoreNetModel:
         s, a, g2, sd = self._coef(t_prev)
         return img, self.unet(img, s), a, g2, sd
 
-    def step(self, us_prev, v_prev, v_next, t_prev, key):
-        """(us_new [N, p, c], log_w [N]) from ONE score evaluation (transition_sampler + likelihood_logpdf)."""
+    def step(self, us_prev, v_prev, v_next, t_prev, key, row_offset=0, rows_total=None):
+        """(us_new [N, p, c], log_w [N]) from ONE score evaluation (transition_sampler + likelihood_logpdf).
+
+        ``row_offset`` / ``rows_total``: the N particles are rows [row_offset, row_offset + N) of a larger (sharded)
+        particle set; the transition noise is the matching slice of ``normal(key, (rows_total, p, c))``."""
         us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
         v_prev = dev(v_prev, F32).reshape(self.q, self.c)
         v_next = dev(v_next, F32).reshape(self.q, self.c)
@@ -295,7 +298,7 @@ class ScoreNetModel:
         us_new = torch.empty_like(us_prev)
         lw = torch.empty((B,), dtype=F32, device=us_prev.device)
         ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, v_next=v_next, key=key,
-                    us_new=us_new, lw=lw)
+                    us_new=us_new, lw=lw, row_offset=row_offset, rows_total=rows_total)
         return us_new, lw
 
     def transition_sampler(self, us_prev, v_prev, t_prev, key, **kwargs):

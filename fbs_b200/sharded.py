@@ -1,0 +1,163 @@
+"""Particle-sharded CSMC sweep: ONE chain whose particle set is block-partitioned over the ranks of a
+``torch.distributed`` group (BASELINE.json configs[4]: a CelebA-HQ-shaped score network with a very large particle set
+on 8 GPUs).  Everything else in this package shards by independent chains and needs no communication
+(fbs_b200/parallel.py); this module is the one place with a data-path exchange.
+
+Per time step (csmc.py:132-148), with N particles, rank r owning rows [r n, (r + 1) n), n = N / G:
+
+1. **weights** -- every rank holds the unnormalised log-weights of its n children; ONE all-gather of N floats gives
+   every rank the full vector.  Normalisation, the cumulative sum and the conditional resampling are then computed
+   redundantly and deterministically on every rank by the same kernel as on one GPU, so the ancestor indices are
+   *bit-identical to the unsharded sweep for any G* -- the summation-order contract of DESIGN.md needs no
+   "offset of shard totals" arithmetic whose rounding would depend on G.  Cost: 4 N bytes per step (64 KB at
+   N = 16384), against 4 du bytes *per moved particle* (12 KB at CelebA-64 inpainting) for step 2.
+2. **particle exchange** -- child j of rank r needs parent row A[j], which lives on rank A[j] // n.  Every rank knows
+   all of A, hence both its send and its receive lists without a handshake; the rows travel as one batch of
+   point-to-point sends/receives (NCCL over NVLink / NVSwitch; gloo in the CPU tests).  With ``killing`` resampling
+   surviving particles keep their own slot (resamplings.py:72-74), so only killed particles move.
+3. **transition + weight** on the local parents: one score-network evaluation per rank on its n particles, the
+   transition noise being rows [r n, (r + 1) n) of the same ``normal(key, (N, p, c))`` array as unsharded.
+
+The result is the sweep of fbs_b200.samplers.csmc.csmc.forward_pass_nn, row-partitioned.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class ParticleShard:
+    """Block partition of N particle rows over the ranks of a process group."""
+
+    def __init__(self, N: int, rank: int, world: int):
+        if N % world:
+            raise ValueError(f'the particle count ({N}) must be a multiple of the number of ranks ({world})')
+        self.N, self.rank, self.world = int(N), int(rank), int(world)
+        self.n = self.N // self.world
+        self.lo, self.hi = self.rank * self.n, (self.rank + 1) * self.n
+
+    def owner(self, rows):
+        return rows // self.n
+
+
+def exchange_plan(A, shard: ParticleShard):
+    """Send / receive lists of rank ``shard.rank`` for the global ancestor vector ``A`` (int64 [N], identical on all ranks).
+
+    Returns ``(send_rows, recv_pos)``: ``send_rows[d]`` = local row indices this rank sends to rank d (in increasing
+    child order), ``recv_pos[s]`` = local child positions filled by what rank s sends (same order).  ``d == rank``
+    entries describe the local copies.
+    """
+    A = A.to(torch.int64)
+    own = torch.div(A, shard.n, rounding_mode='floor')          # rank owning each child's parent
+    send_rows, recv_pos = [], []
+    mine = A[shard.lo:shard.hi]
+    src = own[shard.lo:shard.hi]
+    for r in range(shard.world):
+        recv_pos.append(torch.nonzero(src == r, as_tuple=False).reshape(-1))            # my children fed by rank r
+        seg = A[r * shard.n:(r + 1) * shard.n]                                          # parents of rank r's children
+        send_rows.append(seg[own[r * shard.n:(r + 1) * shard.n] == shard.rank] - shard.lo)  # ... that are mine
+    assert int(sum(p.numel() for p in recv_pos)) == shard.n
+    return send_rows, recv_pos, mine
+
+
+def exchange_rows(rows_local, A, shard: ParticleShard, group=None):
+    """parents[j] = rows_global[A[lo + j]] for the n children of this rank; ``rows_local`` = rows [lo, hi) of the global
+    array (any trailing shape).  One batch of point-to-point transfers; returns ``(parents_local, moved_rows)``."""
+    send_rows, recv_pos, _ = exchange_plan(A, shard)
+    out = torch.empty_like(rows_local)
+    ops, bufs = [], []
+    for r in range(shard.world):
+        if r == shard.rank:
+            out[recv_pos[r]] = rows_local[send_rows[r]]
+            continue
+        if send_rows[r].numel():
+            payload = rows_local[send_rows[r]].contiguous()
+            bufs.append(payload)
+            ops.append(dist.P2POp(dist.isend, payload, r if group is None else dist.get_global_rank(group, r), group))
+        if recv_pos[r].numel():
+            buf = torch.empty((recv_pos[r].numel(),) + tuple(rows_local.shape[1:]), dtype=rows_local.dtype, device=rows_local.device)
+            bufs.append((buf, recv_pos[r]))
+            ops.append(dist.P2POp(dist.irecv, buf, r if group is None else dist.get_global_rank(group, r), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    moved = 0
+    for b in bufs:
+        if isinstance(b, tuple):
+            out[b[1]] = b[0]
+            moved += b[1].numel()
+    return out, moved
+
+
+def all_gather_rows(x_local, shard: ParticleShard, group=None):
+    """Concatenation over ranks of equally sized local pieces (the N log-weights of a step)."""
+    full = torch.empty((shard.N,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
+    return full
+
+
+def forward_pass_sharded(key, us_star, bs_star, vs, model, init, cond_resampling, nsamples, group=None, history=False):
+    """csmc.py:132-164 for one chain over a :class:`fbs_b200.nn.ScoreNetModel`, particle rows sharded over ``group``.
+
+    Arguments as ``forward_pass_nn`` (identical on every rank).  Returns a dict with this rank's shard:
+    ``us_last [n, p, c]``, the FULL ``log_ws_last [N]`` (identical on every rank), ``lo`` / ``hi``, ``moved`` = rows received
+    from other ranks per step, and with ``history`` the local ``uss [K + 1, n, p, c]`` plus the full ``As [K, N]`` /
+    ``log_wss [K + 1, N]``.
+    """
+    from .samplers.csmc.csmc import NormalInit, DegenerateInit, _scheme_of
+    from ._tensor import dev, empty, ptr, stream
+    from . import random as frandom, _native as nat
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    scheme = _scheme_of(cond_resampling, 'conditional')
+    k = dev(key, torch.uint32).reshape(2)
+    K, p, q, c = model.K, model.p, model.q, model.c
+    us_star = dev(us_star, torch.float32).reshape(K + 1, p, c)
+    v = dev(vs, torch.float32).reshape(K + 1, q, c)
+    bs = dev(bs_star, torch.int32).reshape(K + 1)
+    bs_host = [int(b) for b in bs.cpu().tolist()]
+    ks = frandom.split(k, 2)
+    key_init, key_scan = ks[0].contiguous(), ks[1].contiguous()
+    sk = frandom.split(frandom.split(key_scan, K), 2).contiguous()
+    ts = model.ts
+    N = int(nsamples) + 1 if isinstance(init, NormalInit) else init.nparticles
+    shard = ParticleShard(N, rank, world)
+    lo, hi, n = shard.lo, shard.hi, shard.n
+
+    def pin(us_local, row, value):
+        if lo <= row < hi:
+            us_local[row - lo].copy_(value)
+
+    if isinstance(init, NormalInit):
+        us = frandom.normal(key_init, (N, p, c))[lo:hi].contiguous()               # rows of the same global draw
+        pin(us, bs_host[0], us_star[0])
+        lw_local = model.likelihood_logpdf(v[0], us, v[1], ts[0])
+        lw = all_gather_rows(lw_local, shard, group)
+    elif isinstance(init, DegenerateInit):
+        us = us_star[0:1].expand(n, p, c).contiguous()
+        lw = torch.full((N,), init.init_log_w, dtype=torch.float32, device=us.device)
+    else:
+        raise TypeError('init must be a DegenerateInit or NormalInit')
+    log_w = lw - torch.logsumexp(lw, dim=0)
+    As = log_wss = uss = None
+    if history:
+        As = empty((K, N), torch.int32)
+        log_wss = empty((K + 1, N), torch.float32)
+        uss = empty((K + 1, n, p, c), torch.float32)
+        log_wss[0].copy_(log_w)
+        uss[0].copy_(us)
+    A = empty((1, N), torch.int32)
+    moved = []
+    for kk in range(K):
+        w = torch.exp(log_w).contiguous()
+        nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(sk[kk, 0]), ptr(w), ptr(bs[kk:kk + 1]), ptr(bs[kk + 1:kk + 2]), 1,
+                 1, N, ptr(A))                                                     # identical on every rank
+        parents, mv = exchange_rows(us, A[0], shard, group)
+        moved.append(mv)
+        us, lw_local = model.step(parents, v[kk], v[kk + 1], ts[kk], sk[kk, 1], row_offset=lo, rows_total=N)
+        pin(us, bs_host[kk + 1], us_star[kk + 1])
+        lw = all_gather_rows(lw_local, shard, group)
+        log_w = lw - torch.logsumexp(lw, dim=0)
+        if history:
+            As[kk].copy_(A[0])
+            log_wss[kk + 1].copy_(log_w)
+            uss[kk + 1].copy_(us)
+    return dict(N=N, lo=lo, hi=hi, us_last=us, log_ws_last=log_w, moved=moved, As=As, log_wss=log_wss, uss=uss)

@@ -282,10 +282,12 @@ int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, c
                               int64_t B, int32_t p, int32_t q, int32_t c, float* img);
 /* transition_sampler + likelihood_logpdf (inpainting.py:122-147) from ONE score evaluation: rd = -a x + g2 score;
  * us_new = u + rd_u dt + sd normal(key, (B, p, c)) (NULL: skip), mean_out = u + rd_u dt (NULL: skip),
- * lw[b] = sum logN(v_next; v_prev + rd_v dt, sd) (NULL: skip). */
+ * lw[b] = sum logN(v_next; v_prev + rd_v dt, sd) (NULL: skip).  The B particles of this call are rows
+ * [row_offset, row_offset + B) of a particle set of rows_total rows (a particle-sharded sweep draws its slice of the
+ * SAME normal(key, (rows_total, p, c)) array; unsharded: row_offset = 0, rows_total = B). */
 int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
                        const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
-                       float dt, float sd, float* us_new, float* mean_out, float* lw);
+                       float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw);
 /* dst[b, :] = src[idx[b], :]  (the ancestor gather, csmc.py:140). */
 int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, float* dst);
 int fbs_nn_f32_to_bf16(fbs_stream_t s, const float* x, int64_t n, void* y);

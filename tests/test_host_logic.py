@@ -108,3 +108,50 @@ def test_two_process_gloo_partition(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert 'GLOO_OK' in res.stdout
+
+
+_GLOO_SHARD_SCRIPT = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from fbs_b200.sharded import ParticleShard, exchange_rows, all_gather_rows, exchange_plan
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+g = torch.Generator().manual_seed(0)          # identical on every rank
+N, D = 12, 5
+rows = torch.randn(N, D, generator=g)
+for trial in range(6):
+    A = torch.randint(0, N, (N,), generator=g)
+    if trial == 0:
+        A = torch.arange(N)                   # nothing moves
+    if trial == 1:
+        A = torch.full((N,), N - 1)           # everything comes from the last rank
+    sh = ParticleShard(N, rank, world)
+    got, moved = exchange_rows(rows[sh.lo:sh.hi].clone(), A, sh)
+    assert torch.equal(got, rows[A[sh.lo:sh.hi]]), (trial, rank)
+    want_moved = int((A[sh.lo:sh.hi] // sh.n != rank).sum())
+    assert moved == want_moved, (moved, want_moved)
+    full = all_gather_rows(rows[sh.lo:sh.hi, 0].contiguous(), sh)
+    assert torch.equal(full, rows[:, 0])
+try:
+    ParticleShard(7, rank, world)
+    raise SystemExit('expected ValueError')
+except ValueError:
+    pass
+dist.barrier()
+if rank == 0:
+    print('GLOO_SHARD_OK')
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_particle_shard_exchange_gloo(tmp_path, world):
+    """fbs_b200/sharded.py (config 5: particle set sharded over ranks): the all-gather of the weights and the
+    point-to-point exchange of resampled particle rows reproduce rows_global[A] on every rank, for any ancestor vector."""
+    script = tmp_path / 'gloo_shard.py'
+    script.write_text(_GLOO_SHARD_SCRIPT)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
+           '--master-port', str(29540 + world), str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert 'GLOO_SHARD_OK' in res.stdout
