@@ -176,6 +176,112 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------------------------
+# secondary workloads (short; reported under "secondary", never the headline value)
+# ----------------------------------------------------------------------------------------------
+UNET_FLOPS = {(28, 28, 1): 2.788e9, (64, 64, 3): 14.635e9}   # per evaluation, SURVEY.md App. D
+
+
+def _score_model(shape, K, seed=0):
+    import fbs_b200
+    from fbs_b200 import sdes
+    from fbs_b200.nn import ScoreUNet, ScoreNetModel, random_unet_params
+    H, W, C = shape
+    T = 2.0
+    ts = np.linspace(0., T, K + 1)
+    sde = sdes.StationaryLinLinearSDE(beta_min=0.02, beta_max=5., t0=0., T=T)
+    side = 15 if H == 28 else H // 2                                   # inpaint-15 (MNIST) / inpaint-32 (CelebA-64)
+    off = (H - side) // 2
+    rect = np.array([(i + off) * W + (j + off) for i in range(side) for j in range(side)], dtype=np.int32)
+    obs = np.setdiff1d(np.arange(H * W, dtype=np.int32), rect)
+    net = ScoreUNet(random_unet_params(seed, C), shape, dt=T / 200)
+    return ScoreNetModel(net, sde, ts, T, rect, obs), ts, rect, obs
+
+
+def secondary_mnist(nparticles=101, steps=12):
+    """configs[3]: MNIST 28x28 inpainting-15, nparticles + 1 = 101 particles ('gibbs-eb-ef', imgs_gibbs.sh:37-38), random-init
+    score U-Net: CSMC steps (resample + gather + ONE score evaluation + EM step + weights) through forward_pass_nn."""
+    import torch
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    from fbs_b200 import random as fr
+    shape = (28, 28, 1)
+    model, ts, rect, obs = _score_model(shape, steps)
+    rng = np.random.default_rng(0)
+    us_star = rng.standard_normal((steps + 1, rect.size, 1)).astype(np.float32)
+    vs = rng.uniform(size=(steps + 1, obs.size, 1)).astype(np.float32)
+    bs = np.zeros((steps + 1,), np.int32)
+    init = csmc.DegenerateInit(nparticles)
+    args = (fr.PRNGKey(3), us_star, bs, vs, model, init, R.killing.scheme, nparticles)
+    csmc.forward_pass_nn(*args, history=False)          # warm-up: CUDA graph capture
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    csmc.forward_pass_nn(*args, history=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # the network alone (graph replays back to back)
+    x = torch.randn(nparticles, *shape, device='cuda')
+    model.unet(x, 0.5)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(10):
+        model.unet(x, 0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    net_ms = e0.elapsed_time(e1) / 10
+    flops = UNET_FLOPS[shape] * nparticles
+    peak = 1391.3
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'])
+    except Exception:
+        pass
+    return {'workload': 'configs[3]: MNIST 28x28 inpaint-15, 101 particles, random-init fbs/nn score U-Net (12.99 M parameters), '
+                        'score GEMMs on tcgen05 (bf16 operands, fp32 accumulate)',
+            'value': nparticles * steps / (ms * 1e-3), 'unit': 'particle-steps/s', 'steps': steps, 'ms_per_csmc_step': ms / steps,
+            'dtype': 'bf16', 'score_net_ms_per_eval': net_ms,
+            'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + fused norm / attention kernels (one score evaluation)',
+                         'achieved': flops / (net_ms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': flops / (net_ms * 1e-3) / 1e12 / peak, 'traffic': None,
+                         'flops_per_particle_step': UNET_FLOPS[shape], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained'}}
+
+
+def secondary_sharded(world, rank, per_rank=16, steps=4):
+    """configs[4]: CelebA-HQ-shaped (64x64x3, inpaint-32) random-init score U-Net, ONE chain whose particle set is sharded over
+    the ranks (fbs_b200/sharded.py): all-gather of the weights + NCCL exchange of resampled particles per step."""
+    import torch
+    import torch.distributed as dist
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    from fbs_b200.sharded import forward_pass_sharded
+    from fbs_b200 import random as fr
+    shape = (64, 64, 3)
+    N = per_rank * world
+    model, ts, rect, obs = _score_model(shape, steps)
+    rng = np.random.default_rng(0)
+    us_star = rng.standard_normal((steps + 1, rect.size, 3)).astype(np.float32)
+    vs = rng.uniform(size=(steps + 1, obs.size, 3)).astype(np.float32)
+    bs = np.zeros((steps + 1,), np.int32)
+    init = csmc.DegenerateInit(N)
+    args = (fr.PRNGKey(5), us_star, bs, vs, model, init, R.killing, N)
+    forward_pass_sharded(*args)                                       # warm-up
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = forward_pass_sharded(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {'workload': 'configs[4]: CelebA-HQ-shaped 64x64x3 inpaint-32, random-init score U-Net, one chain, particle set '
+                        f'sharded over {world} GPUs ({per_rank} particles per GPU, weak)',
+            'value': N * steps / (ms * 1e-3), 'unit': 'particle-steps/s', 'n_particles': N, 'steps': steps,
+            'ms_per_csmc_step': ms / steps, 'moved_rows_per_step': float(np.mean(r['moved'])),
+            'collectives_per_step': 'all_gather(4 N bytes) + batch_isend_irecv(moved rows x 4 du bytes)', 'dtype': 'bf16'}
+
+
 WORKLOAD_NAME = ('configs[1]: toy Gaussian pseudo-marginal MCMC scaled out (experiments/toy/gp_pmcmc.py; d=100, K=200, '
                  'N=100, stratified, pCN delta=0.005), independent chains partitioned over GPUs')
 
@@ -294,6 +400,23 @@ def run_gpu(args):
     e2e_ms = float(t.item())
     e2e_value = psteps_per_step / (e2e_ms * 1e-3)
 
+    secondary = {}
+    if not args.no_secondary:
+        # a secondary workload must never take the headline line (or another rank) down
+        if rank == 0:
+            try:
+                secondary['mnist_score_net'] = secondary_mnist()
+            except Exception as e:
+                secondary['mnist_score_net'] = {'error': repr(e)[:300]}
+        if world > 1:
+            try:
+                dist.barrier()
+                sh = secondary_sharded(world, rank)
+            except Exception as e:
+                sh = {'error': repr(e)[:300]}
+            if rank == 0:
+                secondary['celeba_particle_sharded'] = sh
+
     if rank == 0:
         peak, peak_src = measured_peak()
         k_ms = float(np.mean(kern_ms))
@@ -325,6 +448,7 @@ def run_gpu(args):
                          'note': 'nominal HBM roofline of SURVEY 8(d); the persistent kernel keeps particles in shared '
                                  'memory, so the binding resource is the FMA/ALU pipe (see DESIGN.md)'},
             'cpu_baseline': cpu,
+            'secondary': secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -339,6 +463,7 @@ def main():
     ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
     ap.add_argument('--chains', type=int, default=4096, help='chains per GPU (weak scaling)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary (score network / particle-sharded) workloads')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

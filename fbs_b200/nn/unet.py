@@ -46,6 +46,82 @@ def _pack_stride2(w):
     return _pack(np.ascontiguousarray(k2).reshape(2, 2, 4 * cin, cout))
 
 
+def unet_param_shapes(in_ch, dim=64, dim_mults=(1, 2, 4), heads=4, dim_head=32):
+    """name -> shape of every parameter of ``UNet(dim, dim_mults, upsampling='pixel_shuffle')`` (fbs/nn/unet.py:279-368),
+    flax layouts (HWIO convolution kernels, [in, out] dense kernels)."""
+    sh = {}
+
+    def conv(name, k, cin, cout, bias=True):
+        sh[name + '.kernel'] = (k, k, cin, cout)
+        if bias:
+            sh[name + '.bias'] = (cout,)
+
+    def res(name, cin, d):
+        conv(name + '.conv_0', 3, cin, d)
+        conv(name + '.conv_1', 3, d, d)
+        for nm in ('norm_0', 'norm_1'):
+            sh[f'{name}.{nm}.scale'] = (d,)
+            sh[f'{name}.{nm}.bias'] = (d,)
+        sh[name + '.time_mlp.dense_0.kernel'] = (4 * dim, 2 * d)
+        sh[name + '.time_mlp.dense_0.bias'] = (2 * d,)
+        if cin != d:
+            conv(name + '.res_conv_0', 1, cin, d)
+
+    def attn(name, c, linear=True):
+        sh[name + '.norm.scale'] = (c,)
+        conv(name + '.attn.to_qkv.conv_0', 1, c, 3 * heads * dim_head, bias=False)
+        conv(name + '.attn.to_out.conv_0', 1, heads * dim_head, c)
+        if linear:
+            sh[name + '.attn.to_out.norm_0.scale'] = (c,)
+
+    nres = len(dim_mults)
+    conv('init.conv_0', 7, in_ch, dim)
+    for i, (a, b) in enumerate(((dim, 4 * dim), (4 * dim, 4 * dim))):
+        sh[f'time.dense_{i}.kernel'] = (a, b)
+        sh[f'time.dense_{i}.bias'] = (b,)
+    c = dim
+    for ind in range(nres):
+        res(f'down_{ind}.resblock_0', c, c)
+        res(f'down_{ind}.resblock_1', c, c)
+        attn(f'down_{ind}.attnblock_0', c)
+        if ind < nres - 1:
+            conv(f'down_{ind}.downsample_0', 4, c, dim * dim_mults[ind])
+            c = dim * dim_mults[ind]
+    mid = dim * dim_mults[-1]
+    conv(f'down_{nres - 1}.conv_0', 3, c, mid)
+    res('mid.resblock_0', mid, mid)
+    attn('mid.attenblock_0', mid, linear=False)
+    res('mid.resblock_1', mid, mid)
+    for ind in reversed(range(nres)):
+        d_in = dim * dim_mults[ind]
+        d_out = dim * dim_mults[ind - 1] if ind > 0 else dim
+        res(f'up_{ind}.resblock_0', d_in + d_out, d_in)
+        res(f'up_{ind}.resblock_1', d_in + d_out, d_in)
+        attn(f'up_{ind}.attnblock_0', d_in)
+        if ind > 0:
+            conv(f'up_{ind}.upsample_0.conv_0', 3, d_in, 4 * d_in)
+            conv(f'up_{ind}.upsample_0.conv_1', 3, d_in, d_out)
+    conv('up_0.conv_0', 3, dim, dim)
+    res('final.resblock_0', 2 * dim, dim)
+    conv('final.conv_0', 1, dim, in_ch)
+    return sh
+
+
+def random_unet_params(seed, in_ch, dim=64, dim_mults=(1, 2, 4)):
+    """Random-init weights of the architecture (there is no network access for checkpoints): kernels N(0, 1 / fan_in)
+    as flax's default lecun_normal, biases 0, norm scales 1 -- what ``nn.init`` gives (fbs/nn/base.py:30)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, shape in unet_param_shapes(in_ch, dim, dim_mults).items():
+        if name.endswith('.kernel'):
+            out[name] = (rng.standard_normal(shape) / math.sqrt(int(np.prod(shape[:-1])))).astype(np.float32)
+        elif name.endswith('.scale'):
+            out[name] = np.ones(shape, np.float32)
+        else:
+            out[name] = np.zeros(shape, np.float32)
+    return out
+
+
 class ScoreUNet:
     def __init__(self, params, image_shape, dt, dim=64, dim_mults=(1, 2, 4), groups=8, heads=4, dim_head=32, device=None):
         self.H, self.W, self.Cimg = (int(s) for s in image_shape)

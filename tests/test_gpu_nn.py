@@ -305,3 +305,32 @@ def test_nn_gibbs_kernel_runs():
     # bs_star_next is randint(key_csmc_bwd_bs, (K + 1,), 0, nparticles)   (gibbs.py:156)
     kc = jr.split(jr.split(key, 3)[1], 4)
     np.testing.assert_array_equal(bs_next, jr.randint(kc[3], (K + 1,), 0, N))
+
+
+def test_sharded_sweep_single_rank_equals_unsharded():
+    """fbs_b200/sharded.py with a one-rank NCCL group is the unsharded sweep (the 2-GPU equality is checked by
+    scripts/sharded_check.py under torchrun; the exchange logic for G > 1 by the gloo tests on CPU)."""
+    import torch.distributed as dist
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    from fbs_b200.sharded import forward_pass_sharded
+    K, N = 3, 6
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(13)
+    us_star = rng.standard_normal((K + 1, rect.size, 1)).astype(np.float32)
+    vs = np.cumsum(0.05 * rng.standard_normal((K + 1, obs.size, 1)), axis=0).astype(np.float32)
+    bs_star = jr.randint(jr.PRNGKey(2), (K + 1,), 0, N).astype(np.int32)
+    key = jr.PRNGKey(17)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group('nccl', init_method='tcp://127.0.0.1:29577', rank=0, world_size=1)
+    try:
+        for init in (csmc.DegenerateInit(N), csmc.NormalInit(model)):
+            r = forward_pass_sharded(key, us_star, bs_star, vs, model, init, R.killing, N, history=True)
+            full = csmc.forward_pass_nn(key, us_star, bs_star, vs, model, init, R.killing.scheme, N, history=True)
+            assert torch.equal(r['As'], full['As'][0])
+            assert torch.equal(r['log_wss'], full['log_wss'][0])
+            assert torch.equal(r['uss'].reshape(full['uss'].shape[1:]), full['uss'][0])
+            assert r['moved'] == [0] * K
+    finally:
+        if created:
+            dist.destroy_process_group()
