@@ -176,12 +176,17 @@ class AffineGaussianModel:
         return ctypes.byref(self._struct)
 
     def workspace(self, B: int):
-        """(tensor, nbytes) scratch for the tiled sweep kernel: per-chain step vectors of all K steps."""
+        """(tensor, nbytes) scratch for the tiled sweep kernel: per-chain step vectors of all K steps.  One buffer per
+        CUDA stream: chunks of chains pipelined on different streams (samplers/smc.py) must not share scratch."""
         self.device_arrays()
         nbytes = int(nat.lib().fbs_sweep_workspace_bytes(ctypes.byref(self._struct), int(B)))
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=self._dev['MT'].device)
-        return self._ws, nbytes
+        if not isinstance(self._ws, dict):
+            self._ws = {}
+        sid = torch.cuda.current_stream().cuda_stream
+        ws = self._ws.get(sid)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._ws[sid] = torch.empty((nbytes,), dtype=torch.uint8, device=self._dev['MT'].device)
+        return ws, nbytes
 
     def step_index(self, t_prev) -> int:
         t = float(t_prev.item() if isinstance(t_prev, torch.Tensor) else t_prev)

@@ -64,6 +64,48 @@ def pcn_proposal(key, delta: float, x, mean, sampler):
     return out(o, host)
 
 
+PIPELINE_MIN_CHAINS = 512     # host-buffer calls with at least this many chains are chunked over CUDA streams
+PIPELINE_CHUNKS = 4
+_streams = []
+
+
+def _pmcmc_kernel_pipelined(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler, transition_sampler,
+                            likelihood_logpdf, resampling, nparticles, delta, which_u, kwargs):
+    """Host-buffer call on many chains: the chains are independent, so they are cut into chunks that run on separate CUDA
+    streams -- chunk c's kernels overlap chunk c + 1's host-to-device copies and chunk c - 1's device-to-host copies
+    (both PCIe directions busy while the SMs work).  Results land in page-locked buffers returned as numpy views."""
+    k_all = np.asarray(key) if not isinstance(key, torch.Tensor) else key
+    B = k_all.shape[0]
+    nchunks = min(PIPELINE_CHUNKS, B // (PIPELINE_MIN_CHAINS // 2))
+    while len(_streams) < nchunks:
+        _streams.append(torch.cuda.Stream())
+    bounds = [(c * B // nchunks, (c + 1) * B // nchunks) for c in range(nchunks)]
+
+    def host_t(x):
+        return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+
+    k_h, uT_h, le_h, ys_h = host_t(key), host_t(uT), host_t(log_ell), host_t(ys)
+    y0_d = dev(y0, torch.float32)
+    outs = None
+    cur = torch.cuda.current_stream()
+    for c, (lo, hi) in enumerate(bounds):
+        st = _streams[c]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            args = [t[lo:hi].to(y0_d.device, non_blocking=True) for t in (k_h, uT_h, le_h, ys_h)]
+            r = pmcmc_kernel(args[0], args[1], args[2], args[3], y0_d, ts, fwd_ys_sampler, sde, ref_sampler, transition_sampler,
+                             likelihood_logpdf, resampling, nparticles, delta=delta, which_u=which_u, **kwargs)
+            flat = list(r[:3]) + list(r[3])
+            if outs is None:
+                outs = [torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True) for t in flat]
+            for o, t in zip(outs, flat):
+                o[lo:hi].copy_(t, non_blocking=True)
+    for st in _streams[:nchunks]:
+        st.synchronize()
+    res = [o.numpy() for o in outs]
+    return res[0], res[1], res[2], MCMCState(*res[3:])
+
+
 def pmcmc_kernel(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler, transition_sampler,
                  likelihood_logpdf, resampling, nparticles, delta=None, which_u=0, **kwargs):
     """One pseudo-marginal MCMC step targeting p(u_T | v_T = y0); same arguments as the reference (smc.py:171-184).
@@ -72,6 +114,10 @@ def pmcmc_kernel(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler,
     """
     model = _model_of(transition_sampler, likelihood_logpdf)
     host = is_host(key)
+    if host and np.ndim(key) == 2 and np.shape(key)[0] >= PIPELINE_MIN_CHAINS and getattr(model, '_pipeline_warm', False):
+        # (the first call runs unchunked: it creates the model's cached device arrays on one stream)
+        return _pmcmc_kernel_pipelined(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler, transition_sampler,
+                                       likelihood_logpdf, resampling, nparticles, delta, which_u, kwargs)
     k = dev(key, torch.uint32)
     single = k.dim() == 1
     k = k.reshape(-1, 2)
@@ -104,6 +150,7 @@ def pmcmc_kernel(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler,
     state = MCMCState(acceptance_prob=acc_prob, is_accepted=is_acc.bool(), prop_log_ell=prop_log_ell,
                       log_ell=old_log_ell)
     res = [uT_d, le_d, ys_d]
+    model._pipeline_warm = True
     if single:
         res = [t[0] for t in res]
         state = MCMCState(*[t[0] for t in state])

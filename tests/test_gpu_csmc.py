@@ -389,3 +389,26 @@ def test_pmcmc_kernel_composition(delta):
             np.testing.assert_array_equal(uT2[b], uT[b])
             assert le2[b] == log_ell[b]
     assert 0 < st.is_accepted.sum() < B
+
+
+def test_pmcmc_kernel_host_pipeline_equals_unchunked(monkeypatch):
+    """Host-buffer pmcmc_kernel on many chains is chunked over CUDA streams (H2D / kernels / D2H overlapped); chains are
+    independent, so the result must equal the unchunked call bit for bit."""
+    from fbs_b200.samplers import pmcmc_kernel, stratified
+    from fbs_b200.samplers import smc as psmc
+    d, N, K, B = 4, 16, 10, 96
+    p = gp_problem(d, K=K)
+    om32 = oracle_model(p, np.float32)
+    pm, sde = product_model(p)
+    keys = jr.split(jr.PRNGKey(5), B)
+    uT = jr.normal(jr.PRNGKey(1), (B, d))
+    ys = np.stack([om32.fwd_ys_sampler(k, p['y0']) for k in jr.split(jr.PRNGKey(2), B)])
+    log_ell = np.zeros(B, np.float32)
+    kw = dict(ts=p['ts'], fwd_ys_sampler=pm.fwd_ys_sampler, sde=sde, ref_sampler=pm.ref_sampler,
+              transition_sampler=pm.transition_sampler, likelihood_logpdf=pm.likelihood_logpdf, resampling=stratified,
+              nparticles=N, delta=0.3)
+    a = pmcmc_kernel(keys, uT, log_ell, ys, p['y0'], **kw)            # unchunked (also warms the model)
+    monkeypatch.setattr(psmc, 'PIPELINE_MIN_CHAINS', 32)
+    b = pmcmc_kernel(keys, uT, log_ell, ys, p['y0'], **kw)            # 3 chunks of 32 chains
+    for x, y in zip(list(a[:3]) + list(a[3]), list(b[:3]) + list(b[3])):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
