@@ -351,6 +351,12 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   }
   p.h_tiles = (a->H + p.BH - 1) / p.BH;
   const int n_tiles = (a->B + p.BNb - 1) / p.BNb;
+  // few M tiles (the 7x7 / 14x14 levels): a CTA streams its whole K loop through ONE SM's L2 port, so prefer narrower N
+  // tiles until the grid covers the machine about twice
+  while (ntile > 64 && ntile % 32 == 0 && (int64_t)n_tiles * p.h_tiles * (a->Cout / ntile) < 2 * sm_count() &&
+         (!p.pixel_shuffle || true))
+    ntile /= 2;
+  p.ntile = ntile;
   const size_t stage = (size_t)A_STAGE_BYTES + (size_t)ntile * 128;
   // short K loops (9..54 blocks) and small tiles: prologue / epilogue latency matters more than ring depth, so keep the
   // ring shallow enough for 2-3 CTAs to share an SM and overlap one CTA's epilogue with another's main loop
