@@ -303,6 +303,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'NONE'      # keep stdout to the ONE JSON line (NCCL prints its version there)
         dist.init_process_group('nccl', device_id=dev)
 
     d, K, N, C = D_TOY, K_STEPS, N_PART, args.chains
