@@ -522,6 +522,7 @@ int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
                                 float init_log_w, int scheme, int64_t B, int64_t N, int32_t* As, float* log_wss,
                                 float* uss, float* log_ws_last, float* us_last, void* workspace,
                                 size_t workspace_bytes) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   int rc = check_model(model);
   if (rc) return rc;
   FBS_REQUIRE(keys && us_star && bs_star && vs, "csmc_forward: null input");
@@ -549,6 +550,7 @@ int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
                                 const float* u0s, int scheme, int64_t B, int64_t N, float* uT, float* log_ell,
                                 int32_t* inds, float* log_ws_hist, float* us_hist, void* workspace,
                                 size_t workspace_bytes) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   int rc = check_model(model);
   if (rc) return rc;
   FBS_REQUIRE(keys && vs && u0s, "pmcmc_filter: null input");

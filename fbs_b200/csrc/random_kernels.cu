@@ -116,9 +116,9 @@ static int grid_for(int64_t total, int threads) {
 
 template <int MODE>
 static int launch_fill(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, float lo, float hi, void* out) {
-  FBS_REQUIRE(keys && out, "random fill: null pointer");
   FBS_REQUIRE(B >= 0 && n >= 0 && n < 0xFFFFFFFFll, "random fill: bad sizes B=%lld n=%lld", (long long)B, (long long)n);
-  if (B == 0 || n == 0) return FBS_OK;
+  if (B == 0 || n == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
+  FBS_REQUIRE(keys && out, "random fill: null pointer");
   const int64_t total = B * ((n + 1) / 2);
   random_fill_kernel<MODE><<<grid_for(total, 256), 256, 0, as_stream(s)>>>(keys, B, (uint32_t)n, lo, hi, out);
   return check_launch("random_fill_kernel");
@@ -154,9 +154,9 @@ int fbs_random_normal_f32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64
 
 int fbs_random_randint_i32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, int32_t minval, int32_t maxval,
                            int32_t* out) {
-  FBS_REQUIRE(keys && out, "randint: null pointer");
   FBS_REQUIRE(B >= 0 && n >= 0 && n < 0xFFFFFFFFll, "randint: bad sizes");
   if (B == 0 || n == 0) return FBS_OK;
+  FBS_REQUIRE(keys && out, "randint: null pointer");
   uint32_t span = maxval > minval ? (uint32_t)((int64_t)maxval - (int64_t)minval) : 1u;
   uint32_t mult = 65536u % span;
   mult = (mult * mult) % span;
@@ -166,9 +166,9 @@ int fbs_random_randint_i32(fbs_stream_t s, const uint32_t* keys, int64_t B, int6
 
 int fbs_random_choice_f32(fbs_stream_t s, const uint32_t* keys, const float* p, int64_t B, int64_t N, int64_t n,
                           int32_t* out) {
-  FBS_REQUIRE(keys && p && out, "choice: null pointer");
   FBS_REQUIRE(B >= 0 && N >= 1 && n >= 0, "choice: bad sizes");
   if (B == 0 || n == 0) return FBS_OK;
+  FBS_REQUIRE(keys && p && out, "choice: null pointer");
   const size_t per_warp = (size_t)N * sizeof(float);
   if (per_warp > 200 * 1024) {
     set_error("choice: N=%lld exceeds the single-warp shared-memory scan limit", (long long)N);

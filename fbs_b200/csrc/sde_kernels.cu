@@ -267,6 +267,7 @@ extern "C" {
 int fbs_ou_forward_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0, int x0_batched, const float* F,
                             const float* sqrtQ, int64_t B, int64_t K, int64_t D, int64_t du, int rev, float* out_u,
                             float* out_v) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(keys && x0 && F && sqrtQ, "ou_forward_path: null input");
   FBS_REQUIRE(B >= 0 && K >= 1 && D >= 1 && K * D < 0xFFFFFFFFll, "ou_forward_path: bad sizes");
   FBS_REQUIRE(rev ? (du >= 0 && du <= D && (out_u || out_v)) : (out_u != nullptr && du == D),
@@ -280,6 +281,7 @@ int fbs_ou_forward_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x
 int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0, int x0_batched, const float* AT,
                            const float* a, const float* ddt, const float* disp, int64_t B, int64_t K, int64_t m,
                            int64_t D, int64_t du, int rev, float* out_u, float* out_v) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(keys && x0 && AT && a && ddt && disp, "em_affine_path: null input");
   FBS_REQUIRE(B >= 0 && K >= 1 && m >= 1 && D >= 1 && D <= 8192 && m * D < 0xFFFFFFFFll, "em_affine_path: bad sizes");
   FBS_REQUIRE(rev ? (du >= 0 && du <= D && (out_u || out_v)) : (out_u != nullptr && du == D),
@@ -299,6 +301,7 @@ int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0
 int fbs_force_move_f32(fbs_stream_t s, const uint32_t* keys, const float* log_ws_last, int weights_are_log,
                        const float* us_last, const int32_t* k, int64_t B, int64_t N, int64_t du, int32_t* idx,
                        float* alpha, float* x0) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(keys && log_ws_last && k && idx, "force_move: null input");
   FBS_REQUIRE(!x0 || us_last, "force_move: x0 requested without us_last");
   FBS_REQUIRE(B >= 0 && N >= 1 && du >= 0, "force_move: bad sizes");
@@ -322,6 +325,7 @@ int fbs_force_move_f32(fbs_stream_t s, const uint32_t* keys, const float* log_ws
 
 int fbs_pcn_combine_f32(fbs_stream_t s, double delta, const float* x, const float* mean, const float* r0,
                         const float* r1, int64_t B, int64_t n, float* out) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(x && mean && r0 && r1 && out, "pcn_combine: null pointer");
   FBS_REQUIRE(B >= 0 && n >= 1 && delta > 0, "pcn_combine: bad arguments");
   if (B == 0) return FBS_OK;
@@ -335,6 +339,7 @@ int fbs_pcn_combine_f32(fbs_stream_t s, double delta, const float* x, const floa
 int fbs_mh_accept_f32(fbs_stream_t s, const uint32_t* keys_mh, const float* prop_uTs, const float* prop_log_ell,
                       const float* prop_ys, int64_t B, int64_t N, int64_t du, int64_t ny, int32_t which_u, float* uT,
                       float* log_ell, float* ys, float* acceptance_prob, uint8_t* is_accepted) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(keys_mh && prop_uTs && prop_log_ell && prop_ys && uT && log_ell && ys, "mh_accept: null pointer");
   FBS_REQUIRE(B >= 0 && N >= 1 && which_u >= 0 && which_u < N, "mh_accept: bad sizes");
   if (B == 0) return FBS_OK;
@@ -349,6 +354,7 @@ int fbs_mh_accept_f32(fbs_stream_t s, const uint32_t* keys_mh, const float* prop
 int fbs_gaussian_ref_sample_f32(fbs_stream_t s, const uint32_t* keys, const float* yT, const float* a, const float* Bm,
                                 const float* c, const float* L, int64_t B, int64_t N, int64_t du, int64_t dv,
                                 float* out) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(keys && yT && a && Bm && c && L && out, "gaussian_ref_sample: null pointer");
   FBS_REQUIRE(B >= 0 && N >= 1 && du >= 1 && dv >= 1, "gaussian_ref_sample: bad sizes");
   if (B == 0) return FBS_OK;
@@ -370,6 +376,7 @@ int fbs_gaussian_ref_sample_f32(fbs_stream_t s, const uint32_t* keys, const floa
 int fbs_backward_scan_f32(fbs_stream_t s, const uint32_t* keys, const int32_t* As, const float* uss,
                           const float* log_w_T, int64_t B, int64_t K, int64_t N, int64_t du, float* xs_star,
                           int32_t* bs_star) {
+  if (B == 0) return FBS_OK;  // an empty batch is a no-op (its buffers may be NULL)
   FBS_REQUIRE(keys && As && uss && log_w_T && xs_star && bs_star, "backward_scan: null pointer");
   FBS_REQUIRE(B >= 0 && K >= 1 && N >= 1 && du >= 1, "backward_scan: bad sizes");
   if (B == 0) return FBS_OK;

@@ -412,3 +412,62 @@ def test_pmcmc_kernel_host_pipeline_equals_unchunked(monkeypatch):
     b = pmcmc_kernel(keys, uT, log_ell, ys, p['y0'], **kw)            # 3 chunks of 32 chains
     for x, y in zip(list(a[:3]) + list(a[3]), list(b[:3]) + list(b[3])):
         np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+
+
+@pytest.mark.parametrize('d,N,K,B', [(8, 128, 3, 3), (4, 2, 2, 1), (100, 64, 3, 5), (52, 100, 3, 2), (124, 100, 2, 2),
+                                     (20, 30, 5, 301)])
+def test_forward_pass_tensor_core_kernel_shapes(d, N, K, B, monkeypatch):
+    """Edge shapes of the tcgen05 sweep kernel (sweep_v3.cu): full 128 MMA rows, a single tiny chain, odd chain counts
+    (the second warp group runs one chain fewer), padded K / N dimensions, the widest accumulator (2 x 128 columns), and
+    more chain pairs than SMs.  Teacher-forced against the oracle, and equal ancestors to the general kernel."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    p = gp_problem(d, K=K)
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N, seed=21)
+    init = csmc.DegenerateInit(N)
+    args = (keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf, pm.transition_sampler,
+            pm.likelihood_logpdf, R.killing, N)
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v3')
+    As, log_wss, uss = csmc.forward_pass(*args)
+    nb = min(B, 4)
+    _check_forward_history(p, om64, keys[:nb], us_star[:nb], bs_star[:nb], vs[:nb], As[:nb], log_wss[:nb], uss[:nb], 'killing', False)
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v1')
+    A1, l1, u1 = csmc.forward_pass(*args)
+    np.testing.assert_array_equal(A1[:, 0], As[:, 0])
+    np.testing.assert_allclose(u1[:, 1], uss[:, 1], rtol=1e-5, atol=1e-5)
+
+
+def test_forward_pass_explicit_final_on_tensor_cores(monkeypatch):
+    """explicit_final=True with an even particle count (nparticles = 9 -> 10 rows) takes the tcgen05 kernel, including
+    its extra GEMM for the initial weights."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    d, N, K, B = 8, 9, 6, 5
+    p = gp_problem(d, K=K, sde_kind='lin')
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N + 1, seed=8)
+    init = csmc.NormalInit(pm)
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v3')
+    As, log_wss, uss = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, R.killing, N)
+    assert As.shape == (B, K, N + 1)
+    _check_forward_history(p, om64, keys, us_star, bs_star, vs, As, log_wss, uss, 'killing', True)
+
+
+def test_empty_batch_is_a_no_op():
+    """Zero chains: every batched entry point returns empty outputs and launches nothing that faults."""
+    import torch
+    from fbs_b200.samplers import pmcmc_filter_step, stratified
+    from fbs_b200.samplers.csmc import resamplings as R
+    from fbs_b200 import random as fr
+    p = gp_problem(4, K=5)
+    pm, _ = product_model(p)
+    keys = torch.empty((0, 2), dtype=torch.uint32, device='cuda')
+    uT, le = pmcmc_filter_step(keys, torch.empty((0, 6, 4), device='cuda'), torch.empty((0, 8, 4), device='cuda'), p['ts'],
+                               pm.transition_sampler, pm.likelihood_logpdf, stratified, 8)
+    assert tuple(uT.shape) == (0, 8, 4) and tuple(le.shape) == (0,)
+    idx = R.killing(keys, torch.empty((0, 16), device='cuda'), 0, 0, True)
+    assert tuple(idx.shape) == (0, 16)
+    assert tuple(fr.normal(keys, (3,)).shape) == (0, 3)
+    torch.cuda.synchronize()
