@@ -409,8 +409,16 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
   } else {
     // =============================== worker group g ===============================
     // roles inside a group (gw = warp of the group): 0..3 "E" epilogue + noise, 4 "R" resampling only, 5.. "X" noise only
-    const int g = (warp - 1) / GWARPS;
-    const int gt = tid - 32 - g * GTHREADS, gw = gt >> 5;
+    // warp -> (group, role).  A warp lives on scheduler (warp % 4); the four light warps (MMA 0, R 5 and 10, TMA 15) sit on
+    // four different schedulers and every scheduler gets exactly three of the twelve noise warps -- with the plain
+    // "group g = warps 1 + 7 g .." numbering one scheduler had four noise warps and another two, and the step waited for
+    // the crowded one.  E warps of a group keep four distinct TMEM lane quadrants (warp % 4).
+    //   warp:   1  2  3  4  5  6  7 |  8  9 10 11 12 13 14
+    //   group:  0  0  0  0  0  0  0 |  1  1  1  1  1  1  1
+    //   gw:     0  1  2  3  4  5  6 |  0  1  4  3  5  6  2        (0..3 E, 4 R, 5..6 X)
+    const int g = warp >= 8 ? 1 : 0;
+    const int gw = g == 0 ? warp - 1 : ((0x2653410 >> (4 * (warp - 8))) & 0xF);
+    const int gt = 32 * gw + lane;
     const bool is_E = gw < 4, is_R = gw == 4, is_noise = !is_R;
     const int nt = gw < 4 ? gt : gt - 32;  // index among the NOISE_THREADS noise threads
     const int xt = gt - 160;               // index among the 64 X threads
