@@ -199,7 +199,7 @@ struct Layout {
   uint32_t a_lbo, b_lbo, blk_bytes, img_bytes, stage_bytes, a_bytes;
   // byte offsets.  Group g: A operands at A + g * 2 * a_bytes (hi, then lo), small arrays at grp + g * grp_bytes + <field>
   uint32_t A, ring, bars, tmem, grp, grp_bytes;
-  uint32_t cvs, lwraw, lw, w, cum, idx, tmp, keys, scal, skeys, pin;
+  uint32_t cvs, lwraw, lw, w, cum, idx, tmp, keys, scal, skeys, pin, ub;
   uint32_t total;
 };
 
@@ -245,6 +245,7 @@ __host__ __device__ inline Layout make_layout(int N, int du, int dv, int stages_
   L.scal = take(16);
   L.skeys = take(64);                       // 2 slots (step parity) x (resampling key, transition key)
   L.pin = take((uint32_t)(du + 4) * 4u);    // pinned reference particle of the step + its slot
+  L.ub = take((2 * ROWS + 4) * 4);          // resampling uniforms of the step, drawn before the weights arrive
   L.grp_bytes = o;
   L.total = L.grp + GROUPS * L.grp_bytes;
   return L;
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     float* scal = reinterpret_cast<float*>(gb + L.scal);
     Key* skeys = reinterpret_cast<Key*>(gb + L.skeys);  // slot k & 1: [0] resampling key, [1] transition key of step k
     float* pin = reinterpret_cast<float*>(gb + L.pin);  // [0, du): u*_{k+1}, [du]: its slot b*_{k+1} (as int bits)
+    float* ub = reinterpret_cast<float*>(gb + L.ub);    // killing: U1 at [0, N), U2 at [ROWS, ROWS + N), U_J at [2 ROWS]
     const float logN = logf((float)N);
     const uint32_t tmem_g = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
     const uint32_t lbo = L.a_lbo;
@@ -738,9 +740,132 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             }
             __syncwarp();
           }
+          const bool fastk = p.mode == MODE_CSMC && p.scheme == FBS_RESAMPLE_KILLING;
+          if (fastk) {  // the three uniform streams of conditional killing (resamplings.py:66,71,74,84)
+            Key k1, k2, k3;
+            split3(skeys[2 * (k & 1)], k1, k2, k3);
+            const uint32_t h = ((uint32_t)N + 1u) >> 1;
+            for (uint32_t b = lane; b < h; b += 32) {
+              uint32_t a0, a1, c0, c1;
+              random_bits_block(k1, N, b, a0, a1);
+              random_bits_block(k2, N, b, c0, c1);
+              ub[b] = bits_to_unit(a0);
+              ub[ROWS + b] = bits_to_unit(c0);
+              if (b + h < (uint32_t)N) {
+                ub[b + h] = bits_to_unit(a1);
+                ub[ROWS + b + h] = bits_to_unit(c1);
+              }
+            }
+            uint32_t x0 = 0u, x1 = 0u;  // choice(key_3, N, (), p): random_bits(key_3, 1) = block (0, 0), word 0
+            threefry2x32(k3.k0, k3.k1, x0, x1);
+            if (lane == 0) ub[2 * ROWS] = bits_to_unit(x0);
+            __syncwarp();
+          }
           bar_ER_sync();
           const Key kres = skeys[2 * (k & 1)];
-          if (fast) {
+          if (fastk) {
+            // conditional killing (resamplings.py:40-88) + weights of the resampled parents (csmc.py:139-146), the warp's 4
+            // elements per lane (q = lane + 32 j) in registers; the same float operations in the same order as
+            // warp_cond_killing / warp_normalise_v3, hence the same bits
+            const int32_t* bsp = p.bs_star + (size_t)chain * (K + 1);
+            const int ci = bsp[k], cj = bsp[k + 1];
+            const float fn = (float)N;
+            float wv[4];
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              wv[j] = 0.f;
+              if (q < N) {
+                wv[j] = expf(lw[q]);  // csmc.py:139
+                w[q] = wv[j];
+                m = fmaxf(m, wv[j]);
+              }
+            }
+            const float w_max = warp_max(m);
+            __syncwarp();
+            const float total = warp_seq_cumsum(w, cum, N, lane);
+            float r[4];
+            int lo[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              const bool killed = q < N && __fmul_rn(ub[q < N ? q : 0], w_max) >= wv[j];
+              r[j] = __fmul_rn(total, __fsub_rn(1.0f, ub[ROWS + (q < N ? q : 0)]));
+              lo[j] = 0;
+              hi[j] = killed ? N : 0;
+              if (!killed) lo[j] = q;
+            }
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (lo[j] < hi[j]) {
+                  const int mid = (lo[j] + hi[j]) >> 1;
+                  if (cum[mid] < r[j]) lo[j] = mid + 1; else hi[j] = mid;
+                }
+              }
+            }
+            __syncwarp();  // every search done before cum is reused
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              if (q < N) {
+                tmp[q] = lo[j];
+                cum[q] = (q == ci) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(wv[j], w_max)), fn);  // J_prob (:79)
+              }
+            }
+            __syncwarp();
+            if (lane == 0) {
+              float acc = 0.f;
+              int q = 0;
+              for (; q + 8 <= N; q += 8) {
+                float x[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) x[t] = cum[q + t];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, x[t]);
+              }
+              for (; q < N; ++q) acc = __fadd_rn(acc, cum[q]);
+              cum[ci] = fmaxf(__fsub_rn(1.0f, acc), 0.f);  // :80-82
+            }
+            __syncwarp();
+            warp_seq_cumsum(cum, cum, N, lane);
+            const int J = choice_from_cum(cum, N, ub[2 * ROWS]);  // :84
+            int shift = (cj - J) % N;
+            if (shift < 0) shift += N;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              v[j] = -INFINITY;
+              if (q < N) {
+                int src = q - shift;
+                if (src < 0) src += N;
+                const int a = (q == cj) ? ci : tmp[src];  // roll + pin (:85-86)
+                idx[q] = a;
+                v[j] = lwraw[a];  // csmc.py:145 on the resampled parents
+                if (p.As) p.As[((size_t)chain * K + k) * N + q] = a;
+              }
+            }
+            float mm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+            mm = warp_max(mm);
+            if (!(fabsf(mm) < INFINITY)) mm = 0.f;
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (lane + 32 * j < N) sacc += expf(v[j] - mm);
+            sacc = warp_sum_v3(sacc);
+            const float lse = logf(sacc) + mm;  // csmc.py:146
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              if (q < N) {
+                lw[q] = v[j] - lse;
+                if (p.log_wss) p.log_wss[((size_t)chain * (K + 1) + k + 1) * N + q] = v[j] - lse;
+              }
+            }
+          } else if (fast) {
             // pmcmc_filter_step (smc.py:144-148) with the warp's 4 elements per lane (q = lane + 32 j) in registers;
             // same operation order as warp_normalise_v3 / warp_systematic_or_stratified, hence the same bits
             float v[4];
