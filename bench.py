@@ -247,6 +247,45 @@ def secondary_mnist(nparticles=101, steps=12):
                          'flops_per_particle_step': UNET_FLOPS[shape], 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained'}}
 
 
+
+def secondary_gibbs(chains=2048, steps=3):
+    """configs[0] scaled out: the particle-Gibbs sweep of experiments/toy/gp_gibbs.py (d = 100, K = 200, N = 100, conditional
+    killing resampling, explicit backward / forced move), device resident, gibbs_kernel through the public API."""
+    import torch
+    import fbs_b200
+    from fbs_b200 import sdes, parallel, random as fr
+    from fbs_b200.samplers import gibbs_kernel
+    d, K, N = D_TOY, K_STEPS, N_PART
+    jm, jc, y0 = gp_setup(d)
+    ts = np.linspace(0., 1., K + 1)
+    sde = sdes.StationaryConstLinearSDE(a=-0.5, b=1.)
+    model = fbs_b200.AffineGaussianModel.from_linear_sde(sde, jm, jc, d, ts, T=1.)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    y0_d = torch.from_numpy(y0).to(dev)
+    x0 = torch.zeros((chains, d), device=dev)
+    bs = torch.zeros((chains, K + 1), dtype=torch.int32, device=dev)
+
+    def sweep(i, x0, bs):
+        keys = torch.from_numpy(parallel.chain_keys(fr.PRNGKey(900 + i), chains, 0, 1)).to(dev)
+        x0, _, bs, _ = gibbs_kernel(keys, x0, y0_d, None, bs, ts, model.fwd_sampler, sde, model.unpack, N,
+                                    model.transition_sampler, model.transition_logpdf, model.likelihood_logpdf)
+        return x0, bs
+
+    for i in range(3):
+        x0, bs = sweep(i, x0, bs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        x0, bs = sweep(3 + i, x0, bs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'workload': 'configs[0] scaled out: particle-Gibbs sweep (gp_gibbs.py; d=100, K=200, N=100, conditional killing), '
+                        f'{chains} chains, device resident', 'value': chains * N * K / (ms * 1e-3), 'unit': 'particle-steps/s',
+            'ms_per_sweep': ms, 'steps': steps, 'dtype': 'f32'}
+
+
 def secondary_sharded(world, rank, per_rank=16, steps=4):
     """configs[4]: CelebA-HQ-shaped (64x64x3, inpaint-32) random-init score U-Net, ONE chain whose particle set is sharded over
     the ranks (fbs_b200/sharded.py): all-gather of the weights + NCCL exchange of resampled particles per step."""
@@ -410,6 +449,10 @@ def run_gpu(args):
     if not args.no_secondary:
         # a secondary workload must never take the headline line (or another rank) down
         if rank == 0:
+            try:
+                secondary['gibbs_sweep'] = secondary_gibbs()
+            except Exception as e:
+                secondary['gibbs_sweep'] = {'error': repr(e)[:300]}
             try:
                 secondary['mnist_score_net'] = secondary_mnist()
             except Exception as e:

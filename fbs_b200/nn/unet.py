@@ -377,6 +377,20 @@ class ScoreNetModel:
                     us_new=us_new, lw=lw, row_offset=row_offset, rows_total=rows_total)
         return us_new, lw
 
+    def mean_and_logw(self, us_prev, v_prev, v_next, t_prev):
+        """(transition mean [N, p, c], log-weight [N], sd) from ONE score evaluation: what pmcmc_filter_step needs, since the
+        transition of the RESAMPLED particles is the gathered mean plus fresh noise (smc.py:144-150)."""
+        us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
+        v_prev = dev(v_prev, F32).reshape(self.q, self.c)
+        v_next = dev(v_next, F32).reshape(self.q, self.c)
+        B = us_prev.shape[0]
+        img, score, a, g2, sd = self._score(us_prev, v_prev, t_prev)
+        mean = torch.empty_like(us_prev)
+        lw = torch.empty((B,), dtype=F32, device=us_prev.device)
+        ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, v_next=v_next, mean_out=mean,
+                    lw=lw)
+        return mean, lw, sd
+
     def transition_sampler(self, us_prev, v_prev, t_prev, key, **kwargs):
         """inpainting.py:122-128."""
         us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
@@ -435,6 +449,19 @@ class ScoreNetModel:
         xy0 = self.concat(x0, y0)
         path = forward_path(dev(key, torch.uint32).reshape(2), xy0.reshape(-1), *self._fwd_coef)
         return path.reshape(self.K + 1, self.unet.H, self.unet.W, self.c)
+
+    def fwd_ys_sampler(self, key, y0, **kwargs):
+        """inpainting.py:155-157: simulate_cond_forward(key, y0, ts) on the observed pixels alone -> [K + 1, q, c]."""
+        from ..sdes.linear import step_coefficients, forward_path
+        if not hasattr(self, '_fwd_coef'):
+            self._fwd_coef = step_coefficients(self.sde, self.ts)
+        k = dev(key, torch.uint32)
+        path = forward_path(k.reshape(2), dev(y0, F32).reshape(-1), *self._fwd_coef)
+        return path.reshape(self.K + 1, self.q, self.c)
+
+    def ref_sampler(self, key, _, n, **kwargs):
+        """inpainting.py:160-161: N(0, I) reference draw of the unobserved pixels -> [n, p, c]."""
+        return frandom.normal(dev(key, torch.uint32).reshape(2), (int(n), self.p, self.c))
 
     def fwd_sampler_reversed(self, key, x0, y0):
         """(us, vs) = (path_x[::-1], path_y[::-1]) of one forward-noising draw (gibbs.py:127-130), flattened per step."""

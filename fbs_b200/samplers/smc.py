@@ -15,6 +15,8 @@ from .._tensor import dev, empty, ptr, stream, out, is_host
 from .. import random as frandom
 from .common import MCMCState
 from .csmc.csmc import _model_of, _scheme_of
+from ..nn.unet import ScoreNetModel
+from ..nn import ops as nnops
 
 
 def pmcmc_filter_step(key, vs_bridge, u0s, ts, transition_sampler, likelihood_logpdf, resampling, nparticles,
@@ -27,6 +29,14 @@ def pmcmc_filter_step(key, vs_bridge, u0s, ts, transition_sampler, likelihood_lo
     single = k.dim() == 1
     k = k.reshape(-1, 2)
     B, K, N = k.shape[0], model.K, int(nparticles)
+    if isinstance(model, ScoreNetModel):
+        if B != 1 or return_history:
+            raise NotImplementedError('score-network chains run one at a time, without history')
+        uT, log_ell = _pmcmc_filter_step_nn(k[0], vs_bridge, u0s, model, resampling, N)
+        res = (uT.reshape(1, N, model.du), log_ell.reshape(1))
+        if single:
+            res = tuple(t[0] for t in res)
+        return tuple(out(t, host) for t in res)
     v = dev(vs_bridge, torch.float32).reshape(B, K + 1, model.dv)
     u0 = dev(u0s, torch.float32).reshape(B, N, model.du)
     uT = empty((B, N, model.du), torch.float32)
@@ -43,6 +53,26 @@ def pmcmc_filter_step(key, vs_bridge, u0s, ts, transition_sampler, likelihood_lo
     if single:
         res = tuple(t[0] for t in res)
     return tuple(out(t, host) for t in res)
+
+
+def _pmcmc_filter_step_nn(key, vs_bridge, u0s, model, resampling, N):
+    """smc.py:115-158 over a ScoreNetModel, one chain: per step ONE score evaluation gives the weights of the current
+    particles and their transition means; the resampled particles' transition is the gathered mean plus fresh noise."""
+    K, p, c = model.K, model.p, model.c
+    v = dev(vs_bridge, torch.float32).reshape(K + 1, model.q, c)
+    us = dev(u0s, torch.float32).reshape(N, p, c).contiguous()
+    sk = frandom.split(frandom.split(key, K), 2).contiguous()       # [K, (proposal, resampling), 2]   smc.py:142,154
+    log_ell = torch.zeros((), dtype=torch.float32, device=us.device)
+    logN = np.float32(math.log(N))
+    gathered = torch.empty_like(us)
+    for kk in range(K):
+        mean, lw, sd = model.mean_and_logw(us, v[kk], v[kk + 1], model.ts[kk])          # smc.py:144
+        c_ = torch.logsumexp(lw, dim=0)
+        log_ell = log_ell - logN + c_                                                   # smc.py:146
+        inds = resampling(torch.exp(lw - c_).contiguous(), sk[kk, 1].contiguous())      # smc.py:147-148
+        nnops.gather_rows(mean, inds.reshape(N).to(torch.int32), gathered)              # smc.py:149-150
+        us = gathered + sd * frandom.normal(sk[kk, 0].contiguous(), (N, p, c))
+    return us, log_ell
 
 
 def pcn_proposal(key, delta: float, x, mean, sampler):
@@ -168,6 +198,14 @@ def bootstrap_filter(transition_sampler, measurement_cond_pdf, vs, ts, init_samp
     single = k.dim() == 1
     k = k.reshape(-1, 2)
     B, K, N = k.shape[0], model.K, int(nparticles)
+    if isinstance(model, ScoreNetModel):
+        if B != 1:
+            raise NotImplementedError('score-network chains run one at a time')
+        res = _bootstrap_filter_nn(k[0], vs, model, init_sampler, resampling, N, return_last)
+        res = tuple(t.unsqueeze(0) for t in res)
+        if single:
+            res = tuple(t[0] for t in res)
+        return tuple(out(t, host) for t in res)
     v = dev(vs, torch.float32).reshape(B, K + 1, model.dv)
     ks = frandom.split(k, 2)                                                       # smc.py:77
     key_init, key_steps = ks[:, 0].contiguous(), ks[:, 1].contiguous()
@@ -195,6 +233,30 @@ def bootstrap_filter(transition_sampler, measurement_cond_pdf, vs, ts, init_samp
     return tuple(out(t, host) for t in res)
 
 
+def _bootstrap_filter_nn(key, vs, model, init_sampler, resampling, N, return_last):
+    """smc.py:58-88 over a ScoreNetModel, one chain: ONE score evaluation per step feeds the proposal and the weights."""
+    K, p, c = model.K, model.p, model.c
+    v = dev(vs, torch.float32).reshape(K + 1, model.q, c)
+    ks = frandom.split(key, 2)                                                     # smc.py:77
+    us = dev(init_sampler(ks[0].contiguous(), v[0], N), torch.float32).reshape(N, p, c).contiguous()
+    sk = frandom.split(frandom.split(ks[1].contiguous(), K), 2).contiguous()       # [K, (proposal, resampling), 2]
+    log_nell = torch.zeros((), dtype=torch.float32, device=us.device)
+    logN = np.float32(math.log(N))
+    hist = [us]
+    for kk in range(K):
+        us_new, lw = model.step(us, v[kk], v[kk + 1], model.ts[kk], sk[kk, 0].contiguous())      # smc.py:63,65
+        c_ = torch.logsumexp(lw, dim=0)
+        log_nell = log_nell - (c_ - logN)                                          # smc.py:67
+        inds = resampling(torch.exp(lw - c_).contiguous(), sk[kk, 1].contiguous())  # smc.py:68-69
+        us = torch.empty_like(us_new)
+        nnops.gather_rows(us_new, inds.reshape(N).to(torch.int32), us)             # smc.py:72
+        if not return_last:
+            hist.append(us)
+    if return_last:
+        return us.reshape(N, model.du), log_nell
+    return torch.stack(hist, dim=0).reshape(K + 1, N, model.du), log_nell
+
+
 def bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf, *args, **kwargs):
     """smc.py:91-112 (the unsplit ``key`` draws u_T, as written upstream)."""
     model = _model_of(transition_logpdf)
@@ -216,7 +278,10 @@ def bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf, *args
     u = uT
     traj = []
     for q, t in enumerate(range(K - 1, -1, -1)):                                   # smc.py:110-111
-        lw = model._eval(t, None, fu[:, t].contiguous(), None, v[:, t].contiguous(), u.contiguous(), 'tlp')
+        if isinstance(model, ScoreNetModel):
+            lw = model.transition_logpdf(u[0], fu[0, t], v[0, t], model.ts[t]).reshape(1, N)
+        else:
+            lw = model._eval(t, None, fu[:, t].contiguous(), None, v[:, t].contiguous(), u.contiguous(), 'tlp')
         w = torch.exp(lw - torch.logsumexp(lw, dim=-1, keepdim=True)).contiguous()
         idx = frandom.choice(skeys[:, q].contiguous(), N, (), p=w).reshape(B).long()
         u = fu[ar, t, idx]

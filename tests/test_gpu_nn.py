@@ -334,3 +334,60 @@ def test_sharded_sweep_single_rank_equals_unsharded():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_nn_pmcmc_filter_step_and_bootstrap_filter_one_step():
+    """pmcmc_filter_step (smc.py:115-158) and bootstrap_filter (smc.py:58-88) over the score network against the oracle
+    closures for K = 1 (one step is not chaotic): evidence, resampled indices on identical weights, particles."""
+    from fbs_b200.samplers import pmcmc_filter_step, bootstrap_filter, stratified
+    from oracle import resampling as orx
+    K, N = 1, 8
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(31)
+    u0s = rng.standard_normal((N, rect.size, 1)).astype(np.float32)
+    vs = np.cumsum(0.05 * rng.standard_normal((K + 1, obs.size, 1)), axis=0).astype(np.float32)
+    key = jr.PRNGKey(12)
+    uT, log_ell = pmcmc_filter_step(key, vs, u0s, ts, model.transition_sampler, model.likelihood_logpdf, stratified, N)
+    key_prop, key_res = jr.split(jr.split(key, K)[0], 2)
+    mean, lw, sd = model.mean_and_logw(u0s, vs[0], vs[1], ts[0])
+    mean, lw = mean.cpu().numpy(), lw.cpu().numpy().astype(np.float64)
+    c = np.log(np.exp(lw - lw.max()).sum()) + lw.max()
+    np.testing.assert_allclose(log_ell, c - math.log(N), rtol=1e-5, atol=1e-4)
+    inds = orx.stratified(np.exp(lw - c).astype(np.float32), key_res)
+    want = mean[inds] + np.float32(sd) * jr.normal(key_prop, u0s.shape)
+    np.testing.assert_allclose(uT.reshape(want.shape), want, rtol=1e-5, atol=1e-5)
+    # the mean / weights themselves against the fp32 oracle network
+    want_us, want_lw = _oracle_step(params, sde, T, T / K, rect, obs, u0s, vs[0], vs[1], ts[0], key_prop)
+    np.testing.assert_allclose(lw - lw.mean(), want_lw - want_lw.mean(), rtol=0, atol=5e-2 * max(1.0, float(np.ptp(want_lw))))
+    # bootstrap filter: same step, proposal first then resampling of the children
+    def init_sampler(key_, v0, n):
+        return u0s
+    us_bf, nell = bootstrap_filter(model.transition_sampler, model.likelihood_logpdf, vs, ts, init_sampler, key, N, stratified)
+    k_init, k_steps = jr.split(key, 2)
+    kp, kr = jr.split(jr.split(k_steps, K)[0], 2)
+    children = mean + np.float32(sd) * jr.normal(kp, u0s.shape)
+    inds = orx.stratified(np.exp(lw - c).astype(np.float32), kr)
+    np.testing.assert_allclose(us_bf.reshape(children.shape), children[inds], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(nell, -(c - math.log(N)), rtol=1e-5, atol=1e-4)
+
+
+def test_nn_pmcmc_kernel_and_gibbs_init_run():
+    """pmcmc_kernel (smc.py:171-258) and gibbs_init (gibbs.py:23-65, filter and smoother) over the score network."""
+    from fbs_b200.samplers import pmcmc_kernel, gibbs_init, stratified
+    K, N = 3, 6
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(41)
+    y0 = rng.uniform(size=(obs.size, 1)).astype(np.float32)
+    key = jr.PRNGKey(3)
+    ys = model.fwd_ys_sampler(jr.PRNGKey(4), y0).cpu().numpy()
+    uT = rng.standard_normal((rect.size, 1)).astype(np.float32)
+    for delta in (None, 0.1):
+        uT2, le2, ys2, st = pmcmc_kernel(key, uT, np.float32(-1e30), ys, y0, ts, model.fwd_ys_sampler, sde, model.ref_sampler,
+                                         model.transition_sampler, model.likelihood_logpdf, stratified, N, delta=delta)
+        assert bool(st.is_accepted) and np.isfinite(le2) and np.isfinite(uT2).all() and ys2.shape == (K + 1, obs.size)
+        assert uT2.shape == (rect.size,)
+    for method in ('filter', 'smoother'):
+        x0, us_star = gibbs_init(key, y0, (rect.size, 1), ts, model.fwd_sampler, sde, model.unpack, model.transition_sampler,
+                                 model.transition_logpdf, model.likelihood_logpdf, N, method=method)
+        assert x0.shape == (rect.size,) and us_star.shape == (K + 1, rect.size)
+        assert np.isfinite(x0).all() and np.isfinite(us_star).all()
