@@ -49,6 +49,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -114,7 +117,7 @@ struct Params {
   int ntile;          // N tile: multiple of 16, <= 256, divides Cout
   int kh, kw, off_h, off_w;
   int BW, BH, BNb;    // pixel box of one M tile: BW * BH * BNb <= 128, BW == W
-  int h_tiles, stages;
+  int h_tiles, m_tiles, stages;
   int pixel_shuffle;
   const float* bias;
   const float* residual;
@@ -125,6 +128,8 @@ struct Params {
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const Params p) {
+  // Persistent: CTA c runs tiles c, c + gridDim.x, ...; the accumulator is double buffered in tensor memory so that the
+  // epilogue of tile i overlaps the TMA / MMA main loop of tile i + 1.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,24 +138,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   unsigned char* ring = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
   uint64_t* empty = full + MAX_STAGES;
-  uint64_t* accum = empty + MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  uint64_t* acc_full = empty + MAX_STAGES;   // [2]: accumulator buffer written by the MMA warp
+  uint64_t* acc_empty = acc_full + 2;        // [2]: ... drained by the four epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int mt = blockIdx.x, nt = blockIdx.y;
-  const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
   const int ctot = p.C0 + p.C1;
   const int kblocks = p.kh * p.kw * (ctot / KBLK);
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.ntile) tmem_cols <<= 1;
+  const int n_ntiles = p.Cout / p.ntile;
+  const int ntiles = p.m_tiles * n_ntiles;
+  uint32_t acc_cols = 32;  // columns of one accumulator buffer (power of two >= ntile)
+  while (acc_cols < (uint32_t)p.ntile) acc_cols <<= 1;
 
   if (warp == 0) {
-    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_alloc(tmem_slot, 2 * acc_cols);
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(full + s, 1);
         mbar_init(empty + s, 1);
       }
-      mbar_init(accum, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(acc_full + i, 1);
+        mbar_init(acc_empty + i, 4);  // one arrival per epilogue warp
+      }
       fence_barrier_init();
     }
   }
@@ -163,21 +172,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(KBLK * p.BW * p.BH * p.BNb) * 2u;
       uint32_t s = 0, ph = 1;
-      int kcol = 0;  // column of this K-block in the weight matrix
-      for (int ty = 0; ty < p.kh; ++ty) {
-        for (int tx = 0; tx < p.kw; ++tx) {
-          for (int c = 0; c < ctot; c += KBLK, kcol += KBLK) {
-            mbar_wait(empty + s, ph);
-            unsigned char* dst = ring + (size_t)s * stage_bytes;
-            mbar_expect_tx(full + s, a_bytes + b_stage_bytes);
-            if (c < p.C0)
-              tma_load_4d(dst, &tmA0, full + s, c, p.off_w + tx, h0 + p.off_h + ty, n0);
-            else
-              tma_load_4d(dst, &tmA1, full + s, c - p.C0, p.off_w + tx, h0 + p.off_h + ty, n0);
-            tma_load_2d(dst + A_STAGE_BYTES, &tmB, full + s, kcol, nt * p.ntile);
-            if (++s == (uint32_t)p.stages) {
-              s = 0;
-              ph ^= 1u;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int mt = t / n_ntiles, nt = t - mt * n_ntiles;  // N tiles of one M tile are neighbours: the A boxes hit in L2
+        const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
+        int kcol = 0;  // column of this K-block in the weight matrix
+        for (int ty = 0; ty < p.kh; ++ty) {
+          for (int tx = 0; tx < p.kw; ++tx) {
+            for (int c = 0; c < ctot; c += KBLK, kcol += KBLK) {
+              mbar_wait(empty + s, ph);
+              unsigned char* dst = ring + (size_t)s * stage_bytes;
+              mbar_expect_tx(full + s, a_bytes + b_stage_bytes);
+              if (c < p.C0)
+                tma_load_4d(dst, &tmA0, full + s, c, p.off_w + tx, h0 + p.off_h + ty, n0);
+              else
+                tma_load_4d(dst, &tmA1, full + s, c - p.C0, p.off_w + tx, h0 + p.off_h + ty, n0);
+              tma_load_2d(dst + A_STAGE_BYTES, &tmB, full + s, kcol, nt * p.ntile);
+              if (++s == (uint32_t)p.stages) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
           }
         }
@@ -189,21 +202,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       // instruction descriptor: D fp32, A / B bf16, both K-major, N, M
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       uint32_t s = 0, ph = 0;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(full + s, ph);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(acc_empty + buf, ((it >> 1) & 1u) ^ 1u);  // passes on a fresh barrier; then waits for the epilogue of tile it - 2
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
-        const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + A_STAGE_BYTES);
+        const uint32_t d_tmem = tmem_base + buf * acc_cols;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
+          const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < KBLK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row: +2 in the address field
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(empty + s);
-        if (++s == (uint32_t)p.stages) {
-          s = 0;
-          ph ^= 1u;
+          for (int k = 0; k < KBLK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row: +2 in the address field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty + s);
+          if (++s == (uint32_t)p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
+        umma_commit(acc_full + buf);
       }
-      umma_commit(accum);
     }
     __syncwarp();
   } else {
@@ -211,65 +231,74 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp & 3;
     const int r = 32 * q + lane;
     const int w = r % p.BW, hh = (r / p.BW) % p.BH, nn = r / (p.BW * p.BH);
-    const int h = h0 + hh, n = n0 + nn;
-    const bool valid = r < p.BW * p.BH * p.BNb && h < p.H && n < p.B;
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
-    const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-    for (int c0 = 0; c0 < p.ntile; c0 += 32) {
-      float acc[32];
-      tmem_ld32(trow + c0, acc);
-      if (!valid) continue;
-      const int cg = nt * p.ntile + c0;  // first global output channel of this chunk
-      const int nc = min(32, p.ntile - c0);
-      if (p.bias) {
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int mt = t / n_ntiles, nt = t - mt * n_ntiles;
+      const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
+      const int h = h0 + hh, n = n0 + nn;
+      const bool valid = r < p.BW * p.BH * p.BNb && h < p.H && n < p.B;
+      const uint32_t buf = it & 1u;
+      mbar_wait(acc_full + buf, (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + buf * acc_cols + ((uint32_t)(32 * q) << 16);
+      const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+        float acc[32];
+        tmem_ld32(trow + c0, acc);
+        if (!valid) continue;
+        const int cg = nt * p.ntile + c0;  // first global output channel of this chunk
+        const int nc = min(32, p.ntile - c0);
+        if (p.bias) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < nc) acc[c] += __ldg(p.bias + cg + c);
-      }
-      size_t obase;
-      if (p.pixel_shuffle) {
-        // channel = (h2 * 2 + w2) * Cq + cq  ->  pixel (2h + h2, 2w + w2), channel cq   (fbs/nn/utils.py:53-57)
-        const int Cq = p.Cout >> 2;
-        const int blk = cg / Cq, cq = cg - blk * Cq;  // a 32-channel chunk never straddles a block (Cq % 32 == 0)
-        const int h2 = blk >> 1, w2 = blk & 1;
-        obase = (((size_t)n * (2 * p.H) + (2 * h + h2)) * (2 * p.W) + (2 * w + w2)) * Cq + cq;
-      } else {
-        obase = pix * p.Cout + cg;
-      }
-      if (p.residual) {
+          for (int c = 0; c < 32; ++c)
+            if (c < nc) acc[c] += __ldg(p.bias + cg + c);
+        }
+        size_t obase;
+        if (p.pixel_shuffle) {
+          // channel = (h2 * 2 + w2) * Cq + cq  ->  pixel (2h + h2, 2w + w2), channel cq   (fbs/nn/utils.py:53-57)
+          const int Cq = p.Cout >> 2;
+          const int blk = cg / Cq, cq = cg - blk * Cq;  // a 32-channel chunk never straddles a block (Cq % 32 == 0)
+          const int h2 = blk >> 1, w2 = blk & 1;
+          obase = (((size_t)n * (2 * p.H) + (2 * h + h2)) * (2 * p.W) + (2 * w + w2)) * Cq + cq;
+        } else {
+          obase = pix * p.Cout + cg;
+        }
+        if (p.residual) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          if (c < nc) {
-            const float4 rv = *reinterpret_cast<const float4*>(p.residual + obase + c);
-            acc[c] += rv.x; acc[c + 1] += rv.y; acc[c + 2] += rv.z; acc[c + 3] += rv.w;
+          for (int c = 0; c < 32; c += 4) {
+            if (c < nc) {
+              const float4 rv = *reinterpret_cast<const float4*>(p.residual + obase + c);
+              acc[c] += rv.x; acc[c + 1] += rv.y; acc[c + 2] += rv.z; acc[c + 3] += rv.w;
+            }
+          }
+        }
+        if (p.out_f32) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            if (c < nc) *reinterpret_cast<float4*>(p.out_f32 + obase + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        }
+        if (p.out_bf16) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            if (c < nc) {
+              __align__(16) __nv_bfloat162 v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(acc[c + 2 * j], acc[c + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(p.out_bf16 + obase + c) = *reinterpret_cast<const uint4*>(v);
+            }
           }
         }
       }
-      if (p.out_f32) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          if (c < nc) *reinterpret_cast<float4*>(p.out_f32 + obase + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-      }
-      if (p.out_bf16) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          if (c < nc) {
-            __align__(16) __nv_bfloat162 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(acc[c + 2 * j], acc[c + 2 * j + 1]);
-            *reinterpret_cast<uint4*>(p.out_bf16 + obase + c) = *reinterpret_cast<const uint4*>(v);
-          }
-        }
-      }
+      // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + buf);
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, 2 * acc_cols);
   }
 }
 
@@ -351,22 +380,20 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   }
   p.h_tiles = (a->H + p.BH - 1) / p.BH;
   const int n_tiles = (a->B + p.BNb - 1) / p.BNb;
-  // few M tiles (the 7x7 / 14x14 levels): a CTA streams its whole K loop through ONE SM's L2 port, so prefer narrower N
-  // tiles until the grid covers the machine about twice
-  while (ntile > 64 && ntile % 32 == 0 && (int64_t)n_tiles * p.h_tiles * (a->Cout / ntile) < 2 * sm_count() &&
-         (!p.pixel_shuffle || true))
-    ntile /= 2;
+  p.m_tiles = n_tiles * p.h_tiles;
+  // few M tiles (the 7x7 / 14x14 levels): a CTA streams its K loop through ONE SM's L2 port, so prefer narrower N tiles
+  // until there are about two tiles per SM
+  while (ntile > 64 && ntile % 32 == 0 && (int64_t)p.m_tiles * (a->Cout / ntile) < 2 * sm_count()) ntile /= 2;
   p.ntile = ntile;
   const size_t stage = (size_t)A_STAGE_BYTES + (size_t)ntile * 128;
-  // short K loops (9..54 blocks) and small tiles: prologue / epilogue latency matters more than ring depth, so keep the
-  // ring shallow enough for 2-3 CTAs to share an SM and overlap one CTA's epilogue with another's main loop
-  int stages = ntile <= 128 ? 3 : 4;
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
     set_error("nn_conv: tile does not fit shared memory");
     return FBS_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage + (2 * MAX_STAGES + 1) * 8 + 16;
+  const size_t smem = 1024 + stages * stage + (2 * MAX_STAGES + 4) * 8 + 16;
   CUtensorMap tmA0, tmA1, tmB;
   const int Hin = a->Hin > 0 ? a->Hin : a->H, Win = a->Win > 0 ? a->Win : a->W;
   int rc = make_act_map(&tmA0, a->in0, a->B, Hin, Win, a->C0, p.BW, p.BH, p.BNb);
@@ -381,7 +408,8 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     set_error("nn_conv: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
   }
-  dim3 grid((unsigned)(n_tiles * p.h_tiles), (unsigned)(a->Cout / ntile));
+  const int64_t tiles = (int64_t)p.m_tiles * (a->Cout / ntile);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   conv_gemm_kernel<<<grid, NTHREADS, smem, as_stream(s)>>>(tmA0, tmA1, tmB, p);
   return check_launch("conv_gemm_kernel");
 }
