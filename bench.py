@@ -487,7 +487,7 @@ def run_gpu(args):
                        'mh_acceptance_rate_last_step': acc_rate},
             'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms, 'steps': e2e_steps, 'warmup': e2e_warm,
-                    'how': 'numpy in / numpy out through fbs_b200.samplers.pmcmc_kernel; chains chunked over 4 CUDA streams so that '
+                    'how': 'numpy in / numpy out through fbs_b200.samplers.pmcmc_kernel; chains chunked over 8 CUDA streams so that '
                            'H2D, kernels and D2H (page-locked staging) overlap'},
             'gpu_launches': int(launches),
             'clocks': clk,
@@ -512,7 +512,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--chains', type=int, default=4096, help='chains per GPU (weak scaling)')
+    ap.add_argument('--chains', type=int, default=4144, help='chains per GPU (weak scaling); 4144 = 14 full waves of 148 SMs x 2 chains per CTA')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary (score network / particle-sharded) workloads')
     args = ap.parse_args()

@@ -95,7 +95,7 @@ def pcn_proposal(key, delta: float, x, mean, sampler):
 
 
 PIPELINE_MIN_CHAINS = 512     # host-buffer calls with at least this many chains are chunked over CUDA streams
-PIPELINE_CHUNKS = 4
+PIPELINE_CHUNKS = int(__import__('os').environ.get('FBS_PIPELINE_CHUNKS', '8'))
 _streams = []
 
 
