@@ -100,6 +100,120 @@ __global__ void step_transition_kernel(int du, int dv, const float* __restrict__
   }
 }
 
+// (2b) fused transition + weight for SMALL state dimensions (du, dv <= 16): one thread per particle PAIR (n, n + N/2) --
+// the two particles whose noise comes from the same threefry blocks -- with the parent, the drift and the children in
+// registers, the step matrix and the chain's constant drift part in shared memory (broadcast reads), 8-byte vector
+// loads / stores of the particle rows.  Per particle: du (du + dv) + dv (du + dv) FMAs, du normals (~65 instructions
+// each): the kernel is bound by the in-kernel RNG, not by HBM (profiles/r1_hbm_kernels.md).
+template <int DUT, int DVT>
+__global__ void __launch_bounds__(128) step_transition_small_kernel(
+    int du, int dv, const float* __restrict__ MTk, const float* __restrict__ mk, const float* __restrict__ dtp,
+    const float* __restrict__ sdp, const float* __restrict__ lnp, int k, const uint32_t* __restrict__ step_keys,
+    const float* __restrict__ us_prev, const int32_t* __restrict__ A, const float* __restrict__ v,
+    const float* __restrict__ v_prev, const float* __restrict__ u_star, const int32_t* __restrict__ b_cur, int64_t B, int N,
+    int blocks_per_chain, float* __restrict__ us_out, float* __restrict__ lw_out) {
+  constexpr int DT = DUT + DVT;
+  __shared__ float Ms[DUT][DT];  // Ms[j][i] = M_k[i][j], u inputs only
+  __shared__ float cs[DT];       // m_k + M_k[:, du:] v_prev  (u rows), and for v rows: (v - v_prev) - dt (m + M v_prev)
+  const int D = du + dv, half = N / 2;
+  const float dt = dtp[k], sd = sdp[k], lognorm = lnp[k];
+  const float inv_s2 = 1.0f / (sd * sd);
+  for (int64_t blk = blockIdx.x; blk < B * blocks_per_chain; blk += gridDim.x) {
+    const int64_t b = blk / blocks_per_chain;
+    const int pb = (int)(blk - b * blocks_per_chain);
+    __syncthreads();
+    for (int t = threadIdx.x; t < DUT * DT; t += blockDim.x) {
+      const int j = t / DT, i = t - j * DT;
+      const int ii = i < DUT ? i : du + (i - DUT);  // padded column -> model row
+      const bool ok = j < du && (i < DUT ? i < du : i - DUT < dv);
+      Ms[j][i] = ok ? __ldg(MTk + (size_t)j * D + ii) : 0.f;
+    }
+    if (threadIdx.x < DT) {
+      const int i = threadIdx.x;
+      const int ii = i < DUT ? i : du + (i - DUT);
+      const bool ok = i < DUT ? i < du : i - DUT < dv;
+      float acc = 0.f;
+      if (ok) {
+        acc = mk[ii];
+        for (int j = 0; j < dv; ++j) acc = fmaf(__ldg(MTk + (size_t)(du + j) * D + ii), v_prev[b * dv + j], acc);
+        if (i >= DUT) acc = (v[b * dv + (i - DUT)] - v_prev[b * dv + (i - DUT)]) - dt * acc;
+      }
+      cs[i] = acc;
+    }
+    __syncthreads();
+    const int n = pb * blockDim.x + threadIdx.x;
+    if (n >= half) continue;
+    Key key_res, key_tr;
+    split2(Key{step_keys[2 * b], step_keys[2 * b + 1]}, key_res, key_tr);  // csmc.py:136
+    const int bc = b_cur[b];
+    const uint32_t nel = (uint32_t)N * du;
+    float u[2][DUT], child[2][DUT];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int nn = n + s2 * half;
+      const float* parent = us_prev + ((size_t)b * N + A[b * N + nn]) * du;
+#pragma unroll
+      for (int j = 0; j < DUT; j += 2) {  // rows are 8-byte aligned when du is even
+        if (j + 1 < du) {
+          const float2 x = *reinterpret_cast<const float2*>(parent + j);
+          u[s2][j] = x.x;
+          u[s2][j + 1] = x.y;
+        } else {
+          u[s2][j] = j < du ? parent[j] : 0.f;
+          if (j + 1 < DUT) u[s2][j + 1] = 0.f;
+        }
+      }
+    }
+    // drift: u rows -> means, v rows -> residuals
+    float ss[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < DUT; ++j) {
+        const float mji = Ms[j][i];
+        a0 = fmaf(mji, u[0][j], a0);
+        a1 = fmaf(mji, u[1][j], a1);
+      }
+      if (i < DUT) {
+        child[0][i] = u[0][i] + dt * (a0 + cs[i]);
+        child[1][i] = u[1][i] + dt * (a1 + cs[i]);
+      } else {
+        const float r0 = cs[i] - dt * a0, r1 = cs[i] - dt * a1;
+        ss[0] = fmaf(r0, r0, ss[0]);
+        ss[1] = fmaf(r1, r1, ss[1]);
+      }
+    }
+    // noise: block e = n * du + i gives element e (particle n) and e + N du / 2 (particle n + N/2)
+#pragma unroll
+    for (int i = 0; i < DUT; ++i) {
+      if (i < du) {
+        uint32_t y0, y1;
+        random_bits_block(key_tr, nel, (uint32_t)n * du + i, y0, y1);
+        child[0][i] += sd * bits_to_normal(y0);
+        child[1][i] += sd * bits_to_normal(y1);
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int nn = n + s2 * half;
+      float* dst = us_out + ((size_t)b * N + nn) * du;
+      const bool pinned = nn == bc;
+#pragma unroll
+      for (int j = 0; j < DUT; j += 2) {
+        if (j + 1 < du) {
+          float2 x = make_float2(child[s2][j], child[s2][j + 1]);
+          if (pinned) x = *reinterpret_cast<const float2*>(u_star + (size_t)b * du + j);
+          *reinterpret_cast<float2*>(dst + j) = x;
+        } else if (j < du) {
+          dst[j] = pinned ? u_star[(size_t)b * du + j] : child[s2][j];
+        }
+      }
+      lw_out[(size_t)b * N + nn] = -0.5f * (ss[s2] * inv_s2 + lognorm);
+    }
+  }
+}
+
 // (3) log_ws -= logsumexp(log_ws): one CTA per chain.
 __global__ void step_normalise_kernel(float* __restrict__ lw, int64_t B, int N) {
   __shared__ float red[32];
@@ -165,10 +279,26 @@ extern "C" int fbs_csmc_step_affine_f32(fbs_stream_t s, const fbs_affine_model_t
   int64_t blocks = (B * N + 7) / 8;  // 8 warps (children) per CTA
   const int64_t cap2 = (int64_t)sm_count() * 8;
   if (blocks > cap2) blocks = cap2;
-  step_transition_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(du, dv, MTk, mk, model->dt, model->sd, model->lognorm, k,
-                                                                step_keys, 1, us_prev, A_out, v, v_prev, u_star, b_star,
-                                                                nullptr, B, (int)N, us_out, log_ws_out, nullptr);
-  rc = check_launch("step_transition_kernel");
+  if (du <= 16 && dv <= 16 && du % 2 == 0 && N % 2 == 0) {
+    // small state: thread per particle pair, everything in registers
+    const int bpc = (int)((N / 2 + 127) / 128);
+    int64_t nblk = B * bpc;
+    if (nblk > cap2 * 4) nblk = cap2 * 4;
+    if (du == 10 && dv == 10)
+      step_transition_small_kernel<10, 10><<<(int)nblk, 128, 0, as_stream(s)>>>(du, dv, MTk, mk, model->dt, model->sd, model->lognorm,
+                                                                              k, step_keys, us_prev, A_out, v, v_prev, u_star,
+                                                                              b_star, B, (int)N, bpc, us_out, log_ws_out);
+    else
+      step_transition_small_kernel<16, 16><<<(int)nblk, 128, 0, as_stream(s)>>>(du, dv, MTk, mk, model->dt, model->sd, model->lognorm,
+                                                                              k, step_keys, us_prev, A_out, v, v_prev, u_star,
+                                                                              b_star, B, (int)N, bpc, us_out, log_ws_out);
+    rc = check_launch("step_transition_small_kernel");
+  } else {
+    step_transition_kernel<<<(int)blocks, 256, 0, as_stream(s)>>>(du, dv, MTk, mk, model->dt, model->sd, model->lognorm, k,
+                                                                  step_keys, 1, us_prev, A_out, v, v_prev, u_star, b_star,
+                                                                  nullptr, B, (int)N, us_out, log_ws_out, nullptr);
+    rc = check_launch("step_transition_kernel");
+  }
   if (rc) return rc;
   step_normalise_kernel<<<(int)(B > cap ? cap : B), 256, 0, as_stream(s)>>>(log_ws_out, B, (int)N);
   return check_launch("step_normalise_kernel");

@@ -171,6 +171,32 @@ def forward_pass(key, us_star, bs_star, vs, ts, init_sampler, init_likelihood_lo
     return tuple(out(t, host) for t in res)
 
 
+
+def csmc_step(model, k, step_keys, us_prev, log_ws, vs_k1, vs_k, u_star_k1, b_star_k, b_star_k1, cond_resampling):
+    """One CSMC step (the scan body csmc.py:132-148) for particle sets held in global memory -- the per-timestep fused
+    kernels (``fbs_csmc_step_affine_f32``: ancestors, fused transition + weight, normalise).  Batched over chains:
+    ``step_keys [B, 2]`` (= keys[k] of csmc.py:157), ``us_prev [B, N, du]``, ``log_ws [B, N]`` normalised, ``vs_k1`` / ``vs_k``
+    ``[B, dv]`` (v and v_prev), ``u_star_k1 [B, du]``, ``b_star_k`` / ``b_star_k1 [B]``.  Returns ``(A, us, log_ws)``."""
+    if not isinstance(model, AffineGaussianModel):
+        raise TypeError('csmc_step needs an AffineGaussianModel')
+    scheme = _scheme_of(cond_resampling, 'conditional')
+    host = is_host(step_keys)
+    kk = dev(step_keys, torch.uint32).reshape(-1, 2)
+    B = kk.shape[0]
+    up = dev(us_prev, torch.float32).reshape(B, -1, model.du)
+    N = up.shape[1]
+    lw = dev(log_ws, torch.float32).reshape(B, N)
+    v1, v0 = dev(vs_k1, torch.float32).reshape(B, model.dv), dev(vs_k, torch.float32).reshape(B, model.dv)
+    ustar = dev(u_star_k1, torch.float32).reshape(B, model.du)
+    b0, b1 = dev(b_star_k, torch.int32).reshape(B), dev(b_star_k1, torch.int32).reshape(B)
+    A = empty((B, N), torch.int32)
+    us = empty((B, N, model.du), torch.float32)
+    lw_out = empty((B, N), torch.float32)
+    nat.call('fbs_csmc_step_affine_f32', stream(), model.struct(), int(k), scheme, ptr(kk), ptr(up), ptr(lw), ptr(v1), ptr(v0),
+             ptr(ustar), ptr(b0), ptr(b1), B, N, ptr(A), ptr(us), ptr(lw_out))
+    return tuple(out(t, host) for t in (A, us, lw_out))
+
+
 def normalise(log_weights, log_space=False):
     """csmc.py:273-292 on device tensors / numpy (tiny helper, not on the fused path)."""
     host = is_host(log_weights)

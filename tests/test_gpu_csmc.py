@@ -471,3 +471,39 @@ def test_empty_batch_is_a_no_op():
     assert tuple(idx.shape) == (0, 16)
     assert tuple(fr.normal(keys, (3,)).shape) == (0, 3)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('d,N,B', [(10, 64, 5), (10, 1000, 3), (6, 16, 4), (2, 2, 2), (20, 32, 3), (10, 33, 2)])
+@pytest.mark.parametrize('scheme', ['killing', 'multinomial'])
+def test_per_timestep_step_kernels(d, N, B, scheme):
+    """fbs_csmc_step_affine_f32 (the per-timestep kernels for particle sets in global memory; register-resident
+    transition kernel for du, dv <= 16, general one otherwise) against the oracle's scan body (csmc.py:132-148)."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    K = 6
+    p = gp_problem(d, K=K)
+    om64 = oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    rng = np.random.default_rng(d * 1000 + N)
+    k = 3
+    step_keys = jr.split(jr.PRNGKey(N), B)
+    us_prev = rng.standard_normal((B, N, d)).astype(np.float32)
+    lw = rng.standard_normal((B, N)).astype(np.float32)
+    lw = (lw - np.log(np.exp(lw.astype(np.float64)).sum(-1, keepdims=True))).astype(np.float32)
+    v0, v1 = rng.standard_normal((B, d)).astype(np.float32), rng.standard_normal((B, d)).astype(np.float32)
+    ustar = rng.standard_normal((B, d)).astype(np.float32)
+    b0 = rng.integers(0, N, size=B).astype(np.int32)
+    b1 = rng.integers(0, N, size=B).astype(np.int32)
+    A, us, lw_out = csmc.csmc_step(pm, k, step_keys, us_prev, lw, v1, v0, ustar, b0, b1, getattr(R, scheme))
+    for b in range(B):
+        key_res, key_tr = jr.split(step_keys[b], 2)
+        want_A = getattr(ocr, scheme)(key_res, np.exp(lw[b]).astype(np.float32), b0[b], b1[b], True)
+        assert (A[b] == want_A).mean() >= 1 - 2e-3            # expf ULP ties, as in the sweep tests
+        parents = us_prev[b][A[b]].astype(np.float64)
+        want = om64.transition_mean(parents, v0[b].astype(np.float64), om64.ts[k]) \
+            + np.float64(om64.transition_sd(om64.ts[k])) * jr.normal(key_tr, (N, d))
+        want[b1[b]] = ustar[b]
+        np.testing.assert_allclose(us[b], want, rtol=1e-5, atol=2e-5)
+        np.testing.assert_array_equal(us[b][b1[b]], ustar[b])
+        want_lw = ocsmc.normalise(om64.likelihood_logpdf(v1[b].astype(np.float64), parents, v0[b].astype(np.float64), om64.ts[k]),
+                                  log_space=True)
+        np.testing.assert_allclose(lw_out[b], want_lw, atol=LW_ATOL)
