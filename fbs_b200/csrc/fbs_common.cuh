@@ -30,6 +30,19 @@ inline int check_launch(const char* what) {
 
 inline cudaStream_t as_stream(fbs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Tiled resampling (resample_kernels.cu): chains in shared-memory tiles, one thread per chain for the sequential sums.
+// expw: weights are log-weights (exp applied on load); split_first: key_resampling = split(key)[0] (csmc.py:136).
+// Returns FBS_ERR_UNSUPPORTED, without touching the error string, when a chain's rows do not fit in shared memory.
+int launch_resample_tile(cudaStream_t st, int scheme, const uint32_t* keys, const float* weights, const int32_t* iv,
+                         const int32_t* jv, int conditional, int clip, int expw, int split_first, int64_t B, int64_t N,
+                         int32_t* out);
+
+// Tensor-core per-timestep transition + weight kernel (step_tc.cu).  Returns FBS_OK, an error, or -1 (not eligible).
+int launch_step_transition_tc(cudaStream_t st, const fbs_affine_model_t* model, int k, const uint32_t* step_keys,
+                              const float* us_prev, const int32_t* A, const float* v, const float* v_prev,
+                              const float* u_star, const int32_t* b_cur, int64_t B, int64_t N, float* us_out,
+                              float* lw_out);
+
 // Number of SMs of the current device (cached per thread; B200: 148).
 int sm_count();
 

@@ -2,6 +2,7 @@
 // fbs/samplers/csmc/csmc.py:132-148 as three launches -- ancestors, fused transition + weight,
 // normalise.  The persistent whole-sweep kernel (csmc_kernels.cu) is the fast path when the
 // particle set of a chain fits in shared memory; this is the general one.
+#include <stdlib.h>
 #include "fbs_common.cuh"
 #include "fbs_resample.cuh"
 
@@ -263,23 +264,36 @@ extern "C" int fbs_csmc_step_affine_f32(fbs_stream_t s, const fbs_affine_model_t
   FBS_REQUIRE(us_prev != us_out, "csmc_step: us_out must not alias us_prev");
   if (B == 0) return FBS_OK;
   const int du = model->du, dv = model->dv, D = du + dv;
+  int rc = launch_resample_tile(as_stream(s), scheme, step_keys, log_ws, b_star_prev, b_star, 1, 0, 1, 1, B, N, A_out);
+  const bool tiled = rc != FBS_ERR_UNSUPPORTED;
+  if (tiled && rc) return rc;
   const size_t smem = ((size_t)3 * N + 1) * sizeof(float);
-  if (smem > 200 * 1024) {
+  if (!tiled && smem > 200 * 1024) {
     set_error("csmc_step: N=%lld exceeds the single-warp resampling limit (multi-CTA scan not built yet)", (long long)N);
     return FBS_ERR_UNSUPPORTED;
   }
-  if (smem > 48 * 1024) cudaFuncSetAttribute(step_ancestors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t cap = (int64_t)sm_count() * 8;
-  step_ancestors_kernel<<<(int)(B > cap ? cap : B), 32, smem, as_stream(s)>>>(scheme, step_keys, log_ws, b_star_prev,
-                                                                           b_star, B, (int)N, A_out);
-  int rc = check_launch("step_ancestors_kernel");
-  if (rc) return rc;
+  if (!tiled) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(step_ancestors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    step_ancestors_kernel<<<(int)(B > cap ? cap : B), 32, smem, as_stream(s)>>>(scheme, step_keys, log_ws, b_star_prev,
+                                                                             b_star, B, (int)N, A_out);
+    rc = check_launch("step_ancestors_kernel");
+    if (rc) return rc;
+  }
   const float* MTk = model->MT + (size_t)k * D * D;
   const float* mk = model->m + (size_t)k * D;
   int64_t blocks = (B * N + 7) / 8;  // 8 warps (children) per CTA
   const int64_t cap2 = (int64_t)sm_count() * 8;
   if (blocks > cap2) blocks = cap2;
-  if (du <= 16 && dv <= 16 && du % 2 == 0 && N % 2 == 0) {
+  const char* impl = getenv("FBS_STEP_IMPL");  // "cuda" pins the CUDA-core kernels (tests compare the two)
+  rc = (impl != nullptr && impl[0] == 'c') ? -1
+                                           : launch_step_transition_tc(as_stream(s), model, k, step_keys, us_prev, A_out, v,
+                                                                       v_prev, u_star, b_star, B, N, us_out, log_ws_out);
+  if (rc > 0) return rc;
+  if (rc == 0) {
+    // done on the tensor cores
+  } else if (du <= 16 && dv <= 16 && du % 2 == 0 && N % 2 == 0) {
     // small state: thread per particle pair, everything in registers
     const int bpc = (int)((N / 2 + 127) / 128);
     int64_t nblk = B * bpc;

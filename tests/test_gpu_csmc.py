@@ -473,11 +473,13 @@ def test_empty_batch_is_a_no_op():
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize('d,N,B', [(10, 64, 5), (10, 1000, 3), (6, 16, 4), (2, 2, 2), (20, 32, 3), (10, 33, 2)])
+@pytest.mark.parametrize('d,N,B', [(10, 64, 5), (10, 1000, 3), (6, 16, 4), (2, 2, 2), (20, 32, 3), (10, 33, 2),
+                                   (100, 256, 3), (100, 100, 2), (32, 130, 2), (40, 64, 3), (100, 1026, 2)])
 @pytest.mark.parametrize('scheme', ['killing', 'multinomial'])
 def test_per_timestep_step_kernels(d, N, B, scheme):
     """fbs_csmc_step_affine_f32 (the per-timestep kernels for particle sets in global memory; register-resident
-    transition kernel for du, dv <= 16, general one otherwise) against the oracle's scan body (csmc.py:132-148)."""
+    transition kernel for du, dv <= 16, the tcgen05 kernel for du >= 32 and even N, the general one otherwise) against
+    the oracle's scan body (csmc.py:132-148)."""
     from fbs_b200.samplers.csmc import csmc, resamplings as R
     K = 6
     p = gp_problem(d, K=K)
@@ -507,3 +509,26 @@ def test_per_timestep_step_kernels(d, N, B, scheme):
         want_lw = ocsmc.normalise(om64.likelihood_logpdf(v1[b].astype(np.float64), parents, v0[b].astype(np.float64), om64.ts[k]),
                                   log_space=True)
         np.testing.assert_allclose(lw_out[b], want_lw, atol=LW_ATOL)
+
+
+@pytest.mark.parametrize('d,N,B', [(100, 256, 4), (64, 100, 3), (36, 2050, 2)])
+def test_step_tensor_core_vs_cuda_core(d, N, B, monkeypatch):
+    """The tcgen05 per-timestep kernel (split-TF32 GEMM in TMEM) against the CUDA-core kernel of the same entry point:
+    identical ancestors and noise, drift within float32 rounding."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    p = gp_problem(d, K=4)
+    pm, _ = product_model(p)
+    rng = np.random.default_rng(d + N)
+    step_keys = jr.split(jr.PRNGKey(N + 1), B)
+    us_prev = rng.standard_normal((B, N, d)).astype(np.float32)
+    lw = np.full((B, N), -np.log(N), np.float32)
+    v0, v1 = rng.standard_normal((B, d)).astype(np.float32), rng.standard_normal((B, d)).astype(np.float32)
+    ustar = rng.standard_normal((B, d)).astype(np.float32)
+    b0 = rng.integers(0, N, size=B).astype(np.int32)
+    b1 = rng.integers(0, N, size=B).astype(np.int32)
+    got = csmc.csmc_step(pm, 2, step_keys, us_prev, lw, v1, v0, ustar, b0, b1, R.killing)
+    monkeypatch.setenv('FBS_STEP_IMPL', 'cuda')
+    want = csmc.csmc_step(pm, 2, step_keys, us_prev, lw, v1, v0, ustar, b0, b1, R.killing)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(got[2], want[2], atol=2e-4)

@@ -73,6 +73,37 @@ def test_unconditional_indices_exact(N, kind):
     assert (np.diff(got, axis=1) >= 0).all()
 
 
+@pytest.mark.parametrize('N', [2, 10, 33, 100, 101, 257, 1000])
+def test_many_chains_exact(N):
+    """Enough chains that the tiled kernel holds many chains per CTA (one thread per chain for the sequential sums,
+    items of several chains inside one warp) and a ragged last tile."""
+    from fbs_b200.samplers.csmc import resamplings as RC
+    from fbs_b200.samplers import resampling as R
+    rng = np.random.default_rng(N)
+    B = 148 * 4 * 3 + 37 if N <= 101 else 700
+    w = np.concatenate([_weights(rng, B - B // 2, N, 'random'), _weights(rng, B // 2, N, 'peaked')])
+    keys = jr.split(jr.PRNGKey(N + 11), B)
+    i = rng.integers(0, N, B).astype(np.int32)
+    j = rng.integers(0, N, B).astype(np.int32)
+    check = rng.choice(B, 48, replace=False).tolist() + [0, B - 1]
+    for name in ('killing', 'multinomial'):
+        got = getattr(RC, name)(keys, w, i, j, True)
+        got_u = getattr(RC, name)(keys, w, conditional=False)
+        for b in check:
+            np.testing.assert_array_equal(got[b], getattr(ocr, name)(keys[b], w[b], int(i[b]), int(j[b]), True),
+                                          err_msg=f'{name} cond b={b}')
+            np.testing.assert_array_equal(got_u[b], getattr(ocr, name)(keys[b], w[b], conditional=False),
+                                          err_msg=f'{name} uncond b={b}')
+        assert (got[np.arange(B), j] == i).all()
+    got_s = RC.systematic(keys, w, conditional=False)
+    for b in check:
+        np.testing.assert_array_equal(got_s[b], ocr.systematic(keys[b], w[b], conditional=False))
+    for name in ('stratified', 'systematic', 'killing'):
+        got = getattr(R, name)(w, keys)
+        for b in check:
+            np.testing.assert_array_equal(got[b], getattr(orx, name)(w[b], keys[b]), err_msg=f'{name} b={b}')
+
+
 def test_single_vector_and_killing_identity():
     from fbs_b200.samplers.csmc import resamplings as R
     key = jr.PRNGKey(1)
