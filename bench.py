@@ -286,6 +286,117 @@ def secondary_gibbs(chains=2048, steps=3):
             'ms_per_sweep': ms, 'steps': steps, 'dtype': 'f32'}
 
 
+def secondary_sb(chains=16384, steps=3, d=10, K=100, N=64):
+    """configs[2]: particle Gibbs through a Gaussian Schroedinger bridge (experiments/sb/gibbs.py: d = 10, K = 100, T = 1,
+    forward sampler = Euler--Maruyama with 10 sub-steps, obs_var = 0.1, reference N(1, a a^T)), batched over conditioning
+    targets, device resident, gibbs_kernel through the public API."""
+    import torch
+    import fbs_b200
+    from fbs_b200 import parallel, random as fr
+    from fbs_b200.samplers import gibbs_kernel
+    rng = np.random.default_rng(3)
+    zs = np.linspace(0., 5., d)
+    cov = np.exp(-np.abs(zs[None] - zs[:, None]))
+    obs_var = 0.1
+    jm = np.zeros(2 * d)
+    jc = np.block([[cov, cov], [cov, cov + obs_var * np.eye(d)]])
+    a_ = rng.normal(size=(2 * d, 2 * d))
+    ts = np.linspace(0., 1., K + 1)
+    model = fbs_b200.AffineGaussianModel.from_gaussian_sb(jm, jc, np.ones(2 * d), a_ @ a_.T, d, ts, sig=1., em_nsteps=10)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    # one conditioning target per chain (sb/gibbs.py loops over 100 ids; here they are batched)
+    y0 = (rng.normal(size=(chains, d)) @ np.linalg.cholesky(cov + obs_var * np.eye(d)).T).astype(np.float32)
+    y0_d = torch.from_numpy(y0).to(dev)
+    x0 = torch.zeros((chains, d), device=dev)
+    bs = torch.zeros((chains, K + 1), dtype=torch.int32, device=dev)
+
+    def sweep(i, x0, bs):
+        keys = torch.from_numpy(parallel.chain_keys(fr.PRNGKey(700 + i), chains, 0, 1)).to(dev)
+        x0, _, bs, _ = gibbs_kernel(keys, x0, y0_d, None, bs, ts, model.fwd_sampler, None, model.unpack, N,
+                                    model.transition_sampler, model.transition_logpdf, model.likelihood_logpdf)
+        return x0, bs
+
+    for i in range(3):
+        x0, bs = sweep(i, x0, bs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        x0, bs = sweep(3 + i, x0, bs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if not bool(torch.isfinite(x0).all()):
+        raise RuntimeError('Gaussian SB Gibbs sweep produced non-finite samples')
+    value = chains * N * K / (ms * 1e-3)
+    peak = measured_peak()[0]
+    achieved = value * (8 * d + 16) / 1e9
+    return {'workload': f'configs[2]: Gaussian Schroedinger bridge particle Gibbs (sb/gibbs.py; d={d}, K={K}, N={N}, EM forward '
+                        f'sampler m=10), {chains} conditioning targets, device resident', 'value': value,
+            'unit': 'particle-steps/s', 'ms_per_sweep': ms, 'steps': steps, 'dtype': 'f32',
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'algorithmic_bytes_per_particle_step': 8 * d + 16}}
+
+
+def secondary_hbm_kernels(shapes=None, steps=None):
+    """The stand-alone resampling kernels and the per-timestep fused step (ancestors + transition / weight + normalise) of
+    north_star items (1)-(2), each timed alone with CUDA events against the HBM roofline with the algorithmic bytes of
+    SURVEY 8(d): 8 B per particle for resampling, 8 du + 16 B per particle-step for the transition."""
+    import torch
+    import fbs_b200
+    from fbs_b200 import sdes, _native as nat, random as fr
+    from fbs_b200._tensor import ptr, stream
+    peak = measured_peak()[0]
+    dev = torch.device('cuda', torch.cuda.current_device())
+
+    def timeit(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = []
+    for B, N in (shapes or ((65536, 100), (262144, 100), (16384, 1024), (1024, 16384))):
+        w = torch.rand(B, N, device=dev)
+        w /= w.sum(dim=1, keepdim=True)
+        keys = fr.split(torch.from_numpy(fr.PRNGKey(1)).to(dev), B)
+        idx = torch.empty(B, N, dtype=torch.int32, device=dev)
+        for name, scheme in (('stratified', nat.RESAMPLE_STRATIFIED), ('killing', nat.RESAMPLE_KILLING)):
+            ms = timeit(lambda: nat.call('fbs_resample_f32', stream(), scheme, ptr(keys), ptr(w), B, N, ptr(idx)), steps or 10)
+            gbs = 8 * B * N / ms / 1e6
+            out.append({'kernel': f'fbs_resample_f32 {name}', 'chains': B, 'N': N, 'ms': ms, 'achieved': gbs, 'unit': 'GB/s',
+                        'frac': gbs / peak, 'algorithmic_bytes_per_particle': 8})
+        del w, keys, idx
+    for d, B, N in ((10, 256, 16384), (100, 64, 16384)):
+        K = 4
+        jm, jc, y0 = gp_setup(d)
+        ts = np.linspace(0., 1., K + 1)
+        model = fbs_b200.AffineGaussianModel.from_linear_sde(sdes.StationaryConstLinearSDE(a=-0.5, b=1.), jm, jc, d, ts, T=1.)
+        us = torch.randn(B, N, d, device=dev)
+        us2 = torch.empty_like(us)
+        lw = torch.full((B, N), -float(np.log(N)), device=dev)
+        lw2 = torch.empty_like(lw)
+        A = torch.empty(B, N, dtype=torch.int32, device=dev)
+        v, vp, ustar = (torch.randn(B, d, device=dev) for _ in range(3))
+        b0 = torch.zeros(B, dtype=torch.int32, device=dev)
+        keys = fr.split(torch.from_numpy(fr.PRNGKey(2)).to(dev), B)
+        ms = timeit(lambda: nat.call('fbs_csmc_step_affine_f32', stream(), model.struct(), 1, nat.RESAMPLE_KILLING, ptr(keys),
+                                     ptr(us), ptr(lw), ptr(v), ptr(vp), ptr(ustar), ptr(b0), ptr(b0), B, N, ptr(A), ptr(us2),
+                                     ptr(lw2)), steps or 5)
+        gbs = (8 * d + 16) * B * N / ms / 1e6
+        out.append({'kernel': 'fbs_csmc_step_affine_f32 (ancestors + transition/weight + normalise, 3 launches)', 'd': d, 'chains': B,
+                    'N': N, 'ms': ms, 'achieved': gbs, 'unit': 'GB/s', 'frac': gbs / peak,
+                    'algorithmic_bytes_per_particle_step': 8 * d + 16, 'particle_steps_per_s': B * N / ms * 1e3})
+    return {'bound': 'hbm', 'peak': peak, 'note': 'in-kernel threefry2x32 (jax.random-compatible) bounds these kernels by instruction issue '
+            'below the HBM roofline; see profiles/r1_hbm_kernels.md', 'kernels': out}
+
+
 def secondary_sharded(world, rank, per_rank=16, steps=4):
     """configs[4]: CelebA-HQ-shaped (64x64x3, inpaint-32) random-init score U-Net, ONE chain whose particle set is sharded over
     the ranks (fbs_b200/sharded.py): all-gather of the weights + NCCL exchange of resampled particles per step."""
@@ -453,6 +564,14 @@ def run_gpu(args):
                 secondary['gibbs_sweep'] = secondary_gibbs()
             except Exception as e:
                 secondary['gibbs_sweep'] = {'error': repr(e)[:300]}
+            try:
+                secondary['gaussian_sb_gibbs'] = secondary_sb()
+            except Exception as e:
+                secondary['gaussian_sb_gibbs'] = {'error': repr(e)[:300]}
+            try:
+                secondary['hbm_kernels'] = secondary_hbm_kernels()
+            except Exception as e:
+                secondary['hbm_kernels'] = {'error': repr(e)[:300]}
             try:
                 secondary['mnist_score_net'] = secondary_mnist()
             except Exception as e:

@@ -19,6 +19,7 @@
 //               in the staging tile, coalesced 16-byte stores.
 // Operand layout, descriptors and the split-TF32 scheme are those of sweep_v3.cu (element (r, k) at
 // (k / 4) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 4) * 4, LBO = 2048 for the 128-row particle operand).
+#include <stdlib.h>
 #include "fbs_common.cuh"
 #include "fbs_rng.cuh"
 
@@ -26,7 +27,7 @@ namespace fbs {
 namespace steptc {
 
 constexpr int ROWS = 128, PAIRS = 64;
-constexpr int WORKERS = 256, NTHREADS = WORKERS + 64;
+constexpr int MAX_WW = 16;  // worker warps: 8 (parents of the next tile prefetched into registers) or 16 (no prefetch)
 constexpr int MAX_STAGES = 4;
 constexpr uint32_t A_LBO = ROWS * 16;
 
@@ -45,6 +46,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {  // off the critical path: back off
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done) __nanosleep(64);
   } while (!done);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -96,7 +108,7 @@ __device__ __forceinline__ uint32_t a_off(int r, int cg) {
 }
 
 // barrier of the MMA warp and the workers (the TMA producer warp runs free)
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS - 32) : "memory"); }
+__device__ __forceinline__ void cta_sync(int nthreads) { asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); }
 
 struct Params {
   int du, dv, N, k;
@@ -109,6 +121,7 @@ struct Params {
   const int32_t* b_cur;
   float *us_out, *lw_out;
   int stages, tiles_per_chain;
+  long long* dbg;  // optional phase timers (cycles, CTA 0, first worker thread): see fbs_debug_step_tc_timers
 };
 
 struct Layout {
@@ -142,14 +155,16 @@ __host__ __device__ inline Layout make_layout(int du, int dv, int stages) {
   L.nz = take((uint32_t)ROWS * L.nzs * 4u);
   L.ring = take((uint32_t)stages * L.stage_bytes);
   L.cs = take((uint32_t)L.nout * 4u);
-  L.ss = take(2 * ROWS * 4);
+  L.ss = take((MAX_WW / 4) * ROWS * 4);
   L.bars = take((2 * MAX_STAGES + 1) * 8);
   L.misc = take(64);
   L.total = o;
   return L;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const Params p) {
+template <int WW, bool PRE>
+__global__ void __launch_bounds__(32 * WW + 64, 1) step_transition_tc_kernel(const Params p) {
+  constexpr int WORKERS = 32 * WW, NTHREADS = WORKERS + 64, HS = WW / 4, QSLOTS = 4 * WW;
   extern __shared__ __align__(1024) unsigned char smem[];
   const Layout L = make_layout(p.du, p.dv, p.stages);
   const int du = p.du, dv = p.dv, N = p.N, half = N / 2, D = du + dv;
@@ -187,7 +202,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
   const unsigned char* img = reinterpret_cast<const unsigned char*>(p.MTc) + (size_t)p.k * L.nkb * L.stage_bytes;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(L.nout >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
   const int64_t tiles = p.B * p.tiles_per_chain;
+  // a CTA owns a contiguous run of tiles: consecutive tiles mostly belong to the same chain (its constants are reused)
+  const int64_t per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = blockIdx.x * per_cta;
+  const int64_t tile_end = tile_begin + per_cta < tiles ? tile_begin + per_cta : tiles;
   const int wt = tid - 64;            // worker thread index (warps 2..9)
+  const int step_r = WORKERS / L.ncg, step_c = WORKERS - step_r * L.ncg;  // (row, column group) stride of a worker
+  long long tprev = 0;
+  const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+#define FBS_TICK(slot)                                 \
+  if (timing) {                                        \
+    const long long tnow = clock64();                  \
+    p.dbg[slot] += tnow - tprev;                       \
+    tprev = tnow;                                      \
+  }
   uint32_t g = 0;                     // K-blocks streamed / consumed so far (ring position)
   uint32_t it = 0;                    // tiles done by this CTA (accumulator barrier parity)
   int64_t prev_b = -1;
@@ -196,51 +224,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
     // ---- TMA producer (free running, synchronised with the MMA warp through the ring's mbarriers only): the K-blocks
     //      of the step matrix once per tile, in consumption order
     if (lane == 0) {
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
         for (int kb = 0; kb < L.nkb; ++kb, ++g) {
           const uint32_t slot = g % (uint32_t)p.stages, use = g / (uint32_t)p.stages;
-          if (use > 0) mbar_wait(empty + slot, (use - 1) & 1u);
+          if (use > 0) mbar_wait_sleep(empty + slot, (use - 1) & 1u);
           mbar_expect_tx(full + slot, L.stage_bytes);
           bulk_g2s(ring + slot * L.stage_bytes, img + (size_t)kb * L.stage_bytes, L.stage_bytes, full + slot);
         }
       }
     }
   } else
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-    const int64_t b = tile / p.tiles_per_chain;
-    const int p0 = (int)(tile - b * p.tiles_per_chain) * PAIRS;
-    const int npairs = min(PAIRS, half - p0);
+  {
+  // ---- gather plumbing (workers).  A quarter-warp covers 8 distinct rows (conflict-free 16-byte shared stores); a thread
+  //      always works on the same tile row and loads full 32-byte sectors (two column groups) of its parent row.  The
+  //      parents of the NEXT tile are fetched into registers while the current tile's noise / epilogue run.
+  constexpr int NJ = 16 / (QSLOTS / 16);  // du8 <= 128: at most 16 column-group pairs per row, QSLOTS / 16 quarter-slots per row group
+  const int qslot = warp >= 2 ? (warp - 2) * 4 + (lane >> 3) : 0;  // < QSLOTS
+  const int grow = (qslot & 15) * 8 + (lane & 7);  // this thread's tile row in the gather
+  const int ncp = (L.ncgA + 1) / 2;
+  float4 pre[NJ][2];
+  int pre_idx = 0;
+  auto tile_coords = [&](int64_t tile, int64_t& b, int& p0, int& npairs) {
+    b = tile / p.tiles_per_chain;
+    p0 = (int)(tile - b * p.tiles_per_chain) * PAIRS;
+    npairs = min(PAIRS, half - p0);
+  };
+  auto fetch_index = [&](int64_t tile) {  // ancestor of this thread's gather row in `tile`
+    pre_idx = -1;
+    if (tile < tile_end) {
+      int64_t b; int p0, npairs;
+      tile_coords(tile, b, p0, npairs);
+      if ((grow & (PAIRS - 1)) < npairs) {
+        const int n = grow < PAIRS ? p0 + grow : half + p0 + (grow - PAIRS);
+        pre_idx = __ldg(p.A + (size_t)b * N + n);
+      }
+    }
+  };
+  auto fetch_parent = [&](int64_t tile) {
+    const int64_t b = tile < tile_end ? tile / p.tiles_per_chain : 0;
+    const float4* parent = reinterpret_cast<const float4*>(p.us_prev + ((size_t)b * N + (pre_idx < 0 ? 0 : pre_idx)) * du);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int cp = (qslot >> 4) + (QSLOTS / 16) * j, cg0 = 2 * cp, cg1 = cg0 + 1;
+      pre[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pre[j][1] = pre[j][0];
+      if (pre_idx >= 0 && cp < ncp) {
+        if (cg0 < L.ncg) pre[j][0] = __ldg(parent + cg0);
+        if (cg1 < L.ncg) pre[j][1] = __ldg(parent + cg1);
+      }
+    }
+  };
+  auto store_operands = [&]() {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int cp = (qslot >> 4) + (QSLOTS / 16) * j, cg0 = 2 * cp, cg1 = cg0 + 1;
+      if (cp < ncp) {
+        const float4 x0 = pre[j][0], x1 = pre[j][1];
+        {
+          const float4 h = make_float4(tf32_rn(x0.x), tf32_rn(x0.y), tf32_rn(x0.z), tf32_rn(x0.w));
+          *reinterpret_cast<float4*>(Ahi + a_off(grow, cg0)) = h;
+          *reinterpret_cast<float4*>(Alo + a_off(grow, cg0)) = make_float4(x0.x - h.x, x0.y - h.y, x0.z - h.z, x0.w - h.w);
+        }
+        if (cg1 < L.ncgA) {
+          const float4 h = make_float4(tf32_rn(x1.x), tf32_rn(x1.y), tf32_rn(x1.z), tf32_rn(x1.w));
+          *reinterpret_cast<float4*>(Ahi + a_off(grow, cg1)) = h;
+          *reinterpret_cast<float4*>(Alo + a_off(grow, cg1)) = make_float4(x1.x - h.x, x1.y - h.y, x1.z - h.z, x1.w - h.w);
+        }
+      }
+    }
+  };
+  if (PRE && warp >= 2) {
+    fetch_index(tile_begin);
+    fetch_parent(tile_begin);
+  }
+
+  for (int64_t tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    int64_t b; int p0, npairs;
+    tile_coords(tile, b, p0, npairs);
     // row r of the tile <-> particle n(r); rows r in [npairs, 64) and [64 + npairs, 128) are empty
     auto row_particle = [&](int r) { return r < PAIRS ? p0 + r : half + p0 + (r - PAIRS); };
     auto row_valid = [&](int r) { return (r & (PAIRS - 1)) < npairs; };
 
+    if (timing) tprev = clock64();
     if (warp >= 2) {
-      // ---- gather + split: a quarter-warp covers 8 distinct rows (conflict-free 16-byte shared stores), each thread
-      //      loads one full 32-byte sector (two column groups) of its parent row
-      const int qslot = (warp - 2) * 4 + (lane >> 3);
-      const int ncp = (L.ncgA + 1) / 2;
-      for (int item = qslot; item < 16 * ncp; item += 32) {
-        const int rg = item & 15, cp = item >> 4;
-        const int r = rg * 8 + (lane & 7);
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-        const int cg0 = 2 * cp, cg1 = cg0 + 1;
-        if (row_valid(r)) {
-          const int n = row_particle(r);
-          const float* parent = p.us_prev + ((size_t)b * N + p.A[(size_t)b * N + n]) * du;
-          if (cg0 < L.ncg) x0 = __ldg(reinterpret_cast<const float4*>(parent) + cg0);
-          if (cg1 < L.ncg) x1 = __ldg(reinterpret_cast<const float4*>(parent) + cg1);
-        }
-        {
-          const float4 h = make_float4(tf32_rn(x0.x), tf32_rn(x0.y), tf32_rn(x0.z), tf32_rn(x0.w));
-          *reinterpret_cast<float4*>(Ahi + a_off(r, cg0)) = h;
-          *reinterpret_cast<float4*>(Alo + a_off(r, cg0)) = make_float4(x0.x - h.x, x0.y - h.y, x0.z - h.z, x0.w - h.w);
-        }
-        if (cg1 < L.ncgA) {
-          const float4 h = make_float4(tf32_rn(x1.x), tf32_rn(x1.y), tf32_rn(x1.z), tf32_rn(x1.w));
-          *reinterpret_cast<float4*>(Ahi + a_off(r, cg1)) = h;
-          *reinterpret_cast<float4*>(Alo + a_off(r, cg1)) = make_float4(x1.x - h.x, x1.y - h.y, x1.z - h.z, x1.w - h.w);
-        }
+      if (!PRE) {
+        fetch_index(tile);
+        fetch_parent(tile);
       }
+      store_operands();  // tf32 split of the (prefetched) parents into the UMMA operands
       // ---- the chain's constant vectors: u rows  c_u = m + M[:, du:] v_prev;  v rows  (v - v_prev) - dt (m + M[:, du:] v_prev)
       if (b != prev_b) {
         for (int o = wt; o < L.nout; o += WORKERS) {
@@ -265,11 +336,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
         }
       }
       fence_proxy_async();  // the operand stores must be visible to the tensor core (async proxy)
+      FBS_TICK(0)  // gather + split + constants
     }
     prev_b = b;
     tc_fence_before();
-    cta_sync();  // #1: operands, constants and the transition key are in place; the previous tile's stores are done
+    cta_sync(NTHREADS - 32);  // #1: operands, constants and the transition key are in place; the previous tile's stores are done
     tc_fence_after();
+    FBS_TICK(1)  // barrier #1
 
     if (warp == 0) {
       // ---- MMA issuer
@@ -294,11 +367,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
     } else if (warp >= 2) {
       // ---- noise in the shadow of the GEMM: task (pair, column group) = 4 threefry blocks = 4 normals for particle
       //      p0 + pair and 4 for its partner, element e = n * du + i of normal(key_tr, (N, du))
+      if (PRE) fetch_index(tile + 1);
       const uint32_t k0 = misc[2], k1 = misc[3];
       const uint32_t hblk = (uint32_t)half * (uint32_t)du;
       const int ntasks = npairs * L.ncg;
-      for (int t = wt; t < ntasks; t += WORKERS) {
-        const int pr = t / L.ncg, cg = t - pr * L.ncg;
+      int pr = wt / L.ncg, cg = wt - pr * L.ncg;
+      for (int t = wt; t < ntasks; t += WORKERS, pr += step_r, cg += step_c) {
+        if (cg >= L.ncg) { cg -= L.ncg; ++pr; }
         const uint32_t e = (uint32_t)(p0 + pr) * (uint32_t)du + 4u * (uint32_t)cg;
         uint32_t x0[4] = {e, e + 1u, e + 2u, e + 3u};
         uint32_t x1[4] = {e + hblk, e + hblk + 1u, e + hblk + 2u, e + hblk + 3u};
@@ -311,10 +386,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
         *reinterpret_cast<float4*>(nz + (size_t)pr * L.nzs + 4 * cg) = lo4;
         *reinterpret_cast<float4*>(nz + (size_t)(pr + PAIRS) * L.nzs + 4 * cg) = hi4;
       }
+      FBS_TICK(2)  // noise
+      if (PRE) fetch_parent(tile + 1);  // in flight during the epilogue
       // the noise rows are read by other threads (row owners) below: a worker-only barrier
-      asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(WORKERS) : "memory");
+      FBS_TICK(3)  // worker barrier
       mbar_wait(acc_full, it & 1u);
       tc_fence_after();
+      FBS_TICK(4)  // accumulator wait
       // ---- epilogue: thread = accumulator row (TMEM lane quadrant = warp % 4), the two threads of a row split the
       //      8-column chunks
       const int r = 32 * (warp & 3) + lane;
@@ -324,27 +403,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
       const bool pinned = valid && n == p.b_cur[b];
       const uint32_t trow = tbase + ((uint32_t)(32 * (warp & 3)) << 16);
       const int nuc = L.du8 / 8, nvc = (L.nout - L.du8) / 8;
-      const int uc0 = hs ? (nuc + 1) / 2 : 0, uc1 = hs ? nuc : (nuc + 1) / 2;
-      const int vc0 = hs ? (nvc + 1) / 2 : 0, vc1 = hs ? nvc : (nvc + 1) / 2;
+      const int uc0 = nuc * hs / HS, uc1 = nuc * (hs + 1) / HS;
+      const int vc0 = nvc * hs / HS, vc1 = nvc * (hs + 1) / HS;
       float ss = 0.f;
-      for (int c = vc0; c < vc1; ++c) {
-        uint32_t acc[8];
-        tmem_ld8_issue(trow + (uint32_t)(L.du8 + 8 * c), acc);
+      for (int c = vc0; c < vc1; c += 4) {  // four 8-column loads in flight per wait
+        uint32_t acc[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c + u < vc1) tmem_ld8_issue(trow + (uint32_t)(L.du8 + 8 * (c + u)), acc[u]);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float resid = cs[L.du8 + 8 * c + q] - dt * __uint_as_float(acc[q]);
-          ss = fmaf(resid, resid, ss);
+        for (int u = 0; u < 4; ++u) {
+          if (c + u < vc1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float resid = cs[L.du8 + 8 * (c + u) + q] - dt * __uint_as_float(acc[u][q]);
+              ss = fmaf(resid, resid, ss);
+            }
+          }
         }
       }
       ssp[hs * ROWS + r] = ss;
-      for (int c = uc0; c < uc1; ++c) {
-        uint32_t acc[8];
-        tmem_ld8_issue(trow + (uint32_t)(8 * c), acc);
+      for (int c2 = uc0; c2 < uc1; c2 += 2) {  // two 8-column loads in flight per wait
+        uint32_t acc2[2][8];
+        tmem_ld8_issue(trow + (uint32_t)(8 * c2), acc2[0]);
+        if (c2 + 1 < uc1) tmem_ld8_issue(trow + (uint32_t)(8 * (c2 + 1)), acc2[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int hq = 0; hq < 2; ++hq) {
-          const int cg = 2 * c + hq;
+        for (int hq2 = 0; hq2 < 4; ++hq2) {
+          const int c = c2 + (hq2 >> 1), hq = hq2 & 1;
+          const uint32_t* acc = acc2[hq2 >> 1];
+          const int cg = c < uc1 ? 2 * c + hq : L.ncg;
           if (cg < L.ncg) {
             const float4 ph = *reinterpret_cast<const float4*>(Ahi + a_off(r, cg));
             const float4 pl = *reinterpret_cast<const float4*>(Alo + a_off(r, cg));
@@ -361,29 +450,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) step_transition_tc_kernel(const P
         }
       }
     }
+    FBS_TICK(5)  // epilogue
     tc_fence_before();
-    cta_sync();  // #2: accumulator and operands are free again, the children are staged
+    cta_sync(NTHREADS - 32);  // #2: accumulator and operands are free again, the children are staged
     tc_fence_after();
+    FBS_TICK(6)  // barrier #2
     if (warp >= 2) {
       // ---- coalesced stores: the two runs of npairs consecutive particle rows, 16 bytes per thread
       const int nvec = 2 * npairs * L.ncg;
-      for (int t = wt; t < nvec; t += WORKERS) {
-        const int rr = t / L.ncg, cg = t - rr * L.ncg;
+      int rr = wt / L.ncg, cg = wt - rr * L.ncg;
+      for (int t = wt; t < nvec; t += WORKERS, rr += step_r, cg += step_c) {
+        if (cg >= L.ncg) { cg -= L.ncg; ++rr; }
         const int r = rr < npairs ? rr : PAIRS + (rr - npairs);
         const int n = row_particle(r);
         *(reinterpret_cast<float4*>(p.us_out + ((size_t)b * N + n) * du) + cg) =
             *reinterpret_cast<const float4*>(nz + (size_t)r * L.nzs + 4 * cg);
       }
       if (wt < ROWS && row_valid(wt))
-        p.lw_out[(size_t)b * N + row_particle(wt)] = -0.5f * ((ssp[wt] + ssp[ROWS + wt]) * inv_s2 + lognorm);
+      {
+        float ss = ssp[wt];
+#pragma unroll
+        for (int h2 = 1; h2 < HS; ++h2) ss += ssp[h2 * ROWS + wt];
+        p.lw_out[(size_t)b * N + row_particle(wt)] = -0.5f * (ss * inv_s2 + lognorm);
+      }
+      FBS_TICK(7)  // stores
     }
+  }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
+#undef FBS_TICK
+static long long* g_step_tc_dbg = nullptr;
+
 }  // namespace steptc
+
+// Test / profiling hook: device buffer of 8 int64 that CTA 0 accumulates its per-phase cycle counts into (NULL = off).
+extern "C" int fbs_debug_step_tc_timers(long long* dev_buf) {
+  steptc::g_step_tc_dbg = dev_buf;
+  return FBS_OK;
+}
 
 // Returns FBS_OK, an error, or -1 when the shape is not eligible (the caller falls back to the CUDA-core kernels).
 int launch_step_transition_tc(cudaStream_t st, const fbs_affine_model_t* model, int k, const uint32_t* step_keys,
@@ -392,7 +500,7 @@ int launch_step_transition_tc(cudaStream_t st, const fbs_affine_model_t* model, 
                               float* lw_out) {
   using namespace steptc;
   const int du = model->du, dv = model->dv;
-  if (model->MTc == nullptr || du % 4 != 0 || du < 32 || (N & 1) || N < 2 || N >= (1 << 24)) return -1;
+  if (model->MTc == nullptr || du % 4 != 0 || du < 32 || du > 128 || (N & 1) || N < 2 || N >= (1 << 24)) return -1;
   if ((uint64_t)N * (uint64_t)du >= (1ull << 32)) return -1;
   int stages = MAX_STAGES;
   Layout L = make_layout(du, dv, stages);
@@ -404,15 +512,20 @@ int launch_step_transition_tc(cudaStream_t st, const fbs_affine_model_t* model, 
   p.step_keys = step_keys; p.us_prev = us_prev; p.A = A; p.v = v; p.v_prev = v_prev; p.u_star = u_star; p.b_cur = b_cur;
   p.us_out = us_out; p.lw_out = lw_out;
   p.stages = stages;
+  p.dbg = g_step_tc_dbg;
   p.tiles_per_chain = (int)((N / 2 + PAIRS - 1) / PAIRS);
   const int64_t tiles = B * p.tiles_per_chain;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  cudaError_t e = cudaFuncSetAttribute(step_transition_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
+  const int grid = (int)((tiles + per_cta - 1) / per_cta);
+  const char* ww = getenv("FBS_STEP_TC_WARPS");  // "8": eight worker warps with register prefetch; default sixteen
+  const bool eight = ww != nullptr && ww[0] == '8';
+  auto kern = eight ? step_transition_tc_kernel<8, true> : step_transition_tc_kernel<16, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) {
     set_error("step_tc: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
   }
-  step_transition_tc_kernel<<<grid, NTHREADS, L.total, st>>>(p);
+  kern<<<grid, eight ? 320 : 576, L.total, st>>>(p);
   return check_launch("step_transition_tc_kernel");
 }
 

@@ -139,6 +139,11 @@ typedef struct {
  * kernel; Bimg is ONE step of the MTc image (nkb = K8 / 8 blocks). */
 int fbs_debug_umma_gemm(fbs_stream_t s, const float* A, const float* Bimg, int32_t K8, int32_t nout, float* D);
 
+/* Profiling hook of the tcgen05 per-timestep kernel: a device buffer of 8 int64 into which CTA 0 accumulates the
+ * cycles it spends per phase (gather, barrier, noise, worker barrier, accumulator wait, epilogue, barrier, stores);
+ * NULL switches it off (default).  Not thread safe; for scripts/step_tc_phases.py only. */
+int fbs_debug_step_tc_timers(long long* dev_buf);
+
 /* Scratch the tiled sweep kernel needs for B chains (per-chain step vectors of all K steps); pass a device
  * buffer of at least this many bytes as `workspace` to fbs_csmc_forward_affine_f32 / fbs_pmcmc_filter_affine_f32.
  * With workspace == NULL (or too small) the general kernel runs instead. */
