@@ -2,6 +2,7 @@
 // Reference: fbs/sdes/linear.py:190-225, fbs/sdes/simulators.py:53-106, fbs/samplers/gibbs.py:171-214,
 // fbs/samplers/smc.py:161-168,244-258, experiments/toy/gp_gibbs.py:138-141.
 #include <math.h>
+#include <stdlib.h>
 #include "fbs_common.cuh"
 #include "fbs_resample.cuh"
 
@@ -84,6 +85,140 @@ __global__ void em_affine_path_kernel(const uint32_t* __restrict__ keys, const f
       for (int d = tid; d < D; d += blockDim.x) store_path(cur[d], b, k + 1, d, K, D, du, rev, out_u, out_v);
     }
     __syncthreads();
+  }
+}
+
+// euler_maruyama with an affine drift, ONE THREAD PER CHAIN (small D, many chains -- the Gaussian Schroedinger-bridge
+// forward sampler of experiments/sb/gibbs.py:141-143 batched over conditioning targets): the state lives in registers, the
+// m sub-step matrices of an interval are staged in shared memory with cp.async one interval ahead (all threads read the
+// same element: broadcast), and both outputs of every threefry block are used -- element e of normal(keys[k], (m, D)) is
+// drawn together with element e + m D / 2, which a later sub-step reads back from a per-thread shared-memory stash.
+template <int DT>
+__global__ void __launch_bounds__(64) em_affine_path_tpc_kernel(
+    const uint32_t* __restrict__ keys, const float* __restrict__ x0, int x0_batched, const float* __restrict__ AT,
+    const float* __restrict__ a, const float* __restrict__ ddt, const float* __restrict__ disp, int64_t B, int K, int m,
+    int D, int du, int rev, float* __restrict__ out_u, float* __restrict__ out_v) {
+  extern __shared__ __align__(16) float sm[];
+  const int nt = blockDim.x, tid = threadIdx.x;
+  const uint32_t n = (uint32_t)m * D, h = (n + 1u) >> 1;
+  const int per_k = m * D * D, per_ka = m * D, per_buf = (per_k + per_ka + 3) & ~3;
+  float* mat = sm;                       // [2][per_buf]: AT of the m sub-steps, then a of the m sub-steps
+  float* stash = sm + 2 * per_buf;       // [h][nt]: second outputs of the threefry blocks, read by a later sub-step
+  float* epsb = stash + (size_t)h * nt;  // [D][nt]: this sub-step's normals
+  const int64_t b = blockIdx.x * (int64_t)nt + tid;
+  const bool active = b < B;
+  const int64_t bb = active ? b : B - 1;  // idle threads of the last CTA shadow a real chain (no stores)
+  const Key key{keys[2 * bb], keys[2 * bb + 1]};
+  float x[DT];
+#pragma unroll
+  for (int i = 0; i < DT; ++i) {
+    x[i] = i < D ? x0[(x0_batched ? bb * D : 0) + i] : 0.f;
+    if (active && i < D) store_path(x[i], b, 0, i, K, D, du, rev, out_u, out_v);
+  }
+  auto stage = [&](int k, int buf) {
+    float* dst = mat + buf * per_buf;
+    const float* srcA = AT + (size_t)k * per_k;
+    const float* srca = a + (size_t)k * per_ka;
+    for (int t = tid; t < per_k + per_ka; t += nt) {
+      const float* src = t < per_k ? srcA + t : srca + (t - per_k);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + t)), "l"(src)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  for (int k = 0; k < K; ++k) {
+    if (k + 1 < K) {
+      stage(k + 1, (k + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* buf = mat + (k & 1) * per_buf;
+    const Key key_k = split_key(key, (uint32_t)K, (uint32_t)k);  // simulators.py:81
+    const float hh = ddt[k];
+    const float sq = sqrtf(hh);
+    for (int q = 0; q < m; ++q) {
+      const float* Aq = buf + q * D * D;
+      const float* aq = buf + per_k + q * D;
+      const float g = disp[k * m + q];
+      float acc[DT];
+#pragma unroll
+      for (int i = 0; i < DT; ++i) acc[i] = 0.f;
+      if ((D & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < DT; ++j) {
+          if (j < D) {
+            const float xj = x[j];
+#pragma unroll
+            for (int i = 0; i < DT; i += 4) {
+              if (i < D) {
+                const float4 w = *reinterpret_cast<const float4*>(Aq + j * D + i);
+                acc[i] = fmaf(w.x, xj, acc[i]);
+                if (i + 1 < DT) acc[i + 1] = fmaf(w.y, xj, acc[i + 1]);
+                if (i + 2 < DT) acc[i + 2] = fmaf(w.z, xj, acc[i + 2]);
+                if (i + 3 < DT) acc[i + 3] = fmaf(w.w, xj, acc[i + 3]);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < DT; ++j) {
+          if (j < D) {
+            const float xj = x[j];
+#pragma unroll
+            for (int i = 0; i < DT; ++i)
+              if (i < D) acc[i] = fmaf(Aq[j * D + i], xj, acc[i]);
+          }
+        }
+      }
+      // the sub-step's normals -> epsb (a ROLLED loop: unrolled over D the kernel outgrows the instruction cache, and with
+      // one warp per scheduler every fetch miss is exposed); four threefry blocks in lockstep where the group allows it
+#pragma unroll 1
+      for (int i0 = 0; i0 < D; i0 += 4) {
+        const uint32_t e0 = (uint32_t)q * D + i0;
+        const int cnt = min(4, D - i0);
+        if (cnt == 4 && e0 + 3u < h && e0 + 3u + h < n) {
+          uint32_t y0[4] = {e0, e0 + 1u, e0 + 2u, e0 + 3u};
+          uint32_t y1[4] = {e0 + h, e0 + h + 1u, e0 + h + 2u, e0 + h + 3u};
+          threefry2x32_x4(key_k.k0, key_k.k1, y0, y1);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            epsb[(size_t)(i0 + r) * nt + tid] = bits_to_normal(y0[r]);
+            stash[(size_t)(e0 + r) * nt + tid] = bits_to_normal(y1[r]);
+          }
+        } else {
+          for (int r = 0; r < cnt; ++r) {
+            const uint32_t e = e0 + r;
+            float eps;
+            if (e < h) {
+              uint32_t y0, y1;
+              random_bits_block(key_k, n, e, y0, y1);
+              eps = bits_to_normal(y0);
+              if (e + h < n) stash[(size_t)e * nt + tid] = bits_to_normal(y1);
+            } else {
+              eps = stash[(size_t)(e - h) * nt + tid];
+            }
+            epsb[(size_t)(i0 + r) * nt + tid] = eps;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < DT; ++i) {
+        if (i < D) {
+          const float drift = acc[i] + aq[i];
+          x[i] = x[i] + drift * hh + g * sq * epsb[(size_t)i * nt + tid];  // simulators.py:87
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < DT; ++i)
+        if (i < D) store_path(x[i], b, k + 1, i, K, D, du, rev, out_u, out_v);
+    }
+    __syncthreads();  // buffer (k & 1) is refilled by the next iteration's stage(k + 2)
   }
 }
 
@@ -287,6 +422,33 @@ int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0
   FBS_REQUIRE(rev ? (du >= 0 && du <= D && (out_u || out_v)) : (out_u != nullptr && du == D),
               "em_affine_path: bad output configuration");
   if (B == 0) return FBS_OK;
+  {
+    // many chains of a small system: one thread per chain
+    const int nt = 32;
+    const size_t per_buf = ((size_t)(m * D * D + m * D) + 3) & ~(size_t)3;
+    const size_t smem_tpc = (2 * per_buf + (size_t)((m * D + 1) / 2 + D) * nt) * sizeof(float);
+    const char* impl = getenv("FBS_EM_IMPL");  // "cta" pins the CTA-per-chain kernel (tests compare the two)
+    if (D <= 32 && B >= 1024 && smem_tpc <= 100 * 1024 && !(impl != nullptr && impl[0] == 'c')) {
+      const int grid_tpc = (int)((B + nt - 1) / nt);
+#define FBS_EM_TPC(DT)                                                                                               \
+  do {                                                                                                               \
+    if (smem_tpc > 48 * 1024)                                                                                        \
+      cudaFuncSetAttribute(em_affine_path_tpc_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tpc); \
+    em_affine_path_tpc_kernel<DT><<<grid_tpc, nt, smem_tpc, as_stream(s)>>>(keys, x0, x0_batched, AT, a, ddt, disp, B,  \
+                                                                           (int)K, (int)m, (int)D, (int)du, rev, out_u, \
+                                                                           out_v);                                   \
+  } while (0)
+      if (D <= 4) FBS_EM_TPC(4);
+      else if (D <= 8) FBS_EM_TPC(8);
+      else if (D <= 12) FBS_EM_TPC(12);
+      else if (D <= 16) FBS_EM_TPC(16);
+      else if (D <= 20) FBS_EM_TPC(20);
+      else if (D <= 24) FBS_EM_TPC(24);
+      else FBS_EM_TPC(32);
+#undef FBS_EM_TPC
+      return check_launch("em_affine_path_tpc_kernel");
+    }
+  }
   int threads = (int)((D + 31) / 32 * 32);
   if (threads > 256) threads = 256;
   const size_t smem = 2 * (size_t)D * sizeof(float);
