@@ -127,98 +127,243 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // LinearAttention core (unet.py:227-239): q softmax over the head dimension, k softmax over the pixels,
 // context = k^T (v / P), out = context^T (q / sqrt(d)).  One CTA per (sample, head); dim_head = 32.
 // qkv: bf16 [B, P, 3 * heads * 32] (q | k | v, each (head, d));  out: bf16 [B, P, heads * 32].
+//
+// Both contractions (32 x P x 32 and P x 32 x 32 per head: tiny, but 1.6 MFLOP per CTA of scalar FMAs was the whole run
+// time) run on the tensor cores with warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- far too small for a
+// tcgen05 tile.  Global traffic is 16-byte loads; tiles of 128 pixels are staged in shared memory as bf16 rows padded to
+// 80 bytes (conflict-free ldmatrix); exp(k - max) and the q softmax are applied while staging.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __global__ void __launch_bounds__(256) linear_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int P, int heads,
                                                                __nv_bfloat16* __restrict__ out) {
-  constexpr int TN = 128;  // pixels per shared-memory tile
-  __shared__ float ek[TN][33], vt[TN][32];
-  __shared__ float ctx[32][33];
+  constexpr int TN = 128, LDS = 40;  // pixels per tile; shared-memory row stride in bf16 (32 + 8 pad)
+  __shared__ __align__(16) unsigned char raw[2 * TN * LDS * 2];
+  __nv_bfloat16 (*at)[LDS] = reinterpret_cast<__nv_bfloat16 (*)[LDS]>(raw);                 // exp(k - max) tile, then the softmaxed q tile
+  __nv_bfloat16 (*vt)[LDS] = reinterpret_cast<__nv_bfloat16 (*)[LDS]>(raw + TN * LDS * 2);  // v tile
+  float (*pb)[32][33] = reinterpret_cast<float (*)[32][33]>(raw);                           // 4 partial contexts (after the tiles)
+  __shared__ __align__(16) __nv_bfloat16 cb[32][LDS];  // context [d][e], bf16
+  __shared__ float red[64][33];
   __shared__ float kmax[32], ksum[32];
-  __shared__ float part[8][32];
+  __shared__ float ctx[32][33];
   const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
   const int HD = heads * 32, ld = 3 * HD;
   const __nv_bfloat16* q = qkv + (size_t)b * P * ld + hd * 32;
   const __nv_bfloat16* k = q + HD;
   const __nv_bfloat16* v = k + HD;
-  const int d = threadIdx.x & 31, sl = threadIdx.x >> 5;  // 8 warps
-  // column max of k over the pixels
-  float m = -INFINITY;
-  for (int n = sl; n < P; n += 8) m = fmaxf(m, __bfloat162float(k[(size_t)n * ld + d]));
-  part[sl][d] = m;
-  __syncthreads();
-  if (sl == 0) {
-    float t = part[0][d];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cgp = tid & 3, prow = tid >> 2;  // this thread stages channels [8 cgp, 8 cgp + 8) of pixels prow and prow + 64 of a tile
+  auto load8 = [&](const __nv_bfloat16* base, int n, float (&f)[8]) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(base + (size_t)n * ld + 8 * cgp);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-    for (int j = 1; j < 8; ++j) t = fmaxf(t, part[j][d]);
-    kmax[d] = t;
-  }
-  __syncthreads();
-  // context[d][e] = sum_n exp(k[n,d] - kmax[d]) v[n,e]: tiles of TN pixels staged (exp applied) in shared memory;
-  // thread (d, e-block of 4: e in [4 sl, 4 sl + 4)) accumulates over the tile
-  const float km = kmax[d];
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ks = 0.f;
-  for (int n0 = 0; n0 < P; n0 += TN) {
-    __syncthreads();
-    for (int n = sl; n < TN; n += 8) {
-      const bool ok = n0 + n < P;
-      ek[n][d] = ok ? __expf(__bfloat162float(k[(size_t)(n0 + n) * ld + d]) - km) : 0.f;
-      vt[n][d] = ok ? __bfloat162float(v[(size_t)(n0 + n) * ld + d]) : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h2[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
     }
-    __syncthreads();
-#pragma unroll 8
-    for (int n = 0; n < TN; ++n) {
-      const float e = ek[n][d];
-      const float4 vv = *reinterpret_cast<const float4*>(&vt[n][4 * sl]);
-      a0 = fmaf(e, vv.x, a0); a1 = fmaf(e, vv.y, a1); a2 = fmaf(e, vv.z, a2); a3 = fmaf(e, vv.w, a3);
-      ks += e;
-    }
-  }
-  if (sl == 0) ksum[d] = ks;
-  __syncthreads();
+  };
+  auto store8 = [&](__nv_bfloat16 (*tile)[LDS], int row, const float (&f)[8]) {
+    __align__(16) __nv_bfloat162 h2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(&tile[row][8 * cgp]) = *reinterpret_cast<const uint4*>(h2);
+  };
+  // ---- column max of k over the pixels
   {
-    const float sc = 1.0f / (ksum[d] * (float)P);  // softmax denominator and v / (H W)
-    ctx[d][4 * sl + 0] = a0 * sc; ctx[d][4 * sl + 1] = a1 * sc; ctx[d][4 * sl + 2] = a2 * sc; ctx[d][4 * sl + 3] = a3 * sc;
-  }
-  __syncthreads();
-  // out[n][e] = sum_d ctx[d][e] softmax_d(q[n,:])[d] / sqrt(32): per tile of TN pixels the softmaxed q goes to shared
-  // memory TRANSPOSED (reusing the k tile), then every thread computes a 4 pixel x 4 channel block from 16-byte reads
-  const float inv_sqrt_d = 0.17677669529663687f;
-  float (*qsT)[TN + 4] = reinterpret_cast<float (*)[TN + 4]>(&ek[0][0]);  // [32][TN + 4] fills the ek tile exactly; +4: 4-way instead of 32-way store conflicts
-  float (*ctx4)[32] = reinterpret_cast<float (*)[32]>(&vt[0][0]);  // aligned copy of the context inside the v tile
-  __syncthreads();
-  for (int t = threadIdx.x; t < 32 * 32; t += 256) ctx4[t >> 5][t & 31] = ctx[t >> 5][t & 31];
-  const int eb = threadIdx.x & 7, nb = threadIdx.x >> 3;  // channels 4 eb .. 4 eb + 3, pixels 4 nb .. 4 nb + 3 of the tile
-  for (int n0 = 0; n0 < P; n0 += TN) {
+    float mx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
+    for (int n = prow; n < P; n += 64) {
+      float f[8];
+      load8(k, n, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], f[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[prow][8 * cgp + j] = mx[j];
     __syncthreads();
-    for (int n = sl; n < TN; n += 8) {
-      const bool ok = n0 + n < P;
-      const float qv = ok ? __bfloat162float(q[(size_t)(n0 + n) * ld + d]) : 0.f;
-      const float qm = warp_maxf(qv);
-      const float qe = __expf(qv - qm);
-      qsT[d][n] = qe / warp_sum(qe) * inv_sqrt_d;
+    if (tid < 32) {
+      float t = red[0][tid];
+      for (int r = 1; r < 64; ++r) t = fmaxf(t, red[r][tid]);
+      kmax[tid] = t;
     }
     __syncthreads();
+  }
+  // ---- context[d][e] = sum_n exp(k[n,d] - kmax[d]) v[n,e]: A = (exp k)^T through ldmatrix.trans, B = v through ldmatrix.trans;
+  //      warp w takes pixels [16 w, 16 w + 16) of every tile (one k16 step) and keeps a full 32 x 32 partial in registers
+  float km[8], ks[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    km[j] = kmax[8 * cgp + j];
+    ks[j] = 0.f;
+  }
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  for (int n0 = 0; n0 < P; n0 += TN) {
+    __syncthreads();
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int row = prow + 64 * hlf, n = n0 + row;
+      float fk[8], fv[8];
+      if (n < P) {
+        load8(k, n, fk);
+        load8(v, n, fv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          fk[j] = __expf(fk[j] - km[j]);
+          ks[j] += fk[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fk[j] = fv[j] = 0.f;
+      }
+      store8(at, row, fk);
+      store8(vt, row, fv);
+    }
+    __syncthreads();
+    const int r0 = 16 * warp;
+    uint32_t a[2][4], bv[2][4];
+    // A (m = d, k = pixel) from at[pixel][d]: matrices (pix 0-7, d 0-7), (pix 0-7, d 8-15), (pix 8-15, d 0-7), (pix 8-15, d 8-15)
+    const int arow = r0 + (lane & 7) + 8 * (lane >> 4), acol = 8 * ((lane >> 3) & 1);
+    ldmatrix_x4_trans(a[0], &at[arow][acol]);
+    ldmatrix_x4_trans(a[1], &at[arow][acol + 16]);
+    // B (k = pixel, n = e) from vt[pixel][e]: matrices (pix 0-7, e0), (pix 8-15, e0), (pix 0-7, e0 + 8), (pix 8-15, e0 + 8)
+    const int brow = r0 + (lane & 7) + 8 * ((lane >> 3) & 1), bcol = 8 * (lane >> 4);
+    ldmatrix_x4_trans(bv[0], &vt[brow][bcol]);
+    ldmatrix_x4_trans(bv[1], &vt[brow][bcol + 16]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[mt][nt], a[mt], bv[nt >> 1][2 * (nt & 1)], bv[nt >> 1][2 * (nt & 1) + 1]);
+  }
+  // ---- reduce the partial contexts of the 8 warps (fixed order: the result must not depend on scheduling) and the
+  //      softmax denominators
+  __syncthreads();  // the tiles are dead: their storage holds the partials now
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[prow][8 * cgp + j] = ks[j];
+  {
+    const int g = lane >> 2, tg = lane & 3;
+    for (int round = 0; round < 2; ++round) {
+      if ((warp >> 2) == round) {
+        float (*dstp)[33] = pb[warp & 3];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float* r0p = &dstp[16 * mt + g][8 * nt + 2 * tg];
+            float* r1p = &dstp[16 * mt + g + 8][8 * nt + 2 * tg];
+            if (round == 0) {
+              r0p[0] = acc[mt][nt][0]; r0p[1] = acc[mt][nt][1];
+              r1p[0] = acc[mt][nt][2]; r1p[1] = acc[mt][nt][3];
+            } else {
+              r0p[0] += acc[mt][nt][0]; r0p[1] += acc[mt][nt][1];
+              r1p[0] += acc[mt][nt][2]; r1p[1] += acc[mt][nt][3];
+            }
+          }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < 32) {
+    float t = 0.f;
+    for (int r = 0; r < 64; ++r) t += red[r][tid];
+    ksum[tid] = t;
+  }
+  for (int t = tid; t < 32 * 32; t += 256) {
+    const int d = t >> 5, e = t & 31;
+    ctx[d][e] = (pb[0][d][e] + pb[1][d][e]) + (pb[2][d][e] + pb[3][d][e]);
+  }
+  __syncthreads();
+  for (int t = tid; t < 32 * 32; t += 256) {
+    const int d = t >> 5, e = t & 31;
+    cb[d][e] = __float2bfloat16_rn(ctx[d][e] / (ksum[d] * (float)P));  // softmax denominator and v / (H W)
+  }
+  __syncthreads();
+  // ---- out[n][e] = sum_d softmax_d(q[n,:])[d] / sqrt(32) ctx[d][e]: A = q tile (row major), B = context through ldmatrix.trans
+  const float inv_sqrt_d = 0.17677669529663687f;
+  uint32_t bc[2][2][4];  // [k step (d 0-15 / 16-31)][e half][matrices (d lo, e0), (d hi, e0), (d lo, e0 + 8), (d hi, e0 + 8)]
+  {
+    const int brow = (lane & 7) + 8 * ((lane >> 3) & 1), bcol = 8 * (lane >> 4);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      ldmatrix_x4_trans(bc[kk][0], &cb[16 * kk + brow][bcol]);
+      ldmatrix_x4_trans(bc[kk][1], &cb[16 * kk + brow][bcol + 16]);
+    }
+  }
+  for (int n0 = 0; n0 < P; n0 += TN) {
+    __syncthreads();
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int row = prow + 64 * hlf, n = n0 + row;
+      float f[8];
+      if (n < P) {
+        load8(q, n, f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      float m = f[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) m = fmaxf(m, f[j]);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));  // the 4 threads of a pixel are adjacent lanes
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] = __expf(f[j] - m);
+        sum += f[j];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float sc = inv_sqrt_d / sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= sc;
+      store8(at, row, f);
+    }
+    __syncthreads();
+    const int r0 = 16 * warp;
+    uint32_t a[2][4];
+    // A (m = pixel, k = d), row major: matrices (pix 0-7, d 0-7), (pix 8-15, d 0-7), (pix 0-7, d 8-15), (pix 8-15, d 8-15)
+    const int arow = r0 + (lane & 7) + 8 * ((lane >> 3) & 1), acol = 8 * (lane >> 4);
+    ldmatrix_x4(a[0], &at[arow][acol]);
+    ldmatrix_x4(a[1], &at[arow][acol + 16]);
     float o[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-#pragma unroll 8
-    for (int dd = 0; dd < 32; ++dd) {
-      const float4 q4 = *reinterpret_cast<const float4*>(&qsT[dd][4 * nb]);
-      const float4 c4 = *reinterpret_cast<const float4*>(&ctx4[dd][4 * eb]);
-      const float qa[4] = {q4.x, q4.y, q4.z, q4.w}, ca[4] = {c4.x, c4.y, c4.z, c4.w};
+      for (int c = 0; c < 4; ++c) o[nt][c] = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(qa[i], ca[j], o[i][j]);
+      for (int kk = 0; kk < 2; ++kk) mma_bf16_16816(o[nt], a[kk], bc[kk][nt >> 1][2 * (nt & 1)], bc[kk][nt >> 1][2 * (nt & 1) + 1]);
     }
+    const int g = lane >> 2, tg = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = n0 + 4 * nb + i;
+    for (int hh = 0; hh < 2; ++hh) {
+      const int n = n0 + r0 + g + 8 * hh;
       if (n < P) {
-        __align__(8) __nv_bfloat162 w2[2] = {__floats2bfloat162_rn(o[i][0], o[i][1]), __floats2bfloat162_rn(o[i][2], o[i][3])};
-        *reinterpret_cast<uint2*>(out + ((size_t)b * P + n) * HD + hd * 32 + 4 * eb) = *reinterpret_cast<const uint2*>(w2);
+        __nv_bfloat16* dst = out + ((size_t)b * P + n) * HD + hd * 32 + 2 * tg;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<__nv_bfloat162*>(dst + 8 * nt) = __floats2bfloat162_rn(o[nt][2 * hh], o[nt][2 * hh + 1]);
       }
     }
   }

@@ -222,6 +222,110 @@ __global__ void __launch_bounds__(64) em_affine_path_tpc_kernel(
   }
 }
 
+// The same integrator with a chain split over T = 2 or 4 adjacent lanes (lane t owns coordinates [t DO, (t + 1) DO),
+// DO = D / T <= 8): T times as many warps for the same number of chains -- what the serial sub-step chain needs to
+// hide its latencies when there are only tens of thousands of chains.  The matvec exchanges the state by warp shuffles.
+template <int T>
+__global__ void __launch_bounds__(128) em_affine_path_split_kernel(
+    const uint32_t* __restrict__ keys, const float* __restrict__ x0, int x0_batched, const float* __restrict__ AT,
+    const float* __restrict__ a, const float* __restrict__ ddt, const float* __restrict__ disp, int64_t B, int K, int m,
+    int D, int du, int rev, float* __restrict__ out_u, float* __restrict__ out_v) {
+  constexpr int DOT = 8;
+  extern __shared__ __align__(16) float sm[];
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+  const int cpc = nt / T, cl = tid / T, t = tid % T, lbase = lane & ~(T - 1);
+  const int DO = D / T;
+  const uint32_t n = (uint32_t)m * D, h = (n + 1u) >> 1;
+  const int per_k = m * D * D, per_ka = m * D, per_buf = (per_k + per_ka + 3) & ~3;
+  float* mat = sm;                   // [2][per_buf]
+  float* stash = sm + 2 * per_buf;   // [h][cpc + 1]
+  const int sst = cpc + 1;
+  const int64_t b = blockIdx.x * (int64_t)cpc + cl;
+  const bool active = b < B;
+  const int64_t bb = active ? b : B - 1;
+  const Key key{keys[2 * bb], keys[2 * bb + 1]};
+  float x[DOT];
+#pragma unroll
+  for (int r = 0; r < DOT; ++r) {
+    x[r] = r < DO ? x0[(x0_batched ? bb * D : 0) + t * DO + r] : 0.f;
+    if (active && r < DO) store_path(x[r], b, 0, t * DO + r, K, D, du, rev, out_u, out_v);
+  }
+  auto stage = [&](int k, int buf) {
+    float* dst = mat + buf * per_buf;
+    const float* srcA = AT + (size_t)k * per_k;
+    const float* srca = a + (size_t)k * per_ka;
+    for (int i = tid; i < per_k + per_ka; i += nt) {
+      const float* src = i < per_k ? srcA + i : srca + (i - per_k);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(src)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, 0);
+  for (int k = 0; k < K; ++k) {
+    if (k + 1 < K) {
+      stage(k + 1, (k + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* buf = mat + (k & 1) * per_buf;
+    const Key key_k = split_key(key, (uint32_t)K, (uint32_t)k);  // simulators.py:81
+    const float hh = ddt[k];
+    const float sq = sqrtf(hh);
+    for (int q = 0; q < m; ++q) {
+      const float* Aq = buf + q * D * D + t * DO;
+      const float* aq = buf + per_k + q * D + t * DO;
+      const float g = disp[k * m + q];
+      float acc[DOT];
+#pragma unroll
+      for (int r = 0; r < DOT; ++r) acc[r] = 0.f;
+#pragma unroll
+      for (int tt = 0; tt < T; ++tt) {
+#pragma unroll
+        for (int r = 0; r < DOT; ++r) {
+          const float xj = __shfl_sync(0xffffffffu, x[r], lbase + tt);  // coordinate j = tt DO + r of this chain
+          if (r < DO) {
+            const float* row = Aq + (tt * DO + r) * D;
+#pragma unroll
+            for (int ro = 0; ro < DOT; ++ro)
+              if (ro < DO) acc[ro] = fmaf(row[ro], xj, acc[ro]);
+          }
+        }
+      }
+      // normals: element e = q D + i comes from threefry block e (first output) or block e - h (second output, stashed)
+      float eps[DOT];
+      const uint32_t e0 = (uint32_t)q * D + t * DO;
+#pragma unroll
+      for (int r = 0; r < DOT; ++r) {
+        eps[r] = 0.f;
+        if (r < DO && e0 + r < h) {
+          uint32_t y0, y1;
+          random_bits_block(key_k, n, e0 + r, y0, y1);
+          eps[r] = bits_to_normal(y0);
+          if (e0 + r + h < n) stash[(size_t)(e0 + r) * sst + cl] = bits_to_normal(y1);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < DOT; ++r) {
+        if (r < DO) {
+          if (e0 + r >= h) eps[r] = stash[(size_t)(e0 + r - h) * sst + cl];
+          const float drift = acc[r] + aq[r];
+          x[r] = x[r] + drift * hh + g * sq * eps[r];  // simulators.py:87
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < DOT; ++r)
+        if (r < DO) store_path(x[r], b, k + 1, t * DO + r, K, D, du, rev, out_u, out_v);
+    }
+    __syncthreads();
+  }
+}
+
 // force_move + x0 selection.  One warp per chain.
 __global__ void force_move_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ log_ws, int is_log,
                                   const float* __restrict__ us_last, const int32_t* __restrict__ kk, int64_t B, int N,
@@ -427,8 +531,31 @@ int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0
     const int nt = 32;
     const size_t per_buf = ((size_t)(m * D * D + m * D) + 3) & ~(size_t)3;
     const size_t smem_tpc = (2 * per_buf + (size_t)((m * D + 1) / 2 + D) * nt) * sizeof(float);
-    const char* impl = getenv("FBS_EM_IMPL");  // "cta" pins the CTA-per-chain kernel (tests compare the two)
-    if (D <= 32 && B >= 1024 && smem_tpc <= 100 * 1024 && !(impl != nullptr && impl[0] == 'c')) {
+    const char* impl = getenv("FBS_EM_IMPL");  // "cta" / "tpc" pin the CTA-per-chain / thread-per-chain kernels (tests)
+    const bool pinned_cta = impl != nullptr && impl[0] == 'c';
+    const bool pinned_tpc = impl != nullptr && impl[0] == 't';
+    const int T = (D % 4 == 0 && D <= 32) ? 4 : ((D % 2 == 0 && D <= 16) ? 2 : 0);
+    if (T != 0 && B >= 1024 && !pinned_cta && !pinned_tpc) {
+      // a chain over T lanes: 32 chains (T = 4) or 64 chains (T = 2) per 128-thread CTA
+      const int cpc = 128 / T;
+      const size_t smem_sp = (2 * per_buf + (size_t)((m * D + 1) / 2) * (cpc + 1)) * sizeof(float);
+      if (smem_sp <= 100 * 1024) {
+        const int grid_sp = (int)((B + cpc - 1) / cpc);
+        if (T == 4) {
+          if (smem_sp > 48 * 1024)
+            cudaFuncSetAttribute(em_affine_path_split_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
+          em_affine_path_split_kernel<4><<<grid_sp, 128, smem_sp, as_stream(s)>>>(keys, x0, x0_batched, AT, a, ddt, disp, B, (int)K,
+                                                                                (int)m, (int)D, (int)du, rev, out_u, out_v);
+        } else {
+          if (smem_sp > 48 * 1024)
+            cudaFuncSetAttribute(em_affine_path_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
+          em_affine_path_split_kernel<2><<<grid_sp, 128, smem_sp, as_stream(s)>>>(keys, x0, x0_batched, AT, a, ddt, disp, B, (int)K,
+                                                                                (int)m, (int)D, (int)du, rev, out_u, out_v);
+        }
+        return check_launch("em_affine_path_split_kernel");
+      }
+    }
+    if (D <= 32 && B >= 1024 && smem_tpc <= 100 * 1024 && !pinned_cta) {
       const int grid_tpc = (int)((B + nt - 1) / nt);
 #define FBS_EM_TPC(DT)                                                                                               \
   do {                                                                                                               \

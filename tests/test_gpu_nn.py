@@ -102,7 +102,7 @@ def test_norms_and_attention_match_oracle_pieces():
     ops.layernorm(x.cuda(), gamma.cuda(), residual=res.cuda(), out_f32=out)
     np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2e-5)
     # attention cores on a given qkv
-    for P_, linear in ((196, True), (49, False), (300, False)):
+    for P_, linear in ((196, True), (784, True), (100, True), (49, False), (300, False)):
         qkv = _bf(torch.randn(B, P_, 1, 384, generator=g)).float()
         q, k, v = ou._split_heads(qkv, 4)
         if linear:

@@ -95,10 +95,10 @@ def test_euler_maruyama_affine_matches_oracle(m):
         sdes.euler_maruyama(keys, x0, ts, lambda x, t: x, dispersion)
 
 
-@pytest.mark.parametrize('D,m', [(20, 10), (8, 10), (6, 1), (5, 3), (32, 2), (2, 1)])
+@pytest.mark.parametrize('D,m', [(20, 10), (8, 10), (6, 1), (5, 3), (32, 2), (2, 1), (12, 3), (14, 2)])
 def test_euler_maruyama_thread_per_chain_kernel(D, m, monkeypatch):
-    """>= 1024 chains of a small system run one thread per chain (registers + shared-memory noise stash): same paths as the
-    CTA-per-chain kernel on every chain, and the oracle's on a few."""
+    """>= 1024 chains of a small system run one thread per chain, or one chain over 2 / 4 lanes when D allows (registers +
+    shared-memory noise stash): same paths as the CTA-per-chain kernel on every chain, and the oracle's on a few."""
     from fbs_b200 import sdes
     rng = np.random.default_rng(D * 10 + m)
     K = 7
@@ -110,10 +110,13 @@ def test_euler_maruyama_thread_per_chain_kernel(D, m, monkeypatch):
     B = 1100
     keys = jr.split(jr.PRNGKey(D + m), B)
     x0 = rng.normal(size=(B, D)).astype(np.float32)
-    got = sdes.euler_maruyama(keys, x0, ts, drift, dispersion, integration_nsteps=m, return_path=True)
+    got = sdes.euler_maruyama(keys, x0, ts, drift, dispersion, integration_nsteps=m, return_path=True)   # lane-split if D allows
+    monkeypatch.setenv('FBS_EM_IMPL', 'tpc')
+    got_tpc = sdes.euler_maruyama(keys, x0, ts, drift, dispersion, integration_nsteps=m, return_path=True)
     monkeypatch.setenv('FBS_EM_IMPL', 'cta')
     ref = sdes.euler_maruyama(keys, x0, ts, drift, dispersion, integration_nsteps=m, return_path=True)
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got_tpc, ref, rtol=1e-5, atol=1e-6)
     for b in (0, 517, B - 1):
         want = osdes.euler_maruyama(keys[b], x0[b], ts,
                                     lambda x, t: (x @ (A0 * (1. + t)).T + a0 * np.cos(t)).astype(np.float32),
