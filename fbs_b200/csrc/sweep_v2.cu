@@ -19,6 +19,24 @@
 
 namespace fbs {
 
+// Four threefry blocks -> 8 scaled normals: elements b .. b + 3 and b + hblk .. b + hblk + 3 of normal(key, (2 hblk,)).
+struct V2Noise8 {
+  float lo[4], hi[4];
+};
+static __device__ __noinline__ V2Noise8 v2_noise_task(uint32_t k0, uint32_t k1, uint32_t b, uint32_t hblk, float scale) {
+  uint32_t x0[4] = {b, b + 1u, b + 2u, b + 3u};
+  uint32_t x1[4] = {b + hblk, b + hblk + 1u, b + hblk + 2u, b + hblk + 3u};
+  threefry2x32_x4(k0, k1, x0, x1);
+  V2Noise8 r;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    r.lo[c] = scale * bits_to_normal(x0[c]);
+    r.hi[c] = scale * bits_to_normal(x1[c]);
+  }
+  return r;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA bulk copy (global -> shared)
 // ------------------------------------------------------------------------------------------------
@@ -386,17 +404,18 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_v2_kernel(const SweepParams p) 
 
     // transition noise of the tile in registers: element (n, i), n < half shares its threefry block with (n + half, i)
     float nz[4][8];
+    // (four threefry blocks in lockstep per call of a NON-inlined task: inlined 16 times the noise alone is ~40 KB of
+    //  straight-line code and the step loop stalls on instruction fetch; out-of-range elements of the tile draw from
+    //  counters nobody reads)
     auto make_noise = [&](Key ktr, float scale) {
+      const uint32_t hblk = (uint32_t)half * (uint32_t)du;  // nel / 2: element e shares its block with e + hblk
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        const int n = n0 + s;
+        const V2Noise8 r8 = v2_noise_task(ktr.k0, ktr.k1, (uint32_t)(n0 + s) * du + 4u * ti, hblk, scale);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int i = 4 * ti + q;
-          uint32_t y0 = 0u, y1 = 0u;
-          if (n < half && i < du) random_bits_block(ktr, nel, (uint32_t)n * du + i, y0, y1);
-          nz[q][s] = scale * bits_to_normal(y0);
-          nz[q][4 + s] = scale * bits_to_normal(y1);
+          nz[q][s] = r8.lo[q];
+          nz[q][4 + s] = r8.hi[q];
         }
       }
     };
