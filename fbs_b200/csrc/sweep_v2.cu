@@ -182,6 +182,98 @@ __global__ void __launch_bounds__(256) stepvec_kernel(const SweepParams p, int d
   }
 }
 
+// The same precompute as a register-tiled GEMM: per slot, ws[:, slot, :] = epilogue(vs[:, kp, :] (chains x dv) * Mv_k (dv x DP)).
+// A CTA keeps the slot's matrix in shared memory (columns already in the workspace's padded order) and walks over tiles of
+// 64 chains; a thread owns 8 chains x 8 outputs (two groups of 4 columns): four 16-byte shared loads per 64 FMAs.  Same summation order
+// as stepvec_kernel (j ascending, then + m), hence the same bits.
+constexpr int SV_CH = 64;
+__global__ void __launch_bounds__(256, 2) stepvec_tiled_kernel(const SweepParams p, int dup, int DP, int DP8) {
+  extern __shared__ __align__(16) float sv2[];
+  const int du = p.du, dv = p.dv, D = du + dv, K = p.K;
+  const int vst = dv | 1;                   // odd row stride of the chain-major v tile
+  float* Ws = sv2;                          // [dv][DP8]
+  float* Vt = sv2 + (size_t)dv * DP8;       // [SV_CH][vst]  v_prev of the tile's chains
+  const int tid = threadIdx.x, ng = DP8 / 8;
+  const int og = tid % ng, cg = tid / ng;   // output group (2 x 4 columns), chain group (8 chains)
+  const bool worker = cg < SV_CH / 8;
+  const int64_t ntiles = (p.B + SV_CH - 1) / SV_CH;
+  // work items (slot, chain tile), slot major, split into contiguous runs over a persistent grid: the slot's matrix is
+  // reloaded only when the slot changes
+  const int64_t items = (int64_t)(K + 1) * ntiles;
+  const int64_t per = (items + gridDim.x - 1) / gridDim.x;
+  const int64_t it0 = blockIdx.x * per, it1 = it0 + per < items ? it0 + per : items;
+  int cur_slot = -1;
+  for (int64_t it = it0; it < it1; ++it) {
+    const int slot = (int)(it / ntiles);
+    const int64_t tile = it - (int64_t)slot * ntiles;
+    const int k = slot < K ? slot : 0;
+    const int kv = slot < K ? slot + 1 : 0, kp = slot < K ? slot : 1;
+    const float dt = p.dt[k];
+    const int64_t b0 = tile * SV_CH;
+    const int nb = (int)min((int64_t)SV_CH, p.B - b0);
+    __syncthreads();
+    if (slot != cur_slot) {
+      const float* MTk = p.MT + (size_t)k * D * D + (size_t)du * D;  // rows du.. : inputs v
+      for (int j = tid / 32; j < dv; j += blockDim.x / 32)
+        for (int col = tid % 32; col < DP8; col += 32) {
+          float w = 0.f;
+          if (col < du) w = __ldg(MTk + (size_t)j * D + col);
+          else if (col >= dup && col - dup < dv) w = __ldg(MTk + (size_t)j * D + du + (col - dup));
+          Ws[(size_t)j * DP8 + col] = w;
+        }
+      cur_slot = slot;
+    }
+    for (int c = tid / 32; c < SV_CH; c += blockDim.x / 32) {
+      const float* src = p.vs + ((size_t)(b0 + (c < nb ? c : 0)) * (K + 1) + kp) * dv;
+      for (int j = tid % 32; j < dv; j += 32) Vt[c * vst + j] = c < nb ? src[j] : 0.f;
+    }
+    __syncthreads();
+    if (!worker) continue;
+    float acc[8][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[c][o] = 0.f;
+    const float* vbase = Vt + (size_t)(8 * cg) * vst;
+#pragma unroll 2
+    for (int j = 0; j < dv; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(Ws + (size_t)j * DP8 + 4 * og);          // columns [4 og, 4 og + 4)
+      const float4 wb = *reinterpret_cast<const float4*>(Ws + (size_t)j * DP8 + 4 * (og + ng));   // and [4 (og + ng), ..): 16-byte lane stride
+      const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float vv = vbase[c * vst + j];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[c][o] = fmaf(ww[o], vv, acc[c][o]);
+      }
+    }
+    // epilogue: u columns  m + acc;  v columns  (v - v_prev) - dt (m + acc);  padding columns 0
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = 8 * cg + c;
+      if (ch >= nb) continue;
+      const float* vrow_p = p.vs + ((size_t)(b0 + ch) * (K + 1) + kp) * dv;
+      const float* vrow_c = p.vs + ((size_t)(b0 + ch) * (K + 1) + kv) * dv;
+      float r[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int col = o < 4 ? 4 * og + o : 4 * (og + ng) + (o - 4);
+        float x = 0.f;
+        if (col < du) {
+          x = p.m[(size_t)k * D + col] + acc[c][o];
+        } else if (col >= dup && col - dup < dv) {
+          const int q = col - dup;
+          x = (vrow_c[q] - vrow_p[q]) - dt * (p.m[(size_t)k * D + du + q] + acc[c][o]);
+        }
+        r[o] = x;
+      }
+      float* dst = p.ws + ((size_t)(b0 + ch) * (K + 1) + slot) * DP;
+      if (4 * og + 4 <= DP) *reinterpret_cast<float4*>(dst + 4 * og) = make_float4(r[0], r[1], r[2], r[3]);
+      if (4 * (og + ng) + 4 <= DP) *reinterpret_cast<float4*>(dst + 4 * (og + ng)) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
 __device__ __forceinline__ float warp_sum_v2(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -638,6 +730,20 @@ static int launch_variant(cudaStream_t st, SweepParams& p, int grid, int threads
 int launch_stepvec(void* stream, SweepParams& p) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int dup = (p.du + 3) / 4 * 4, DP = dup + (p.dv + 3) / 4 * 4;
+  {
+    const int DP8 = (DP + 7) / 8 * 8, ng = DP8 / 8;
+    const size_t sm2 = ((size_t)p.dv * DP8 + (size_t)SV_CH * (p.dv | 1)) * sizeof(float);
+    const char* impl = getenv("FBS_STEPVEC_IMPL");  // "old" pins the thread-per-output kernel
+    if (ng * (SV_CH / 8) <= 256 && sm2 <= 110 * 1024 && p.B >= SV_CH && !(impl != nullptr && impl[0] == 'o')) {
+      cudaFuncSetAttribute(stepvec_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+      const int64_t items = (int64_t)(p.K + 1) * ((p.B + SV_CH - 1) / SV_CH);
+      const int64_t slots = 2 * (int64_t)sm_count();  // two CTAs per SM, persistent
+      int threads = ng * (SV_CH / 8);
+      threads = (threads + 31) / 32 * 32;
+      stepvec_tiled_kernel<<<(unsigned)(items < slots ? items : slots), threads, sm2, st>>>(p, dup, DP, DP8);
+      return check_launch("stepvec_tiled_kernel");
+    }
+  }
   dim3 grid((unsigned)((p.B + CV_CH - 1) / CV_CH), (unsigned)(p.K + 1));
   const size_t sm = (size_t)2 * p.dv * CV_CH * sizeof(float);
   if (sm > 48 * 1024) cudaFuncSetAttribute(stepvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
