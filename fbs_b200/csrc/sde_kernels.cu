@@ -454,6 +454,69 @@ __global__ void gaussian_ref_sample_kernel(const uint32_t* __restrict__ keys, co
 }
 
 
+// The same sampler as a register-tiled GEMM (du % 4 == 0): persistent CTAs keep L in shared memory, a chain's N x du
+// normals are drawn into shared memory (both outputs of every threefry block used) and every thread forms 4 x 4 blocks of
+// eps @ L from one 16-byte and four broadcast shared loads per 16 FMAs.  Same summation order (j ascending, then + mean).
+__global__ void __launch_bounds__(256, 2) gaussian_ref_sample_tiled_kernel(
+    const uint32_t* __restrict__ keys, const float* __restrict__ yT, const float* __restrict__ a,
+    const float* __restrict__ Bm, const float* __restrict__ c, const float* __restrict__ Lm, int64_t B, int N, int du, int dv,
+    float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* Ls = smem;                              // [du][du]
+  float* eps = Ls + (size_t)du * du;             // [N4][du], rows >= N zero
+  float* mean = eps + (size_t)((N + 3) / 4 * 4) * du;  // [du]
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int n4 = (N + 3) / 4, i4 = du / 4;
+  for (int t = tid; t < du * du; t += NT) Ls[t] = __ldg(Lm + t);
+  for (int t = N * du + tid; t < n4 * 4 * du; t += NT) eps[t] = 0.f;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const Key key{keys[2 * b], keys[2 * b + 1]};
+    __syncthreads();
+    for (int i = tid; i < du; i += NT) {
+      float acc = 0.f;
+      for (int j = 0; j < dv; ++j) acc = fmaf(Bm[(size_t)i * dv + j], yT[b * dv + j] - c[j], acc);
+      mean[i] = a[i] + acc;
+    }
+    const uint32_t nel = (uint32_t)N * du, h = (nel + 1u) >> 1;
+    for (uint32_t blk = tid; blk < h; blk += NT) {
+      uint32_t y0, y1;
+      random_bits_block(key, nel, blk, y0, y1);
+      eps[blk] = bits_to_normal(y0);
+      if (blk + h < nel) eps[blk + h] = bits_to_normal(y1);
+    }
+    __syncthreads();
+    for (int t = tid; t < n4 * i4; t += NT) {
+      const int nb = t / i4, ib = t - nb * i4;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
+      const float* e0 = eps + (size_t)(4 * nb) * du;
+#pragma unroll 4
+      for (int j = 0; j < du; ++j) {
+        const float4 l4 = *reinterpret_cast<const float4*>(Ls + (size_t)j * du + 4 * ib);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float e = e0[r * du + j];
+          acc[r][0] = fmaf(e, l4.x, acc[r][0]);
+          acc[r][1] = fmaf(e, l4.y, acc[r][1]);
+          acc[r][2] = fmaf(e, l4.z, acc[r][2]);
+          acc[r][3] = fmaf(e, l4.w, acc[r][3]);
+        }
+      }
+      const float4 m4 = *reinterpret_cast<const float4*>(mean + 4 * ib);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = 4 * nb + r;
+        if (n < N)
+          *reinterpret_cast<float4*>(out + (b * N + n) * du + 4 * ib) =
+              make_float4(m4.x + acc[r][0], m4.y + acc[r][1], m4.z + acc[r][2], m4.w + acc[r][3]);
+      }
+    }
+  }
+}
+
 // backward_scanning_pass (csmc.py:230-270): B_T ~ Cat(normalise(log_w_T)), then B_{t-1} = A_t[B_t].
 // One warp per chain.
 __global__ void backward_scan_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ As,
@@ -647,6 +710,16 @@ int fbs_gaussian_ref_sample_f32(fbs_stream_t s, const uint32_t* keys, const floa
   FBS_REQUIRE(keys && yT && a && Bm && c && L && out, "gaussian_ref_sample: null pointer");
   FBS_REQUIRE(B >= 0 && N >= 1 && du >= 1 && dv >= 1, "gaussian_ref_sample: bad sizes");
   if (B == 0) return FBS_OK;
+  {
+    const size_t smem_t = ((size_t)du * du + (size_t)((N + 3) / 4 * 4) * du + (size_t)du) * sizeof(float);
+    if (du % 4 == 0 && smem_t <= 110 * 1024 && B >= 64) {
+      cudaFuncSetAttribute(gaussian_ref_sample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+      const int64_t slots = 2 * (int64_t)sm_count();
+      gaussian_ref_sample_tiled_kernel<<<(int)(B < slots ? B : slots), 256, smem_t, as_stream(s)>>>(
+          keys, yT, a, Bm, c, L, B, (int)N, (int)du, (int)dv, out);
+      return check_launch("gaussian_ref_sample_tiled_kernel");
+    }
+  }
   const size_t smem = ((size_t)du + (size_t)N * du) * sizeof(float);
   if (smem > 220 * 1024) {
     set_error("gaussian_ref_sample: N*du=%lld too large for shared memory", (long long)(N * du));

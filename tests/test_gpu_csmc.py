@@ -532,3 +532,19 @@ def test_step_tensor_core_vs_cuda_core(d, N, B, monkeypatch):
     np.testing.assert_array_equal(got[0], want[0])
     np.testing.assert_allclose(got[1], want[1], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(got[2], want[2], atol=2e-4)
+
+
+@pytest.mark.parametrize('d,N,B', [(12, 10, 80), (100, 100, 70), (8, 7, 300), (10, 16, 90)])
+def test_ref_sampler_tiled_and_plain_match_oracle(d, N, B):
+    """ref_sampler (gp_gibbs.py:138-141; fbs_gaussian_ref_sample_f32): the register-tiled kernel (du % 4 == 0, >= 64 chains)
+    and the plain one (d = 10) against the oracle: noise bit-pinned, Cholesky product within float32 rounding."""
+    p = gp_problem(d, K=4)
+    om32 = oracle_model(p, np.float32)
+    pm, _ = product_model(p)
+    rng = np.random.default_rng(d + N)
+    keys = jr.split(jr.PRNGKey(d * 7 + N), B)
+    yT = rng.standard_normal((B, d)).astype(np.float32)
+    got = pm.ref_sampler(keys, yT, N)
+    assert got.shape == (B, N, d)
+    for b in (0, 1, B // 2, B - 1):
+        np.testing.assert_allclose(got[b], om32.ref_sampler(keys[b], yT[b], N), rtol=2e-5, atol=2e-5)
