@@ -221,6 +221,20 @@ def secondary_mnist(nparticles=101, steps=12):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # several conditioning targets at once (inpainting.py:205-210 loops over them; here C chains share every score evaluation)
+    chains = 8
+    us_c = rng.standard_normal((chains, steps + 1, rect.size, 1)).astype(np.float32)
+    vs_c = rng.uniform(size=(chains, steps + 1, obs.size, 1)).astype(np.float32)
+    bs_c = np.zeros((chains, steps + 1), np.int32)
+    keys_c = fr.split(fr.PRNGKey(4), chains)
+    args_c = (keys_c, us_c, bs_c, vs_c, model, init, R.killing.scheme, nparticles)
+    csmc.forward_pass_nn_chains(*args_c)
+    torch.cuda.synchronize()
+    e0.record()
+    csmc.forward_pass_nn_chains(*args_c)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_c = e0.elapsed_time(e1)
     # the network alone (graph replays back to back)
     x = torch.randn(nparticles, *shape, device='cuda')
     model.unet(x, 0.5)
@@ -241,6 +255,10 @@ def secondary_mnist(nparticles=101, steps=12):
                         'score GEMMs on tcgen05 (bf16 operands, fp32 accumulate)',
             'value': nparticles * steps / (ms * 1e-3), 'unit': 'particle-steps/s', 'steps': steps, 'ms_per_csmc_step': ms / steps,
             'dtype': 'bf16', 'score_net_ms_per_eval': net_ms,
+            'batched_targets': {'chains': chains, 'value': chains * nparticles * steps / (ms_c * 1e-3), 'unit': 'particle-steps/s',
+                                'ms_per_csmc_step': ms_c / steps,
+                                'how': 'forward_pass_nn_chains: 8 conditioning targets x 101 particles through one score '
+                                       'evaluation per step (bit-identical per chain to the single-target sweep)'},
             'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + fused norm / attention kernels (one score evaluation)',
                          'achieved': flops / (net_ms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': flops / (net_ms * 1e-3) / 1e12 / peak, 'traffic': None,

@@ -377,6 +377,30 @@ class ScoreNetModel:
                     us_new=us_new, lw=lw, row_offset=row_offset, rows_total=rows_total)
         return us_new, lw
 
+    def step_chains(self, us_prev, v_prev, v_next, t_prev, keys):
+        """:meth:`step` for C independent chains (conditioning targets) at once: ``us_prev [C, N, p, c]``, ``v_prev`` /
+        ``v_next [C, q, c]``, ``keys [C, 2]`` -> ``(us_new [C, N, p, c], log_w [C, N])``.  The C x N images go through ONE
+        score evaluation (the network is launch / latency bound at N = 101: batching targets is what fills the GPU); image
+        assembly, noise and weights stay per chain, so every chain gets exactly the numbers of its own :meth:`step`."""
+        us_prev = dev(us_prev, F32)
+        C_, N = us_prev.shape[0], us_prev.shape[1]
+        us_prev = us_prev.reshape(C_, N, self.p, self.c)
+        v_prev = dev(v_prev, F32).reshape(C_, self.q, self.c)
+        v_next = dev(v_next, F32).reshape(C_, self.q, self.c)
+        keys = dev(keys, torch.uint32).reshape(C_, 2).contiguous()
+        B = C_ * N
+        img = self.unet._buf(B, 'closure_img', (B, self.unet.H, self.unet.W, self.c), F32)
+        for ci in range(C_):
+            ops.assemble_image(us_prev[ci], v_prev[ci], self.unobs, self.obs, img[ci * N:(ci + 1) * N])
+        s, a, g2, sd = self._coef(t_prev)
+        score = self.unet(img, s)
+        us_new = torch.empty_like(us_prev)
+        lw = torch.empty((C_, N), dtype=F32, device=us_prev.device)
+        for ci in range(C_):
+            ops.em_step(img[ci * N:(ci + 1) * N], score[ci * N:(ci + 1) * N], self.unobs, self.obs, N, self.p, self.q, self.c,
+                        a, g2, self.dt, sd, v_next=v_next[ci], key=keys[ci], us_new=us_new[ci], lw=lw[ci])
+        return us_new, lw
+
     def mean_and_logw(self, us_prev, v_prev, v_next, t_prev):
         """(transition mean [N, p, c], log-weight [N], sd) from ONE score evaluation: what pmcmc_filter_step needs, since the
         transition of the RESAMPLED particles is the gathered mean plus fresh noise (smc.py:144-150)."""

@@ -120,6 +120,53 @@ def forward_pass_nn(key, us_star, bs_star, vs, model, init, scheme, nsamples, hi
                 log_ws_last=log_w.unsqueeze(0).contiguous(), us_last=us.reshape(1, N, p * c).contiguous())
 
 
+def forward_pass_nn_chains(keys, us_star, bs_star, vs, model, init, scheme, nsamples):
+    """:func:`forward_pass_nn` for C independent chains / conditioning targets in one go (``keys [C, 2]``,
+    ``us_star [C, K + 1, p, c]``, ``vs [C, K + 1, q, c]``, ``bs_star [C, K + 1]``): per step ONE batched conditional-resampling
+    launch, ONE ancestor gather and ONE score-network evaluation over the C x N particles.  Chain c's result equals
+    ``forward_pass_nn(keys[c], us_star[c], bs_star[c], vs[c], ...)`` bit for bit.  Returns the last step (no history)."""
+    k = dev(keys, torch.uint32).reshape(-1, 2)
+    C = k.shape[0]
+    K, p, q, c = model.K, model.p, model.q, model.c
+    us_star = dev(us_star, torch.float32).reshape(C, K + 1, p, c)
+    v = dev(vs, torch.float32).reshape(C, K + 1, q, c)
+    bs = dev(bs_star, torch.int32).reshape(C, K + 1).contiguous()
+    ks = frandom.split(k, 2)                                                       # [C, 2, 2]   csmc.py:150
+    key_scan = ks[:, 1].contiguous()
+    sk = frandom.split(frandom.split(key_scan, K).reshape(C * K, 2), 2).reshape(C, K, 2, 2)   # csmc.py:157,136
+    ts = model.ts
+    if isinstance(init, NormalInit):
+        N = int(nsamples) + 1
+        us = torch.stack([frandom.normal(ks[ci, 0].contiguous(), (N, p, c)) for ci in range(C)]).contiguous()
+        for ci in range(C):
+            us[ci].index_copy_(0, bs[ci, 0:1].long(), us_star[ci, 0:1])
+        lw = torch.stack([model.likelihood_logpdf(v[ci, 0], us[ci], v[ci, 1], ts[0]) for ci in range(C)])
+    elif isinstance(init, DegenerateInit):
+        N = init.nparticles
+        us = us_star[:, 0:1].expand(C, N, p, c).contiguous()
+        lw = torch.full((C, N), init.init_log_w, dtype=torch.float32, device=us.device)
+    else:
+        raise TypeError('init_sampler / init_likelihood_logpdf must come from DegenerateInit or NormalInit')
+    log_w = lw - torch.logsumexp(lw, dim=1, keepdim=True)
+    A = empty((C, N), torch.int32)
+    us_prev = torch.empty_like(us)
+    base = (torch.arange(C, device=us.device, dtype=torch.int32) * N).reshape(C, 1)
+    rows = torch.arange(C, device=us.device)
+    for kk in range(K):
+        w = torch.exp(log_w).contiguous()
+        # (the contiguous copies must stay referenced until the launch: a temporary freed right after ptr() hands its block
+        #  to the next temporary, and the kernel would read the last copy three times)
+        k_res, b_prev, b_cur = sk[:, kk, 0].contiguous(), bs[:, kk].contiguous(), bs[:, kk + 1].contiguous()
+        nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(k_res), ptr(w), ptr(b_prev), ptr(b_cur), 1, C, N,
+                 ptr(A))                                                           # csmc.py:139, all chains
+        a_glob = (A + base).reshape(C * N).contiguous()
+        nnops.gather_rows(us.reshape(C * N, p * c), a_glob, us_prev.reshape(C * N, p * c))
+        us, lw = model.step_chains(us_prev, v[:, kk], v[:, kk + 1], ts[kk], sk[:, kk, 1])   # csmc.py:142,145
+        us[rows, bs[:, kk + 1].long()] = us_star[:, kk + 1]                        # csmc.py:143
+        log_w = lw - torch.logsumexp(lw, dim=1, keepdim=True)                      # csmc.py:146
+    return dict(N=N, log_ws_last=log_w.contiguous(), us_last=us.reshape(C, N, p * c).contiguous())
+
+
 def forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples, history=True):
     """Device-level forward pass on batched device tensors.  Returns a dict of device tensors."""
     if isinstance(model, ScoreNetModel):

@@ -84,8 +84,9 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
         r = forward_pass_device(key_csmc_fwd, us, bs, vs, model, init, killing.scheme, N, history=False)
         idx = empty((B,), torch.int32)
         x0_new = empty((B, model.du), torch.float32)
+        b_last = bs[:, -1].contiguous()                                            # kept referenced until the launch
         nat.call('fbs_force_move_f32', stream(), ptr(key_csmc_x0), ptr(r['log_ws_last']), 1, ptr(r['us_last']),
-                 ptr(bs[:, -1].contiguous()), B, r['N'], model.du, ptr(idx), None, ptr(x0_new))   # gibbs.py:152-154
+                 ptr(b_last), B, r['N'], model.du, ptr(idx), None, ptr(x0_new))   # gibbs.py:152-154
         us_star_next, _ = _fwd_reversed(model, fwd_sampler, unpack, key_csmc_bwd_us, x0_new, y0_d, kwargs)  # :155
         us_star_next = us_star_next.reshape(B, K + 1, model.du)
         bs_star_next = frandom.randint(key_csmc_bwd_bs, (K + 1,), 0, N)            # gibbs.py:156

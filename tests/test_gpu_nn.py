@@ -391,3 +391,24 @@ def test_nn_pmcmc_kernel_and_gibbs_init_run():
                                  model.transition_logpdf, model.likelihood_logpdf, N, method=method)
         assert x0.shape == (rect.size,) and us_star.shape == (K + 1, rect.size)
         assert np.isfinite(x0).all() and np.isfinite(us_star).all()
+
+
+def test_nn_forward_pass_batched_chains_equals_single_chains():
+    """forward_pass_nn_chains (C conditioning targets through ONE score evaluation per step) gives every chain exactly the
+    result of its own forward_pass_nn: the batching is a scheduling decision, not a numerical one."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    K, N, C = 3, 6, 3
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(21)
+    us_star = rng.standard_normal((C, K + 1, rect.size, 1)).astype(np.float32)
+    vs = np.cumsum(0.05 * rng.standard_normal((C, K + 1, obs.size, 1)), axis=1).astype(np.float32)
+    bs_star = np.stack([jr.randint(jr.PRNGKey(30 + ci), (K + 1,), 0, N) for ci in range(C)]).astype(np.int32)
+    keys = jr.split(jr.PRNGKey(23), C)
+    for init in (csmc.DegenerateInit(N), csmc.NormalInit(model)):
+        got = csmc.forward_pass_nn_chains(keys, us_star, bs_star, vs, model, init, R.killing.scheme, N)
+        n_part = got['N']
+        assert tuple(got['us_last'].shape) == (C, n_part, rect.size) and tuple(got['log_ws_last'].shape) == (C, n_part)
+        for ci in range(C):
+            one = csmc.forward_pass_nn(keys[ci], us_star[ci], bs_star[ci], vs[ci], model, init, R.killing.scheme, N, history=False)
+            assert torch.equal(got['us_last'][ci], one['us_last'][0]), f'chain {ci}: particles differ'
+            assert torch.equal(got['log_ws_last'][ci], one['log_ws_last'][0]), f'chain {ci}: weights differ'
