@@ -415,7 +415,7 @@ def secondary_hbm_kernels(shapes=None, steps=None):
             'below the HBM roofline; see profiles/r1_hbm_kernels.md', 'kernels': out}
 
 
-def secondary_sharded(world, rank, per_rank=16, steps=4):
+def secondary_sharded(world, rank, per_rank=128, steps=4):
     """configs[4]: CelebA-HQ-shaped (64x64x3, inpaint-32) random-init score U-Net, ONE chain whose particle set is sharded over
     the ranks (fbs_b200/sharded.py): all-gather of the weights + NCCL exchange of resampled particles per step."""
     import torch
