@@ -474,7 +474,8 @@ def test_empty_batch_is_a_no_op():
 
 
 @pytest.mark.parametrize('d,N,B', [(10, 64, 5), (10, 1000, 3), (6, 16, 4), (2, 2, 2), (20, 32, 3), (10, 33, 2),
-                                   (100, 256, 3), (100, 100, 2), (32, 130, 2), (40, 64, 3), (100, 1026, 2)])
+                                   (100, 256, 3), (100, 100, 2), (32, 130, 2), (40, 64, 3), (100, 1026, 2), (32, 2, 1), (128, 66, 2),
+                                   (36, 4, 150)])
 @pytest.mark.parametrize('scheme', ['killing', 'multinomial'])
 def test_per_timestep_step_kernels(d, N, B, scheme):
     """fbs_csmc_step_affine_f32 (the per-timestep kernels for particle sets in global memory; register-resident
