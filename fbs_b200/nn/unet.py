@@ -488,7 +488,15 @@ class ScoreNetModel:
         return frandom.normal(dev(key, torch.uint32).reshape(2), (int(n), self.p, self.c))
 
     def fwd_sampler_reversed(self, key, x0, y0):
-        """(us, vs) = (path_x[::-1], path_y[::-1]) of one forward-noising draw (gibbs.py:127-130), flattened per step."""
+        """(us, vs) = (path_x[::-1], path_y[::-1]) of one forward-noising draw (gibbs.py:127-130), flattened per step.
+        With keys ``[C, 2]`` (several conditioning targets): ``x0 [C, p c]``, ``y0 [C, q c]`` or shared -> ``[C, K + 1, .]``."""
+        k = dev(key, torch.uint32).reshape(-1, 2)
+        if k.shape[0] > 1:
+            C_ = k.shape[0]
+            x0c = dev(x0, F32).reshape(C_, self.p * self.c)
+            y0c = dev(y0, F32).reshape(-1, self.q * self.c)
+            parts = [self.fwd_sampler_reversed(k[ci], x0c[ci], y0c[ci if y0c.shape[0] > 1 else 0]) for ci in range(C_)]
+            return torch.cat([a for a, _ in parts]).contiguous(), torch.cat([b for _, b in parts]).contiguous()
         path = self.fwd_sampler(key, dev(x0, F32).reshape(self.p, self.c), dev(y0, F32).reshape(self.q, self.c))
         px, py = self.unpack(path)
         return (torch.flip(px, dims=[0]).reshape(1, self.K + 1, self.du).contiguous(),

@@ -170,6 +170,10 @@ def forward_pass_nn_chains(keys, us_star, bs_star, vs, model, init, scheme, nsam
 def forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples, history=True):
     """Device-level forward pass on batched device tensors.  Returns a dict of device tensors."""
     if isinstance(model, ScoreNetModel):
+        if dev(key, torch.uint32).numel() > 2:                                     # several conditioning targets
+            if history:
+                raise NotImplementedError('the batched score-network sweep keeps no history (use explicit_backward=True)')
+            return forward_pass_nn_chains(key, us_star, bs_star, vs, model, init, scheme, nsamples)
         return forward_pass_nn(key, us_star, bs_star, vs, model, init, scheme, nsamples, history)
     k = dev(key, torch.uint32).reshape(-1, 2)
     B = k.shape[0]

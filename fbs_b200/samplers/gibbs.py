@@ -56,7 +56,8 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
     (gibbs.py:68-168): ``(x0, us_star, bs_star, bs_star_next != bs_star)``.
 
     ``us_star`` is ignored, as upstream (gibbs.py:91-92).  With keys ``[B, 2]``: ``x0 [B, du]``,
-    ``bs_star [B, K+1]``, ``y0 [dv]`` shared.
+    ``bs_star [B, K+1]``, ``y0 [dv]`` shared or ``[B, dv]`` (one conditioning target per chain; with a score-network model the
+    B chains share every score evaluation -- the reference loops over test images, inpainting.py:205-210).
     """
     if marg_y:
         raise NotImplementedError('marg_y=True (Doob bridge for y) is not part of the accelerated path')
@@ -66,8 +67,8 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
     single = k.dim() == 1
     k = k.reshape(-1, 2)
     B, K, N = k.shape[0], model.K, int(nparticles)
-    if isinstance(model, ScoreNetModel) and B != 1:
-        raise NotImplementedError('image chains run one at a time (the reference loops over test images, inpainting.py:205-210)')
+    if isinstance(model, ScoreNetModel) and B != 1 and not explicit_backward:
+        raise NotImplementedError('several image chains at once need explicit_backward=True (the batched sweep keeps no history)')
     x0_d = dev(x0, torch.float32).reshape(B, model.du)
     y0_d = dev(y0, torch.float32).reshape(-1, model.dv)
     bs = dev(bs_star, torch.int32).reshape(B, K + 1)

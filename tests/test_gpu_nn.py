@@ -412,3 +412,27 @@ def test_nn_forward_pass_batched_chains_equals_single_chains():
             one = csmc.forward_pass_nn(keys[ci], us_star[ci], bs_star[ci], vs[ci], model, init, R.killing.scheme, N, history=False)
             assert torch.equal(got['us_last'][ci], one['us_last'][0]), f'chain {ci}: particles differ'
             assert torch.equal(got['log_ws_last'][ci], one['log_ws_last'][0]), f'chain {ci}: weights differ'
+
+
+@pytest.mark.parametrize('explicit_final', [True, False])
+def test_nn_gibbs_kernel_batched_targets_equals_single_targets(explicit_final):
+    """gibbs_kernel over the score network with keys [C, 2] and one y0 per chain: every chain gets exactly what its own
+    single-target call returns (the C chains only share the score evaluations)."""
+    from fbs_b200.samplers import gibbs_kernel
+    K, N, C = 3, 5, 3
+    params, model, sde, ts, T, rect, obs = _inpaint_problem(K, N)
+    rng = np.random.default_rng(8)
+    x0 = rng.standard_normal((C, rect.size)).astype(np.float32)
+    y0 = rng.uniform(size=(C, obs.size)).astype(np.float32)
+    bs_star = np.stack([jr.randint(jr.PRNGKey(40 + ci), (K + 1,), 0, N) for ci in range(C)]).astype(np.int32)
+    keys = jr.split(jr.PRNGKey(77), C)
+    kw = dict(explicit_backward=True, explicit_final=explicit_final)
+    args = (ts, model.fwd_sampler, sde, model.unpack, N, model.transition_sampler, model.transition_logpdf, model.likelihood_logpdf)
+    x0n, us_next, bs_next, changed = gibbs_kernel(keys, x0, y0, None, bs_star, *args, **kw)
+    assert x0n.shape == (C, rect.size) and us_next.shape == (C, K + 1, rect.size) and bs_next.shape == (C, K + 1)
+    for ci in range(C):
+        a, b, c_, d = gibbs_kernel(keys[ci], x0[ci], y0[ci], None, bs_star[ci], *args, **kw)
+        np.testing.assert_array_equal(x0n[ci], a)
+        np.testing.assert_array_equal(us_next[ci], b)
+        np.testing.assert_array_equal(bs_next[ci], c_)
+        np.testing.assert_array_equal(changed[ci], d)
