@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -64,16 +64,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        """Wall-clock mark (start / end of the timed region)."""
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken inside [t0, t1] (the timed region).  The sampler is started before the warm-up steps
+        (nvidia-smi needs a few hundred ms to come up -- longer than a short timed region); if no sample landed inside the
+        region itself, the samples of the warm-up steps (same kernels, same load) are used and the result says so."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        inside = [ln for ts_, ln in self.lines if t0 is None or (t0 <= ts_ <= t1 + 0.1)]
+        window = 'timed region'
+        if not inside:
+            inside = [ln for _, ln in self.lines]
+            window = 'warm-up + timed region (no sample landed inside the timed region itself)'
+        for ln in inside:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -85,7 +97,7 @@ class ClockSampler:
                 if val.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 def measured_peak():
@@ -510,27 +522,29 @@ def run_gpu(args):
         uT_, le_, ys_, st = pmcmc_kernel(keys, uT_, le_, ys_, y0_d, **kw)
         return (uT_, le_, ys_), st
 
+    clocks = ClockSampler(local)
+    clocks.start()                     # before the warm-up: nvidia-smi takes a few hundred ms to deliver its first sample
     state = (uT, log_ell, ys)
     for i in range(args.warmup):
         state, st = one_step(i, state)
     barrier()
 
     # ---- device-resident timed region -------------------------------------------------------
-    clocks = ClockSampler(local)
-    clocks.start()
     nat.TIMED['fbs_pmcmc_filter_affine_f32'] = []
     nat.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_clk0 = clocks.mark()
     ev0.record()
     for i in range(args.steps):
         state, st = one_step(args.warmup + i, state)
     ev1.record()
     barrier()
+    t_clk1 = clocks.mark()
     launches = nat.launch_count()
     ms_total = ev0.elapsed_time(ev1)
     kern_ms = [a.elapsed_time(b) for a, b in nat.TIMED.pop('fbs_pmcmc_filter_affine_f32')]
-    clk = clocks.stop()
+    clk = clocks.stop(t_clk0, t_clk1)
     acc_rate = float(st.is_accepted.float().mean().item())
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
