@@ -440,7 +440,7 @@ def secondary_sharded(world, rank, per_rank=128, steps=4):
     model, ts, rect, obs = _score_model(shape, steps)
     rng = np.random.default_rng(0)
     us_star = rng.standard_normal((steps + 1, rect.size, 3)).astype(np.float32)
-    vs = rng.uniform(size=(steps + 1, obs.size, 3)).astype(np.float32)
+    vs = np.cumsum(0.05 * rng.standard_normal((steps + 1, obs.size, 3)), axis=0).astype(np.float32)   # a noised path: particles get killed and move
     bs = np.zeros((steps + 1,), np.int32)
     init = csmc.DegenerateInit(N)
     args = (fr.PRNGKey(5), us_star, bs, vs, model, init, R.killing, N)
@@ -459,7 +459,10 @@ def secondary_sharded(world, rank, per_rank=128, steps=4):
                         f'sharded over {world} GPUs ({per_rank} particles per GPU, weak)',
             'value': N * steps / (ms * 1e-3), 'unit': 'particle-steps/s', 'n_particles': N, 'steps': steps,
             'ms_per_csmc_step': ms / steps, 'moved_rows_per_step': float(np.mean(r['moved'])),
-            'collectives_per_step': 'all_gather(4 N bytes) + batch_isend_irecv(moved rows x 4 du bytes)', 'dtype': 'bf16'}
+            'exchange': r.get('exchange'),
+            'collectives_per_step': 'all_gather(4 N bytes) of the log-weights; parent rows read from the owners over NVLink inside '
+                                    'the gather kernel (CUDA IPC peer memory; FBS_SHARD_EXCHANGE=nccl: batch_isend_irecv)',
+            'dtype': 'bf16'}
 
 
 WORKLOAD_NAME = ('configs[1]: toy Gaussian pseudo-marginal MCMC scaled out (experiments/toy/gp_pmcmc.py; d=100, K=200, '
@@ -654,6 +657,8 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        from fbs_b200.sharded import close_peer_buffers
+        close_peer_buffers()
         dist.destroy_process_group()
 
 

@@ -77,6 +77,10 @@ SIGNATURES = {
     'fbs_nn_assemble_image_f32': ([_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p], _int),
     'fbs_nn_em_step_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _i64, _i64, _p, _p, _p], _int),
     'fbs_gather_rows_f32': ([_p, _p, _p, _i64, _i64, _p], _int),
+    'fbs_gather_rows_peer_f32': ([_p, _p, _p, _i64, _i64, _i64, _p], _int),
+    'fbs_ipc_export': ([_p, _p, _p], _int),
+    'fbs_ipc_import': ([_p, _i64, _p], _int),
+    'fbs_ipc_release': ([_p, _i64], _int),
     'fbs_nn_f32_to_bf16': ([_p, _p, _i64, _p], _int),
 }
 

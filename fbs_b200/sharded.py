@@ -11,15 +11,21 @@ Per time step (csmc.py:132-148), with N particles, rank r owning rows [r n, (r +
    *bit-identical to the unsharded sweep for any G* -- the summation-order contract of DESIGN.md needs no
    "offset of shard totals" arithmetic whose rounding would depend on G.  Cost: 4 N bytes per step (64 KB at
    N = 16384), against 4 du bytes *per moved particle* (12 KB at CelebA-64 inpainting) for step 2.
-2. **particle exchange** -- child j of rank r needs parent row A[j], which lives on rank A[j] // n.  Every rank knows
-   all of A, hence both its send and its receive lists without a handshake; the rows travel as one batch of
-   point-to-point sends/receives (NCCL over NVLink / NVSwitch; gloo in the CPU tests).  With ``killing`` resampling
-   surviving particles keep their own slot (resamplings.py:72-74), so only killed particles move.
+2. **particle exchange** -- child j of rank r needs parent row A[j], which lives on rank A[j] // n.  On GPUs the ancestor
+   gather reads it straight from the owner's memory: every rank's particle rows live in two ping-pong buffers shared with
+   the other ranks through CUDA IPC, and ``fbs_gather_rows_peer_f32`` loads each parent row over NVLink inside the gather
+   kernel (no staging, no send / receive lists).  The all-gather of step 1 doubles as the ordering point: a rank's new rows
+   are written before it joins the collective, so they are complete before any peer's next gather runs, and the buffer a
+   rank overwrites was last read before the previous collective.  ``FBS_SHARD_EXCHANGE=nccl`` selects the alternative --
+   every rank knows all of A, hence its send and receive lists without a handshake, and the rows travel as one batch of
+   point-to-point sends / receives (also what the gloo CPU tests exercise).  With ``killing`` resampling surviving
+   particles keep their own slot (resamplings.py:72-74), so only killed particles move.
 3. **transition + weight** on the local parents: one score-network evaluation per rank on its n particles, the
    transition noise being rows [r n, (r + 1) n) of the same ``normal(key, (N, p, c))`` array as unsharded.
 
 The result is the sweep of fbs_b200.samplers.csmc.csmc.forward_pass_nn, row-partitioned.
 """
+import os
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -88,6 +94,83 @@ def exchange_rows(rows_local, A, shard: ParticleShard, group=None):
     return out, moved
 
 
+class PeerRows:
+    """This rank's particle rows as two ping-pong buffers ``[2, n, row]`` that the other ranks of the box can read directly:
+    the buffers are exported with CUDA IPC, the 64-byte handles travel through ``all_gather_object``, and every rank holds a
+    device table ``[2, G]`` of pointers (its own buffer + the imports) for ``fbs_gather_rows_peer_f32``."""
+
+    def __init__(self, shard: ParticleShard, row: int, device, group=None):
+        import ctypes as C
+        from . import _native as nat
+        self.shard, self.row, self.group = shard, int(row), group
+        self.buf = torch.empty((2, shard.n, self.row), dtype=torch.float32, device=device)
+        self._imports = []
+        bases = [None] * shard.world
+        bases[shard.rank] = self.buf.data_ptr()
+        if shard.world > 1:
+            handle = (C.c_ubyte * 64)()
+            off = C.c_int64(0)
+            nat.call('fbs_ipc_export', self.buf.data_ptr(), handle, C.byref(off))
+            mine = (bytes(handle), int(off.value))
+            everyone = [None] * shard.world
+            dist.all_gather_object(everyone, mine, group=group)
+            for r, (hb, o) in enumerate(everyone):
+                if r == shard.rank:
+                    continue
+                hbuf = (C.c_ubyte * 64).from_buffer_copy(hb)
+                out = C.c_void_p()
+                nat.call('fbs_ipc_import', hbuf, o, C.byref(out))
+                self._imports.append((out.value, o))
+                bases[r] = out.value
+        slot_bytes = shard.n * self.row * 4
+        self.table = torch.tensor([[b + s * slot_bytes for b in bases] for s in range(2)], dtype=torch.int64, device=device)
+        self.cur = 0
+
+    def local(self):
+        """This rank's current rows ``[n, row]`` (a view of the shared buffer)."""
+        return self.buf[self.cur]
+
+    def gather(self, parents_global, out):
+        """``out[j] = rows_global[parents_global[j]]``: every parent row is loaded from the GPU that owns it."""
+        from . import _native as nat
+        from ._tensor import ptr, stream
+        nat.call('fbs_gather_rows_peer_f32', stream(), ptr(self.table[self.cur]), ptr(parents_global), out.shape[0], self.row,
+                 self.shard.n, ptr(out))
+
+    def publish(self, rows):
+        """Write the step's new rows into the other buffer and make it current.  The caller's next collective (the all-gather of
+        the log-weights) is the point after which the peers read it."""
+        self.cur ^= 1
+        self.buf[self.cur].copy_(rows.reshape(self.shard.n, self.row))
+
+    def close(self):
+        from . import _native as nat
+        for p_, o in self._imports:
+            nat.call('fbs_ipc_release', p_, o)
+        self._imports = []
+
+
+_PEER_CACHE = {}
+
+
+def _peer_rows(shard: ParticleShard, row: int, device, group=None) -> PeerRows:
+    """One :class:`PeerRows` per (group, partition, row size): exporting / importing the IPC handles costs milliseconds, a
+    sweep step microseconds.  Reuse across sweeps is safe: after a sweep's last all-gather no rank reads the buffers, and the
+    next sweep starts with a collective after its initial rows are written."""
+    key = (id(group), shard.N, shard.rank, shard.world, int(row), str(device))
+    pr = _PEER_CACHE.get(key)
+    if pr is None:
+        pr = _PEER_CACHE[key] = PeerRows(shard, row, device, group)
+    return pr
+
+
+def close_peer_buffers():
+    """Release every imported peer buffer (call on all ranks, after the last sharded sweep, before destroying the group)."""
+    for pr in _PEER_CACHE.values():
+        pr.close()
+    _PEER_CACHE.clear()
+
+
 def all_gather_rows(x_local, shard: ParticleShard, group=None):
     """Concatenation over ranks of equally sized local pieces (the N log-weights of a step)."""
     full = torch.empty((shard.N,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
@@ -146,18 +229,40 @@ def forward_pass_sharded(key, us_star, bs_star, vs, model, init, cond_resampling
         uss[0].copy_(us)
     A = empty((1, N), torch.int32)
     moved = []
+    # particle exchange: 'peer' = the gather kernel loads parent rows from the owners' memory over NVLink (CUDA IPC, default on
+    # GPUs); 'nccl' = one batch of point-to-point sends / receives (also what the gloo CPU tests exercise)
+    mode = os.environ.get('FBS_SHARD_EXCHANGE', 'peer' if us.is_cuda else 'nccl')
+    peer = None
+    if mode == 'peer':
+        peer = _peer_rows(shard, p * c, us.device, group)                          # IPC set-up once per (group, shape)
+        peer.cur = 0
+        peer.buf[0].copy_(us.reshape(n, p * c))
+        if world > 1:
+            dist.all_reduce(torch.zeros(1, device=us.device), group=group)         # every rank's initial rows are in place
+        moved_dev = []
     for kk in range(K):
         w = torch.exp(log_w).contiguous()
         nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(sk[kk, 0]), ptr(w), ptr(bs[kk:kk + 1]), ptr(bs[kk + 1:kk + 2]), 1,
                  1, N, ptr(A))                                                     # identical on every rank
-        parents, mv = exchange_rows(us, A[0], shard, group)
-        moved.append(mv)
+        if peer is not None:
+            mine = A[0, lo:hi].contiguous()
+            parents = torch.empty((n, p, c), dtype=torch.float32, device=us.device)
+            peer.gather(mine, parents)
+            moved_dev.append(((mine < lo) | (mine >= hi)).sum())
+        else:
+            parents, mv = exchange_rows(us, A[0], shard, group)
+            moved.append(mv)
         us, lw_local = model.step(parents, v[kk], v[kk + 1], ts[kk], sk[kk, 1], row_offset=lo, rows_total=N)
         pin(us, bs_host[kk + 1], us_star[kk + 1])
+        if peer is not None:
+            peer.publish(us)
         lw = all_gather_rows(lw_local, shard, group)
         log_w = lw - torch.logsumexp(lw, dim=0)
         if history:
             As[kk].copy_(A[0])
             log_wss[kk + 1].copy_(log_w)
             uss[kk + 1].copy_(us)
-    return dict(N=N, lo=lo, hi=hi, us_last=us, log_ws_last=log_w, moved=moved, As=As, log_wss=log_wss, uss=uss)
+    if peer is not None:
+        moved = [int(m) for m in torch.stack(moved_dev).cpu().tolist()] if moved_dev else []
+    return dict(N=N, lo=lo, hi=hi, us_last=us, log_ws_last=log_w, moved=moved, As=As, log_wss=log_wss, uss=uss,
+                exchange=mode)

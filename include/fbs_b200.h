@@ -295,6 +295,19 @@ int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, con
                        float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw);
 /* dst[b, :] = src[idx[b], :]  (the ancestor gather, csmc.py:140). */
 int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, float* dst);
+
+/* Particle-sharded sweep (one chain over the GPUs of an NVSwitch box; no upstream counterpart): the ancestor gather over
+ * PEER MEMORY.  srcs: device array of one pointer per rank to that rank's particle rows [rows_per_rank, row] (the local
+ * buffer for the calling rank, CUDA-IPC imports for the others); idx: GLOBAL parent row of each of the B local children.
+ * dst[b, :] = srcs[idx[b] / rows_per_rank][idx[b] % rows_per_rank, :] -- NVLink loads inside the kernel. */
+int fbs_gather_rows_peer_f32(fbs_stream_t s, const float* const* srcs, const int32_t* idx, int64_t B, int64_t row,
+                             int64_t rows_per_rank, float* dst);
+/* CUDA IPC plumbing for the above (host side; the 64-byte handles travel through the caller's own channel).  export:
+ * handle of the allocation containing dev_ptr and dev_ptr's offset inside it; import: the peer's view of that address
+ * (peer access enabled lazily); release: closes an import. */
+int fbs_ipc_export(const void* dev_ptr, unsigned char* handle64, int64_t* offset);
+int fbs_ipc_import(const unsigned char* handle64, int64_t offset, void** out_ptr);
+int fbs_ipc_release(void* imported_ptr, int64_t offset);
 int fbs_nn_f32_to_bf16(fbs_stream_t s, const float* x, int64_t n, void* y);
 
 #ifdef __cplusplus

@@ -57,4 +57,6 @@ dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     out['sharded_s'] = float(t.item())
     print(json.dumps(out), flush=True)
+from fbs_b200.sharded import close_peer_buffers
+close_peer_buffers()
 dist.destroy_process_group()

@@ -333,6 +333,8 @@ def test_sharded_sweep_single_rank_equals_unsharded():
             assert r['moved'] == [0] * K
     finally:
         if created:
+            from fbs_b200.sharded import close_peer_buffers
+            close_peer_buffers()
             dist.destroy_process_group()
 
 
