@@ -438,3 +438,19 @@ def test_nn_gibbs_kernel_batched_targets_equals_single_targets(explicit_final):
         np.testing.assert_array_equal(us_next[ci], b)
         np.testing.assert_array_equal(bs_next[ci], c_)
         np.testing.assert_array_equal(changed[ci], d)
+
+
+def test_peer_gather_kernel_owner_arithmetic():
+    """fbs_gather_rows_peer_f32 with a pointer table of three LOCAL buffers standing in for three ranks (the CUDA-IPC imports
+    need several processes: scripts/sharded_check.py): dst[b] = bufs[idx[b] // n][idx[b] % n]."""
+    from fbs_b200 import _native as nat
+    from fbs_b200._tensor import ptr, stream
+    n, G = 5, 3
+    for row in (12, 7):                                     # 16-byte vector path and scalar path
+        bufs = [torch.randn(n, row, device='cuda') for _ in range(G)]
+        table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device='cuda')
+        idx = torch.tensor([14, 0, 7, 7, 3, 10, 4, 5], dtype=torch.int32, device='cuda')
+        dst = torch.empty(idx.numel(), row, device='cuda')
+        nat.call('fbs_gather_rows_peer_f32', stream(), ptr(table), ptr(idx), idx.numel(), row, n, ptr(dst))
+        want = torch.cat(bufs)[idx.long()]
+        assert torch.equal(dst, want)
