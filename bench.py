@@ -647,7 +647,11 @@ def run_gpu(args):
             'clocks': clk,
             'roofline': {'bound': 'hbm', 'kernel': 'sweep_v3_kernel (fbs_pmcmc_filter_affine_f32; tcgen05 split-TF32 GEMM + in-kernel threefry + resampling)',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'peak_source': peak_src,
+                         'traffic': (int((traffic or {}).get('dram_bytes_per_launch') * C / (traffic or {}).get('chains', C))
+                                     if (traffic or {}).get('dram_bytes_per_launch') else None),
+                         'traffic_source': (f"{(traffic or {}).get('source')}; captured at {(traffic or {}).get('chains')} chains, "
+                                            f"scaled to this launch's {C}" if traffic else None),
+                         'peak_source': peak_src,
                          'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / ms_per_step,
                          'algorithmic_bytes_per_particle_step': ALG_BYTES_PER_PARTICLE_STEP,
                          'note': 'nominal HBM roofline of SURVEY 8(d); the persistent kernel keeps particles in shared '
