@@ -110,6 +110,17 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def rng_bound(normals_per_s):
+    """The kernel's normal draws per second against the stand-alone rate of the jax.random-compatible generator (threefry2x32 +
+    XLA's erf_inv) measured by scripts/rng_microbench_normals.cu -- the resource that actually binds."""
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, 'profiles', 'rng_peaks.json')))['normals_per_s'])
+    except Exception:
+        return None
+    return {'achieved': normals_per_s / 1e9, 'peak': peak / 1e9, 'unit': 'G normals/s per GPU', 'frac': normals_per_s / peak,
+            'note': 'every particle-step draws du normals in the kernel; peak = stand-alone generator micro-benchmark'}
+
+
 def recorded_traffic():
     """dram read+write bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -652,6 +663,7 @@ def run_gpu(args):
                          'traffic_source': (f"{(traffic or {}).get('source')}; captured at {(traffic or {}).get('chains')} chains, "
                                             f"scaled to this launch's {C}" if traffic else None),
                          'peak_source': peak_src,
+                         'rng_bound': rng_bound(value / world * d),
                          'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / ms_per_step,
                          'algorithmic_bytes_per_particle_step': ALG_BYTES_PER_PARTICLE_STEP,
                          'note': 'nominal HBM roofline of SURVEY 8(d); the persistent kernel keeps particles in shared '
