@@ -289,7 +289,7 @@ def secondary_mnist(nparticles=101, steps=12):
 
 
 
-def secondary_gibbs(chains=2048, steps=3):
+def secondary_gibbs(chains=2072, steps=3):   # 7 full waves of 148 SMs x 2 chains per CTA
     """configs[0] scaled out: the particle-Gibbs sweep of experiments/toy/gp_gibbs.py (d = 100, K = 200, N = 100, conditional
     killing resampling, explicit backward / forced move), device resident, gibbs_kernel through the public API."""
     import torch
