@@ -223,9 +223,39 @@ __global__ void __launch_bounds__(256, 2) stepvec_tiled_kernel(const SweepParams
         }
       cur_slot = slot;
     }
-    for (int c = tid / 32; c < SV_CH; c += blockDim.x / 32) {
-      const float* src = p.vs + ((size_t)(b0 + (c < nb ? c : 0)) * (K + 1) + kp) * dv;
-      for (int j = tid % 32; j < dv; j += 32) Vt[c * vst + j] = c < nb ? src[j] : 0.f;
+    if ((dv & 3) == 0) {
+      // 16-byte loads, all of a warp's rows in flight before the first shared store
+      const int nw = blockDim.x / 32, q4 = dv / 4;
+      for (int c0 = tid / 32; c0 < SV_CH; c0 += 4 * nw) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * nw;
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < nb && (tid % 32) < q4)
+            x[u] = __ldg(reinterpret_cast<const float4*>(p.vs + ((size_t)(b0 + c) * (K + 1) + kp) * dv) + (tid % 32));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * nw;
+          if (c < SV_CH) {
+            for (int j4 = tid % 32; j4 < q4; j4 += 32) {
+              float4 y = x[u];
+              if (j4 != (tid % 32)) {
+                y = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < nb) y = __ldg(reinterpret_cast<const float4*>(p.vs + ((size_t)(b0 + c) * (K + 1) + kp) * dv) + j4);
+              }
+              float* d = Vt + c * vst + 4 * j4;
+              d[0] = y.x; d[1] = y.y; d[2] = y.z; d[3] = y.w;
+            }
+          }
+        }
+      }
+    } else {
+      for (int c = tid / 32; c < SV_CH; c += blockDim.x / 32) {
+        const float* src = p.vs + ((size_t)(b0 + (c < nb ? c : 0)) * (K + 1) + kp) * dv;
+        for (int j = tid % 32; j < dv; j += 32) Vt[c * vst + j] = c < nb ? src[j] : 0.f;
+      }
     }
     __syncthreads();
     if (!worker) continue;
@@ -248,6 +278,58 @@ __global__ void __launch_bounds__(256, 2) stepvec_tiled_kernel(const SweepParams
       }
     }
     // epilogue: u columns  m + acc;  v columns  (v - v_prev) - dt (m + acc);  padding columns 0
+    if (((du | dv | dup) & 3) == 0) {
+      // every 4-column group is entirely u, v or padding: the group's m once per tile, v as ONE 16-byte load per chain,
+      // v_prev from the shared-memory tile
+      float4 mg[2];
+      int kind[2], q0[2];  // 0 padding, 1 u, 2 v; first column inside its part
+#pragma unroll
+      for (int hq = 0; hq < 2; ++hq) {
+        const int col = hq == 0 ? 4 * og : 4 * (og + ng);
+        kind[hq] = col < du ? 1 : ((col >= dup && col - dup < dv) ? 2 : 0);
+        q0[hq] = kind[hq] == 2 ? col - dup : col;
+        mg[hq] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kind[hq]) mg[hq] = __ldg(reinterpret_cast<const float4*>(p.m + (size_t)k * D + (kind[hq] == 2 ? du : 0) + q0[hq]));
+      }
+      float4 vcur[8];
+      if (kind[0] == 2 || kind[1] == 2) {
+        const int qv = kind[0] == 2 ? q0[0] : q0[1];  // (a thread has at most one v group when dup >= 4 ng ... both may be v)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int ch = 8 * cg + c;
+          vcur[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ch < nb && !(kind[0] == 2 && kind[1] == 2))
+            vcur[c] = __ldg(reinterpret_cast<const float4*>(p.vs + ((size_t)(b0 + ch) * (K + 1) + kv) * dv + qv));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int ch = 8 * cg + c;
+        if (ch >= nb) continue;
+        float* dst = p.ws + ((size_t)(b0 + ch) * (K + 1) + slot) * DP;
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          const int col = hq == 0 ? 4 * og : 4 * (og + ng);
+          if (col + 4 > DP) continue;
+          const float a0 = acc[c][4 * hq + 0], a1 = acc[c][4 * hq + 1], a2 = acc[c][4 * hq + 2], a3 = acc[c][4 * hq + 3];
+          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kind[hq] == 1) {
+            r4 = make_float4(mg[hq].x + a0, mg[hq].y + a1, mg[hq].z + a2, mg[hq].w + a3);
+          } else if (kind[hq] == 2) {
+            float4 vc4 = vcur[c];
+            if (kind[0] == 2 && kind[1] == 2)
+              vc4 = __ldg(reinterpret_cast<const float4*>(p.vs + ((size_t)(b0 + ch) * (K + 1) + kv) * dv + q0[hq]));
+            const float* vp = Vt + (size_t)ch * vst + q0[hq];
+            r4.x = (vc4.x - vp[0]) - dt * (mg[hq].x + a0);
+            r4.y = (vc4.y - vp[1]) - dt * (mg[hq].y + a1);
+            r4.z = (vc4.z - vp[2]) - dt * (mg[hq].z + a2);
+            r4.w = (vc4.w - vp[3]) - dt * (mg[hq].w + a3);
+          }
+          *reinterpret_cast<float4*>(dst + col) = r4;
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int ch = 8 * cg + c;
