@@ -816,7 +816,8 @@ int launch_stepvec(void* stream, SweepParams& p) {
     const int DP8 = (DP + 7) / 8 * 8, ng = DP8 / 8;
     const size_t sm2 = ((size_t)p.dv * DP8 + (size_t)SV_CH * (p.dv | 1)) * sizeof(float);
     const char* impl = getenv("FBS_STEPVEC_IMPL");  // "old" pins the thread-per-output kernel
-    if (ng * (SV_CH / 8) <= 256 && sm2 <= 110 * 1024 && p.B >= SV_CH && !(impl != nullptr && impl[0] == 'o')) {
+    // (narrow systems keep the thread-per-output kernel: with fewer than 8 output groups most of a tiled CTA idles)
+    if (ng >= 8 && ng * (SV_CH / 8) <= 256 && sm2 <= 110 * 1024 && p.B >= SV_CH && !(impl != nullptr && impl[0] == 'o')) {
       cudaFuncSetAttribute(stepvec_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       const int64_t items = (int64_t)(p.K + 1) * ((p.B + SV_CH - 1) / SV_CH);
       const int64_t slots = 2 * (int64_t)sm_count();  // two CTAs per SM, persistent
