@@ -105,23 +105,43 @@ class PeerRows:
         self.shard, self.row, self.group = shard, int(row), group
         self.buf = torch.empty((2, shard.n, self.row), dtype=torch.float32, device=device)
         self._imports = []
+        self.error = None
         bases = [None] * shard.world
         bases[shard.rank] = self.buf.data_ptr()
         if shard.world > 1:
-            handle = (C.c_ubyte * 64)()
-            off = C.c_int64(0)
-            nat.call('fbs_ipc_export', self.buf.data_ptr(), handle, C.byref(off))
-            mine = (bytes(handle), int(off.value))
+            # every rank goes through the same collectives whatever happens locally (a rank that raised before a collective
+            # would leave the others waiting in it); failures are agreed on afterwards
+            mine = None
+            try:
+                handle = (C.c_ubyte * 64)()
+                off = C.c_int64(0)
+                nat.call('fbs_ipc_export', self.buf.data_ptr(), handle, C.byref(off))
+                mine = (bytes(handle), int(off.value))
+            except Exception as e:                                   # noqa: BLE001
+                self.error = repr(e)
             everyone = [None] * shard.world
             dist.all_gather_object(everyone, mine, group=group)
-            for r, (hb, o) in enumerate(everyone):
-                if r == shard.rank:
-                    continue
-                hbuf = (C.c_ubyte * 64).from_buffer_copy(hb)
-                out = C.c_void_p()
-                nat.call('fbs_ipc_import', hbuf, o, C.byref(out))
-                self._imports.append((out.value, o))
-                bases[r] = out.value
+            if self.error is None and all(x is not None for x in everyone):
+                try:
+                    for r, (hb, o) in enumerate(everyone):
+                        if r == shard.rank:
+                            continue
+                        hbuf = (C.c_ubyte * 64).from_buffer_copy(hb)
+                        out = C.c_void_p()
+                        nat.call('fbs_ipc_import', hbuf, o, C.byref(out))
+                        self._imports.append((out.value, o))
+                        bases[r] = out.value
+                except Exception as e:                               # noqa: BLE001
+                    self.error = repr(e)
+            elif self.error is None:
+                self.error = 'a peer could not export its buffer'
+            ok = torch.tensor([0 if self.error else 1], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.error = self.error or 'a peer could not import the buffers'
+                self.close()
+                self.table = None
+                return
         slot_bytes = shard.n * self.row * 4
         self.table = torch.tensor([[b + s * slot_bytes for b in bases] for s in range(2)], dtype=torch.int64, device=device)
         self.cur = 0
@@ -235,6 +255,9 @@ def forward_pass_sharded(key, us_star, bs_star, vs, model, init, cond_resampling
     peer = None
     if mode == 'peer':
         peer = _peer_rows(shard, p * c, us.device, group)                          # IPC set-up once per (group, shape)
+        if peer.table is None:
+            raise RuntimeError('peer-memory particle exchange is unavailable on this box (' + str(peer.error) + '); '
+                               'set FBS_SHARD_EXCHANGE=nccl for the send / receive exchange')   # raised on EVERY rank
         peer.cur = 0
         peer.buf[0].copy_(us.reshape(n, p * c))
         if world > 1:
