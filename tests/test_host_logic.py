@@ -155,3 +155,29 @@ def test_particle_shard_exchange_gloo(tmp_path, world):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert 'GLOO_SHARD_OK' in res.stdout
+
+
+def test_bench_clock_sampler_windows_samples_to_the_timed_region():
+    """bench.ClockSampler.stop keeps the nvidia-smi samples that fall inside the timed region and says when it had to fall
+    back to the warm-up samples (a 0.3 s region can end before nvidia-smi's first sample)."""
+    import bench
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+    line = '0, {sm}, 1965, 3996, 700.0, Not Active, Not Active, Not Active, {cap}'
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [(10.0, line.format(sm=1200, cap='Not Active')), (11.0, line.format(sm=1965, cap='Active')),
+               (11.2, line.format(sm=1950, cap='Not Active')), (13.0, line.format(sm=300, cap='Not Active'))]
+    r = s.stop(10.9, 11.3)
+    assert r['samples'] == 2 and r['sm_mhz'] == 1957.5 and r['sm_max_mhz'] == 1965.0
+    assert r['reasons'] == ['sw_power_cap'] and r['window'] == 'timed region'
+    s2 = bench.ClockSampler(0)
+    s2.proc = FakeProc()
+    s2.lines = [(10.0, line.format(sm=1965, cap='Not Active'))]
+    r2 = s2.stop(20.0, 20.3)
+    assert r2['samples'] == 1 and r2['window'].startswith('warm-up')
+    rb = bench.rng_bound(1.0e11)
+    assert rb is not None and abs(rb['frac'] - 1.0e11 / 423.5e9) < 1e-9

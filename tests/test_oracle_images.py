@@ -52,3 +52,25 @@ def test_result_layouts(tmp_path):
     assert sorted(z.files) == ['gp_cov', 'gp_mean', 'samples'] and z['samples'].shape == (2, 5, 10)
     with pytest.raises(ValueError):
         results.save_restored_images(str(tmp_path / 'x'), imgs[0])
+
+
+def test_product_masks_host_paths_match_oracle():
+    """The parts of fbs_b200.data.ImageRestore that need no random draw (fixed super-resolution mask, unpack / concat on numpy
+    arrays) against the oracle -- on CPU; the random masks are checked on the GPU (tests/test_gpu_images.py)."""
+    from fbs_b200.data import ImageRestore
+    shape = (28, 28, 1)
+    ds = ImageRestore('supr-4', shape, sr_random=False)
+    assert ds.unobs_shape == (735, 1)
+    m = ds.gen_mask(jr.PRNGKey(0))
+    unobs, obs = oi.gen_supr_mask(jr.PRNGKey(0), shape, 4, False)
+    np.testing.assert_array_equal(m.obs_inds_ravelled, obs)
+    np.testing.assert_array_equal(m.unobs_inds_ravelled, unobs)
+    img = np.random.default_rng(2).random((2, 28, 28, 1)).astype(np.float32)
+    x, y = ds.unpack(img, m)
+    wx, wy = oi.unpack(img, shape, unobs, obs)
+    np.testing.assert_array_equal(x, wx)
+    np.testing.assert_array_equal(y, wy)
+    np.testing.assert_array_equal(ds.concat(x, y, m), img)
+    assert ImageRestore('inpaint-15', shape).unobs_shape == (225, 1)
+    with pytest.raises(ValueError):
+        ImageRestore('denoise-3', shape)
