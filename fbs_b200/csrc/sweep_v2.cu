@@ -830,7 +830,10 @@ int launch_stepvec(void* stream, SweepParams& p) {
   dim3 grid((unsigned)((p.B + CV_CH - 1) / CV_CH), (unsigned)(p.K + 1));
   const size_t sm = (size_t)2 * p.dv * CV_CH * sizeof(float);
   if (sm > 48 * 1024) cudaFuncSetAttribute(stepvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  stepvec_kernel<<<grid, 256, sm, st>>>(p, dup, DP);
+  // thread i owns output i: a CTA wider than D only idles (narrow systems: 32 or 64 threads, many CTAs per SM)
+  int sv_threads = (p.du + p.dv + 31) / 32 * 32;
+  if (sv_threads > 256) sv_threads = 256;
+  stepvec_kernel<<<grid, sv_threads, sm, st>>>(p, dup, DP);
   return check_launch("stepvec_kernel");
 }
 
