@@ -42,6 +42,7 @@ SIGNATURES = {
     'fbs_last_error': ([], C.c_char_p),
     'fbs_launch_count': ([], _i64),
     'fbs_reset_launch_count': ([], None),
+    'fbs_debug_set_option': ([C.c_char_p, _int], _int),
     'fbs_random_bits_u32': ([_p, _p, _i64, _i64, _p], _int),
     'fbs_random_split': ([_p, _p, _i64, _i64, _p], _int),
     'fbs_random_uniform_f32': ([_p, _p, _i64, _i64, _f32, _f32, _p], _int),
@@ -61,6 +62,8 @@ SIGNATURES = {
                                      C.c_size_t], _int),
     'fbs_backward_scan_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p], _int),
     'fbs_pmcmc_filter_affine_f32': ([_p, _M, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p, _p, _p, C.c_size_t], _int),
+    'fbs_bootstrap_filter_affine_f32': ([_p, _M, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p, _p], _int),
+    'fbs_backward_sample_affine_f32': ([_p, _M, _int, _p, _p, _p, _p, _int, _i64, _i64, _p, _p], _int),
     'fbs_force_move_f32': ([_p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _p, _p, _p], _int),
     'fbs_pcn_combine_f32': ([_p, _f64, _p, _p, _p, _p, _i64, _i64, _p], _int),
     'fbs_mh_accept_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p], _int),
@@ -76,8 +79,8 @@ SIGNATURES = {
     'fbs_nn_space_to_depth_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),
     'fbs_nn_assemble_image_f32': ([_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p], _int),
     'fbs_nn_em_step_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _i64, _i64, _p, _p, _p], _int),
-    'fbs_gather_rows_f32': ([_p, _p, _p, _i64, _i64, _p], _int),
-    'fbs_gather_rows_peer_f32': ([_p, _p, _p, _i64, _i64, _i64, _p], _int),
+    'fbs_gather_rows_f32': ([_p, _p, _p, _i64, _i64, _i64, _p], _int),
+    'fbs_gather_rows_peer_f32': ([_p, _p, _p, _i64, _i64, _i64, _i64, _p], _int),
     'fbs_ipc_export': ([_p, _p, _p], _int),
     'fbs_ipc_import': ([_p, _i64, _p], _int),
     'fbs_ipc_release': ([_p, _i64], _int),
@@ -107,6 +110,40 @@ def lib():
     return _lib
 
 
+# Implementation pins for tests / A-B measurements.  The C library never reads the environment; the Python layer maps the
+# FBS_* variables onto fbs_debug_set_option whenever their values change (checked per call: a few dict lookups).
+_ENV_OPTS = {
+    'FBS_SWEEP_IMPL': ('sweep_impl', {'v1': 1, 'v2': 2, 'v3': 3}),
+    'FBS_SWEEP_VERBOSE': ('sweep_verbose', None),
+    'FBS_STEP_IMPL': ('step_impl', {'cuda': 1}),
+    'FBS_STEP_TC_WARPS': ('step_tc_warps', None),
+    'FBS_STEPVEC_IMPL': ('stepvec_impl', {'old': 1}),
+    'FBS_SWEEP_G': ('sweep_g', None),
+    'FBS_V3_TWOPASS': ('v3_twopass', None),
+    'FBS_EM_IMPL': ('em_impl', {'cta': 1, 'tpc': 2}),
+    'FBS_V3_VARIANT': ('v3_variant', None),
+}
+_env_seen = {}
+
+
+def _sync_env_options(handle):
+    for env, (name, table) in _ENV_OPTS.items():
+        raw = os.environ.get(env)
+        if _env_seen.get(env) == raw:
+            continue
+        _env_seen[env] = raw
+        if raw is None or raw == '':
+            val = 0
+        elif table is not None:
+            if raw not in table:
+                raise ValueError(f'{env}={raw!r}: expected one of {sorted(table)}')
+            val = table[raw]
+        else:
+            val = int(raw)
+        if handle.fbs_debug_set_option(name.encode(), val) != 0:
+            raise NativeError(handle.fbs_last_error().decode('utf-8', 'replace'))
+
+
 # name -> list of (start_event, end_event): filled when a caller asks for per-kernel device timing
 # (bench.py uses it to time the dominant kernel inside a whole step without a profiler).
 TIMED = {}
@@ -114,6 +151,7 @@ TIMED = {}
 
 def call(name, *args):
     handle = lib()
+    _sync_env_options(handle)
     rec = TIMED.get(name)
     if rec is not None:
         import torch

@@ -203,6 +203,32 @@ __device__ void children_phase(const SweepParams& p, const SmemLayout& L, float*
   const float sd = p.sd[k];
   const uint32_t nel = (uint32_t)N * du;
   const uint32_t h = (nel + 1u) >> 1;
+  if (p.mode == MODE_BOOTSTRAP) {
+    // smc.py:63,72: us_new = mean(us) + sd eps (row n of the noise belongs to particle n), then us = us_new[inds]
+    float* Qw = sm + L.Q;
+    for (int t = tid; t < nchains * (int)h; t += NT) {
+      const int g = t / (int)h;
+      const uint32_t b = (uint32_t)(t - g * (int)h);
+      uint32_t y0, y1;
+      random_bits_block(ktr[g], nel, b, y0, y1);
+      {
+        const int n = b / du, i = b - n * du;
+        Qw[(size_t)i * Rp + g * N + n] += sd * bits_to_normal(y0);
+      }
+      const uint32_t e = b + h;
+      if (e < nel) {
+        const int n = e / du, i = e - n * du;
+        Qw[(size_t)i * Rp + g * N + n] += sd * bits_to_normal(y1);
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < nchains * N * du; t += NT) {
+      const int i = t / (nchains * N), r = t - i * (nchains * N), g = r / N;
+      P[(size_t)i * Rp + r] = Q[(size_t)i * Rp + g * N + idx[r]];
+    }
+    __syncthreads();
+    return;
+  }
   if ((N & 1) == 0) {
     // N even: element (n, i) pairs with (n + N/2, i); map threads with n fastest (bank-conflict free).
     const int hn = N >> 1;
@@ -282,7 +308,7 @@ __global__ void __launch_bounds__(1024, 1) sweep_affine_kernel(const SweepParams
       scal[tid] = 0.f;
     }
     __syncthreads();
-    if (p.mode == MODE_PMCMC) {
+    if (p.mode != MODE_CSMC) {
       for (int t = tid; t < R * du; t += NT) {
         const int r = t / du, i = t - r * du;
         P[(size_t)i * Rp + r] = p.u0s[(size_t)chain0 * N * du + t];
@@ -315,7 +341,7 @@ __global__ void __launch_bounds__(1024, 1) sweep_affine_kernel(const SweepParams
         __syncthreads();
         for (int t = tid; t < nchains * du; t += NT) {  // csmc.py:152
           const int g = t / du, i = t - g * du;
-          const int b0 = p.bs_star[(size_t)(chain0 + g) * (K + 1)];
+          const int b0 = clamp_index(p.bs_star[(size_t)(chain0 + g) * (K + 1)], N);
           P[(size_t)i * Rp + g * N + b0] = p.us_star[(size_t)(chain0 + g) * (K + 1) * du + i];
         }
         __syncthreads();
@@ -378,7 +404,8 @@ __global__ void __launch_bounds__(1024, 1) sweep_affine_kernel(const SweepParams
           if (p.lw_hist)
             for (int q = lane; q < N; q += 32) p.lw_hist[((size_t)(chain0 + g) * K + k) * N + q] = lwg[q];
           const float c = warp_normalise(lwg, N, lane);  // smc.py:145,147
-          if (lane == 0) scal[g] = (scal[g] - logN) + c;  // smc.py:146
+          if (lane == 0) scal[g] = p.mode == MODE_BOOTSTRAP ? scal[g] - (c - logN)   // smc.py:67 (negative log-likelihood)
+                                                            : (scal[g] - logN) + c;  // smc.py:146
           for (int q = lane; q < N; q += 32) wg[q] = expf(lwg[q]);
           __syncwarp();
           if (p.scheme == FBS_RESAMPLE_KILLING)
@@ -396,7 +423,7 @@ __global__ void __launch_bounds__(1024, 1) sweep_affine_kernel(const SweepParams
       if (p.mode == MODE_CSMC) {
         for (int t = tid; t < nchains * du; t += NT) {  // csmc.py:143
           const int g = t / du, i = t - g * du;
-          const int bj = p.bs_star[(size_t)(chain0 + g) * (K + 1) + k + 1];
+          const int bj = clamp_index(p.bs_star[(size_t)(chain0 + g) * (K + 1) + k + 1], N);
           P[(size_t)i * Rp + g * N + bj] = p.us_star[((size_t)(chain0 + g) * (K + 1) + k + 1) * du + i];
         }
         __syncthreads();
@@ -440,15 +467,20 @@ __global__ void __launch_bounds__(1024, 1) sweep_affine_kernel(const SweepParams
 static int launch_sweep(fbs_stream_t s, SweepParams& p) {
   const int D = p.du + p.dv;
   {
-    const char* impl = getenv("FBS_SWEEP_IMPL");
+    const int impl = p.mode == MODE_BOOTSTRAP ? 1 : debug_opt(OPT_SWEEP_IMPL);
     // preference: tcgen05 kernel (v3) -> tiled CUDA-core kernel (v2) -> general kernel (v1); each returns -1 when the
     // shape is not eligible.  FBS_SWEEP_IMPL = v1 | v2 | v3 pins the choice (tests / A-B measurements).
-    const bool only1 = impl && impl[1] == '1', only2 = impl && impl[1] == '2';
-    const bool verbose = getenv("FBS_SWEEP_VERBOSE") != nullptr;
+    const bool only1 = impl == 1, only2 = impl == 2;
+    const bool verbose = debug_opt(OPT_SWEEP_VERBOSE) != 0;
     if (!only1 && !only2) {
       const int rc = launch_sweep_v3(s, p);
       if (verbose) fprintf(stderr, "[fbs] sweep v3 (tcgen05) -> %d\n", rc);
       if (rc >= 0) return rc;
+      if (impl == 3) {
+        set_error("sweep: the tcgen05 kernel was pinned (sweep_impl = 3) but the shape N=%lld du=%d dv=%d is not eligible",
+                  (long long)p.N, p.du, p.dv);
+        return FBS_ERR_UNSUPPORTED;
+      }
     }
     if (!only1) {
       const int rc = launch_sweep_v2(s, p);
@@ -543,6 +575,26 @@ int fbs_csmc_forward_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
     p.MTc = model->MTc;
     p.ws = static_cast<float*>(workspace);
   }
+  return launch_sweep(s, p);
+}
+
+int fbs_bootstrap_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* step_keys,
+                                    const float* vs, const float* u0s, int scheme, int64_t B, int64_t N, float* uT,
+                                    float* log_nell, int32_t* inds, float* log_ws_hist, float* us_hist) {
+  if (B == 0) return FBS_OK;
+  int rc = check_model(model);
+  if (rc) return rc;
+  FBS_REQUIRE(step_keys && vs && u0s, "bootstrap_filter: null input");
+  FBS_REQUIRE(N >= 1 && N < (1 << 20), "bootstrap_filter: bad sizes");
+  FBS_REQUIRE(scheme >= FBS_RESAMPLE_MULTINOMIAL && scheme <= FBS_RESAMPLE_STRATIFIED, "bootstrap_filter: bad scheme %d",
+              scheme);
+  SweepParams p{};
+  p.K = model->K; p.du = model->du; p.dv = model->dv;
+  p.MT = model->MT; p.m = model->m; p.dt = model->dt; p.sd = model->sd; p.lognorm = model->lognorm;
+  p.keys = step_keys; p.vs = vs; p.u0s = u0s;
+  p.mode = MODE_BOOTSTRAP; p.scheme = scheme;
+  p.B = B; p.N = (int)N;
+  p.uT = uT; p.log_ell = log_nell; p.inds = inds; p.lw_hist = log_ws_hist; p.us_hist = us_hist;
   return launch_sweep(s, p);
 }
 

@@ -46,4 +46,20 @@ int launch_step_transition_tc(cudaStream_t st, const fbs_affine_model_t* model, 
 // Number of SMs of the current device (cached per thread; B200: 148).
 int sm_count();
 
+// Implementation-selection knobs for tests and A/B measurements (fbs_debug_set_option): relaxed atomics, default 0 = the
+// library's own choice.  The library never reads the environment.
+enum DebugOpt {
+  OPT_SWEEP_IMPL = 0,   // 1 / 2 / 3: pin the general / tiled / tcgen05 sweep kernel
+  OPT_SWEEP_VERBOSE,    // 1: print the sweep kernel chosen to stderr
+  OPT_STEP_IMPL,        // 1: CUDA-core per-timestep transition kernel
+  OPT_STEP_TC_WARPS,    // 8: eight-warp variant of the tcgen05 per-timestep kernel
+  OPT_STEPVEC_IMPL,     // 1: thread-per-output step-vector kernel
+  OPT_SWEEP_G,          // > 0: chains per CTA of the tiled sweep kernel
+  OPT_V3_TWOPASS,       // 1: two-pass GEMM in the tcgen05 sweep kernel
+  OPT_EM_IMPL,          // 1: CTA-per-chain, 2: thread-per-chain Euler--Maruyama path kernel
+  OPT_V3_VARIANT,       // experimental variants of the tcgen05 sweep kernel (A/B measurements)
+  OPT_COUNT
+};
+int debug_opt(DebugOpt which);
+
 }  // namespace fbs

@@ -11,6 +11,11 @@
 
 namespace fbs {
 
+// Reference-particle indices (bs_star, i, j) address shared / global memory inside the kernels.  JAX clamps an
+// out-of-range gather / scatter index silently; here it is clamped where it is loaded so that a stale bs_star (reused
+// after nparticles changed) cannot corrupt memory.  The Python layer validates the range up front where that costs nothing.
+__device__ __forceinline__ int clamp_index(int b, int n) { return min(max(b, 0), n - 1); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -82,6 +87,8 @@ __device__ __forceinline__ void warp_cond_killing(Key key, const float* w, int n
                                                   float* cum, int* tmp, int* out, int lane) {
   Key key_1, key_2, key_3;
   split3(key, key_1, key_2, key_3);  // :66
+  i = clamp_index(i, n);
+  j = clamp_index(j, n);
   float m = -INFINITY;
   for (int q = lane; q < n; q += 32) m = fmaxf(m, w[q]);
   const float w_max = warp_max(m);  // :69
@@ -128,6 +135,8 @@ __device__ __forceinline__ void warp_cond_killing(Key key, const float* w, int n
 // Conditional multinomial, resamplings.py:10-37.
 __device__ __forceinline__ void warp_cond_multinomial(Key key, const float* w, int n, int i, int j, bool conditional,
                                                       float* cum, int* out, int lane) {
+  i = clamp_index(i, n);
+  j = clamp_index(j, n);
   warp_seq_cumsum(w, cum, n, lane);
   const uint32_t h = ((uint32_t)n + 1u) >> 1;
   for (uint32_t b = lane; b < h; b += 32) {

@@ -4,7 +4,10 @@
 
 namespace fbs {
 
-enum { MODE_CSMC = 0, MODE_PMCMC = 1 };
+// MODE_BOOTSTRAP = the bootstrap filter of smc.py:9-88: the pMCMC filter's weights / resampling, but every particle is
+// propagated BEFORE the resampling (its noise row travels with it: us = us_new[inds], smc.py:63,72) and the evidence is
+// accumulated as a NEGATIVE log-likelihood (smc.py:67).  General kernel only.
+enum { MODE_CSMC = 0, MODE_PMCMC = 1, MODE_BOOTSTRAP = 2 };
 
 struct SweepParams {
   int K, du, dv;

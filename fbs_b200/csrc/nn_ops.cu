@@ -645,11 +645,11 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
 
 // rows of src gathered by an index list: dst[b, :] = src[idx[b], :]  (csmc.py:140, the ancestor gather)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int64_t B,
-                                                          int64_t row, float* __restrict__ dst) {
+                                                          int64_t row, int src_rows, float* __restrict__ dst) {
   const int64_t total = B * row;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = t / row;
-    dst[t] = src[(int64_t)idx[b] * row + (t - b * row)];
+    dst[t] = src[(int64_t)min(max(idx[b], 0), src_rows - 1) * row + (t - b * row)];
   }
 }
 
@@ -773,9 +773,12 @@ int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, con
   return check_launch("em_step_kernel");
 }
 
-int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, float* dst) {
+int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, int64_t src_rows,
+                        float* dst) {
+  if (B == 0) return FBS_OK;
   FBS_REQUIRE(src && idx && dst, "gather_rows: null argument");
-  gather_rows_kernel<<<grid_for(B * row), 256, 0, as_stream(s)>>>(src, idx, B, row, dst);
+  FBS_REQUIRE(src_rows >= 1 && src_rows < (1ll << 31), "gather_rows: bad src_rows");
+  gather_rows_kernel<<<grid_for(B * row), 256, 0, as_stream(s)>>>(src, idx, B, row, (int)src_rows, dst);
   return check_launch("gather_rows_kernel");
 }
 

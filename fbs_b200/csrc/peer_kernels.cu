@@ -15,11 +15,11 @@ namespace fbs {
 template <typename V>
 __global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float* const* __restrict__ srcs,
                                                                const int32_t* __restrict__ idx, int64_t B, int64_t rowv,
-                                                               int rows_per_rank, V* __restrict__ dst) {
+                                                               int rows_per_rank, int rows_total, V* __restrict__ dst) {
   const int64_t total = B * rowv;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = t / rowv;
-    const int g = idx[b];
+    const int g = min(max(idx[b], 0), rows_total - 1);
     const int owner = g / rows_per_rank, local = g - owner * rows_per_rank;
     dst[t] = reinterpret_cast<const V*>(srcs[owner])[(int64_t)local * rowv + (t - b * rowv)];
   }
@@ -93,20 +93,23 @@ int fbs_ipc_release(void* imported_ptr, int64_t offset) {
 }
 
 int fbs_gather_rows_peer_f32(fbs_stream_t s, const float* const* srcs, const int32_t* idx, int64_t B, int64_t row,
-                             int64_t rows_per_rank, float* dst) {
+                             int64_t rows_per_rank, int64_t n_ranks, float* dst) {
   if (B == 0) return FBS_OK;
   FBS_REQUIRE(srcs && idx && dst, "gather_rows_peer: null argument");
-  FBS_REQUIRE(row >= 1 && rows_per_rank >= 1 && rows_per_rank < (1ll << 31), "gather_rows_peer: bad sizes");
+  FBS_REQUIRE(row >= 1 && rows_per_rank >= 1 && n_ranks >= 1 && rows_per_rank * n_ranks < (1ll << 31),
+              "gather_rows_peer: bad sizes");
+  const int rows_total = (int)(rows_per_rank * n_ranks);
   const bool v4 = row % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0;
   const int64_t rowv = v4 ? row / 4 : row;
   int64_t blocks = (B * rowv + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (v4)
-    gather_rows_peer_kernel<float4><<<(int)blocks, 256, 0, as_stream(s)>>>(srcs, idx, B, rowv, (int)rows_per_rank,
+    gather_rows_peer_kernel<float4><<<(int)blocks, 256, 0, as_stream(s)>>>(srcs, idx, B, rowv, (int)rows_per_rank, rows_total,
                                                                           reinterpret_cast<float4*>(dst));
   else
-    gather_rows_peer_kernel<float><<<(int)blocks, 256, 0, as_stream(s)>>>(srcs, idx, B, rowv, (int)rows_per_rank, dst);
+    gather_rows_peer_kernel<float><<<(int)blocks, 256, 0, as_stream(s)>>>(srcs, idx, B, rowv, (int)rows_per_rank, rows_total,
+                                                                         dst);
   return check_launch("gather_rows_peer_kernel");
 }
 

@@ -1,5 +1,7 @@
 // Standalone jax.random kernels behind the C ABI (include/fbs_b200.h) + library bookkeeping.
 #include <stdarg.h>
+#include <string.h>
+#include <atomic>
 #include "fbs_common.cuh"
 #include "fbs_rng.cuh"
 
@@ -25,6 +27,11 @@ int sm_count() {
   }
   return g_sms;
 }
+
+static std::atomic<int> g_opts[OPT_COUNT];
+static const char* const g_opt_names[OPT_COUNT] = {"sweep_impl", "sweep_verbose", "step_impl", "step_tc_warps", "stepvec_impl",
+                                                    "sweep_g", "v3_twopass", "em_impl", "v3_variant"};
+int debug_opt(DebugOpt which) { return g_opts[which].load(std::memory_order_relaxed); }
 
 enum { OUT_BITS = 0, OUT_UNIFORM = 1, OUT_NORMAL = 2 };
 
@@ -134,6 +141,17 @@ int fbs_version(void) { return 100; }
 const char* fbs_last_error(void) { return g_err; }
 int64_t fbs_launch_count(void) { return g_launches; }
 void fbs_reset_launch_count(void) { g_launches = 0; }
+
+int fbs_debug_set_option(const char* name, int value) {
+  FBS_REQUIRE(name != nullptr, "fbs_debug_set_option: null name");
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, g_opt_names[i]) == 0) {
+      g_opts[i].store(value, std::memory_order_relaxed);
+      return FBS_OK;
+    }
+  set_error("fbs_debug_set_option: unknown option '%s'", name);
+  return FBS_ERR_INVALID_ARGUMENT;
+}
 
 int fbs_random_bits_u32(fbs_stream_t s, const uint32_t* keys, int64_t B, int64_t n, uint32_t* out) {
   return launch_fill<OUT_BITS>(s, keys, B, n, 0.f, 1.f, out);

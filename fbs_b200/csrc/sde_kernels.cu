@@ -403,8 +403,11 @@ __global__ void mh_accept_kernel(const uint32_t* __restrict__ keys, const float*
     threefry2x32(key.k0, key.k1, x0, x1);
     const float z = bits_to_unit(x0);                          // smc.py:248
     const float le = log_ell[b], ple = prop_log_ell[b];
-    const float log_acc = fminf(0.f, ple - le);                // smc.py:246
-    const bool acc = logf(z) < log_acc;                        // smc.py:249
+    // smc.py:246: jnp.minimum propagates NaN (CUDA's fminf drops it), so a NaN evidence -- all weights -inf, or a
+    // non-finite score -- rejects the proposal and the chain keeps its last finite state, as upstream
+    const float dl = ple - le;
+    const float log_acc = (dl == dl) ? fminf(0.f, dl) : dl;
+    const bool acc = logf(z) < log_acc;                        // smc.py:249 (false when log_acc is NaN)
     __syncthreads();  // every thread has read log_ell[b] before thread 0 may overwrite it
     if (threadIdx.x == 0) {
       if (acc_prob) acc_prob[b] = expf(log_acc);
@@ -594,9 +597,9 @@ int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0
     const int nt = 32;
     const size_t per_buf = ((size_t)(m * D * D + m * D) + 3) & ~(size_t)3;
     const size_t smem_tpc = (2 * per_buf + (size_t)((m * D + 1) / 2 + D) * nt) * sizeof(float);
-    const char* impl = getenv("FBS_EM_IMPL");  // "cta" / "tpc" pin the CTA-per-chain / thread-per-chain kernels (tests)
-    const bool pinned_cta = impl != nullptr && impl[0] == 'c';
-    const bool pinned_tpc = impl != nullptr && impl[0] == 't';
+    const int impl = debug_opt(OPT_EM_IMPL);  // 1 / 2 pin the CTA-per-chain / thread-per-chain kernels (tests)
+    const bool pinned_cta = impl == 1;
+    const bool pinned_tpc = impl == 2;
     const int T = (D % 4 == 0 && D <= 32) ? 4 : ((D % 2 == 0 && D <= 16) ? 2 : 0);
     if (T != 0 && B >= 1024 && !pinned_cta && !pinned_tpc) {
       // a chain over T lanes: 32 chains (T = 4) or 64 chains (T = 2) per 128-thread CTA

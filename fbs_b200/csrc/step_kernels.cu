@@ -286,8 +286,8 @@ extern "C" int fbs_csmc_step_affine_f32(fbs_stream_t s, const fbs_affine_model_t
   int64_t blocks = (B * N + 7) / 8;  // 8 warps (children) per CTA
   const int64_t cap2 = (int64_t)sm_count() * 8;
   if (blocks > cap2) blocks = cap2;
-  const char* impl = getenv("FBS_STEP_IMPL");  // "cuda" pins the CUDA-core kernels (tests compare the two)
-  rc = (impl != nullptr && impl[0] == 'c') ? -1
+  // OPT_STEP_IMPL = 1 pins the CUDA-core kernels (tests compare the two)
+  rc = (debug_opt(OPT_STEP_IMPL) == 1) ? -1
                                            : launch_step_transition_tc(as_stream(s), model, k, step_keys, us_prev, A_out, v,
                                                                        v_prev, u_star, b_star, B, N, us_out, log_ws_out);
   if (rc > 0) return rc;

@@ -517,8 +517,7 @@ int launch_step_transition_tc(cudaStream_t st, const fbs_affine_model_t* model, 
   const int64_t tiles = B * p.tiles_per_chain;
   const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
   const int grid = (int)((tiles + per_cta - 1) / per_cta);
-  const char* ww = getenv("FBS_STEP_TC_WARPS");  // "8": eight worker warps with register prefetch; default sixteen
-  const bool eight = ww != nullptr && ww[0] == '8';
+  const bool eight = debug_opt(OPT_STEP_TC_WARPS) == 8;  // eight worker warps with register prefetch; default sixteen
   auto kern = eight ? step_transition_tc_kernel<8, true> : step_transition_tc_kernel<16, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) {

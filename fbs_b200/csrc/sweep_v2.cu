@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_v2_kernel(const SweepParams p) 
     } else {  // gibbs.py:133-137
       if (live && u_tile) {
         make_noise(kbase[2 * p.G + g], 1.0f);
-        const int b0 = p.bs_star[(size_t)chain * (K + 1)];
+        const int b0 = clamp_index(p.bs_star[(size_t)chain * (K + 1)], N);
         const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_v2_kernel(const SweepParams p) 
         int bj = -1;
         const float* ustar = nullptr;
         if (p.mode == MODE_CSMC) {
-          bj = p.bs_star[(size_t)chain * (K + 1) + k + 1];
+          bj = clamp_index(p.bs_star[(size_t)chain * (K + 1) + k + 1], N);
           ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
         }
 #pragma unroll
@@ -815,9 +815,9 @@ int launch_stepvec(void* stream, SweepParams& p) {
   {
     const int DP8 = (DP + 7) / 8 * 8, ng = DP8 / 8;
     const size_t sm2 = ((size_t)p.dv * DP8 + (size_t)SV_CH * (p.dv | 1)) * sizeof(float);
-    const char* impl = getenv("FBS_STEPVEC_IMPL");  // "old" pins the thread-per-output kernel
+    const bool old_impl = debug_opt(OPT_STEPVEC_IMPL) == 1;  // pins the thread-per-output kernel
     // (narrow systems keep the thread-per-output kernel: with fewer than 8 output groups most of a tiled CTA idles)
-    if (ng >= 8 && ng * (SV_CH / 8) <= 256 && sm2 <= 110 * 1024 && p.B >= SV_CH && !(impl != nullptr && impl[0] == 'o')) {
+    if (ng >= 8 && ng * (SV_CH / 8) <= 256 && sm2 <= 110 * 1024 && p.B >= SV_CH && !old_impl) {
       cudaFuncSetAttribute(stepvec_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
       const int64_t items = (int64_t)(p.K + 1) * ((p.B + SV_CH - 1) / SV_CH);
       const int64_t slots = 2 * (int64_t)sm_count();  // two CTAs per SM, persistent
@@ -841,7 +841,7 @@ int launch_sweep_v2(void* stream, SweepParams& p) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p.MTp == nullptr || p.ws == nullptr) return -1;
   if (p.N < 2 || (p.N & 1)) return -1;  // the threefry pairing needs an even particle count
-  const char* gforce = getenv("FBS_SWEEP_G");
+  const int gforce = debug_opt(OPT_SWEEP_G);
   // chains per CTA: as many as fit 384 threads (one 8x8 register tile each, <= 168 registers) and shared memory;
   // FBS_SWEEP_G overrides (up to 704 threads) for experiments
   const int max_tiles = gforce ? 704 : 384;
@@ -853,7 +853,7 @@ int launch_sweep_v2(void* stream, SweepParams& p) {
     if ((int64_t)G > p.B && bestG > 0) break;
     bestG = G;
     L = c;
-    if (gforce && G == atoi(gforce)) break;
+    if (gforce && G == gforce) break;
   }
   if (bestG == 0) return -1;
   p.G = bestG;

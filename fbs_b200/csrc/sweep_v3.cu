@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         for (int t = gt; t < N; t += GTHREADS) lw[t] = p.init_log_w;
       } else {  // gibbs.py:133-137
         make_noise(kbase[2], 1.0f, I_0{}, I_3{});
-        const int b0 = p.bs_star[(size_t)chain * (K + 1)];
+        const int b0 = clamp_index(p.bs_star[(size_t)chain * (K + 1)], N);
         const float* u0 = p.us_star + (size_t)chain * (K + 1) * du;
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           if (p.mode == MODE_CSMC) {  // the pinned reference particle of this step
             const float* ustar = p.us_star + ((size_t)chain * (K + 1) + k + 1) * du;
             for (int t = nt; t < du; t += NOISE_THREADS) pin[t] = ustar[t];
-            if (nt == 0) reinterpret_cast<int*>(pin)[du] = p.bs_star[(size_t)chain * (K + 1) + k + 1];
+            if (nt == 0) reinterpret_cast<int*>(pin)[du] = clamp_index(p.bs_star[(size_t)chain * (K + 1) + k + 1], N);
           }
           const Key ktr = skeys[2 * (k & 1) + 1];
           const float sd = __ldg(p.sd + k);
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             // elements per lane (q = lane + 32 j) in registers; the same float operations in the same order as
             // warp_cond_killing / warp_normalise_v3, hence the same bits
             const int32_t* bsp = p.bs_star + (size_t)chain * (K + 1);
-            const int ci = bsp[k], cj = bsp[k + 1];
+            const int ci = clamp_index(bsp[k], N), cj = clamp_index(bsp[k + 1], N);
             const float fn = (float)N;
             float wv[4];
             float m = -INFINITY;
@@ -1133,8 +1133,7 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   if (p.N < 2 || (p.N & 1) || p.N > ROWS) return -1;
   if (p.du % 4 != 0 || p.du < 4) return -1;
   int stages = MAX_STAGES;
-  const char* tp = getenv("FBS_V3_TWOPASS");
-  const int flags = (tp != nullptr && tp[0] == '1') ? 0x100 : 0;  // two-pass GEMM (v columns first): slower, the small-N MMAs are bound by operand fetch
+  const int flags = debug_opt(OPT_V3_TWOPASS) == 1 ? 0x100 : 0;  // two-pass GEMM (v columns first): slower, the small-N MMAs are bound by operand fetch
   Layout L = make_layout(p.N, p.du, p.dv, stages | flags);
   while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, --stages | flags);
   if (L.total > 227 * 1024) return -1;

@@ -83,7 +83,7 @@ def em_step(img, score, unobs, obs, B, p, q, c, a, g2, dt, sd, v_next=None, key=
 
 def gather_rows(src, idx, dst):
     B = idx.shape[0]
-    nat.call('fbs_gather_rows_f32', stream(), ptr(src), ptr(idx), B, src.numel() // src.shape[0], ptr(dst))
+    nat.call('fbs_gather_rows_f32', stream(), ptr(src), ptr(idx), B, src.numel() // src.shape[0], src.shape[0], ptr(dst))
 
 
 def to_bf16(x, y):

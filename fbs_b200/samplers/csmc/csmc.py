@@ -61,6 +61,17 @@ def _model_of(*fns):
     return model
 
 
+def _check_reference_indices(bs_star, n):
+    """``0 <= bs_star < n``, checked when the indices arrive as host data (no device synchronisation is spent on device
+    tensors: the kernels clamp what they load, as a JAX gather would)."""
+    if bs_star is None or (isinstance(bs_star, torch.Tensor) and bs_star.is_cuda):
+        return
+    b = np.asarray(bs_star)
+    if b.size and (b.min() < 0 or b.max() >= n):
+        raise ValueError(f'bs_star must lie in [0, {n}): got [{int(b.min())}, {int(b.max())}] (a reference-particle index from a '
+                         f'run with a different nparticles / explicit_final?)')
+
+
 def _scheme_of(resampling, family):
     if getattr(resampling, 'family', None) != family or not hasattr(resampling, 'scheme'):
         raise TypeError(f'{family} resampling must be one of the fbs_b200 resampling functions')
@@ -187,6 +198,7 @@ def forward_pass_device(key, us_star, bs_star, vs, model, init, scheme, nsamples
         init_mode, N, init_log_w = nat.INIT_DEGENERATE, init.nparticles, init.init_log_w
     else:
         raise TypeError('init_sampler / init_likelihood_logpdf must come from DegenerateInit or NormalInit')
+    _check_reference_indices(bs_star, N)
     res = dict(N=N)
     As = log_wss = uss = None
     if history:
@@ -239,6 +251,8 @@ def csmc_step(model, k, step_keys, us_prev, log_ws, vs_k1, vs_k, u_star_k1, b_st
     lw = dev(log_ws, torch.float32).reshape(B, N)
     v1, v0 = dev(vs_k1, torch.float32).reshape(B, model.dv), dev(vs_k, torch.float32).reshape(B, model.dv)
     ustar = dev(u_star_k1, torch.float32).reshape(B, model.du)
+    _check_reference_indices(b_star_k, N)
+    _check_reference_indices(b_star_k1, N)
     b0, b1 = dev(b_star_k, torch.int32).reshape(B), dev(b_star_k1, torch.int32).reshape(B)
     A = empty((B, N), torch.int32)
     us = empty((B, N, model.du), torch.float32)
@@ -283,7 +297,8 @@ def backward_scanning_pass(key, As, xss, log_w_T):
 
 
 def backward_sampling_pass(key, transition_logpdf, vs, ts, uss, log_ws, *args, **kwargs):
-    """csmc.py:167-227.  Composed step by step from the closure kernels (not a hot path: O(K) launches)."""
+    """csmc.py:167-227.  Affine models: the whole recursion is one launch (``fbs_backward_sample_affine_f32``, mode 0);
+    score-network models: one score evaluation per step."""
     model = _model_of(transition_logpdf)
     host = is_host(key)
     k = dev(key, torch.uint32)
@@ -296,6 +311,15 @@ def backward_sampling_pass(key, transition_logpdf, vs, ts, uss, log_ws, *args, *
     x = x.reshape(B, K1, N, du)
     lw = dev(log_ws, torch.float32).reshape(B, K1, N)
     v = dev(vs, torch.float32).reshape(B, K1, model.dv)
+    if not isinstance(model, ScoreNetModel):
+        xs = empty((B, K1, du), torch.float32)
+        Bs = empty((B, K1), torch.int32)
+        vc, xc, lwc = v.contiguous(), x.contiguous(), lw.contiguous()             # referenced until the launch
+        nat.call('fbs_backward_sample_affine_f32', stream(), model.struct(), 0, ptr(k), ptr(vc), ptr(xc), ptr(lwc), 0, B, N,
+                 ptr(xs), ptr(Bs))
+        if single:
+            xs, Bs = xs[0], Bs[0]
+        return out(xs, host), out(Bs, host)
     keys = frandom.split(k, K1)                                                    # csmc.py:194  [B, K1, 2]
     W_T = torch.exp(lw[:, -1] - torch.logsumexp(lw[:, -1], dim=-1, keepdim=True))  # csmc.py:200
     B_t = frandom.choice(keys[:, -1].contiguous(), N, (), p=W_T).reshape(B).long()
@@ -303,7 +327,7 @@ def backward_sampling_pass(key, transition_logpdf, vs, ts, uss, log_ws, *args, *
     x_t = x[ar, -1, B_t]
     xs, Bs = [x_t], [B_t]
     for q, t in enumerate(range(K1 - 2, -1, -1)):                                  # csmc.py:217
-        G = model._eval(t, None, x[:, t].contiguous(), None, v[:, t].contiguous(), x_t.contiguous(), 'tlp')
+        G = model.transition_logpdf(x_t[0], x[0, t], v[0, t], model.ts[t]).reshape(1, N)
         G = G - G.max(dim=-1, keepdim=True).values                                 # csmc.py:207
         lwt = G + lw[:, t]
         w = torch.exp(lwt - torch.logsumexp(lwt, dim=-1, keepdim=True))           # csmc.py:208-209

@@ -188,8 +188,10 @@ def pmcmc_kernel(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler,
 
 
 def bootstrap_filter(transition_sampler, measurement_cond_pdf, vs, ts, init_sampler, key, nparticles, resampling,
-                     log: bool = True, return_last: bool = True, **kwargs):
-    """smc.py:9-88 -> (samples, negative log-likelihood).  Step-by-step composition (initialisation path)."""
+                     log: bool = True, return_last: bool = True, return_history: bool = False, **kwargs):
+    """smc.py:9-88 -> (samples, negative log-likelihood).  Affine models: the whole K-step scan is ONE launch
+    (``fbs_bootstrap_filter_affine_f32``); ``return_history=True`` (tests) appends the per-step resampling indices and
+    unnormalised log-weights.  Score-network models: one score evaluation per step."""
     if not log:
         raise NotImplementedError('only the log-domain filter is used by the reference drivers')
     model = _model_of(transition_sampler, measurement_cond_pdf)
@@ -206,28 +208,30 @@ def bootstrap_filter(transition_sampler, measurement_cond_pdf, vs, ts, init_samp
         if single:
             res = tuple(t[0] for t in res)
         return tuple(out(t, host) for t in res)
+    scheme = _scheme_of(resampling, 'unconditional')
     v = dev(vs, torch.float32).reshape(B, K + 1, model.dv)
     ks = frandom.split(k, 2)                                                       # smc.py:77
     key_init, key_steps = ks[:, 0].contiguous(), ks[:, 1].contiguous()
-    us = dev(init_sampler(key_init, v[:, 0].contiguous(), N), torch.float32).reshape(B, N, model.du)
-    step_keys = frandom.split(key_steps, K)                                        # [B, K, 2]
-    log_nell = torch.zeros((B,), dtype=torch.float32, device=us.device)
-    hist = [us]
-    logN = np.float32(math.log(N))
-    ar = torch.arange(B, device=us.device)[:, None]
-    for kk in range(K):
-        pk = frandom.split(step_keys[:, kk].contiguous(), 2)                       # smc.py:61
-        key_proposal, key_resampling = pk[:, 0].contiguous(), pk[:, 1].contiguous()
-        vp, vc = v[:, kk].contiguous(), v[:, kk + 1].contiguous()
-        us_new = model._eval(kk, key_proposal, us, None, vp, None, 'us')           # smc.py:63
-        lw = model._eval(kk, None, us, vc, vp, None, 'lw')                         # smc.py:65
-        c = torch.logsumexp(lw, dim=-1)
-        log_nell = log_nell - (c - logN)                                           # smc.py:67
-        inds = resampling(torch.exp(lw - c[:, None]).contiguous(), key_resampling).long()   # smc.py:68-69
-        us = us_new[ar, inds].contiguous()                                         # smc.py:72
-        if not return_last:
-            hist.append(us)
-    res = (us, log_nell) if return_last else (torch.stack(hist, dim=1), log_nell)
+    u0 = dev(init_sampler(key_init, v[:, 0].contiguous(), N), torch.float32).reshape(B, N, model.du).contiguous()   # smc.py:78
+    uT = empty((B, N, model.du), torch.float32)
+    log_nell = empty((B,), torch.float32)
+    # the whole scan (smc.py:58-74,79-84) in one launch; the history is written straight behind the initial set
+    hist = None if return_last else empty((B, K + 1, N, model.du), torch.float32)
+    inds = lwh = None
+    if return_history:
+        inds = empty((B, K, N), torch.int32)
+        lwh = empty((B, K, N), torch.float32)
+    ush = None
+    if hist is not None:
+        hist[:, 0].copy_(u0)
+        ush = empty((B, K, N, model.du), torch.float32)
+    nat.call('fbs_bootstrap_filter_affine_f32', stream(), model.struct(), ptr(key_steps), ptr(v), ptr(u0), scheme, B, N,
+             ptr(uT), ptr(log_nell), ptr(inds), ptr(lwh), ptr(ush))
+    if hist is not None:
+        hist[:, 1:].copy_(ush)
+    res = (uT, log_nell) if return_last else (hist, log_nell)
+    if return_history:
+        res = res + (inds, lwh)
     if single:
         res = tuple(t[0] for t in res)
     return tuple(out(t, host) for t in res)
@@ -268,6 +272,17 @@ def bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf, *args
     fu = dev(filter_us, torch.float32)
     N, du = fu.shape[-2], fu.shape[-1]
     K = model.K
+    if not isinstance(model, ScoreNetModel):
+        # the whole backward recursion in one launch (mode 1 of fbs_backward_sample_affine_f32).  A history without a chain
+        # axis under batched keys is shared by all of them (the reference vmaps over the keys only, test_filters.py:138-141)
+        shared = 1 if (B > 1 and fu.numel() == (K + 1) * N * du) else 0
+        nb = 1 if shared else B
+        fu = fu.reshape(nb, K + 1, N, du).contiguous()
+        v = dev(vs, torch.float32).reshape(nb, K + 1, model.dv).contiguous()
+        xs = empty((B, K + 1, du), torch.float32)
+        nat.call('fbs_backward_sample_affine_f32', stream(), model.struct(), 1, ptr(k), ptr(v), ptr(fu), None, shared, B, N,
+                 ptr(xs), None)
+        return out(xs[0] if single else xs, host)
     fu = fu.reshape(B, K + 1, N, du)
     v = dev(vs, torch.float32).reshape(B, K + 1, model.dv)
     ks = frandom.split(k, 2)                                                       # smc.py:108
@@ -278,10 +293,7 @@ def bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf, *args
     u = uT
     traj = []
     for q, t in enumerate(range(K - 1, -1, -1)):                                   # smc.py:110-111
-        if isinstance(model, ScoreNetModel):
-            lw = model.transition_logpdf(u[0], fu[0, t], v[0, t], model.ts[t]).reshape(1, N)
-        else:
-            lw = model._eval(t, None, fu[:, t].contiguous(), None, v[:, t].contiguous(), u.contiguous(), 'tlp')
+        lw = model.transition_logpdf(u[0], fu[0, t], v[0, t], model.ts[t]).reshape(1, N)
         w = torch.exp(lw - torch.logsumexp(lw, dim=-1, keepdim=True)).contiguous()
         idx = frandom.choice(skeys[:, q].contiguous(), N, (), p=w).reshape(B).long()
         u = fu[ar, t, idx]

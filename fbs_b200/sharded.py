@@ -155,7 +155,7 @@ class PeerRows:
         from . import _native as nat
         from ._tensor import ptr, stream
         nat.call('fbs_gather_rows_peer_f32', stream(), ptr(self.table[self.cur]), ptr(parents_global), out.shape[0], self.row,
-                 self.shard.n, ptr(out))
+                 self.shard.n, self.shard.world, ptr(out))
 
     def publish(self, rows):
         """Write the step's new rows into the other buffer and make it current.  The caller's next collective (the all-gather of

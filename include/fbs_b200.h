@@ -4,8 +4,9 @@
  * Every entry point is `extern "C"`, takes a CUDA stream, DEVICE pointers and sizes, and
  * returns an int status (FBS_OK == 0).  No entry point allocates, frees, synchronises the
  * device or retains a pointer; all buffers (inputs, outputs, scratch) are owned by the
- * caller.  The library keeps no mutable global state besides a thread-local error string,
- * so it is re-entrant from concurrent host threads (the XLA-FFI threading model).
+ * caller.  The library keeps no mutable global state besides a thread-local error string
+ * (and the test-only implementation pins of fbs_debug_set_option), so it is re-entrant
+ * from concurrent host threads (the XLA-FFI threading model).
  *
  * The reference (zgbkdlm/fbs, pure JAX) has no FFI of its own; each function below names
  * the reference Python function (file:line under /root/reference) whose arithmetic it
@@ -56,6 +57,12 @@ const char* fbs_last_error(void);
 /* Number of kernel launches issued through this library on this thread since the last reset. */
 int64_t fbs_launch_count(void);
 void fbs_reset_launch_count(void);
+/* Test / measurement knob: pins one of several equivalent kernel implementations ("sweep_impl" = 1 | 2 | 3, "step_impl",
+ * "step_tc_warps", "stepvec_impl", "sweep_g", "v3_twopass", "em_impl", "sweep_verbose", "v3_variant"; 0 = the library's own choice).
+ * The options are process-wide relaxed atomics -- the only mutable global state of the library -- and never change
+ * results beyond the documented float32 summation-order differences between the implementations.  The library does
+ * not read the environment. */
+int fbs_debug_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------
  * jax.random (threefry2x32, jax 0.4.26 non-partitionable) -- third-party semantics the
@@ -199,6 +206,31 @@ int fbs_pmcmc_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model,
                                 float* log_ell, int32_t* inds, float* log_ws_hist, float* us_hist, void* workspace,
                                 size_t workspace_bytes);
 
+/* bootstrap_filter(transition_sampler, measurement_cond_pdf, vs, ts, init_sampler, key, nparticles, resampling),
+ * fbs/samplers/smc.py:9-88 (log-domain branch :58-74), the whole K-step scan in one launch.  step_keys [B,2] =
+ * key_steps of smc.py:77 (the caller draws u0s with key_init, :78); vs [B,K+1,dv]; u0s [B,N,du].
+ * Every particle is propagated BEFORE the resampling and its noise row travels with it (us = us_new[inds], :63,72).
+ * Out: uT [B,N,du] (the last resampled set), log_nell [B] (NEGATIVE log-likelihood, :67).  Optional history (may be
+ * NULL): inds [B,K,N], log_ws_hist [B,K,N] (unnormalised, :65), us_hist [B,K,N,du] (the resampled set after each step:
+ * with u0s prepended, the `return_last=False` output of :85-88). */
+int fbs_bootstrap_filter_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, const uint32_t* step_keys,
+                                    const float* vs, const float* u0s, int scheme, int64_t B, int64_t N, float* uT,
+                                    float* log_nell, int32_t* inds, float* log_ws_hist, float* us_hist);
+
+/* Backward sampling over a stored particle history, one launch for the whole K-step recursion.
+ * mode 0: backward_sampling_pass(key, transition_logpdf, vs, ts, uss, log_ws), fbs/samplers/csmc/csmc.py:167-227 --
+ *         B_T ~ Cat(normalise(log_ws[-1])) with keys[-1], then for t = K-1..0: G = transition_logpdf(x, uss[t], vs[t], ts[t]),
+ *         w = normalise(G - max G + log_ws[t]), B_t ~ Cat(w) with keys[q] (keys = split(key, K+1), consumed in order).
+ * mode 1: bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf), fbs/samplers/smc.py:91-112 --
+ *         u_T = filter_us[-1][randint(key)] (the UNSPLIT key, :109, as written upstream), then for k = K-1..0:
+ *         w = normalise(transition_logpdf(u, filter_us[k], vs[k], ts[k])), draw with split(split(key)[1], K)[q].
+ * keys [B,2]; vs [B,K+1,dv]; uss [B,K+1,N,du]; log_wss [B,K+1,N] (mode 0; NULL in mode 1).  shared_history != 0: vs, uss,
+ * log_wss carry no chain axis and all B keys walk the SAME stored history (the reference vmaps the smoother over keys
+ * only, tests/test_filters.py:138-141).  Out: xs_star [B,K+1,du]; bs_star [B,K+1] (may be NULL). */
+int fbs_backward_sample_affine_f32(fbs_stream_t s, const fbs_affine_model_t* model, int mode, const uint32_t* keys,
+                                   const float* vs, const float* uss, const float* log_wss, int shared_history, int64_t B,
+                                   int64_t N, float* xs_star, int32_t* bs_star);
+
 /* force_move(key, weights, k), fbs/samplers/gibbs.py:171-214, fused with the selection
  * x0 = uss[-1, idx] (gibbs.py:152-154).  log_ws_last [B,N]: normalised log-weights when weights_are_log != 0
  * (the kernel exponentiates, as gibbs.py:152 does), else the weights themselves.
@@ -293,15 +325,18 @@ int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, c
 int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
                        const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
                        float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw);
-/* dst[b, :] = src[idx[b], :]  (the ancestor gather, csmc.py:140). */
-int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, float* dst);
+/* dst[b, :] = src[clamp(idx[b], 0, src_rows - 1), :]  (the ancestor gather, csmc.py:140; an out-of-range index -- the
+ * unclipped systematic scheme of resamplings.py:120-125 can return N -- is clamped, as a JAX gather does). */
+int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, int64_t src_rows,
+                        float* dst);
 
 /* Particle-sharded sweep (one chain over the GPUs of an NVSwitch box; no upstream counterpart): the ancestor gather over
  * PEER MEMORY.  srcs: device array of one pointer per rank to that rank's particle rows [rows_per_rank, row] (the local
  * buffer for the calling rank, CUDA-IPC imports for the others); idx: GLOBAL parent row of each of the B local children.
- * dst[b, :] = srcs[idx[b] / rows_per_rank][idx[b] % rows_per_rank, :] -- NVLink loads inside the kernel. */
+ * dst[b, :] = srcs[g / rows_per_rank][g % rows_per_rank, :], g = clamp(idx[b], 0, n_ranks rows_per_rank - 1) -- NVLink loads
+ * inside the kernel. */
 int fbs_gather_rows_peer_f32(fbs_stream_t s, const float* const* srcs, const int32_t* idx, int64_t B, int64_t row,
-                             int64_t rows_per_rank, float* dst);
+                             int64_t rows_per_rank, int64_t n_ranks, float* dst);
 /* CUDA IPC plumbing for the above (host side; the 64-byte handles travel through the caller's own channel).  export:
  * handle of the allocation containing dev_ptr and dev_ptr's offset inside it; import: the peer's view of that address
  * (peer access enabled lazily); release: closes an import. */

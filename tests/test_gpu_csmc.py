@@ -166,6 +166,47 @@ def test_closures_match_oracle():
 @pytest.mark.parametrize('d,N,K,B', [(1, 10, 10, 4), (10, 100, 10, 3), (10, 25, 16, 7), (100, 100, 3, 2), (6, 8, 8, 150)])
 @pytest.mark.parametrize('scheme', ['stratified', 'systematic', 'killing'])
 def test_pmcmc_filter_step_teacher_forced(d, N, K, B, scheme):
+    _check_pmcmc_filter(d, N, K, B, scheme)
+
+
+@pytest.mark.parametrize('mode', ['csmc-killing', 'pmcmc-stratified'])
+def test_bench_shape_teacher_forced_on_tensor_cores(mode, monkeypatch):
+    """The benchmarked configuration at its own size -- d = 100, K = 200, N = 100 (bench.py; gp_gibbs.py / gp_pmcmc.py) --
+    through the tcgen05 kernel PINNED (sweep_impl = 3 fails instead of falling back), an odd number of chains (the second
+    warp group of the last CTA idles), every one of the 200 steps of every chain re-derived by the oracle: K = 200 cycles
+    the TMA ring and the mbarrier phase bits ~50x more often than the K <= 4 shapes above."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v3')
+    d, N, K, B = 100, 100, 200, 5
+    if mode == 'pmcmc-stratified':
+        _check_pmcmc_filter(d, N, K, B, 'stratified')
+        return
+    p = gp_problem(d, K=K)
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N, seed=77)
+    init = csmc.DegenerateInit(N)
+    As, log_wss, uss = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, R.killing, N)
+    assert As.shape == (B, K, N)
+    _check_forward_history(p, om64, keys, us_star, bs_star, vs, As, log_wss, uss, 'killing', False)
+
+
+def test_pinned_tensor_core_kernel_refuses_ineligible_shapes(monkeypatch):
+    """sweep_impl = 3 must not silently fall back: an odd particle count is not eligible for the tcgen05 kernel."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v3')
+    d, N, K, B = 8, 130, 3, 1
+    p = gp_problem(d, K=K)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, oracle_model(p, np.float32), B, N)
+    init = csmc.DegenerateInit(N)
+    with pytest.raises(NotImplementedError):
+        csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf, pm.transition_sampler,
+                          pm.likelihood_logpdf, R.killing, N)
+
+
+def _check_pmcmc_filter(d, N, K, B, scheme):
     from fbs_b200.samplers import smc, resampling as R
     p = gp_problem(d, K=K)
     om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
@@ -389,6 +430,33 @@ def test_pmcmc_kernel_composition(delta):
             np.testing.assert_array_equal(uT2[b], uT[b])
             assert le2[b] == log_ell[b]
     assert 0 < st.is_accepted.sum() < B
+
+
+def test_mh_accept_rejects_nan_evidence():
+    """smc.py:246-249: ``jnp.minimum(0, nan)`` is nan and ``log z < nan`` is False -- a proposal whose evidence is NaN (all
+    weights -inf, a non-finite score) is REJECTED and the chain keeps its last finite state.  (CUDA's fminf would drop the NaN
+    and accept every such proposal.)"""
+    import torch
+    from fbs_b200 import _native as nat
+    from fbs_b200._tensor import ptr, stream
+    B, N, du, ny = 6, 4, 3, 10
+    keys = torch.from_numpy(jr.split(jr.PRNGKey(9), B)).cuda()
+    prop_uTs = torch.randn(B, N, du, device='cuda')
+    prop_ys = torch.randn(B, ny, device='cuda')
+    ple = torch.tensor([float('nan'), 5., float('nan'), float('inf'), -float('inf'), float('nan')], device='cuda')
+    le0 = torch.tensor([0., 0., float('nan'), 0., 0., -float('inf')], device='cuda')
+    uT, ys, le = torch.zeros(B, du, device='cuda'), torch.zeros(B, ny, device='cuda'), le0.clone()
+    acc_prob = torch.empty(B, device='cuda')
+    is_acc = torch.empty(B, dtype=torch.uint8, device='cuda')
+    nat.call('fbs_mh_accept_f32', stream(), ptr(keys), ptr(prop_uTs), ptr(ple), ptr(prop_ys), B, N, du, ny, 0, ptr(uT), ptr(le),
+             ptr(ys), ptr(acc_prob), ptr(is_acc))
+    acc = is_acc.cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(acc, [False, True, False, True, False, False])
+    for b in (0, 2, 4, 5):                                  # rejected: state untouched
+        assert torch.equal(uT[b], torch.zeros(du, device='cuda')) and torch.equal(ys[b], torch.zeros(ny, device='cuda'))
+        assert torch.equal(le[b:b + 1], le0[b:b + 1]) or (torch.isnan(le[b]) and torch.isnan(le0[b]))
+    assert torch.isnan(acc_prob[[0, 2, 5]]).all()
+    assert torch.equal(uT[1], prop_uTs[1, 0]) and float(le[1]) == 5.
 
 
 def test_pmcmc_kernel_host_pipeline_equals_unchunked(monkeypatch):

@@ -1,0 +1,341 @@
+"""Bootstrap filter / backward smoother / backward sampling / gibbs_init on the CUDA path.
+
+Part 1 (teacher-forced parity): every step of ``fbs_bootstrap_filter_affine_f32`` and ``fbs_backward_sample_affine_f32``
+is re-derived by the oracle (oracle/smc.py, oracle/csmc.py) from the kernel's own state one step earlier, as in
+test_gpu_csmc.py: indices exact (up to float32 ``exp`` ties), particles rtol 1e-5, log-weights atol 2e-3.
+
+Part 2 (the reference's own acceptance criteria, re-run on the kernels with the reference's tolerances):
+``/root/reference/tests/test_filters.py:14-143`` (particle filter vs Kalman filter, backward smoother vs GP regression) and
+``/root/reference/tests/test_csmc.py:39-132`` (Gibbs-within-CSMC keeps the prior invariant, ``backward`` False and True).
+The reference builds those models as inline Python closures; here they are ``AffineGaussianModel`` s (helpers.LinearGaussianSSM).
+test_csmc.py's ``tanh`` emission is not affine, so the emission is linear (the criterion -- prior invariance -- is the same).
+"""
+import math
+import numpy as np
+import pytest
+import torch
+from oracle import jax_random as jr
+from oracle import resampling as orx
+from oracle import csmc as ocsmc
+from oracle import smc as osmc
+from helpers import gp_problem, oracle_model, product_model, LinearGaussianSSM
+
+pytestmark = pytest.mark.gpu
+
+
+def _paths(p, om32, B, seed):
+    d = p['d']
+    x0s = jr.normal(jr.PRNGKey(200 + seed), (B, d))
+    vs = np.stack([om32.fwd_sampler(k, x0s[b], p['y0'])[::-1, d:] for b, k in enumerate(jr.split(jr.PRNGKey(300 + seed), B))])
+    return vs.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Part 1: teacher-forced parity
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('d,N,K,B', [(1, 10, 12, 5), (4, 16, 10, 7), (10, 101, 8, 3), (100, 100, 5, 2), (3, 1000, 4, 2)])
+@pytest.mark.parametrize('scheme', ['stratified', 'systematic', 'killing'])
+def test_bootstrap_filter_teacher_forced(d, N, K, B, scheme):
+    """smc.py:58-88 step by step: proposal from the CURRENT particles, weights of the current particles against the next
+    observation, resampling of the PROPOSED particles (noise row travels with its particle), negative log-likelihood."""
+    from fbs_b200.samplers import smc, resampling as R
+    from fbs_b200 import random as fr
+    p = gp_problem(d, K=K)
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    vs = _paths(p, om32, B, seed=3)
+    keys = jr.split(jr.PRNGKey(900 + d), B)
+
+    def init_sampler(key_, v0, n):
+        return fr.normal(key_, (n, d))
+
+    hist, log_nell, inds, lwh = smc.bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, p['ts'], init_sampler, keys,
+                                                     N, getattr(R, scheme), return_last=False, return_history=True)
+    assert hist.shape == (B, K + 1, N, d) and inds.shape == (B, K, N) and log_nell.shape == (B,)
+    last, log_nell2 = smc.bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, p['ts'], init_sampler, keys, N,
+                                           getattr(R, scheme))
+    np.testing.assert_array_equal(last, hist[:, -1])
+    np.testing.assert_array_equal(log_nell2, log_nell)
+    ts = om64.ts
+    mism = 0
+    for b in range(B):
+        key_init, key_steps = jr.split(keys[b])                                       # smc.py:77
+        np.testing.assert_allclose(hist[b, 0], jr.normal(key_init, (N, d)), rtol=0, atol=5e-7)
+        step_keys = jr.split(key_steps, K)
+        acc = np.float32(0.)
+        for k in range(K):
+            key_prop, key_res = jr.split(step_keys[k])                                # smc.py:61
+            us = hist[b, k].astype(np.float64)
+            lw = om64.likelihood_logpdf(vs[b, k + 1].astype(np.float64), us, vs[b, k].astype(np.float64), ts[k])
+            np.testing.assert_allclose(lwh[b, k], lw, rtol=2e-5, atol=2e-3)
+            c = ocsmc.logsumexp(lwh[b, k])
+            acc = np.float32(acc - np.float32(c - np.float32(math.log(N))))           # smc.py:67
+            want_inds = getattr(orx, scheme)(np.exp(lwh[b, k] - c).astype(np.float32), key_res)
+            mism += int((want_inds != inds[b, k]).sum())
+            us_new = om64.transition_mean(us, vs[b, k].astype(np.float64), ts[k]) \
+                + np.float64(om64.transition_sd(ts[k])) * jr.normal(key_prop, (N, d))   # smc.py:63
+            np.testing.assert_allclose(hist[b, k + 1], us_new[inds[b, k]], rtol=1e-5, atol=2e-5)   # smc.py:72
+        np.testing.assert_allclose(log_nell[b], acc, rtol=1e-5, atol=1e-3)
+    assert mism <= max(1, int(2e-4 * B * K * N)), mism
+
+
+def test_bootstrap_filter_single_chain_equals_batch_row():
+    from fbs_b200.samplers import smc, resampling as R
+    from fbs_b200 import random as fr
+    d, N, K, B = 3, 12, 6, 4
+    p = gp_problem(d, K=K)
+    pm, _ = product_model(p)
+    vs = _paths(p, oracle_model(p, np.float32), B, seed=1)
+    keys = jr.split(jr.PRNGKey(5), B)
+    init = lambda key_, v0, n: fr.normal(key_, (n, d))                              # noqa: E731
+    a = smc.bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, p['ts'], init, keys, N, R.stratified,
+                             return_last=False)
+    b = smc.bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs[2], p['ts'], init, keys[2], N, R.stratified,
+                             return_last=False)
+    np.testing.assert_array_equal(a[0][2], b[0])
+    assert a[1][2] == b[1]
+
+
+def _history(p, B, N, seed):
+    """A stored particle history + weights to walk backwards over: a CSMC forward pass of the kernel itself."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as CR
+    from test_gpu_csmc import _inputs
+    om32 = oracle_model(p, np.float32)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N, seed=seed)
+    init = csmc.DegenerateInit(N)
+    As, log_wss, uss = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf,
+                                         pm.transition_sampler, pm.likelihood_logpdf, CR.killing, N)
+    return pm, vs, log_wss, uss
+
+
+@pytest.mark.parametrize('d,N,K,B', [(1, 10, 12, 6), (5, 33, 9, 4), (10, 100, 10, 3), (100, 100, 4, 2), (40, 7, 5, 150)])
+def test_backward_sampling_pass_teacher_forced(d, N, K, B):
+    """csmc.py:167-227: B_T ~ Cat(W_T) with keys[-1]; then G = transition_logpdf(x_{t+1}, uss[t], vs[t], ts[t]),
+    w = normalise(G - max G + log_ws[t]), B_t ~ Cat(w) with keys[q] -- each step re-derived from the kernel's own x_{t+1}."""
+    from fbs_b200.samplers.csmc import csmc
+    p = gp_problem(d, K=K)
+    om64 = oracle_model(p, np.float64)
+    pm, vs, log_wss, uss = _history(p, B, N, seed=31)
+    keys = jr.split(jr.PRNGKey(77 + d), B)
+    xs, bs = csmc.backward_sampling_pass(keys, pm.transition_logpdf, vs, p['ts'], uss, log_wss)
+    assert xs.shape == (B, K + 1, d) and bs.shape == (B, K + 1) and bs.dtype == np.int32
+    mism = 0
+    nb = min(B, 6)
+    for b in range(nb):
+        ks = jr.split(keys[b], K + 1)                                                 # csmc.py:194
+        want = ocsmc.barker_move(ks[-1], ocsmc.normalise(log_wss[b, -1]))             # csmc.py:200-201
+        mism += int(want != bs[b, K])
+        for q, t in enumerate(range(K - 1, -1, -1)):
+            G = om64.transition_logpdf(xs[b, t + 1].astype(np.float64), uss[b, t].astype(np.float64), vs[b, t].astype(np.float64),
+                                       om64.ts[t])
+            G = G - G.max()
+            w = ocsmc.normalise((G + log_wss[b, t]).astype(np.float32))
+            mism += int(int(jr.choice(ks[q], N, (), p=w)) != bs[b, t])
+    for b in range(B):
+        np.testing.assert_array_equal(xs[b], uss[b, np.arange(K + 1), bs[b]])
+        assert bs[b].min() >= 0 and bs[b].max() < N
+    assert mism <= max(1, int(3e-3 * nb * (K + 1))), mism
+    # unbatched call == row of the batched call
+    x1, b1 = csmc.backward_sampling_pass(keys[1], pm.transition_logpdf, vs[1], p['ts'], uss[1], log_wss[1])
+    np.testing.assert_array_equal(x1, xs[1]); np.testing.assert_array_equal(b1, bs[1])
+
+
+@pytest.mark.parametrize('d,N,K,B', [(1, 10, 12, 6), (6, 50, 8, 4), (100, 100, 4, 2), (2, 1000, 5, 3)])
+def test_backward_smoother_teacher_forced(d, N, K, B):
+    """smc.py:91-112: u_T = filter_us[-1][randint(key)] with the UNSPLIT key, then backward draws with split(key)[1]."""
+    from fbs_b200.samplers import smc
+    p = gp_problem(d, K=K)
+    om64 = oracle_model(p, np.float64)
+    pm, vs, _, uss = _history(p, B, N, seed=13)
+    keys = jr.split(jr.PRNGKey(11 + d), B)
+    traj = smc.bootstrap_backward_smoother(keys, uss, vs, p['ts'], pm.transition_logpdf)
+    assert traj.shape == (B, K + 1, d)
+    mism = 0
+    for b in range(B):
+        np.testing.assert_array_equal(traj[b, K], uss[b, K, int(jr.randint(keys[b], (), 0, N))])   # smc.py:109
+        ks = jr.split(jr.split(keys[b], 2)[1], K)
+        for q, t in enumerate(range(K - 1, -1, -1)):
+            lw = om64.transition_logpdf(traj[b, t + 1].astype(np.float64), uss[b, t].astype(np.float64),
+                                        vs[b, t].astype(np.float64), om64.ts[t])
+            w = np.exp(lw - ocsmc.logsumexp(lw)).astype(np.float32)
+            idx = int(jr.choice(ks[q], N, (), p=w))
+            mism += int(not np.array_equal(traj[b, t], uss[b, t, idx]))
+    assert mism <= max(1, int(3e-3 * B * K)), mism
+    # the oracle's whole smoother on the same history (chaotic only through index ties: compare the first chain loosely)
+    want = osmc.bootstrap_backward_smoother(keys[0], uss[0], vs[0], om64.ts, lambda u, up, vp, t: om64.transition_logpdf(
+        u.astype(np.float64), up.astype(np.float64), vp.astype(np.float64), t).astype(np.float32))
+    assert (np.abs(want - traj[0]).max(axis=1) == 0).mean() >= 0.5
+
+
+def test_backward_smoother_shared_history_equals_per_chain_copies():
+    """Batched keys over ONE stored history (the reference vmaps the smoother over keys only, test_filters.py:138-141)."""
+    from fbs_b200.samplers import smc
+    d, N, K = 3, 20, 7
+    p = gp_problem(d, K=K)
+    pm, vs, _, uss = _history(p, 1, N, seed=2)
+    keys = jr.split(jr.PRNGKey(4), 9)
+    a = smc.bootstrap_backward_smoother(keys, uss[0], vs[0], p['ts'], pm.transition_logpdf)
+    b = smc.bootstrap_backward_smoother(keys, np.repeat(uss, 9, 0), np.repeat(vs, 9, 0), p['ts'], pm.transition_logpdf)
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('method', ['filter', 'smoother'])
+def test_gibbs_init_composition(method):
+    """gibbs_init (gibbs.py:23-65, marg_y=False) piece by piece under the oracle's key schedule."""
+    from fbs_b200.samplers import gibbs_init, smc, resampling as R
+    from fbs_b200 import random as fr
+    d, N, K, B = 3, 24, 9, 5
+    p = gp_problem(d, K=K)
+    om32 = oracle_model(p, np.float32)
+    pm, sde = product_model(p)
+    keys = jr.split(jr.PRNGKey(31), B)
+    x0, us_star = gibbs_init(keys, p['y0'], (d,), p['ts'], pm.fwd_sampler, sde, pm.unpack, pm.transition_sampler,
+                             pm.transition_logpdf, pm.likelihood_logpdf, N, method=method, marg_y=False)
+    assert x0.shape == (B, d) and us_star.shape == (B, K + 1, d)
+    for b in range(B):
+        key_fwd, _, key_u0, key_bf, key_fwd2, key_bwd = jr.split(keys[b], 6)           # gibbs.py:39
+        path = om32.fwd_sampler(key_fwd, np.zeros(d, np.float32), p['y0'])             # gibbs.py:41-43 (x0 = zeros)
+        _, vs = pm.fwd_sampler_reversed(key_fwd, np.zeros(d, np.float32), p['y0'])
+        np.testing.assert_allclose(vs, path[::-1, d:], rtol=2e-5, atol=2e-6)
+        u0 = jr.normal(key_u0, (N, d))                                                 # gibbs.py:46-48: ignores the filter's key
+        init = lambda *_: u0                                                           # noqa: E731
+        if method == 'filter':
+            last, _ = smc.bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, p['ts'], init, key_bf, N, R.stratified)
+            np.testing.assert_array_equal(x0[b], last[0])                              # gibbs.py:52-53
+            want = om32.fwd_sampler(key_fwd2, x0[b], p['y0'])[::-1, :d]                # gibbs.py:54
+            np.testing.assert_allclose(us_star[b], want, rtol=2e-5, atol=2e-6)
+        else:
+            uss, _ = smc.bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, p['ts'], init, key_bf, N, R.stratified,
+                                          return_last=False)
+            np.testing.assert_array_equal(uss[0], u0)
+            np.testing.assert_array_equal(x0[b], uss[-1, 0])                           # gibbs.py:59
+            want = smc.bootstrap_backward_smoother(key_bwd, uss, vs, p['ts'], pm.transition_logpdf)   # gibbs.py:60-61
+            np.testing.assert_array_equal(us_star[b], want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Part 2: the reference's acceptance criteria on the kernels
+# ------------------------------------------------------------------------------------------------------------------
+def test_particle_filter_vs_kalman():
+    """tests/test_filters.py:14-87: x_k = F x_{k-1} + y_{k-1} + q_k, y_k = H x_k + y_{k-1} + r_k; 1000 particles, stratified;
+    filtering means / variances against the Kalman filter, rtol = atol = 1e-1 (:86-87), over 8 simulated data sets."""
+    from fbs_b200.samplers import bootstrap_filter, stratified
+    from fbs_b200 import random as fr
+    F, trans_var, H, meas_var, K, N, B = 0.1, 0.1, 1., 1., 20, 1000, 8
+    mod = LinearGaussianSSM(F, 1., H, 1., math.sqrt(trans_var), math.sqrt(meas_var), K)
+    pm = mod.product()
+    rng = np.random.default_rng(666)
+    y0, m0, v0 = 0., 0., 1.
+    ys_all, kf_m, kf_v = [], [], []
+    for _ in range(B):
+        x, y = m0 + math.sqrt(v0) * rng.standard_normal(), y0
+        ys = [y0]
+        for k in range(K):                                                             # :27-32
+            x = F * x + y + math.sqrt(trans_var) * rng.standard_normal()
+            y = H * x + y + math.sqrt(meas_var) * rng.standard_normal()
+            ys.append(y)
+        ys = np.array(ys)
+        mf, vf, ms, vv = m0, v0, [], []
+        for k in range(K):                                                             # :47-61
+            mp, vp = F * mf + ys[k], F * vf * F + trans_var
+            s = vp * H ** 2 + meas_var
+            gain = vp * H / s
+            mf, vf = mp + gain * (ys[k + 1] - (H * mp + ys[k])), vp - vp * H * gain
+            ms.append(mf); vv.append(vf)
+        ys_all.append(ys); kf_m.append(ms); kf_v.append(vv)
+    ys_all, kf_m, kf_v = np.array(ys_all), np.array(kf_m), np.array(kf_v)
+    vs = mod.scale(ys_all)[:, :, None].astype(np.float32)
+    y0_dev = torch.tensor(y0, device='cuda')
+
+    def init_sampler(key_, v0_, n):                                                    # :77-78
+        return y0_dev + math.sqrt(v0) * fr.normal(key_, (n, 1))
+
+    keys = jr.split(jr.PRNGKey(666), B)
+    pf, _ = bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, mod.ts, init_sampler, keys, N, stratified,
+                             log=True, return_last=False)
+    pf = pf[:, 3:, :, 0]                                                               # :82-84: the reference's index shift
+    np.testing.assert_allclose(pf.mean(axis=2), kf_m[:, 2:], rtol=1e-1, atol=1e-1)
+    np.testing.assert_allclose(pf.var(axis=2), kf_v[:, 2:], rtol=1e-1, atol=1e-1)
+
+
+def test_particle_smoother_vs_gp_regression():
+    """tests/test_filters.py:90-143: OU prior observed in unit noise, K = 100; bootstrap filter (4000 particles here -- the
+    one-launch filter keeps the particle set in shared memory; 10 000 upstream) + 1000 backward-smoother trajectories over the
+    shared filter history; trajectory mean against the GP-regression posterior mean, the reference's rtol 2e-1 (:143) plus
+    atol 6e-2 where the posterior mean crosses zero (Monte-Carlo error of 1000 trajectories)."""
+    from fbs_b200.samplers import bootstrap_filter, bootstrap_backward_smoother, stratified
+    from fbs_b200 import random as fr
+    ell = sigma = 1.
+    a = -1 / ell
+    K, T, R_ = 100, 1., 1.
+    dt = T / K
+    ts = np.linspace(0, T, K + 1)
+    Fd = math.exp(a * dt)
+    Qd = sigma ** 2 * (1 - Fd * Fd)                                                    # discretise_lti_sde of the OU prior
+    cov = sigma ** 2 * np.exp(-np.abs(ts[None, :] - ts[:, None]) / ell)
+    rng = np.random.default_rng(666)
+    xs = np.linalg.cholesky(cov) @ rng.standard_normal(K + 1)
+    ys = xs + math.sqrt(R_) * rng.standard_normal(K + 1)
+    gain = cov + R_ * np.eye(K + 1)
+    post_mean = cov @ np.linalg.solve(gain, ys)
+    post_cov = cov - cov @ np.linalg.solve(gain, cov)
+    mod = LinearGaussianSSM(Fd, 0., 1., 0., math.sqrt(Qd), math.sqrt(R_), K)          # likelihood N(y; x_prev, sqrt R) (:124-125)
+    pm = mod.product()
+    vs = mod.scale(ys)[:, None].astype(np.float32)
+
+    def init_sampler(key_, _, n):                                                      # :112-113
+        return float(post_mean[0]) + math.sqrt(post_cov[0, 0]) * fr.normal(key_, (n, 1))
+
+    key = jr.PRNGKey(666)
+    key, sub = jr.split(key)
+    filt = bootstrap_filter(pm.transition_sampler, pm.likelihood_logpdf, vs, mod.ts, init_sampler, sub, 4000, stratified,
+                            log=True, return_last=False)[0]
+    key, sub = jr.split(key)
+    trajs = bootstrap_backward_smoother(jr.split(sub, 1000), filt, vs, mod.ts, pm.transition_logpdf)
+    assert trajs.shape == (1000, K + 1, 1)
+    np.testing.assert_allclose(trajs[:, :, 0].mean(axis=0), post_mean, rtol=2e-1, atol=6e-2)
+
+
+@pytest.mark.parametrize('backward', [False, True])
+def test_csmc_gibbs_keeps_prior_invariant(backward):
+    """tests/test_csmc.py:39-132: alternate y | x and x | y (csmc_kernel, killing, 10 particles, K = 10); the x-marginal must
+    stay the OU prior: mean atol 1e-1 (:130), marginal variances rtol = atol = 1e-1 (:131), covariance atol 2e-1 (:132).
+    256 chains x 300 iterations (100 burn-in) instead of one chain x 2000: the same criteria on 51 200 draws.  The emission is
+    linear, paired as the sweep pairs it (the weight of step k scores vs[k + 1] against the particles of step k, csmc.py:145):
+    y_0 ~ N(x_0, R), y_{k+1} ~ N(x_k, R), which makes the CSMC target exactly p(x | y)."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as CR
+    from fbs_b200 import random as fr
+    ell = sigma = 1.
+    a = -1 / ell
+    K, N, B, iters, burn = 10, 10, 256, 300, 100
+    dt = 1.
+    ts = np.arange(K + 1) * dt
+    Fd = math.exp(a * dt)
+    Qd = sigma ** 2 * (1 - Fd * Fd)
+    R_ = 1.
+    mod = LinearGaussianSSM(Fd, 0., 1., 0., math.sqrt(Qd), math.sqrt(R_), K)
+    pm = mod.product()
+    cov = sigma ** 2 * np.exp(-np.abs(ts[None, :] - ts[:, None]) / ell)
+    rng = np.random.default_rng(0)
+    xs_star = torch.from_numpy((rng.standard_normal((B, K + 1)) @ np.linalg.cholesky(cov).T).astype(np.float32)).cuda()[:, :, None]
+    bs_star = torch.zeros((B, K + 1), dtype=torch.int32, device='cuda')
+    init = csmc.NormalInit(pm)                                                         # init_sampler N(0, stat_var = 1) (:64-65)
+    master = torch.from_numpy(jr.PRNGKey(666)).cuda()
+    out = []
+    for i in range(iters):
+        kk = fr.split(master, 3)
+        master = kk[0].contiguous()
+        src = torch.cat([xs_star[:, :1], xs_star[:, :-1]], dim=1)
+        ys = src + math.sqrt(R_) * fr.normal(fr.split(kk[1].contiguous(), B), (K + 1, 1))          # y | x (:61-62)
+        vs = (ys * mod.c).contiguous()
+        xs_star, bs_star = csmc.csmc_kernel(fr.split(kk[2].contiguous(), B), xs_star, bs_star, vs, mod.ts, init.sampler,
+                                            init.likelihood_logpdf, pm.transition_sampler, pm.transition_logpdf,
+                                            pm.likelihood_logpdf, CR.killing, N, backward=backward)   # x | y (:78-88)
+        if i >= burn:
+            out.append(xs_star[:, :, 0].cpu().numpy())
+    S = np.concatenate(out)
+    c = np.cov(S, rowvar=False)
+    np.testing.assert_allclose(S.mean(axis=0), np.zeros(K + 1), atol=1e-1)
+    np.testing.assert_allclose(np.diag(c), np.diag(cov), rtol=1e-1, atol=1e-1)
+    np.testing.assert_allclose(c, cov, atol=2e-1)

@@ -451,6 +451,6 @@ def test_peer_gather_kernel_owner_arithmetic():
         table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device='cuda')
         idx = torch.tensor([14, 0, 7, 7, 3, 10, 4, 5], dtype=torch.int32, device='cuda')
         dst = torch.empty(idx.numel(), row, device='cuda')
-        nat.call('fbs_gather_rows_peer_f32', stream(), ptr(table), ptr(idx), idx.numel(), row, n, ptr(dst))
+        nat.call('fbs_gather_rows_peer_f32', stream(), ptr(table), ptr(idx), idx.numel(), row, n, G, ptr(dst))
         want = torch.cat(bufs)[idx.long()]
         assert torch.equal(dst, want)

@@ -139,3 +139,30 @@ def test_gaussian_sb_marginals():
     xT = sdes.euler_maruyama(keys, x0, ts, drift, lambda t: 1., integration_nsteps=2, return_path=False)
     np.testing.assert_allclose(xT.mean(0), m1, atol=5e-2)
     np.testing.assert_allclose(np.cov(xT.T), c1, atol=8e-2)
+
+
+def test_ou_and_linear_sde_agree_bitwise_on_the_kernels():
+    """tests/test_sdes.py:149-159 on the CUDA path: ``make_ou_sde(a, b)`` and ``make_linear_sde(StationaryConstLinearSDE(a, b))``
+    give EQUAL discretisations, conditional scores and -- under one key -- bitwise equal forward paths (``assert_array_equal``
+    upstream, :159), batched and unbatched."""
+    from fbs_b200 import sdes
+    a, b = -0.5, 1.
+    ou_disc, ou_score, ou_sim = sdes.make_ou_sde(a, b)
+    lin_disc, lin_score, lin_sim = sdes.make_linear_sde(sdes.StationaryConstLinearSDE(a=a, b=b))
+    F_ou, Q_ou = ou_disc(1.)
+    F_l, Q_l = lin_disc(1., 0.)
+    np.testing.assert_equal(F_ou, F_l)                                           # :149-150
+    np.testing.assert_equal(Q_ou, Q_l)
+    np.testing.assert_equal(ou_score(2.2, 1.1, 1.5), lin_score(2.2, 1.1, 1.5, 0.))   # :152-154
+    key = jr.PRNGKey(666)
+    ts = np.linspace(0., 2., 20)
+    path_ou = ou_sim(key, np.array([2.5], np.float32), ts)                       # :156-159
+    path_lin = lin_sim(key, np.array([2.5], np.float32), ts)
+    assert path_ou.shape == (20, 1)
+    np.testing.assert_array_equal(path_ou, path_lin)
+    keys = jr.split(key, 7)
+    x0 = jr.normal(jr.PRNGKey(1), (7, 5))
+    np.testing.assert_array_equal(ou_sim(keys, x0, ts), lin_sim(keys, x0, ts))
+    # and the path is the oracle's (float32 restatement of linear.py:190-225)
+    _, _, osim = osdes.make_ou_sde(a, b)
+    np.testing.assert_allclose(path_ou, osim(key, np.array([2.5], np.float32), ts), rtol=2e-5, atol=2e-6)
