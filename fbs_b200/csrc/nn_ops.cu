@@ -643,6 +643,27 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
   }
 }
 
+// One Euler--Maruyama sub-step with the drift ALREADY evaluated (a score / drift network, simulators.py:87):
+//   out[b, e] = x[b, e] + drift[b, e] * ddt + gs * normal(key_b, (n,))[e],   gs = dispersion(t) * sqrt(ddt)
+// One thread per threefry block (elements e and e + h of the chain's stream).  Products and sums are rounded one by
+// one, as the NumPy oracle evaluates the expression.
+__global__ void __launch_bounds__(256) em_drift_step_kernel(const uint32_t* __restrict__ keys, const float* __restrict__ x,
+                                                            const float* __restrict__ drift, int64_t B, uint32_t n, float ddt,
+                                                            float gs, float* __restrict__ out) {
+  const uint32_t h = (n + 1u) >> 1;
+  const int64_t total = B * (int64_t)h;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / h;
+    const uint32_t e = (uint32_t)(t - b * h);
+    uint32_t y0, y1;
+    random_bits_block(Key{keys[2 * b], keys[2 * b + 1]}, n, e, y0, y1);
+    const int64_t o = b * (int64_t)n;
+    out[o + e] = __fadd_rn(__fadd_rn(x[o + e], __fmul_rn(drift[o + e], ddt)), __fmul_rn(gs, bits_to_normal(y0)));
+    if (e + h < n)
+      out[o + e + h] = __fadd_rn(__fadd_rn(x[o + e + h], __fmul_rn(drift[o + e + h], ddt)), __fmul_rn(gs, bits_to_normal(y1)));
+  }
+}
+
 // rows of src gathered by an index list: dst[b, :] = src[idx[b], :]  (csmc.py:140, the ancestor gather)
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int64_t B,
                                                           int64_t row, int src_rows, float* __restrict__ dst) {
@@ -771,6 +792,15 @@ int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, con
   em_step_kernel<<<(unsigned)B, 256, 0, as_stream(s)>>>(img, score, unobs_idx, obs_idx, v_next, key, B, p, q, c, a, g2, dt, sd,
                                                         row_offset, rows_total, us_new, mean_out, lw);
   return check_launch("em_step_kernel");
+}
+
+int fbs_em_drift_step_f32(fbs_stream_t s, const uint32_t* keys, const float* x, const float* drift, int64_t B, int64_t n,
+                          float ddt, float gs, float* out) {
+  if (B == 0 || n == 0) return FBS_OK;
+  FBS_REQUIRE(keys && x && drift && out, "em_drift_step: null argument");
+  FBS_REQUIRE(n > 0 && n < 0xFFFFFFFFll, "em_drift_step: bad n");
+  em_drift_step_kernel<<<grid_for(B * ((n + 1) / 2)), 256, 0, as_stream(s)>>>(keys, x, drift, B, (uint32_t)n, ddt, gs, out);
+  return check_launch("em_drift_step_kernel");
 }
 
 int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, int64_t src_rows,

@@ -81,6 +81,11 @@ def em_step(img, score, unobs, obs, B, p, q, c, a, g2, dt, sd, v_next=None, key=
              ptr(us_new), ptr(mean_out), ptr(lw))
 
 
+def em_drift_step(keys, x, drift, ddt, gs, out):
+    B = keys.shape[0] if keys.dim() == 2 else 1
+    nat.call('fbs_em_drift_step_f32', stream(), ptr(keys), ptr(x), ptr(drift), B, x.numel() // B, float(ddt), float(gs), ptr(out))
+
+
 def gather_rows(src, idx, dst):
     B = idx.shape[0]
     nat.call('fbs_gather_rows_f32', stream(), ptr(src), ptr(idx), B, src.numel() // src.shape[0], src.shape[0], ptr(dst))

@@ -333,10 +333,20 @@ class ScoreNetModel:
     ``unobs_idx`` / ``obs_idx`` are the mask's ravelled pixel index lists (fbs/data/images.py:258-303); the SDE is a
     scalar linear SDE (``drift(x, t) = a(t) x``).  One network evaluation serves both the transition and the weight
     (:meth:`step`); the bound methods keep the reference's closure signatures.
+
+    ``drift_mode=True`` gives the closures of the Schroedinger-bridge image runs instead (experiments/sb_imgs/supr.py:84-129):
+    the network output IS the reverse drift, ``reverse_drift(uv, t) = nn_drift(uv, T - t, param_bwd)`` (:84-85) -- no
+    ``-a x + g^2 score`` wrapping -- while the dispersion stays the SDE's (:100-101).  With ``fwd_unet`` (a second network,
+    ``param_fwd``) ``fwd_sampler`` is the Euler--Maruyama simulation of the learnt FORWARD drift
+    (``euler_maruyama(key, xy0, ts, nn_drift(., t, param_fwd), sde.dispersion, integration_nsteps=1)``, :132-137) instead of
+    the closed-form noising of a linear SDE.
     """
 
-    def __init__(self, unet: ScoreUNet, sde, ts, T, unobs_idx, obs_idx):
+    def __init__(self, unet: ScoreUNet, sde, ts, T, unobs_idx, obs_idx, drift_mode: bool = False, fwd_unet: ScoreUNet = None):
         self.unet, self.sde, self.T = unet, sde, float(T)
+        self.drift_mode, self.fwd_unet = bool(drift_mode), fwd_unet
+        if fwd_unet is not None and (fwd_unet.H, fwd_unet.W, fwd_unet.Cimg) != (unet.H, unet.W, unet.Cimg):
+            raise ValueError('the forward-drift network must have the image shape of the backward one')
         self.ts = np.asarray(ts, dtype=np.float64)
         self.K = self.ts.shape[0] - 1
         self.dt = self.T / self.K                                   # inpainting.py:58
@@ -349,9 +359,11 @@ class ScoreNetModel:
 
     def _coef(self, t_prev):
         s = self.T - float(t_prev)
-        a = float(self.sde.drift_coef(s))
         g = float(self.sde.dispersion(s))
-        return s, a, g * g, float(np.float32(math.sqrt(self.dt)) * np.float32(g))
+        sd = float(np.float32(math.sqrt(self.dt)) * np.float32(g))
+        if self.drift_mode:                                         # sb_imgs/supr.py:84-85: rd = network output
+            return s, 0.0, 1.0, sd
+        return s, float(self.sde.drift_coef(s)), g * g, sd
 
     def _score(self, us_prev, v_prev, t_prev):
         B = us_prev.shape[0]
@@ -465,8 +477,29 @@ class ScoreNetModel:
         ops.assemble_image(x, y, self.unobs, self.obs, img)
         return img[0]
 
+    def _fwd_sampler_em(self, key, xy0):
+        """sb_imgs/supr.py:132-137 = simulators.py:53-106 with ``integration_nsteps = 1`` and the forward-drift network: per
+        interval k one network evaluation at (x, ts[k]) and ``x += drift ddt + dispersion(ts[k]) sqrt(ddt) normal(keys[k])``."""
+        ts32 = self.ts.astype(np.float32)
+        keys = frandom.split(dev(key, torch.uint32).reshape(2), self.K)                # simulators.py:81
+        x = xy0.reshape(1, self.unet.H, self.unet.W, self.c).contiguous()
+        path = torch.empty((self.K + 1,) + tuple(x.shape[1:]), dtype=F32, device=x.device)
+        path[0].copy_(x[0])
+        for k in range(self.K):
+            ddt = np.float32(np.abs(ts32[k + 1] - ts32[k]))                            # simulators.py:90 (m = 1)
+            gs = np.float32(self.sde.dispersion(float(ts32[k]))) * np.sqrt(ddt)        # simulators.py:87
+            drift = self.fwd_unet(x, float(ts32[k]))
+            ops.em_drift_step(keys[k:k + 1], x, drift, ddt, gs, path[k + 1:k + 2])
+            x = path[k + 1:k + 2]
+        return path
+
     def fwd_sampler(self, key, x0, y0, **kwargs):
-        """inpainting.py:150-152: simulate_cond_forward(key, concat(x0, y0), ts) -> path [K + 1, H, W, c]."""
+        """inpainting.py:150-152: simulate_cond_forward(key, concat(x0, y0), ts) -> path [K + 1, H, W, c]
+        (sb_imgs/supr.py:132-137 when a forward-drift network was given)."""
+        if self.fwd_unet is not None:
+            return self._fwd_sampler_em(key, self.concat(x0, y0))
+        if self.drift_mode:
+            raise NotImplementedError('a drift-mode model needs the forward-drift network (fwd_unet) to sample forward paths')
         from ..sdes.linear import step_coefficients, forward_path
         if not hasattr(self, '_fwd_coef'):
             self._fwd_coef = step_coefficients(self.sde, self.ts)
@@ -476,6 +509,9 @@ class ScoreNetModel:
 
     def fwd_ys_sampler(self, key, y0, **kwargs):
         """inpainting.py:155-157: simulate_cond_forward(key, y0, ts) on the observed pixels alone -> [K + 1, q, c]."""
+        if self.drift_mode:
+            raise NotImplementedError('the learnt forward drift of a Schroedinger bridge couples x and y: no y-only sampler '
+                                      '(sb_imgs/supr.py defines none)')
         from ..sdes.linear import step_coefficients, forward_path
         if not hasattr(self, '_fwd_coef'):
             self._fwd_coef = step_coefficients(self.sde, self.ts)

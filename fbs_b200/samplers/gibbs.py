@@ -13,7 +13,8 @@ from .._tensor import dev, empty, ptr, stream, out, is_host
 from .. import random as frandom
 from ..models import AffineGaussianModel
 from ..nn.unet import ScoreNetModel
-from .csmc.csmc import (DegenerateInit, NormalInit, forward_pass_device, backward_scanning_pass, _model_of)
+from .csmc.csmc import (DegenerateInit, NormalInit, forward_pass_device, backward_scanning_pass, _model_of,
+                        _check_reference_indices)
 from .csmc.resamplings import killing
 from .resampling import stratified
 from .smc import bootstrap_filter, bootstrap_backward_smoother
@@ -49,6 +50,48 @@ def _fwd_reversed(model, fwd_sampler, unpack, key, x0, y0, kwargs):
     return torch.flip(px, dims=[tdim]).contiguous(), torch.flip(py, dims=[tdim]).contiguous()   # gibbs.py:129-130
 
 
+def _gibbs_kernel_pipelined(key, x0, y0, bs_star, ts, fwd_sampler, sde, unpack, nparticles, transition_sampler,
+                            transition_logpdf, likelihood_logpdf, explicit_backward, explicit_final, kwargs):
+    """Host-buffer call on many chains (the reference driver's per-sweep ``np`` copies, gp_gibbs.py:185-190): the chains are
+    independent, so they are cut into chunks that run on separate CUDA streams -- chunk c's kernels overlap chunk c + 1's
+    host-to-device copies and chunk c - 1's device-to-host copies.  Results land in page-locked buffers returned as numpy
+    views.  Chain b's numbers do not depend on the chunking (tests/test_gpu_csmc.py)."""
+    from . import smc as _smc
+    B = np.shape(key)[0]
+    nchunks = max(1, min(_smc.PIPELINE_CHUNKS, B // (_smc.PIPELINE_MIN_CHAINS // 2)))
+    while len(_smc._streams) < nchunks:
+        _smc._streams.append(torch.cuda.Stream())
+    bounds = [(c * B // nchunks, (c + 1) * B // nchunks) for c in range(nchunks)]
+
+    def host_t(x, dtype):
+        if isinstance(x, torch.Tensor):
+            return x
+        np_dt = {torch.float32: np.float32, torch.int32: np.int32, torch.uint32: np.uint32}[dtype]
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(x).astype(np_dt, copy=False)))
+
+    k_h, x0_h, bs_h = host_t(key, torch.uint32), host_t(x0, torch.float32), host_t(bs_star, torch.int32)
+    y0_d = dev(y0, torch.float32)
+    per_chain_y0 = y0_d.dim() == 2 and y0_d.shape[0] == B
+    outs = None
+    cur = torch.cuda.current_stream()
+    d = y0_d.device
+    for c, (lo, hi) in enumerate(bounds):
+        st = _smc._streams[c]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            args = [t[lo:hi].to(d, non_blocking=True) for t in (k_h, x0_h, bs_h)]
+            r = gibbs_kernel(args[0], args[1], y0_d[lo:hi] if per_chain_y0 else y0_d, None, args[2], ts, fwd_sampler, sde, unpack,
+                             nparticles, transition_sampler, transition_logpdf, likelihood_logpdf, marg_y=False,
+                             explicit_backward=explicit_backward, explicit_final=explicit_final, **kwargs)
+            if outs is None:
+                outs = [torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True) for t in r]
+            for o, t in zip(outs, r):
+                o[lo:hi].copy_(t, non_blocking=True)
+    for st in _smc._streams[:nchunks]:
+        st.synchronize()
+    return tuple(o.numpy() for o in outs)
+
+
 def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, nparticles, transition_sampler,
                  transition_logpdf, likelihood_logpdf, marg_y: bool = False, explicit_backward: bool = True,
                  explicit_final: bool = False, **kwargs):
@@ -63,6 +106,12 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
         raise NotImplementedError('marg_y=True (Doob bridge for y) is not part of the accelerated path')
     model = _model_of(transition_sampler, likelihood_logpdf)
     host = is_host(key)
+    from . import smc as _smc
+    if (host and isinstance(model, AffineGaussianModel) and np.ndim(key) == 2 and np.shape(key)[0] >= _smc.PIPELINE_MIN_CHAINS
+            and getattr(model, '_gibbs_pipeline_warm', False)):
+        # (the first call runs unchunked: it creates the model's cached device arrays on one stream)
+        return _gibbs_kernel_pipelined(key, x0, y0, bs_star, ts, fwd_sampler, sde, unpack, nparticles, transition_sampler,
+                                       transition_logpdf, likelihood_logpdf, explicit_backward, explicit_final, kwargs)
     k = dev(key, torch.uint32)
     single = k.dim() == 1
     k = k.reshape(-1, 2)
@@ -71,6 +120,7 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
         raise NotImplementedError('several image chains at once need explicit_backward=True (the batched sweep keeps no history)')
     x0_d = dev(x0, torch.float32).reshape(B, model.du)
     y0_d = dev(y0, torch.float32).reshape(-1, model.dv)
+    _check_reference_indices(bs_star, N + 1 if explicit_final else N)
     bs = dev(bs_star, torch.int32).reshape(B, K + 1)
 
     ks = frandom.split(k, 3)                                                       # gibbs.py:126
@@ -97,6 +147,7 @@ def gibbs_kernel(key, x0, y0, us_star, bs_star, ts, fwd_sampler, sde, unpack, np
         us_star_next, bs_star_next = backward_scanning_pass(kc[:, 1].contiguous(), r['As'], r['uss'],
                                                             r['log_wss'][:, -1].contiguous())
     x0_next = us_star_next[:, -1].contiguous()                                     # gibbs.py:167
+    model._gibbs_pipeline_warm = True
     changed = bs_star_next != bs
     res = (x0_next, us_star_next, bs_star_next, changed)
     if single:

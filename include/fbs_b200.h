@@ -325,6 +325,12 @@ int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, c
 int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
                        const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
                        float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw);
+/* One Euler--Maruyama sub-step of fbs/sdes/simulators.py:87 whose drift has ALREADY been evaluated by a network -- the
+ * forward sampler of the Schroedinger-bridge image runs (experiments/sb_imgs/supr.py:132-137: drift = nn_drift(x, t, param_fwd),
+ * integration_nsteps = 1):  out[b, e] = x[b, e] + drift[b, e] * ddt + gs * normal(keys[b], (n,))[e]  with
+ * gs = dispersion(t) * sqrt(ddt).  keys [B, 2] = the interval's key (split(key, K)[k], simulators.py:81); x, drift, out [B, n]. */
+int fbs_em_drift_step_f32(fbs_stream_t s, const uint32_t* keys, const float* x, const float* drift, int64_t B, int64_t n,
+                          float ddt, float gs, float* out);
 /* dst[b, :] = src[clamp(idx[b], 0, src_rows - 1), :]  (the ancestor gather, csmc.py:140; an out-of-range index -- the
  * unclipped systematic scheme of resamplings.py:120-125 can return N -- is clamped, as a JAX gather does). */
 int fbs_gather_rows_f32(fbs_stream_t s, const float* src, const int32_t* idx, int64_t B, int64_t row, int64_t src_rows,

@@ -482,12 +482,14 @@ def test_pmcmc_kernel_host_pipeline_equals_unchunked(monkeypatch):
         np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
 
 
-@pytest.mark.parametrize('d,N,K,B', [(8, 128, 3, 3), (4, 2, 2, 1), (100, 64, 3, 5), (52, 100, 3, 2), (124, 100, 2, 2),
-                                     (20, 30, 5, 301)])
+@pytest.mark.parametrize('d,N,K,B', [(8, 128, 3, 3), (4, 2, 2, 1), (100, 64, 3, 5), (52, 100, 3, 2), (124, 32, 2, 2),
+                                     (104, 96, 2, 3), (20, 30, 5, 301)])
 def test_forward_pass_tensor_core_kernel_shapes(d, N, K, B, monkeypatch):
     """Edge shapes of the tcgen05 sweep kernel (sweep_v3.cu): full 128 MMA rows, a single tiny chain, odd chain counts
-    (the second warp group runs one chain fewer), padded K / N dimensions, the widest accumulator (2 x 128 columns), and
-    more chain pairs than SMs.  Teacher-forced against the oracle, and equal ancestors to the general kernel."""
+    (the second warp group runs one chain fewer), padded K / N dimensions, the widest accumulator (2 x 128 columns; at
+    d = 124 the operand tiles of N = 100 particles no longer fit shared memory, so N = 32), the widest state whose noise tasks still fit
+    the 12 noise warps (d = 104 at N = 96), and more chain pairs than SMs.  The kernel is PINNED (an ineligible shape fails instead of falling
+    back).  Teacher-forced against the oracle, and equal ancestors to the general kernel."""
     from fbs_b200.samplers.csmc import csmc, resamplings as R
     p = gp_problem(d, K=K)
     om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)

@@ -454,3 +454,137 @@ def test_peer_gather_kernel_owner_arithmetic():
         nat.call('fbs_gather_rows_peer_f32', stream(), ptr(table), ptr(idx), idx.numel(), row, n, G, ptr(dst))
         want = torch.cat(bufs)[idx.long()]
         assert torch.equal(dst, want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Schroedinger-bridge image closures (experiments/sb_imgs/supr.py:84-137): raw-network reverse drift (param_bwd) and the
+# Euler--Maruyama forward sampler whose drift is a second network (param_fwd)
+# ------------------------------------------------------------------------------------------------------------------
+def _sb_problem(K=4):
+    from fbs_b200.nn import ScoreUNet, ScoreNetModel
+    from fbs_b200 import sdes
+    from oracle import sdes as osdes
+    from oracle.sb_images import SBImageModel
+    H = W = 28
+    T = 0.5                                                            # supr.py:45
+    ts = np.linspace(0., T, K + 1)
+    param_b, param_f = ou.init_unet_params(21, 1), ou.init_unet_params(22, 1)
+    obs = np.array([i * W + j for i in range(0, H, 4) for j in range(0, W, 4)], dtype=np.int32)   # supr-4: 49 observed pixels
+    unobs = np.setdiff1d(np.arange(H * W, dtype=np.int32), obs)
+    net_dt = 0.5 / 200                                                 # supr.py:67
+    sde = sdes.StationaryLinLinearSDE(beta_min=0.02, beta_max=5., t0=0., T=T)
+    osde = osdes.StationaryLinLinearSDE(beta_min=0.02, beta_max=5., t0=0., T=T)
+    model = ScoreNetModel(ScoreUNet(param_b, (H, W, 1), dt=net_dt), sde, ts, T, unobs, obs, drift_mode=True,
+                          fwd_unet=ScoreUNet(param_f, (H, W, 1), dt=net_dt))
+    omodel = SBImageModel(param_b, param_f, osde, ts, T, (H, W, 1), unobs, obs, net_dt)
+    return model, omodel, sde, ts, T, unobs, obs
+
+
+def test_sb_image_closures_match_oracle():
+    """transition_sampler / likelihood_logpdf / transition_logpdf in drift mode (supr.py:104-129): noise bit-pinned, drift
+    within the bf16 network tolerance (4e-2 of the drift scale, multiplied by dt)."""
+    K, N = 4, 6
+    model, om, sde, ts, T, unobs, obs = _sb_problem(K)
+    rng = np.random.default_rng(1)
+    us = rng.standard_normal((N, unobs.size, 1)).astype(np.float32)
+    v_prev = rng.uniform(size=(obs.size, 1)).astype(np.float32)
+    v_next = (v_prev + 0.05 * rng.standard_normal(v_prev.shape)).astype(np.float32)
+    u_eval = rng.standard_normal((unobs.size, 1)).astype(np.float32)
+    key = jr.PRNGKey(3)
+    k = 2
+    t_prev = ts[k]
+    drift = om.reverse_drift(om.concat(us, v_prev), t_prev)
+    scale = float(np.abs(drift).max())
+    dt = T / K
+    got_us = model.transition_sampler(us, v_prev, t_prev, key).cpu().numpy()
+    np.testing.assert_allclose(got_us, om.transition_sampler(us, v_prev, t_prev, key), rtol=0, atol=4e-2 * dt * scale + 1e-5)
+    # the noise is exactly normal(key, us.shape) scaled by sqrt(dt) dispersion(T - t): remove the oracle mean and compare
+    sd = np.float32(math.sqrt(dt)) * np.float32(om.reverse_dispersion(t_prev))
+    np.testing.assert_allclose(got_us - om.transition_mean(us, v_prev, t_prev), sd * jr.normal(key, us.shape), rtol=0,
+                               atol=4e-2 * dt * scale + 1e-5)
+    lw = model.likelihood_logpdf(v_next, us, v_prev, t_prev).cpu().numpy()
+    want_lw = om.likelihood_logpdf(v_next, us, v_prev, t_prev)
+    np.testing.assert_allclose(lw - lw.mean(), want_lw - want_lw.mean(), rtol=0, atol=5e-2 * max(1.0, float(np.ptp(want_lw))))
+    tlp = model.transition_logpdf(u_eval, us, v_prev, t_prev).cpu().numpy()
+    want_tlp = om.transition_logpdf(u_eval, us, v_prev, t_prev)
+    np.testing.assert_allclose(tlp, want_tlp, rtol=2e-3, atol=5e-2 * max(1.0, float(np.ptp(want_tlp))))
+    # one fused evaluation == the separate closures
+    us2, lw2 = model.step(us, v_prev, v_next, t_prev, key)
+    np.testing.assert_array_equal(us2.cpu().numpy(), got_us)
+    np.testing.assert_array_equal(lw2.cpu().numpy(), lw)
+    with pytest.raises(NotImplementedError):
+        model.fwd_ys_sampler(key, v_prev)
+
+
+def test_sb_image_forward_sampler_teacher_forced():
+    """fwd_sampler = euler_maruyama(key, concat(x0, y0), ts, nn_drift(., t, param_fwd), sde.dispersion, 1, return_path=True)
+    (supr.py:132-137, simulators.py:81-92), every interval re-derived by the oracle from the kernel's own state."""
+    K = 5
+    model, om, sde, ts, T, unobs, obs = _sb_problem(K)
+    rng = np.random.default_rng(2)
+    x0 = rng.uniform(size=(unobs.size, 1)).astype(np.float32)
+    y0 = rng.uniform(size=(obs.size, 1)).astype(np.float32)
+    key = jr.PRNGKey(9)
+    path = model.fwd_sampler(key, x0, y0).cpu().numpy()
+    assert path.shape == (K + 1, 28, 28, 1)
+    np.testing.assert_array_equal(path[0], om.concat(x0[None], y0)[0])
+    keys = jr.split(key, K)
+    ts32 = ts.astype(np.float32)
+    for k in range(K):
+        ddt = np.float32(ts32[k + 1] - ts32[k])
+        drift = ou.unet_forward(om.param_fwd, path[k][None], float(ts32[k]), om.net_dt)[0]
+        want = path[k] + drift * ddt + np.float32(om.sde.dispersion(ts32[k])) * np.sqrt(ddt) * jr.normal(keys[k], (1, 28, 28, 1))[0]
+        np.testing.assert_allclose(path[k + 1], want, rtol=0, atol=4e-2 * float(ddt) * float(np.abs(drift).max()) + 1e-5)
+    # reversed / unpacked as gibbs_kernel consumes it (gibbs.py:127-130)
+    us, vs = model.fwd_sampler_reversed(key, x0, y0)
+    np.testing.assert_array_equal(us.cpu().numpy()[0], path[::-1].reshape(K + 1, 784)[:, unobs])
+    np.testing.assert_array_equal(vs.cpu().numpy()[0], path[::-1].reshape(K + 1, 784)[:, obs])
+
+
+def test_sb_image_forward_pass_teacher_forced_and_gibbs_kernel():
+    """csmc.py:132-164 and gibbs.py:68-168 (explicit_backward = explicit_final = True as in supr.py:171-176) over the
+    drift-mode closures."""
+    from fbs_b200.samplers import gibbs_kernel
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    from oracle import cond_resampling as ocr, csmc as ocsmc
+    K, N = 4, 5
+    model, om, sde, ts, T, unobs, obs = _sb_problem(K)
+    rng = np.random.default_rng(5)
+    us_star = rng.standard_normal((K + 1, unobs.size, 1)).astype(np.float32)
+    vs = np.cumsum(0.05 * rng.standard_normal((K + 1, obs.size, 1)), axis=0).astype(np.float32)
+    key = jr.PRNGKey(8)
+    init = csmc.NormalInit(model)
+    Np = N + 1
+    bs_star = jr.randint(jr.PRNGKey(6), (K + 1,), 0, N).astype(np.int32)
+    As, log_wss, uss = csmc.forward_pass(key, us_star, bs_star, vs, ts, init.sampler, init.likelihood_logpdf,
+                                         model.transition_sampler, model.likelihood_logpdf, R.killing, N)
+    uss = uss.reshape(K + 1, Np, unobs.size, 1)
+    key_init, key_scan = jr.split(key, 2)
+    u0 = jr.normal(key_init, (Np, unobs.size, 1))
+    u0[bs_star[0]] = us_star[0]
+    np.testing.assert_allclose(uss[0], u0, rtol=0, atol=5e-7)
+    for k, step_key in enumerate(jr.split(key_scan, K)):
+        key_res, key_tr = jr.split(step_key, 2)
+        A = ocr.killing(key_res, np.exp(log_wss[k]).astype(np.float32), bs_star[k], bs_star[k + 1], True)
+        np.testing.assert_array_equal(As[k], A)
+        parents = uss[k][As[k]]
+        want_us = om.transition_sampler(parents, vs[k], ts[k], key_tr)
+        want_us[bs_star[k + 1]] = us_star[k + 1]
+        np.testing.assert_array_equal(uss[k + 1][bs_star[k + 1]], us_star[k + 1])
+        np.testing.assert_allclose(uss[k + 1], want_us, rtol=0, atol=3e-2 * max(1.0, float(np.abs(want_us).max())))
+        want = ocsmc.normalise(om.likelihood_logpdf(vs[k + 1], parents, vs[k], ts[k]).astype(np.float32), log_space=True)
+        np.testing.assert_allclose(log_wss[k + 1], want, rtol=0, atol=5e-2 * max(1.0, float(np.ptp(want))))
+    # the Gibbs kernel of supr.py:171-176
+    x0 = rng.uniform(size=(unobs.size, 1)).astype(np.float32)
+    y0 = rng.uniform(size=(obs.size, 1)).astype(np.float32)
+    gkey = jr.PRNGKey(21)
+    x0n, us_next, bs_next, changed = gibbs_kernel(gkey, x0, y0, None, bs_star, ts, model.fwd_sampler, sde, model.unpack, N,
+                                                  model.transition_sampler, model.transition_logpdf, model.likelihood_logpdf,
+                                                  explicit_backward=True, explicit_final=True)
+    assert x0n.shape == (unobs.size,) and us_next.shape == (K + 1, unobs.size) and np.isfinite(us_next).all()
+    np.testing.assert_array_equal(us_next[-1], x0n)
+    kc = jr.split(jr.split(gkey, 3)[1], 4)
+    np.testing.assert_array_equal(bs_next, jr.randint(kc[3], (K + 1,), 0, N))
+    # us_star_next is the reversed forward path started at the selected x0 (gibbs.py:155)
+    want_path = model.fwd_sampler(kc[2], x0n.reshape(unobs.size, 1), y0).cpu().numpy()
+    np.testing.assert_array_equal(us_next, want_path[::-1].reshape(K + 1, 784)[:, unobs])
