@@ -491,45 +491,97 @@ def secondary_hbm_kernels(shapes=None, steps=None):
             'below the HBM roofline; see profiles/r1_hbm_kernels.md', 'kernels': out}
 
 
-def secondary_sharded(world, rank, per_rank=128, steps=4):
+def secondary_sharded(world, rank, per_rank=512, steps=3, strong_total=1024):
     """configs[4]: CelebA-HQ-shaped (64x64x3, inpaint-32) random-init score U-Net, ONE chain whose particle set is sharded over
-    the ranks (fbs_b200/sharded.py): all-gather of the weights + NCCL exchange of resampled particles per step."""
+    the ranks (fbs_b200/sharded.py): per step one all-gather of the log-weights + the ancestor gather over NVLink peer memory.
+
+    (1) bit-equality of the sharded sweep with the unsharded one, checked IN THIS RUN on every rank at a small particle
+        count; (2) weak scaling, `per_rank` particles per GPU (4096 at 8 GPUs), random reference indices as gibbs_kernel
+        draws them (gibbs.py:156) and 'gibbs-eb-ef' initialisation, the step size chosen so that conditional killing replaces
+        roughly a third of the particles; (3) strong scaling: `strong_total` particles whatever the GPU count."""
     import torch
     import torch.distributed as dist
     from fbs_b200.samplers.csmc import csmc, resamplings as R
     from fbs_b200.sharded import forward_pass_sharded
+    from fbs_b200.nn import ScoreNetModel
     from fbs_b200 import random as fr
     shape = (64, 64, 3)
-    N = per_rank * world
-    model, ts, rect, obs = _score_model(shape, steps)
-    rng = np.random.default_rng(0)
+    base_model, _, rect, obs = _score_model(shape, steps)
+    net, sde = base_model.unet, base_model.sde
+    rng = np.random.default_rng(0)                                     # identical inputs on every rank
     us_star = rng.standard_normal((steps + 1, rect.size, 3)).astype(np.float32)
-    vs = np.cumsum(0.05 * rng.standard_normal((steps + 1, obs.size, 3)), axis=0).astype(np.float32)   # a noised path: particles get killed and move
-    bs = np.zeros((steps + 1,), np.int32)
-    init = csmc.DegenerateInit(N)
-    args = (fr.PRNGKey(5), us_star, bs, vs, model, init, R.killing, N)
-    try:
-        forward_pass_sharded(*args)                                   # warm-up (and the CUDA-IPC set-up of the peer buffers)
-    except RuntimeError as e:
-        if 'peer-memory' not in str(e):
-            raise
-        os.environ['FBS_SHARD_EXCHANGE'] = 'nccl'                     # raised on every rank alike: all ranks take the same branch
-        forward_pass_sharded(*args)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    r = forward_pass_sharded(*args)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    return {'workload': 'configs[4]: CelebA-HQ-shaped 64x64x3 inpaint-32, random-init score U-Net, one chain, particle set '
-                        f'sharded over {world} GPUs ({per_rank} particles per GPU, weak)',
-            'value': N * steps / (ms * 1e-3), 'unit': 'particle-steps/s', 'n_particles': N, 'steps': steps,
-            'ms_per_csmc_step': ms / steps, 'moved_rows_per_step': float(np.mean(r['moved'])),
-            'exchange': r.get('exchange'),
+    row_bytes = rect.size * 3 * 4
+
+    def problem(T_model, N):
+        ts = np.linspace(0., T_model, steps + 1)
+        model = ScoreNetModel(net, sde, ts, T_model, rect, obs)        # dt = T_model / steps, reverse time T_model - t
+        sd = math.sqrt(T_model / steps) * float(sde.dispersion(T_model))
+        vs = np.cumsum(sd * np.random.default_rng(1).standard_normal((steps + 1, obs.size, 3)), axis=0).astype(np.float32)
+        bs = np.random.default_rng(2).integers(0, N - 1, size=steps + 1).astype(np.int32)   # gibbs.py:156: in [0, nparticles)
+        return model, (fr.PRNGKey(5), us_star, bs, vs, model, csmc.NormalInit(model), R.killing, N - 1)
+
+    def run(args, history=False):
+        try:
+            return forward_pass_sharded(*args, history=history)
+        except RuntimeError as e:
+            if 'peer-memory' not in str(e):
+                raise
+            os.environ['FBS_SHARD_EXCHANGE'] = 'nccl'                   # raised on every rank alike: all ranks take the same branch
+            return forward_pass_sharded(*args, history=history)
+
+    def replaced_fraction(r):
+        A = r['ancestors']
+        return float(np.mean([1.0 - torch.unique(A[k]).numel() / A.shape[1] for k in range(A.shape[0])]))
+
+    # (1) sharded == unsharded, bit for bit, in this very run
+    n_small = 8 * world
+    model_s, args_s = problem(0.02, n_small)
+    r = run(args_s, history=True)
+    full = csmc.forward_pass_nn(args_s[0], args_s[1], args_s[2], args_s[3], model_s, args_s[5], R.killing.scheme, n_small - 1,
+                                history=True)
+    same = (torch.equal(r['As'], full['As'][0]) and torch.equal(r['log_wss'], full['log_wss'][0])
+            and torch.equal(r['uss'].reshape(steps + 1, -1, rect.size * 3), full['uss'][0][:, r['lo']:r['hi']]))
+    flag = torch.tensor([1 if same else 0], device='cuda')
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    bit_equal = bool(flag.item())
+    moved_small = float(np.mean(r['moved']))
+
+    # (2) pick the step size whose weight spread makes conditional killing replace about a third of the particles
+    trials = []
+    for T_model in (2.0, 0.2, 0.02, 0.005, 0.001):
+        _, a = problem(T_model, 32 * world)
+        trials.append((abs(replaced_fraction(run(a)) - 0.35), T_model))
+    T_pick = min(trials)[1]
+
+    def timed(N):
+        _, a = problem(T_pick, N)
+        run(a)                                                          # warm-up (CUDA graph of this batch size, IPC set-up)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rr = run(a)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mv = torch.tensor([float(np.mean(rr['moved']))], device='cuda', dtype=torch.float64)
+        dist.all_reduce(mv, op=dist.ReduceOp.SUM)                       # rows crossing NVLink per step, all ranks
+        ms = float(t.item())
+        return {'n_particles': N, 'particles_per_gpu': N // world, 'value': N * steps / (ms * 1e-3), 'unit': 'particle-steps/s',
+                'ms_per_csmc_step': ms / steps, 'moved_rows_per_step': float(mv.item()),
+                'nvlink_bytes_per_step': float(mv.item()) * row_bytes,
+                'fraction_of_particles_replaced_per_step': replaced_fraction(rr), 'exchange': rr.get('exchange')}
+
+    weak = timed(per_rank * world)
+    strong = weak if strong_total == per_rank * world else timed(strong_total)
+    return {'workload': 'configs[4]: CelebA-HQ-shaped 64x64x3 inpaint-32, random-init score U-Net, one chain, particle set sharded '
+                        f'over {world} GPUs; random reference indices, explicit-final initialisation, {steps} steps',
+            'bitwise_equal_to_unsharded_sweep': bit_equal,
+            'bitwise_check': f'{n_small} particles, {steps} steps, ancestors + log-weights + every particle row of the history, on every '
+                             f'rank; {moved_small:.1f} rows per step crossed GPUs on rank 0 during the check',
+            'weak': weak, 'strong': strong, 'value': weak['value'], 'unit': 'particle-steps/s',
+            'moved_rows_per_step': weak['moved_rows_per_step'], 'step_size_T_over_K': T_pick / steps,
             'collectives_per_step': 'all_gather(4 N bytes) of the log-weights; parent rows read from the owners over NVLink inside '
                                     'the gather kernel (CUDA IPC peer memory; FBS_SHARD_EXCHANGE=nccl: batch_isend_irecv)',
             'dtype': 'bf16'}

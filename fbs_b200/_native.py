@@ -78,7 +78,9 @@ SIGNATURES = {
     'fbs_nn_head_conv_f32': ([_p, _p, _i64, _i32, _i32, _p, _p, _p], _int),
     'fbs_nn_space_to_depth_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),
     'fbs_nn_assemble_image_f32': ([_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p], _int),
-    'fbs_nn_em_step_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _i64, _i64, _p, _p, _p], _int),
+    'fbs_nn_em_step_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _i64, _i64, _p, _p, _p, _p, _p],
+                           _int),
+    'fbs_normalise_logw_f32': ([_p, _p, _i64, _i64, _p, _p], _int),
     'fbs_em_drift_step_f32': ([_p, _p, _p, _p, _i64, _i64, _f32, _f32, _p], _int),
     'fbs_gather_rows_f32': ([_p, _p, _p, _i64, _i64, _i64, _p], _int),
     'fbs_gather_rows_peer_f32': ([_p, _p, _p, _i64, _i64, _i64, _i64, _p], _int),

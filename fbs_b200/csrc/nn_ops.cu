@@ -30,6 +30,18 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   float t = lane < nw ? red[lane] : 0.f;
   return warp_sum(t);
 }
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+  return t;
+}
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -605,10 +617,13 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
                                                       const int32_t* __restrict__ unobs, const int32_t* __restrict__ obs,
                                                       const float* __restrict__ v_next, const uint32_t* __restrict__ key, int64_t B,
                                                       int p, int q, int c, float a, float g2, float dt, float sd,
-                                                      int64_t row_offset, int64_t rows_total,
+                                                      int64_t row_offset, int64_t rows_total, const int32_t* __restrict__ pin_row,
+                                                      const float* __restrict__ pin_value,
                                                       float* __restrict__ us_new, float* __restrict__ mean_out, float* __restrict__ lw) {
   __shared__ float red[32];
   const int64_t b = blockIdx.x;
+  // csmc.py:143: the reference particle's slot receives u*_{k+1} instead of a propagated particle
+  const bool pinned = pin_row != nullptr && (row_offset + b) == (int64_t)pin_row[0];
   const int P = p + q;
   const float* xi = img + b * (int64_t)P * c;
   const float* si = score + b * (int64_t)P * c;
@@ -624,7 +639,7 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
       if (mean_out) mean_out[b * (int64_t)p * c + e] = mean;
       if (us_new) {
         const uint32_t el = (uint32_t)((row_offset + b) * p * c + e);
-        us_new[b * (int64_t)p * c + e] = mean + sd * bits_to_normal(random_bits_elem(k, nel, el));
+        us_new[b * (int64_t)p * c + e] = pinned ? pin_value[e] : mean + sd * bits_to_normal(random_bits_elem(k, nel, el));
       }
     }
   }
@@ -640,6 +655,28 @@ __global__ void __launch_bounds__(256) em_step_kernel(const float* __restrict__ 
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) lw[b] = acc;
+  }
+}
+
+// normalise (csmc.py:273-292) of a batch of log-weight vectors: log_w = lw - logsumexp(lw), w = exp(log_w).  One CTA per
+// chain; the reduction order is a function of (N, blockDim) only, so the sharded and the unsharded sweep -- which both run
+// this kernel on the full weight vector -- agree bit for bit.
+__global__ void __launch_bounds__(256) normalise_logw_kernel(const float* __restrict__ lw, int N, float* __restrict__ log_w,
+                                                             float* __restrict__ w) {
+  __shared__ float red[32];
+  const float* x = lw + (int64_t)blockIdx.x * N;
+  float m = -INFINITY;
+  for (int q = threadIdx.x; q < N; q += blockDim.x) m = fmaxf(m, x[q]);
+  m = block_max(m, red);
+  if (!(fabsf(m) < INFINITY)) m = 0.f;  // jax logsumexp: a non-finite maximum is replaced by 0
+  float s = 0.f;
+  for (int q = threadIdx.x; q < N; q += blockDim.x) s += expf(x[q] - m);
+  s = block_sum(s, red);
+  const float lse = logf(s) + m;
+  for (int q = threadIdx.x; q < N; q += blockDim.x) {
+    const float v = x[q] - lse;
+    if (log_w) log_w[(int64_t)blockIdx.x * N + q] = v;
+    if (w) w[(int64_t)blockIdx.x * N + q] = expf(v);
   }
 }
 
@@ -784,14 +821,24 @@ int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, c
 
 int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
                        const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
-                       float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw) {
+                       float dt, float sd, int64_t row_offset, int64_t rows_total, const int32_t* pin_row, const float* pin_value,
+                       float* us_new, float* mean_out, float* lw) {
   FBS_REQUIRE(img && score && unobs_idx && obs_idx, "em_step: null argument");
   FBS_REQUIRE(lw == nullptr || v_next != nullptr, "em_step: v_next missing");
   FBS_REQUIRE(us_new == nullptr || key != nullptr, "em_step: key missing");
   FBS_REQUIRE(row_offset >= 0 && row_offset + B <= rows_total, "em_step: rows [row_offset, row_offset + B) must lie inside rows_total");
+  FBS_REQUIRE((pin_row == nullptr) == (pin_value == nullptr), "em_step: pin_row and pin_value go together");
   em_step_kernel<<<(unsigned)B, 256, 0, as_stream(s)>>>(img, score, unobs_idx, obs_idx, v_next, key, B, p, q, c, a, g2, dt, sd,
-                                                        row_offset, rows_total, us_new, mean_out, lw);
+                                                        row_offset, rows_total, pin_row, pin_value, us_new, mean_out, lw);
   return check_launch("em_step_kernel");
+}
+
+int fbs_normalise_logw_f32(fbs_stream_t s, const float* lw, int64_t B, int64_t N, float* log_w, float* w) {
+  if (B == 0) return FBS_OK;
+  FBS_REQUIRE(lw && (log_w || w), "normalise_logw: null argument");
+  FBS_REQUIRE(N >= 1 && N < (1ll << 31) && B < (1ll << 31), "normalise_logw: bad sizes");
+  normalise_logw_kernel<<<(unsigned)B, 256, 0, as_stream(s)>>>(lw, (int)N, log_w, w);
+  return check_launch("normalise_logw_kernel");
 }
 
 int fbs_em_drift_step_f32(fbs_stream_t s, const uint32_t* keys, const float* x, const float* drift, int64_t B, int64_t n,

@@ -349,17 +349,18 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_nn_assemble_image, NnAssembleImageImpl,
 
 // transition_sampler + likelihood_logpdf from ONE score evaluation -> (us_new, mean, lw)         inpainting.py:122-147
 static ffi::Error NnEmStepImpl(cudaStream_t stream, BufF img, BufF score, BufI unobs_idx, BufI obs_idx, BufF v_next, BufU key,
-                               float a, float g2, float dt, float sd, int32_t row_offset, int32_t rows_total, ResF us_new,
-                               ResF mean_out, ResF lw) {
+                               BufI pin_row, BufF pin_value, float a, float g2, float dt, float sd, int32_t row_offset,
+                               int32_t rows_total, ResF us_new, ResF mean_out, ResF lw) {
   auto d = img.dimensions();  // [B, H, W, c]
   const int32_t p = (int32_t)unobs_idx.element_count(), q = (int32_t)obs_idx.element_count();
   return as_error(fbs_nn_em_step_f32(stream, img.typed_data(), score.typed_data(), unobs_idx.typed_data(), obs_idx.typed_data(),
                                      opt(v_next), opt(key), d[0], p, q, (int32_t)d[3], a, g2, dt, sd, row_offset,
-                                     rows_total > 0 ? rows_total : d[0], opt(*us_new), opt(*mean_out), opt(*lw)));
+                                     rows_total > 0 ? rows_total : d[0], opt(pin_row), opt(pin_value), opt(*us_new),
+                                     opt(*mean_out), opt(*lw)));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_nn_em_step, NnEmStepImpl,
                               FBS_BIND_STREAM().Arg<BufF>().Arg<BufF>().Arg<BufI>().Arg<BufI>().Arg<BufF>().Arg<BufU>()
-                                  .Attr<float>("a").Attr<float>("g2").Attr<float>("dt").Attr<float>("sd")
+                                  .Arg<BufI>().Arg<BufF>().Attr<float>("a").Attr<float>("g2").Attr<float>("dt").Attr<float>("sd")
                                   .Attr<int32_t>("row_offset").Attr<int32_t>("rows_total").Ret<BufF>().Ret<BufF>().Ret<BufF>());
 
 // one Euler--Maruyama sub-step with a network drift (forward sampler of the SB image runs)       sb_imgs/supr.py:132-137
@@ -370,6 +371,14 @@ static ffi::Error EmDriftStepImpl(cudaStream_t stream, BufU keys, BufF x, BufF d
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_em_drift_step, EmDriftStepImpl,
                               FBS_BIND_STREAM().Arg<BufU>().Arg<BufF>().Arg<BufF>().Attr<float>("ddt").Attr<float>("gs").Ret<BufF>());
+
+// normalise + exp of the step's log-weights                                                     csmc.py:146,139
+static ffi::Error NormaliseLogwImpl(cudaStream_t stream, BufF lw, ResF log_w, ResF w) {
+  const int64_t N = lw.dimensions().back();
+  return as_error(fbs_normalise_logw_f32(stream, lw.typed_data(), (int64_t)lw.element_count() / (N > 0 ? N : 1), N, opt(*log_w),
+                                         opt(*w)));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_normalise_logw, NormaliseLogwImpl, FBS_BIND_STREAM().Arg<BufF>().Ret<BufF>().Ret<BufF>());
 
 // the ancestor gather                                                                           csmc.py:140
 static ffi::Error GatherRowsImpl(cudaStream_t stream, BufF src, BufI idx, ResF dst) {

@@ -75,10 +75,16 @@ def assemble_image(us, v, unobs, obs, img):
 
 
 def em_step(img, score, unobs, obs, B, p, q, c, a, g2, dt, sd, v_next=None, key=None, us_new=None, mean_out=None, lw=None,
-            row_offset=0, rows_total=None):
+            row_offset=0, rows_total=None, pin_row=None, pin_value=None):
     nat.call('fbs_nn_em_step_f32', stream(), ptr(img), ptr(score), ptr(unobs), ptr(obs), ptr(v_next), ptr(key), B, p, q, c,
              float(a), float(g2), float(dt), float(sd), int(row_offset), int(B if rows_total is None else rows_total),
-             ptr(us_new), ptr(mean_out), ptr(lw))
+             ptr(pin_row), ptr(pin_value), ptr(us_new), ptr(mean_out), ptr(lw))
+
+
+def normalise_logw(lw, log_w=None, w=None):
+    """``log_w = lw - logsumexp(lw)``, ``w = exp(log_w)`` for ``lw [B, N]`` (or ``[N]``) in one launch."""
+    N = lw.shape[-1]
+    nat.call('fbs_normalise_logw_f32', stream(), ptr(lw), lw.numel() // N, N, ptr(log_w), ptr(w))
 
 
 def em_drift_step(keys, x, drift, ddt, gs, out):

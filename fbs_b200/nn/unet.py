@@ -372,24 +372,27 @@ class ScoreNetModel:
         s, a, g2, sd = self._coef(t_prev)
         return img, self.unet(img, s), a, g2, sd
 
-    def step(self, us_prev, v_prev, v_next, t_prev, key, row_offset=0, rows_total=None):
+    def step(self, us_prev, v_prev, v_next, t_prev, key, row_offset=0, rows_total=None, pin_row=None, pin_value=None, out=None):
         """(us_new [N, p, c], log_w [N]) from ONE score evaluation (transition_sampler + likelihood_logpdf).
 
         ``row_offset`` / ``rows_total``: the N particles are rows [row_offset, row_offset + N) of a larger (sharded)
-        particle set; the transition noise is the matching slice of ``normal(key, (rows_total, p, c))``."""
+        particle set; the transition noise is the matching slice of ``normal(key, (rows_total, p, c))``.
+        ``pin_row`` (device int32 [1], global row) / ``pin_value`` ``[p, c]``: the reference particle written by the same
+        kernel (csmc.py:143).  ``out``: where the new particles go (e.g. straight into a peer-visible buffer)."""
         us_prev = dev(us_prev, F32).reshape(-1, self.p, self.c)
         v_prev = dev(v_prev, F32).reshape(self.q, self.c)
         v_next = dev(v_next, F32).reshape(self.q, self.c)
         key = dev(key, torch.uint32).reshape(2)
         B = us_prev.shape[0]
         img, score, a, g2, sd = self._score(us_prev, v_prev, t_prev)
-        us_new = torch.empty_like(us_prev)
+        us_new = torch.empty_like(us_prev) if out is None else out.view(us_prev.shape)
         lw = torch.empty((B,), dtype=F32, device=us_prev.device)
+        pv = None if pin_value is None else dev(pin_value, F32).reshape(self.p * self.c)
         ops.em_step(img, score, self.unobs, self.obs, B, self.p, self.q, self.c, a, g2, self.dt, sd, v_next=v_next, key=key,
-                    us_new=us_new, lw=lw, row_offset=row_offset, rows_total=rows_total)
+                    us_new=us_new, lw=lw, row_offset=row_offset, rows_total=rows_total, pin_row=pin_row, pin_value=pv)
         return us_new, lw
 
-    def step_chains(self, us_prev, v_prev, v_next, t_prev, keys):
+    def step_chains(self, us_prev, v_prev, v_next, t_prev, keys, pin_rows=None, pin_values=None):
         """:meth:`step` for C independent chains (conditioning targets) at once: ``us_prev [C, N, p, c]``, ``v_prev`` /
         ``v_next [C, q, c]``, ``keys [C, 2]`` -> ``(us_new [C, N, p, c], log_w [C, N])``.  The C x N images go through ONE
         score evaluation (the network is launch / latency bound at N = 101: batching targets is what fills the GPU); image
@@ -410,7 +413,9 @@ class ScoreNetModel:
         lw = torch.empty((C_, N), dtype=F32, device=us_prev.device)
         for ci in range(C_):
             ops.em_step(img[ci * N:(ci + 1) * N], score[ci * N:(ci + 1) * N], self.unobs, self.obs, N, self.p, self.q, self.c,
-                        a, g2, self.dt, sd, v_next=v_next[ci], key=keys[ci], us_new=us_new[ci], lw=lw[ci])
+                        a, g2, self.dt, sd, v_next=v_next[ci], key=keys[ci], us_new=us_new[ci], lw=lw[ci],
+                        pin_row=None if pin_rows is None else pin_rows[ci:ci + 1],
+                        pin_value=None if pin_values is None else pin_values[ci])
         return us_new, lw
 
     def mean_and_logw(self, us_prev, v_prev, v_next, t_prev):

@@ -104,7 +104,10 @@ def forward_pass_nn(key, us_star, bs_star, vs, model, init, scheme, nsamples, hi
         lw = torch.full((N,), init.init_log_w, dtype=torch.float32, device=us.device)
     else:
         raise TypeError('init_sampler / init_likelihood_logpdf must come from DegenerateInit or NormalInit')
-    log_w = lw - torch.logsumexp(lw, dim=0)                                        # csmc.py:155
+    # per step: normalise + exp (one launch), conditional resampling, ancestor gather, image assembly, the score network
+    # (one CUDA-graph replay), Euler--Maruyama step + weights + reference pin (one launch) -- no eager tensor arithmetic
+    log_w, w = empty((N,), torch.float32), empty((N,), torch.float32)
+    nnops.normalise_logw(lw.contiguous(), log_w, w)                                # csmc.py:155 (and the exp of :139)
     As = log_wss = uss = None
     if history:
         As = empty((K, N), torch.int32)
@@ -115,13 +118,12 @@ def forward_pass_nn(key, us_star, bs_star, vs, model, init, scheme, nsamples, hi
     A = empty((1, N), torch.int32)
     us_prev = torch.empty_like(us)
     for kk in range(K):
-        w = torch.exp(log_w).contiguous()
         nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(sk[kk, 0]), ptr(w), ptr(bs[kk:kk + 1]), ptr(bs[kk + 1:kk + 2]), 1,
                  1, N, ptr(A))                                                     # csmc.py:139
         nnops.gather_rows(us, A.reshape(N), us_prev)                               # csmc.py:140
-        us, lw = model.step(us_prev, v[kk], v[kk + 1], ts[kk], sk[kk, 1])          # csmc.py:142,145
-        us.index_copy_(0, bsl[kk + 1:kk + 2], us_star[kk + 1:kk + 2])              # csmc.py:143
-        log_w = lw - torch.logsumexp(lw, dim=0)                                    # csmc.py:146
+        us, lw = model.step(us_prev, v[kk], v[kk + 1], ts[kk], sk[kk, 1], pin_row=bs[kk + 1:kk + 2],
+                            pin_value=us_star[kk + 1])                             # csmc.py:142,143,145
+        nnops.normalise_logw(lw, log_w, w)                                         # csmc.py:146
         if history:
             As[kk].copy_(A[0])
             log_wss[kk + 1].copy_(log_w)
@@ -158,23 +160,22 @@ def forward_pass_nn_chains(keys, us_star, bs_star, vs, model, init, scheme, nsam
         lw = torch.full((C, N), init.init_log_w, dtype=torch.float32, device=us.device)
     else:
         raise TypeError('init_sampler / init_likelihood_logpdf must come from DegenerateInit or NormalInit')
-    log_w = lw - torch.logsumexp(lw, dim=1, keepdim=True)
+    log_w, w = empty((C, N), torch.float32), empty((C, N), torch.float32)
+    nnops.normalise_logw(lw.contiguous(), log_w, w)
     A = empty((C, N), torch.int32)
     us_prev = torch.empty_like(us)
     base = (torch.arange(C, device=us.device, dtype=torch.int32) * N).reshape(C, 1)
-    rows = torch.arange(C, device=us.device)
+    bsT = bs.t().contiguous()                                                      # [K + 1, C]: a step's indices are one row
+    skr = sk[:, :, 0].transpose(0, 1).contiguous()                                 # [K, C, 2] resampling keys
+    skt = sk[:, :, 1].transpose(0, 1).contiguous()                                 # [K, C, 2] transition keys
     for kk in range(K):
-        w = torch.exp(log_w).contiguous()
-        # (the contiguous copies must stay referenced until the launch: a temporary freed right after ptr() hands its block
-        #  to the next temporary, and the kernel would read the last copy three times)
-        k_res, b_prev, b_cur = sk[:, kk, 0].contiguous(), bs[:, kk].contiguous(), bs[:, kk + 1].contiguous()
-        nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(k_res), ptr(w), ptr(b_prev), ptr(b_cur), 1, C, N,
+        nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(skr[kk]), ptr(w), ptr(bsT[kk]), ptr(bsT[kk + 1]), 1, C, N,
                  ptr(A))                                                           # csmc.py:139, all chains
-        a_glob = (A + base).reshape(C * N).contiguous()
+        a_glob = (A + base).reshape(C * N)
         nnops.gather_rows(us.reshape(C * N, p * c), a_glob, us_prev.reshape(C * N, p * c))
-        us, lw = model.step_chains(us_prev, v[:, kk], v[:, kk + 1], ts[kk], sk[:, kk, 1])   # csmc.py:142,145
-        us[rows, bs[:, kk + 1].long()] = us_star[:, kk + 1]                        # csmc.py:143
-        log_w = lw - torch.logsumexp(lw, dim=1, keepdim=True)                      # csmc.py:146
+        us, lw = model.step_chains(us_prev, v[:, kk], v[:, kk + 1], ts[kk], skt[kk], pin_rows=bsT[kk + 1],
+                                   pin_values=us_star[:, kk + 1])                  # csmc.py:142,143,145
+        nnops.normalise_logw(lw, log_w, w)                                         # csmc.py:146
     return dict(N=N, log_ws_last=log_w.contiguous(), us_last=us.reshape(C, N, p * c).contiguous())
 
 

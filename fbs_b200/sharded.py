@@ -157,11 +157,19 @@ class PeerRows:
         nat.call('fbs_gather_rows_peer_f32', stream(), ptr(self.table[self.cur]), ptr(parents_global), out.shape[0], self.row,
                  self.shard.n, self.shard.world, ptr(out))
 
-    def publish(self, rows):
-        """Write the step's new rows into the other buffer and make it current.  The caller's next collective (the all-gather of
-        the log-weights) is the point after which the peers read it."""
+    def next_rows(self):
+        """The OTHER buffer: where the step's kernel writes the new rows directly (no staging copy)."""
+        return self.buf[self.cur ^ 1]
+
+    def flip(self):
+        """Make the buffer written through :meth:`next_rows` current.  The caller's next collective (the all-gather of the
+        log-weights) is the point after which the peers read it."""
         self.cur ^= 1
-        self.buf[self.cur].copy_(rows.reshape(self.shard.n, self.row))
+
+    def publish(self, rows):
+        """Copy rows computed elsewhere into the other buffer and make it current."""
+        self.next_rows().copy_(rows.reshape(self.shard.n, self.row))
+        self.flip()
 
     def close(self):
         from . import _native as nat
@@ -239,7 +247,12 @@ def forward_pass_sharded(key, us_star, bs_star, vs, model, init, cond_resampling
         lw = torch.full((N,), init.init_log_w, dtype=torch.float32, device=us.device)
     else:
         raise TypeError('init must be a DegenerateInit or NormalInit')
-    log_w = lw - torch.logsumexp(lw, dim=0)
+    # per step: normalise + exp (one launch, redundantly on every rank), conditional resampling (ditto), the ancestor gather
+    # over peer memory, image assembly + score network + Euler--Maruyama step / weights / reference pin written straight
+    # into the peer-visible buffer, ONE all-gather of the new log-weights -- no eager tensor arithmetic
+    from .nn import ops as nnops
+    log_w, w = empty((N,), torch.float32), empty((N,), torch.float32)
+    nnops.normalise_logw(lw.contiguous(), log_w, w)
     As = log_wss = uss = None
     if history:
         As = empty((K, N), torch.int32)
@@ -262,30 +275,33 @@ def forward_pass_sharded(key, us_star, bs_star, vs, model, init, cond_resampling
         peer.buf[0].copy_(us.reshape(n, p * c))
         if world > 1:
             dist.all_reduce(torch.zeros(1, device=us.device), group=group)         # every rank's initial rows are in place
-        moved_dev = []
+    A_all = empty((K, N), torch.int32)                                             # every step's ancestors (for `moved`)
+    parents = torch.empty((n, p, c), dtype=torch.float32, device=us.device)
+    lw_full = empty((N,), torch.float32)
     for kk in range(K):
-        w = torch.exp(log_w).contiguous()
+        A = A_all[kk:kk + 1]
         nat.call('fbs_cond_resample_f32', stream(), scheme, ptr(sk[kk, 0]), ptr(w), ptr(bs[kk:kk + 1]), ptr(bs[kk + 1:kk + 2]), 1,
                  1, N, ptr(A))                                                     # identical on every rank
         if peer is not None:
-            mine = A[0, lo:hi].contiguous()
-            parents = torch.empty((n, p, c), dtype=torch.float32, device=us.device)
-            peer.gather(mine, parents)
-            moved_dev.append(((mine < lo) | (mine >= hi)).sum())
+            peer.gather(A[0, lo:hi], parents)                                      # a contiguous slice: no copy
+            us, lw_local = model.step(parents, v[kk], v[kk + 1], ts[kk], sk[kk, 1], row_offset=lo, rows_total=N,
+                                      pin_row=bs[kk + 1:kk + 2], pin_value=us_star[kk + 1], out=peer.next_rows())
+            peer.flip()
         else:
             parents, mv = exchange_rows(us, A[0], shard, group)
             moved.append(mv)
-        us, lw_local = model.step(parents, v[kk], v[kk + 1], ts[kk], sk[kk, 1], row_offset=lo, rows_total=N)
-        pin(us, bs_host[kk + 1], us_star[kk + 1])
-        if peer is not None:
-            peer.publish(us)
-        lw = all_gather_rows(lw_local, shard, group)
-        log_w = lw - torch.logsumexp(lw, dim=0)
+            us, lw_local = model.step(parents, v[kk], v[kk + 1], ts[kk], sk[kk, 1], row_offset=lo, rows_total=N,
+                                      pin_row=bs[kk + 1:kk + 2], pin_value=us_star[kk + 1])
+        dist.all_gather_into_tensor(lw_full, lw_local, group=group)
+        nnops.normalise_logw(lw_full, log_w, w)
         if history:
             As[kk].copy_(A[0])
             log_wss[kk + 1].copy_(log_w)
             uss[kk + 1].copy_(us)
     if peer is not None:
-        moved = [int(m) for m in torch.stack(moved_dev).cpu().tolist()] if moved_dev else []
+        mine = A_all[:, lo:hi]
+        moved = [int(m) for m in ((mine < lo) | (mine >= hi)).sum(dim=1).cpu().tolist()]
+    if peer is not None:
+        us = us.reshape(n, p, c).clone()            # the peer buffers are reused by the next sweep
     return dict(N=N, lo=lo, hi=hi, us_last=us, log_ws_last=log_w, moved=moved, As=As, log_wss=log_wss, uss=uss,
-                exchange=mode)
+                exchange=mode, ancestors=A_all)

@@ -321,10 +321,16 @@ int fbs_nn_assemble_image_f32(fbs_stream_t s, const float* us, const float* v, c
  * us_new = u + rd_u dt + sd normal(key, (B, p, c)) (NULL: skip), mean_out = u + rd_u dt (NULL: skip),
  * lw[b] = sum logN(v_next; v_prev + rd_v dt, sd) (NULL: skip).  The B particles of this call are rows
  * [row_offset, row_offset + B) of a particle set of rows_total rows (a particle-sharded sweep draws its slice of the
- * SAME normal(key, (rows_total, p, c)) array; unsharded: row_offset = 0, rows_total = B). */
+ * SAME normal(key, (rows_total, p, c)) array; unsharded: row_offset = 0, rows_total = B).  pin_row / pin_value (both NULL or
+ * both given): a DEVICE int32 holding the global row b*_{k+1} of the reference particle and its value u*_{k+1} [p c]; that
+ * row of us_new receives pin_value instead of a propagated particle (csmc.py:143) -- no separate scatter launch. */
 int fbs_nn_em_step_f32(fbs_stream_t s, const float* img, const float* score, const int32_t* unobs_idx, const int32_t* obs_idx,
                        const float* v_next, const uint32_t* key, int64_t B, int32_t p, int32_t q, int32_t c, float a, float g2,
-                       float dt, float sd, int64_t row_offset, int64_t rows_total, float* us_new, float* mean_out, float* lw);
+                       float dt, float sd, int64_t row_offset, int64_t rows_total, const int32_t* pin_row, const float* pin_value,
+                       float* us_new, float* mean_out, float* lw);
+/* normalise(log_ws, log_space=True) and its exp (csmc.py:146,139) for B weight vectors [B, N] in one launch:
+ * log_w = lw - logsumexp(lw), w = exp(log_w) (either output may be NULL).  The per-step glue of the score-network sweeps. */
+int fbs_normalise_logw_f32(fbs_stream_t s, const float* lw, int64_t B, int64_t N, float* log_w, float* w);
 /* One Euler--Maruyama sub-step of fbs/sdes/simulators.py:87 whose drift has ALREADY been evaluated by a network -- the
  * forward sampler of the Schroedinger-bridge image runs (experiments/sb_imgs/supr.py:132-137: drift = nn_drift(x, t, param_fwd),
  * integration_nsteps = 1):  out[b, e] = x[b, e] + drift[b, e] * ddt + gs * normal(keys[b], (n,))[e]  with
