@@ -116,7 +116,7 @@ def lib():
 # Implementation pins for tests / A-B measurements.  The C library never reads the environment; the Python layer maps the
 # FBS_* variables onto fbs_debug_set_option whenever their values change (checked per call: a few dict lookups).
 _ENV_OPTS = {
-    'FBS_SWEEP_IMPL': ('sweep_impl', {'v1': 1, 'v2': 2, 'v3': 3}),
+    'FBS_SWEEP_IMPL': ('sweep_impl', {'v1': 1, 'v2': 2, 'v3': 3, 'v4': 4}),
     'FBS_SWEEP_VERBOSE': ('sweep_verbose', None),
     'FBS_STEP_IMPL': ('step_impl', {'cuda': 1}),
     'FBS_STEP_TC_WARPS': ('step_tc_warps', None),

@@ -472,6 +472,16 @@ static int launch_sweep(fbs_stream_t s, SweepParams& p) {
     // shape is not eligible.  FBS_SWEEP_IMPL = v1 | v2 | v3 pins the choice (tests / A-B measurements).
     const bool only1 = impl == 1, only2 = impl == 2;
     const bool verbose = debug_opt(OPT_SWEEP_VERBOSE) != 0;
+    if ((impl == 0 || impl == 4) && p.mode != MODE_BOOTSTRAP) {  // narrow states: one warp per chain (sweep_warp.cu)
+      const int rc = launch_sweep_warp(s, p);
+      if (verbose) fprintf(stderr, "[fbs] sweep v4 (warp per chain) -> %d\n", rc);
+      if (rc >= 0) return rc;
+      if (impl == 4) {
+        set_error("sweep: the warp-per-chain kernel was pinned (sweep_impl = 4) but the shape N=%lld du=%d dv=%d is not eligible",
+                  (long long)p.N, p.du, p.dv);
+        return FBS_ERR_UNSUPPORTED;
+      }
+    }
     if (!only1 && !only2) {
       const int rc = launch_sweep_v3(s, p);
       if (verbose) fprintf(stderr, "[fbs] sweep v3 (tcgen05) -> %d\n", rc);

@@ -49,7 +49,7 @@ int sm_count();
 // Implementation-selection knobs for tests and A/B measurements (fbs_debug_set_option): relaxed atomics, default 0 = the
 // library's own choice.  The library never reads the environment.
 enum DebugOpt {
-  OPT_SWEEP_IMPL = 0,   // 1 / 2 / 3: pin the general / tiled / tcgen05 sweep kernel
+  OPT_SWEEP_IMPL = 0,   // 1 / 2 / 3 / 4: pin the general / tiled / tcgen05 / warp-per-chain sweep kernel
   OPT_SWEEP_VERBOSE,    // 1: print the sweep kernel chosen to stderr
   OPT_STEP_IMPL,        // 1: CUDA-core per-timestep transition kernel
   OPT_STEP_TC_WARPS,    // 8: eight-warp variant of the tcgen05 per-timestep kernel

@@ -40,6 +40,8 @@ struct SweepParams {
 int launch_sweep_v2(void* stream, SweepParams& p);
 // sweep_v3.cu (tcgen05).  Same return convention.
 int launch_sweep_v3(void* stream, SweepParams& p);
+// sweep_warp.cu (one warp per chain, narrow states).  Same return convention.
+int launch_sweep_warp(void* stream, SweepParams& p);
 int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8, int nout, float* D);
 // fills p.ws with the per-chain step vectors of all K + 1 slots (sweep_v2.cu)
 int launch_stepvec(void* stream, SweepParams& p);

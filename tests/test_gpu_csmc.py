@@ -619,3 +619,44 @@ def test_ref_sampler_tiled_and_plain_match_oracle(d, N, B):
     assert got.shape == (B, N, d)
     for b in (0, 1, B // 2, B - 1):
         np.testing.assert_allclose(got[b], om32.ref_sampler(keys[b], yT[b], N), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('d,N,K,B', [(10, 64, 12, 37), (4, 64, 5, 3), (16, 64, 4, 2), (10, 128, 6, 5), (12, 128, 3, 2), (7, 64, 6, 20),
+                                     (10, 64, 260, 2)])
+def test_forward_pass_warp_per_chain_kernel(d, N, K, B, monkeypatch):
+    """sweep_warp.cu (one warp per chain, particles in registers; the Gaussian-SB shape d = 10, N = 64): pinned, teacher-forced
+    against the oracle in both CSMC initialisations, and equal ancestors / particles to the general kernel.  K = 260 takes the
+    variant that reads the step matrices through L1 instead of shared memory."""
+    from fbs_b200.samplers.csmc import csmc, resamplings as R
+    p = gp_problem(d, K=K)
+    om32, om64 = oracle_model(p, np.float32), oracle_model(p, np.float64)
+    pm, _ = product_model(p)
+    keys, us_star, bs_star, vs = _inputs(p, om32, B, N, seed=41)
+    init = csmc.DegenerateInit(N)
+    args = (keys, us_star, bs_star, vs, p['ts'], init.sampler, init.likelihood_logpdf, pm.transition_sampler,
+            pm.likelihood_logpdf, R.killing, N)
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v4')
+    As, log_wss, uss = csmc.forward_pass(*args)
+    nb = min(B, 3) if K < 100 else 1
+    _check_forward_history(p, om64, keys[:nb], us_star[:nb], bs_star[:nb], vs[:nb], As[:nb], log_wss[:nb], uss[:nb], 'killing', False)
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v1')
+    A1, l1, u1 = csmc.forward_pass(*args)
+    np.testing.assert_array_equal(A1[:, 0], As[:, 0])
+    np.testing.assert_allclose(u1[:, 1], uss[:, 1], rtol=1e-5, atol=1e-5)
+    assert (A1 == As).mean() > 0.99
+    if K > 100:
+        return
+    # explicit_final (N - 1 = nparticles; the sweep carries N rows) and the multinomial scheme
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v4')
+    ninit = csmc.NormalInit(pm)
+    As2, lw2, us2 = csmc.forward_pass(keys, us_star, bs_star, vs, p['ts'], ninit.sampler, ninit.likelihood_logpdf,
+                                      pm.transition_sampler, pm.likelihood_logpdf, R.multinomial, N - 1)
+    assert As2.shape == (B, K, N)
+    _check_forward_history(p, om64, keys[:2], us_star[:2], bs_star[:2], vs[:2], As2[:2], lw2[:2], us2[:2], 'multinomial', True)
+
+
+@pytest.mark.parametrize('scheme', ['stratified', 'killing'])
+def test_pmcmc_filter_warp_per_chain_kernel(scheme, monkeypatch):
+    monkeypatch.setenv('FBS_SWEEP_IMPL', 'v4')
+    _check_pmcmc_filter(10, 64, 9, 21, scheme)
+    _check_pmcmc_filter(8, 128, 4, 3, scheme)
