@@ -6,6 +6,6 @@ no CPU fallback: importing is cheap, but the first call needs ``fbs_b200/_lib/li
 (``python -m fbs_b200.build``) and a CUDA device.
 """
 from . import random, sdes, samplers  # noqa: F401
-from .models import AffineGaussianModel  # noqa: F401
+from .models import AffineGaussianModel, TwistedAffineModel  # noqa: F401
 
 __version__ = '0.1.0'

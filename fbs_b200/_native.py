@@ -64,6 +64,8 @@ SIGNATURES = {
     'fbs_pmcmc_filter_affine_f32': ([_p, _M, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p, _p, _p, C.c_size_t], _int),
     'fbs_bootstrap_filter_affine_f32': ([_p, _M, _p, _p, _p, _int, _i64, _i64, _p, _p, _p, _p, _p], _int),
     'fbs_backward_sample_affine_f32': ([_p, _M, _int, _p, _p, _p, _p, _int, _i64, _i64, _p, _p], _int),
+    'fbs_twisted_smc_affine_f32': ([_p, _p, _p, _p, _p, _p, _f32, _f32, _i64, _i64, _p, _p, _int, _p, _int, _i64, _i64, _p, _p,
+                                    _p, _p, _p], _int),
     'fbs_force_move_f32': ([_p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _p, _p, _p], _int),
     'fbs_pcn_combine_f32': ([_p, _f64, _p, _p, _p, _p, _i64, _i64, _p], _int),
     'fbs_mh_accept_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p], _int),

@@ -28,6 +28,22 @@ __device__ __forceinline__ float warp_seq_cumsum(const float* w, float* cum, int
   if (lane == 0) {
     // batches of 8: independent loads first, then the dependent FADD chain (the only serial part), then stores
     int i = 0;
+    if (((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(cum)) & 15) == 0) {
+      // 16-byte aligned rows: two vector loads / stores per 8 elements (the lane issues 12 instead of 24 instructions)
+      for (; i + 8 <= n; i += 8) {
+        float4 a = *reinterpret_cast<const float4*>(w + i), b = *reinterpret_cast<const float4*>(w + i + 4);
+        a.x = acc = __fadd_rn(acc, a.x);
+        a.y = acc = __fadd_rn(acc, a.y);
+        a.z = acc = __fadd_rn(acc, a.z);
+        a.w = acc = __fadd_rn(acc, a.w);
+        b.x = acc = __fadd_rn(acc, b.x);
+        b.y = acc = __fadd_rn(acc, b.y);
+        b.z = acc = __fadd_rn(acc, b.z);
+        b.w = acc = __fadd_rn(acc, b.w);
+        *reinterpret_cast<float4*>(cum + i) = a;
+        *reinterpret_cast<float4*>(cum + i + 4) = b;
+      }
+    }
     for (; i + 8 <= n; i += 8) {
       float x[8];
 #pragma unroll

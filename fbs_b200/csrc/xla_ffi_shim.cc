@@ -189,6 +189,21 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_affine_eval, AffineEvalImpl,
                               FBS_BIND_STREAM().Arg<BufU>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>().FBS_BIND_MODEL()
                                   .Attr<int32_t>("du").Attr<int32_t>("k").Ret<BufF>().Ret<BufF>().Ret<BufF>());
 
+// twisted_smc(...) -> (samples, log_weights)                                                   smc.py:261-309
+static ffi::Error TwistedSmcImpl(cudaStream_t stream, BufU keys, BufF y, BufF x0, BufF MT, BufF Mrow, BufF m, BufF sd, BufF g2,
+                                 float dt, float obs_var, int32_t scheme, ResF samples, ResF log_ws) {
+  auto dm = x0.dimensions();  // [B, N, d]
+  const int64_t K = sd.dimensions()[0] - 1;
+  return as_error(fbs_twisted_smc_affine_f32(stream, MT.typed_data(), Mrow.typed_data(), m.typed_data(), sd.typed_data(),
+                                             g2.typed_data(), dt, obs_var, K, dm[2], keys.typed_data(), y.typed_data(),
+                                             y.dimensions().size() == 2 && y.dimensions()[0] == dm[0] && dm[0] > 1, x0.typed_data(),
+                                             scheme, dm[0], dm[1], samples->typed_data(), log_ws->typed_data(), nullptr, nullptr,
+                                             nullptr));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_twisted_smc, TwistedSmcImpl,
+                              FBS_BIND_STREAM().Arg<BufU>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>()
+                                  .Arg<BufF>().Attr<float>("dt").Attr<float>("obs_var").Attr<int32_t>("scheme").Ret<BufF>().Ret<BufF>());
+
 // force_move(key, weights, k) fused with x0 = uss[-1, idx]  -> (idx, alpha, x0)                 gibbs.py:152-154,171-214
 static ffi::Error ForceMoveImpl(cudaStream_t stream, BufU keys, BufF log_ws_last, BufF us_last, BufI k, int32_t weights_are_log,
                                 ResI idx, ResF alpha, ResF x0) {

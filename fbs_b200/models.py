@@ -289,3 +289,75 @@ class AffineGaussianModel:
                 y = y.expand(B, -1)
             return torch.cat([x, y], dim=1).contiguous()
         return torch.cat([x.reshape(-1), y.reshape(-1)]).contiguous()
+
+
+class TwistedAffineModel:
+    """The closures of the twisted-SMC comparison sampler of the toy experiments (experiments/toy/gp_twisted.py:66-129): the
+    reverse diffusion of the X-marginal of a Gaussian ``N(mean_x, cov_x)`` under a scalar linear SDE (affine drift
+    ``M_t u + m_t``), the Gaussian twisting function ``p~(y | u, t) = N(y; u + reverse_drift(u, t) dt, obs_var)`` and the
+    proposal whose drift adds ``g^2 grad_u log p~`` (analytic here: the denoising estimate is affine in ``u``).
+
+    The bound methods satisfy the callable protocol of ``twisted_smc`` (fbs/samplers/smc.py:261-268) and carry the per-time
+    coefficient tables (time indices 0..K: the scan walks ``ts[1:]``, the initial twisting uses ``ts[0]``) the one-launch
+    kernel ``fbs_twisted_smc_affine_f32`` reads.  Called on their own they raise: the sampler fuses them.
+    """
+
+    def __init__(self, sde: LinearSDE, mean_x, cov_x, obs_var, ts, T=None):
+        ts64 = _host64(ts)
+        self.K = ts64.shape[0] - 1
+        self.T = float(ts64[-1]) if T is None else float(T)
+        self.dt = self.T / self.K                                     # gp_twisted.py:57
+        self.obs_var = float(obs_var)
+        self.ts = ts64.astype(np.float32)
+        mu, Sigma = _host64(mean_x), _host64(cov_x)
+        self.d = d = mu.shape[0]
+        eye = np.eye(d)
+        M = np.empty((self.K + 1, d, d))
+        m = np.empty((self.K + 1, d))
+        g = np.empty((self.K + 1,))
+        ts32 = self.ts.astype(np.float64)
+        for k in range(self.K + 1):
+            s = float(np.float32(self.T) - np.float32(ts32[k]))       # T - t as the float32 closures see it
+            F, Q = sde.transition(s, ts32[0])
+            prec = np.linalg.solve(F * F * Sigma + Q * eye, eye)
+            gk = float(sde.dispersion(s))
+            M[k] = -float(sde.drift_coef(s)) * eye - gk * gk * prec  # reverse_drift, gp_twisted.py:84-85
+            m[k] = gk * gk * (prec @ (F * mu))
+            g[k] = gk
+        FT, QT = sde.transition(self.T, ts32[0])
+        self._ref = (FT * mu, np.linalg.cholesky(FT * FT * Sigma + QT * eye))   # terminal reference, gp_twisted.py:80,108-111
+        self.host = dict(MT=np.ascontiguousarray(np.transpose(M, (0, 2, 1))).astype(np.float32), Mr=M.astype(np.float32),
+                         m=m.astype(np.float32), g2=(g * g).astype(np.float32),
+                         sd=(np.float32(math.sqrt(self.dt)) * g.astype(np.float32)).astype(np.float32))
+        self._dev = None
+
+    def device_arrays(self):
+        if self._dev is None:
+            self._dev = {k: dev(v, torch.float32) for k, v in self.host.items()}
+            self._dev['ref_m'] = dev(self._ref[0], torch.float32)
+            self._dev['ref_LT'] = dev(np.ascontiguousarray(self._ref[1].T), torch.float32)
+        return self._dev
+
+    def init_sampler(self, key, nparticles):
+        """gp_twisted.py:108-111: ``m_ref + normal(key, (n, d)) @ cholesky(cov_ref)^T`` (batched over keys ``[B, 2]``), by the
+        Gaussian reference-sampling kernel (``fbs_gaussian_ref_sample_f32`` with an empty conditioning part)."""
+        host = is_host(key)
+        kk = dev(key, torch.uint32)
+        single = kk.dim() == 1
+        kk = kk.reshape(-1, 2)
+        B = kk.shape[0]
+        a = self.device_arrays()
+        if 'zero1' not in a:
+            a['zero1'] = torch.zeros((max(B, 1),), dtype=torch.float32, device=kk.device)
+            a['zeroB'] = torch.zeros((self.d,), dtype=torch.float32, device=kk.device)
+        if a['zero1'].numel() < B:
+            a['zero1'] = torch.zeros((B,), dtype=torch.float32, device=kk.device)
+        o = empty((B, int(nparticles), self.d), torch.float32)
+        nat.call('fbs_gaussian_ref_sample_f32', stream(), ptr(kk), ptr(a['zero1']), ptr(a['ref_m']), ptr(a['zeroB']), ptr(a['zero1']),
+                 ptr(a['ref_LT']), B, int(nparticles), self.d, 1, ptr(o))
+        return out(o[0] if single else o, host)
+
+    def _fused(self, *_, **__):
+        raise TypeError('the closures of a TwistedAffineModel are consumed by the fused twisted_smc kernel; they are not called')
+
+    transition_logpdf = twisting_logpdf = twisting_prop_sampler = twisting_prop_logpdf = _fused

@@ -300,3 +300,42 @@ def bootstrap_backward_smoother(key, filter_us, vs, ts, transition_logpdf, *args
         traj.append(u)
     res = torch.cat([torch.stack(traj[::-1], dim=1), uT[:, None]], dim=1)
     return out(res[0] if single else res, host)
+
+
+def twisted_smc(key, y, ts, init_sampler, transition_logpdf, twisting_logpdf, twisting_prop_sampler, twisting_prop_logpdf,
+                resampling, nparticles, return_history: bool = False, **kwargs):
+    """Twisted SMC, same arguments and returns as ``fbs.samplers.twisted_smc`` (smc.py:261-309): ``(samples [.., N, d],
+    log_weights [.., N])``.  The four closures must be the bound methods of ONE :class:`fbs_b200.TwistedAffineModel`; the
+    whole K-step scan is one launch (``fbs_twisted_smc_affine_f32``).  Keys ``[B, 2]`` run B independent samplers (``y`` shared
+    or ``[B, d]``).  ``return_history=True`` (tests) appends the per-step resampling indices, particles and normalised log-weights."""
+    from ..models import TwistedAffineModel
+    owners = {id(getattr(f, '__self__', None)) for f in (transition_logpdf, twisting_logpdf, twisting_prop_sampler,
+                                                         twisting_prop_logpdf)}
+    model = getattr(transition_logpdf, '__self__', None)
+    if len(owners) != 1 or not isinstance(model, TwistedAffineModel):
+        raise TypeError('twisted_smc fuses the scan into a CUDA kernel and cannot call opaque Python closures: pass the bound '
+                        'methods of one fbs_b200.TwistedAffineModel (no interpreted fallback exists)')
+    scheme = _scheme_of(resampling, 'unconditional')
+    host = is_host(key)
+    k = dev(key, torch.uint32)
+    single = k.dim() == 1
+    k = k.reshape(-1, 2)
+    B, K, N, d = k.shape[0], model.K, int(nparticles), model.d
+    ks = frandom.split(k, 2)                                                       # smc.py:296
+    key_init, key_filter = ks[:, 0].contiguous(), ks[:, 1].contiguous()
+    x0 = dev(init_sampler(key_init if not single else key_init[0], N), torch.float32).reshape(B, N, d).contiguous()   # smc.py:299
+    yd = dev(y, torch.float32).reshape(-1, d).contiguous()
+    if yd.shape[0] not in (1, B):
+        raise ValueError('y must be one observation or one per key')
+    a = model.device_arrays()
+    samples, log_ws = empty((B, N, d), torch.float32), empty((B, N), torch.float32)
+    inds = xs_hist = lw_hist = None
+    if return_history:
+        inds, xs_hist, lw_hist = empty((B, K, N), torch.int32), empty((B, K, N, d), torch.float32), empty((B, K, N), torch.float32)
+    nat.call('fbs_twisted_smc_affine_f32', stream(), ptr(a['MT']), ptr(a['Mr']), ptr(a['m']), ptr(a['sd']), ptr(a['g2']),
+             float(model.dt), float(model.obs_var), K, d, ptr(key_filter), ptr(yd), int(yd.shape[0] == B and B > 1), ptr(x0), scheme,
+             B, N, ptr(samples), ptr(log_ws), ptr(inds), ptr(xs_hist), ptr(lw_hist))
+    res = (samples, log_ws) + ((inds, xs_hist, lw_hist) if return_history else ())
+    if single:
+        res = tuple(t[0] for t in res)
+    return tuple(out(t, host) for t in res)

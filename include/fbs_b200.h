@@ -231,6 +231,19 @@ int fbs_backward_sample_affine_f32(fbs_stream_t s, const fbs_affine_model_t* mod
                                    const float* vs, const float* uss, const float* log_wss, int shared_history, int64_t B,
                                    int64_t N, float* xs_star, int32_t* bs_star);
 
+/* twisted_smc(key, y, ts, init_sampler, transition_logpdf, twisting_logpdf, twisting_prop_sampler, twisting_prop_logpdf,
+ * resampling, nparticles), fbs/samplers/smc.py:261-309, with the affine closures of experiments/toy/gp_twisted.py:66-129
+ * (reverse_drift(u, t) = M_t u + m_t; twisting N(y; u + reverse_drift dt, obs_var); proposal drift + g^2 grad log twisting) --
+ * the whole scan in one launch.  Coefficient tables over the time indices 0..K (the scan walks ts[1:], the initial twisting
+ * uses ts[0]): MT [K+1,d,d] with MT[t][j][i] = M_t[i][j], Mrow [K+1,d,d] = M_t row-major, m [K+1,d], sd [K+1] =
+ * sqrt(dt) g_t, g2 [K+1] = g_t^2.  keys [B,2] = key_filter of smc.py:296; y [B,d] (y_batched != 0) or [d]; x0 [B,N,d] =
+ * init_sampler(key_init, nparticles) (:299).  Out: samples [B,N,d], log_ws [B,N] (normalised).  Optional history (may be
+ * NULL): inds [B,K,N], xs_hist [B,K,N,d], lw_hist [B,K,N]. */
+int fbs_twisted_smc_affine_f32(fbs_stream_t s, const float* MT, const float* Mrow, const float* m, const float* sd,
+                               const float* g2, float dt, float obs_var, int64_t K, int64_t d, const uint32_t* keys,
+                               const float* y, int y_batched, const float* x0, int scheme, int64_t B, int64_t N,
+                               float* samples, float* log_ws, int32_t* inds, float* xs_hist, float* lw_hist);
+
 /* force_move(key, weights, k), fbs/samplers/gibbs.py:171-214, fused with the selection
  * x0 = uss[-1, idx] (gibbs.py:152-154).  log_ws_last [B,N]: normalised log-weights when weights_are_log != 0
  * (the kernel exponentiates, as gibbs.py:152 does), else the weights themselves.

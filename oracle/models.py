@@ -220,3 +220,70 @@ class GaussianSBModel:
         xy0 = np.concatenate([x0_, y0_]).astype(self.dtype)
         return euler_maruyama(key_, xy0, self.ts, lambda x, t: self.drift(x[None], t)[0], self.dispersion,
                               integration_nsteps=self.em_nsteps, return_path=True, dtype=self.dtype)
+
+
+class TwistedGaussianModel:
+    """Closures of experiments/toy/gp_twisted.py:66-129: the reverse diffusion of the X-MARGINAL of the GP regression model,
+    the Gaussian twisting function p~(y | u, t) = N(y; u + reverse_drift(u, t) dt, obs_var) (:114-116) and the proposal that
+    adds ``g^2 grad_u log p~`` to the drift (:88-90, :122-129).  ``jax.grad`` of the twisting function is written out
+    analytically: with reverse_drift(u, t) = M_t u + m_t the denoising estimate is affine, ``(I + dt M_t) u + dt m_t``, so the
+    gradient is ``(I + dt M_t)^T (y - estimate) / obs_var`` -- exactly what autodiff returns.
+    """
+
+    def __init__(self, sde, mean_x, cov_x, obs_var, ts, T, dtype=np.float64):
+        self.sde, self.T, self.dtype, self.obs_var = sde, T, dtype, float(obs_var)
+        self.ts = np.asarray(ts, dtype=dtype)
+        self.K = self.ts.shape[0] - 1
+        self.dt = T / self.K                                           # gp_twisted.py:57 (python float)
+        self.mean_x, self.cov_x = np.asarray(mean_x, dtype), np.asarray(cov_x, dtype)
+        self.d = self.mean_x.shape[0]
+        self.discretise, _, _ = make_linear_sde(sde, dtype)
+
+    def forward_m_cov(self, t):                                        # :66-68
+        F_, Q_ = self.discretise(t, self.ts[0])
+        return F_ * self.mean_x, (F_ ** 2 * self.cov_x + Q_ * np.eye(self.d, dtype=self.dtype)).astype(self.dtype)
+
+    def affine(self, t):
+        """(M_t, m_t, g_t) with reverse_drift(u, t) = M_t u + m_t (:71-85), float64."""
+        tt = float(self.T) - float(t)
+        mt, covt = self.forward_m_cov(self.dtype(tt))
+        prec = np.linalg.inv(covt.astype(np.float64))
+        g = float(self.sde.dispersion(tt))
+        a_lin = float(self.sde.drift(1.0, tt))
+        return -a_lin * np.eye(self.d) - g * g * prec, g * g * prec @ mt.astype(np.float64), g
+
+    def reverse_drift(self, u, t):                                     # :84-85
+        M, m, _ = self.affine(t)
+        return (u @ M.T + m).astype(self.dtype)
+
+    def init_sampler(self, key_, n):                                   # :108-111
+        m_ref, cov_ref = self.forward_m_cov(self.dtype(self.T))
+        return (m_ref + _normal(key_, (n, self.d), self.dtype) @ np.linalg.cholesky(cov_ref).T).astype(self.dtype)
+
+    def transition_logpdf(self, u, u_prev, t_prev):                    # :99-105
+        _, _, g = self.affine(t_prev)
+        return norm_logpdf(u, u_prev + self.reverse_drift(u_prev, t_prev) * self.dtype(self.dt),
+                           self.dtype(math.sqrt(self.dt) * g)).sum(-1)
+
+    def twisting_logpdf(self, y, u, t):                                # :114-116
+        est = u + self.reverse_drift(u, t) * self.dtype(self.dt)
+        return norm_logpdf(np.asarray(y, self.dtype), est, self.dtype(math.sqrt(self.obs_var))).sum(-1)
+
+    def reverse_cond_drift(self, u, t, y):                             # :88-90
+        M, m, g = self.affine(t)
+        G = np.eye(self.d) + self.dt * M
+        est = u + (u @ M.T + m) * self.dt
+        grad = ((np.asarray(y, np.float64) - est) / self.obs_var) @ G
+        return (u @ M.T + m + g * g * grad).astype(self.dtype)
+
+    def twisting_prop_mean(self, us, t, y):
+        return us + self.reverse_cond_drift(us, t, y) * self.dtype(self.dt)
+
+    def twisting_prop_sampler(self, key_, us, t, y):                   # :122-124
+        _, _, g = self.affine(t)
+        return (self.twisting_prop_mean(us, t, y)
+                + self.dtype(math.sqrt(self.dt) * g) * _normal(key_, us.shape, np.float32).astype(self.dtype)).astype(self.dtype)
+
+    def twisting_prop_logpdf(self, u, u_prev, t, y):                   # :127-129
+        _, _, g = self.affine(t)
+        return norm_logpdf(u, self.twisting_prop_mean(u_prev, t, y), self.dtype(math.sqrt(self.dt) * g)).sum(-1)

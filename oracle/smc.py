@@ -113,3 +113,29 @@ def pmcmc_kernel(key, uT, log_ell, ys, y0, ts, fwd_ys_sampler, sde, ref_sampler,
     if acc_flag:
         return prop_uT, prop_log_ell, prop_ys, state                                 # :255-258
     return uT, log_ell, ys, state
+
+
+def twisted_smc(key, y, ts, init_sampler, transition_logpdf, twisting_logpdf, twisting_prop_sampler, twisting_prop_logpdf,
+                resampling, nparticles, return_hist=False, **kwargs):
+    """smc.py:261-309 (Algorithm 1 of arXiv 2306.17775).  The scan walks ``ts[1:]`` (:305), so "t_prev" below is ts[k + 1]."""
+    nsteps = ts.shape[0] - 1
+    key_init, key_filter = jr.split(key, 2)                                          # :296
+    keys = jr.split(key_filter, nsteps)
+    xs = np.asarray(init_sampler(key_init, nparticles))                              # :299
+    log_ps = twisting_logpdf(y, xs, ts[0], **kwargs)                                 # :300
+    log_ws = (log_ps - logsumexp(log_ps)).astype(log_ps.dtype)                       # :301
+    hist = []
+    for k in range(nsteps):
+        t_prev = ts[k + 1]
+        key_resampling, key_prop = jr.split(keys[k])                                 # :280
+        inds = resampling(np.exp(log_ws).astype(log_ws.dtype), key_resampling)       # :283
+        xs_prev = xs[inds, ...]                                                      # :284
+        log_ps_prev = log_ps[inds, ...]                                              # :285
+        xs = np.asarray(twisting_prop_sampler(key_prop, xs_prev, t_prev, y, **kwargs))   # :288
+        log_ps = twisting_logpdf(y, xs, t_prev, **kwargs)                            # :291
+        log_ws = (transition_logpdf(xs, xs_prev, t_prev) + log_ps
+                  - twisting_prop_logpdf(xs, xs_prev, t_prev, y, **kwargs) - log_ps_prev)   # :292-293
+        log_ws = (log_ws - logsumexp(log_ws)).astype(log_ps.dtype)                   # :294
+        if return_hist:
+            hist.append(dict(inds=inds, xs=xs, log_ws=log_ws))
+    return (xs, log_ws, hist) if return_hist else (xs, log_ws)
