@@ -75,6 +75,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// the same wait with a suspend-time hint: the thread sleeps inside try_wait (woken by the phase completion) instead of
+// re-issuing the probe -- the MMA / TMA warps' polls were ~9 % of the executed instructions (profiles/r1_v3_sweep_hot_lines.txt)
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITH_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra WAITH_DONE;\n\t"
+      "bra WAITH_LOOP;\n\t"
+      "WAITH_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -345,7 +360,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             const uint32_t run = (np / 8u) * 128u;  // bytes of this pass's rows inside one (part, k-chunk) of the image
             const unsigned char* src = img + (size_t)(r0 / 8u) * 128u;
             for (int kb = 0; kb < L.nkb; ++kb, src += L.img_bytes) {
-              mbar_wait(empty + ps, pph);
+              if (stages_flags & 0x200) mbar_wait_hint(empty + ps, pph); else mbar_wait(empty + ps, pph);
               unsigned char* dst = ring + (size_t)ps * L.stage_bytes;
               mbar_expect_tx(full + ps, 4u * run);
 #pragma unroll
@@ -370,7 +385,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
       for (uint32_t t = 0; t < G0; ++t) {
         for (int g = 0; g < GROUPS; ++g) {
           if (g == 1 && t >= G1) break;
-          mbar_wait(ready + g, t & 1u);
+          if (stages_flags & 0x200) mbar_wait_hint(ready + g, t & 1u); else mbar_wait(ready + g, t & 1u);
           tc_fence_after();
           const uint32_t a_hi0 = smem_u32(smem + L.A) + (uint32_t)g * 2u * L.a_bytes;
           const uint32_t d_tmem = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             uint64_t dAl = desc_hi_A | (uint64_t)(((a_hi0 + L.a_bytes) >> 4) & 0x3FFFu);
             const uint64_t a_inc = (uint64_t)((2u * L.a_lbo) >> 4), b_lo_off = (uint64_t)((2u * run) >> 4);
             for (int kb = 0; kb < L.nkb; ++kb) {
-              mbar_wait(full + cs, cph);
+              if (stages_flags & 0x200) mbar_wait_hint(full + cs, cph); else mbar_wait(full + cs, cph);
               tc_fence_after();
               const uint64_t dBh = desc_hi_B | (uint64_t)((ring16 + cs * stage16) & 0x3FFFu);
               const uint64_t dBl = dBh + b_lo_off;
@@ -1133,7 +1148,7 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   if (p.N < 2 || (p.N & 1) || p.N > ROWS) return -1;
   if (p.du % 4 != 0 || p.du < 4) return -1;
   int stages = MAX_STAGES;
-  const int flags = debug_opt(OPT_V3_TWOPASS) == 1 ? 0x100 : 0;  // two-pass GEMM (v columns first): slower, the small-N MMAs are bound by operand fetch
+  const int flags = (debug_opt(OPT_V3_TWOPASS) == 1 ? 0x100 : 0) | ((debug_opt(OPT_V3_VARIANT) & 1) ? 0 : 0x200);  // v3_variant bit 0: the un-hinted mbarrier polls (A/B)  // two-pass GEMM (v columns first): slower, the small-N MMAs are bound by operand fetch
   Layout L = make_layout(p.N, p.du, p.dv, stages | flags);
   while (L.total > 227 * 1024 && stages > 2) L = make_layout(p.N, p.du, p.dv, --stages | flags);
   if (L.total > 227 * 1024) return -1;

@@ -258,7 +258,9 @@ class TwistedGaussianModel:
 
     def init_sampler(self, key_, n):                                   # :108-111
         m_ref, cov_ref = self.forward_m_cov(self.dtype(self.T))
-        return (m_ref + _normal(key_, (n, self.d), self.dtype) @ np.linalg.cholesky(cov_ref).T).astype(self.dtype)
+        # (the float32 random stream of the experiment -- jax_enable_x64 is off, gp_twisted.py:21 -- whatever `dtype` the
+        #  arithmetic of this restatement runs in)
+        return (m_ref + _normal(key_, (n, self.d), np.float32).astype(self.dtype) @ np.linalg.cholesky(cov_ref).T).astype(self.dtype)
 
     def transition_logpdf(self, u, u_prev, t_prev):                    # :99-105
         _, _, g = self.affine(t_prev)

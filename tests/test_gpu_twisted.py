@@ -1,6 +1,6 @@
 """twisted_smc (fbs/samplers/smc.py:261-309) with the closures of experiments/toy/gp_twisted.py:66-129 on the CUDA path:
 teacher-forced against the oracle restatement (oracle/smc.py twisted_smc + oracle/models.py TwistedGaussianModel, float64
-closures; indices exact up to float32 exp ties, particles rtol 1e-5, normalised log-weights atol 2e-3) and a statistical
+closures; indices exact up to float32 exp ties, particles rtol 1e-5, normalised log-weights atol 2e-3 + rtol 1e-5) and a statistical
 check of the conditional samples against the GP-regression posterior the toy driver stores next to them (gp_twisted.py:50-53,151-152)."""
 import numpy as np
 import pytest
@@ -26,7 +26,7 @@ def _problem(d, K, kind='const'):
     return omod, pmod, y0, ts, cov_mat
 
 
-@pytest.mark.parametrize('d,N,K,B,kind', [(1, 10, 8, 4, 'const'), (3, 50, 12, 5, 'const'), (10, 100, 6, 3, 'lin'), (100, 100, 3, 2, 'const'),
+@pytest.mark.parametrize('d,N,K,B,kind', [(1, 10, 8, 4, 'const'), (3, 50, 12, 5, 'const'), (10, 100, 6, 3, 'lin'), (100, 100, 20, 2, 'const'),
                                           (7, 33, 5, 150, 'const')])
 @pytest.mark.parametrize('scheme', ['stratified', 'killing'])
 def test_twisted_smc_teacher_forced(d, N, K, B, kind, scheme):
@@ -43,11 +43,8 @@ def test_twisted_smc_teacher_forced(d, N, K, B, kind, scheme):
     mism = 0
     for b in range(min(B, 4)):
         key_init, key_filter = jr.split(keys[b])                                  # smc.py:296
-        x_prev = omod.init_sampler(key_init, N)                                   # smc.py:299 (float64 Cholesky product)
-        lps_prev = omod.twisting_logpdf(y64, x_prev, omod.ts[0])
-        lw_prev = ocsmc.normalise(lps_prev.astype(np.float32), log_space=True)
-        # the kernel starts from the float32 init of the product model: take ITS particles for the teacher forcing
-        x_prev = np.asarray(pmod.init_sampler(key_init, N).cpu().numpy(), np.float64)
+        # smc.py:299 -- the kernel starts from the float32 init of the product model: take ITS particles for the teacher forcing
+        x_prev = np.asarray(pmod.init_sampler(key_init, N), np.float64)
         np.testing.assert_allclose(x_prev, omod.init_sampler(key_init, N), rtol=2e-5, atol=2e-5)
         lps_prev = omod.twisting_logpdf(y64, x_prev, omod.ts[0])
         lw_prev = ocsmc.normalise(lps_prev.astype(np.float32), log_space=True)
@@ -64,7 +61,9 @@ def test_twisted_smc_teacher_forced(d, N, K, B, kind, scheme):
             lps = omod.twisting_logpdf(y64, x_new, t)
             lws = omod.transition_logpdf(x_new, xp, t) + lps - omod.twisting_prop_logpdf(x_new, xp, t, y64) - lpp   # :291-293
             want_lw = lws - ocsmc.logsumexp(lws)
-            np.testing.assert_allclose(lwh[b, k], want_lw, rtol=0, atol=2e-3, err_msg=f'log-weights b={b} k={k}')
+            # (float32 evaluation of terms of size max|lws|: their rounding, 2^-24 relative each, is the floor of the agreement)
+            np.testing.assert_allclose(lwh[b, k], want_lw, rtol=1e-5, atol=2e-3 + 4e-6 * float(np.abs(lws).max()),
+                                       err_msg=f'log-weights b={b} k={k}')
             x_prev, lps_prev, lw_prev = x_new, lps, lwh[b, k]
     assert mism <= max(1, int(3e-4 * min(B, 4) * K * N)), mism
     # one key == row of the batch
