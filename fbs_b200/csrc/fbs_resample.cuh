@@ -22,8 +22,66 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// cum[i] = sequential cumsum of w (lane 0).  w and cum may alias.  Returns cum[n-1] to all lanes.
+// Summation-order contract for LONG rows (n >= kChunkedMinN; the oracle's jax_random.seq_cumsum / seq_sum follow the same
+// definition): chunks of 8 consecutive elements,
+//   local_c[t] = sequential sum of the chunk's first t + 1 elements,  P_0 = 0,  P_{c+1} = fl(P_c + local_c[last]),
+//   cum[8 c + t] = fl(P_c + local_c[t]).
+// The serial dependency is n / 8 additions instead of n (a 16384-particle row: 8 k instead of 65 k cycles) and the 8-element
+// chunks map onto lanes; rows of the sweep kernels (N <= 128) and every golden file (N <= 257) keep the plain sequential sum.
+constexpr int kChunkedMinN = 1024;
+
+// chunked cumulative sum of a long row by the whole warp; w and cum may alias.  Returns the total to all lanes.
+__device__ __forceinline__ float warp_chunked_cumsum(const float* w, float* cum, int n, int lane, bool store) {
+  float running = 0.f;  // P of the tile's first chunk (uniform over the warp)
+  for (int base = 0; base < n; base += 256) {
+    const int c0 = base + 8 * lane;  // this lane's chunk
+    float loc[8];
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float x = c0 + t < n ? w[c0 + t] : 0.f;
+      acc = __fadd_rn(acc, x);
+      loc[t] = acc;
+    }
+    float myP = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < 32; ++s) {  // P_{c+1} = fl(P_c + total_c), chunk by chunk (the only serial part)
+      const float t = __shfl_sync(0xffffffffu, acc, s);
+      if (lane == s) myP = running;
+      running = __fadd_rn(running, t);
+    }
+    if (store) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (c0 + t < n) cum[c0 + t] = __fadd_rn(myP, loc[t]);
+    }
+  }
+  __syncwarp();
+  return running;
+}
+
+// sequential float32 sum of a row (the oracle's seq_sum): by lane 0 for short rows, chunked for long ones.  To all lanes.
+__device__ __forceinline__ float warp_seq_sum(const float* w, int n, int lane) {
+  if (n >= kChunkedMinN) return warp_chunked_cumsum(w, nullptr, n, lane, false);
+  float acc = 0.f;
+  if (lane == 0) {
+    int q = 0;
+    for (; q + 8 <= n; q += 8) {
+      float x[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) x[t] = w[q + t];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, x[t]);
+    }
+    for (; q < n; ++q) acc = __fadd_rn(acc, w[q]);
+  }
+  return __shfl_sync(0xffffffffu, acc, 0);
+}
+
+// cum[i] = cumsum of w in the contract's order (sequential by lane 0 for n < kChunkedMinN).  w and cum may alias.
+// Returns cum[n-1] to all lanes.
 __device__ __forceinline__ float warp_seq_cumsum(const float* w, float* cum, int n, int lane) {
+  if (n >= kChunkedMinN) return warp_chunked_cumsum(w, cum, n, lane, true);
   float acc = 0.f;
   if (lane == 0) {
     // batches of 8: independent loads first, then the dependent FADD chain (the only serial part), then stores
@@ -115,22 +173,11 @@ __device__ __forceinline__ void warp_cond_killing(Key key, const float* w, int n
 
   // J_prob = (1 - w / w_max) / N, J_prob[i] = max(1 - sum(J_prob with J_prob[i] = 0), 0)   (:79-82)
   const float fn = (float)n;
-  float acc = 0.f;
-  // J_prob computed in parallel into cum[], then two sequential passes by lane 0 (sum, cumulative sum)
+  // J_prob computed in parallel into cum[], then two passes in the contract's summation order (sum, cumulative sum)
   for (int q = lane; q < n; q += 32) cum[q] = (q == i) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(w[q], w_max)), fn);
   __syncwarp();
-  if (lane == 0) {
-    int q = 0;
-    for (; q + 8 <= n; q += 8) {
-      float x[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) x[t] = cum[q + t];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, x[t]);
-    }
-    for (; q < n; ++q) acc = __fadd_rn(acc, cum[q]);
-    cum[i] = fmaxf(__fsub_rn(1.0f, acc), 0.f);
-  }
+  const float acc = warp_seq_sum(cum, n, lane);
+  if (lane == 0) cum[i] = fmaxf(__fsub_rn(1.0f, acc), 0.f);
   __syncwarp();
   warp_seq_cumsum(cum, cum, n, lane);
   // J ~ Cat(J_prob): choice(key_3, N, (), p=J_prob)   (:84) -- random_bits(key_3, 1) = block (0, 0), word 0

@@ -3,7 +3,7 @@
 #include <string.h>
 #include <atomic>
 #include "fbs_common.cuh"
-#include "fbs_rng.cuh"
+#include "fbs_resample.cuh"
 
 namespace fbs {
 
@@ -90,13 +90,7 @@ __global__ void choice_kernel(const uint32_t* __restrict__ keys, const float* __
   float* cum = smem + (size_t)warp * N;
   for (int64_t bch = blockIdx.x * (int64_t)nwarps + warp; bch < B; bch += (int64_t)gridDim.x * nwarps) {
     const float* pb = p + bch * N;
-    float acc = 0.f;
-    if (lane == 0)
-      for (int q = 0; q < N; ++q) {
-        acc = __fadd_rn(acc, pb[q]);
-        cum[q] = acc;
-      }
-    __syncwarp();
+    warp_seq_cumsum(pb, cum, N, lane);  // the contract's summation order (fbs_resample.cuh)
     Key key{keys[2 * bch], keys[2 * bch + 1]};
     const uint32_t h = (n + 1u) >> 1;
     for (uint32_t b = lane; b < h; b += 32) {

@@ -354,14 +354,9 @@ __global__ void force_move_kernel(const uint32_t* __restrict__ keys, const float
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
-    if (lane == 0) {
-      for (int q = 0; q < N; ++q) {
-        const float rest = regular ? __fdiv_rn((q == k) ? 0.f : w[q], temp) : unif;
-        acc = __fadd_rn(acc, rest);
-        cum[q] = acc;
-      }
-    }
+    for (int q = lane; q < N; q += 32) cum[q] = regular ? __fdiv_rn((q == k) ? 0.f : w[q], temp) : unif;
     __syncwarp();
+    acc = warp_seq_cumsum(cum, cum, N, lane);  // the contract's summation order (fbs_resample.cuh)
     uint32_t x0 = 0u, x1 = 0u;
     threefry2x32(key_1.k0, key_1.k1, x0, x1);
     int i = choice_from_cum(cum, N, bits_to_unit(x0));  // gibbs.py:207

@@ -130,17 +130,31 @@ def normal(key, shape=()) -> np.ndarray:
     return (_SQRT2 * erf_inv(u)).astype(np.float32)
 
 
+CHUNKED_MIN_N = 1024   # rows at least this long use the chunked order below (kChunkedMinN in fbs_resample.cuh)
+
+
 def seq_cumsum(w: np.ndarray) -> np.ndarray:
-    """Sequential cumulative sum in the array's own dtype (oracle convention, see __init__)."""
+    """Cumulative sum in the array's own dtype, in the summation order of the oracle convention (see __init__):
+    sequential ``c[i] = fl(c[i-1] + w[i])`` for rows shorter than CHUNKED_MIN_N; for longer rows chunks of 8 consecutive
+    elements, ``local_c`` = sequential sums inside chunk c, ``P_0 = 0``, ``P_{c+1} = fl(P_c + local_c[-1])``,
+    ``c[8 c + t] = fl(P_c + local_c[t])`` -- the serial chain is n / 8 additions, which is what lets a 16384-particle row
+    (BASELINE.json configs[4]) be scanned in microseconds.  XLA fixes no order; this is the contract both sides follow."""
     w = np.asarray(w)
-    return np.cumsum(w, dtype=w.dtype)
+    n = w.shape[0]
+    if w.ndim != 1 or n < CHUNKED_MIN_N:
+        return np.cumsum(w, dtype=w.dtype)
+    pad = (-n) % 8
+    x = np.concatenate([w, np.zeros(pad, dtype=w.dtype)]).reshape(-1, 8)
+    local = np.cumsum(x, axis=1, dtype=w.dtype)
+    P = np.concatenate([np.zeros(1, dtype=w.dtype), np.cumsum(local[:, -1], dtype=w.dtype)[:-1]])
+    return (P[:, None] + local).astype(w.dtype).reshape(-1)[:n]
 
 
 def seq_sum(w: np.ndarray):
     w = np.asarray(w)
     if w.shape[0] == 0:
         return w.dtype.type(0)
-    return np.cumsum(w, dtype=w.dtype)[-1]
+    return seq_cumsum(w)[-1]
 
 
 def randint(key, shape, minval: int, maxval: int) -> np.ndarray:

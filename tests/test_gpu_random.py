@@ -63,7 +63,7 @@ def test_choice_exact():
     from fbs_b200 import random as fr
     rng = np.random.default_rng(0)
     keys = jr.split(jr.PRNGKey(31), 6)
-    for N in (1, 2, 10, 100, 1000):
+    for N in (1, 2, 10, 100, 1000, 1024, 3001):              # >= 1024: the chunked summation order of the contract
         p = rng.random((6, N)).astype(np.float32)
         p /= p.sum(axis=1, keepdims=True)
         p[0, N // 2:] = 0.  # zero tail

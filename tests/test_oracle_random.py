@@ -56,3 +56,27 @@ def test_randint_and_choice():
     # zero-weight tail is never selected, u = 0 maps to the last positive-weight index
     c2 = jr.choice(jr.PRNGKey(5), 4, (1000,), p=np.array([0.5, 0.5, 0., 0.], np.float32))
     assert c2.max() <= 1
+
+
+def test_chunked_summation_contract_matches_its_definition():
+    """seq_cumsum / seq_sum for rows of >= 1024 elements (the summation-order contract the CUDA kernels follow,
+    fbs_resample.cuh kChunkedMinN): chunks of 8, sequential inside a chunk, sequential over the chunk totals -- against a
+    literal scalar-loop evaluation of that definition; shorter rows stay the plain sequential sum."""
+    rng = np.random.default_rng(0)
+    for n in (1023, 1024, 1029, 4096):
+        w = rng.random(n).astype(np.float32)
+        w /= w.sum()
+        got = jr.seq_cumsum(w)
+        if n < jr.CHUNKED_MIN_N:
+            np.testing.assert_array_equal(got, np.cumsum(w, dtype=np.float32))
+            continue
+        P = np.float32(0)
+        want = np.zeros(n, np.float32)
+        for c0 in range(0, n, 8):
+            acc = np.float32(0)
+            for t in range(c0, min(c0 + 8, n)):
+                acc = np.float32(acc + w[t])
+                want[t] = np.float32(P + acc)
+            P = np.float32(P + acc)
+        np.testing.assert_array_equal(got, want)
+        assert jr.seq_sum(w) == want[-1]
