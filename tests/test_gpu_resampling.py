@@ -26,7 +26,7 @@ def _weights(rng, B, N, kind):
     return (w / w.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
 
 
-@pytest.mark.parametrize('N', [1, 2, 3, 10, 33, 100, 101, 1000, 1023, 1024, 1029, 4096, 16384, 20001])
+@pytest.mark.parametrize('N', [1, 2, 3, 10, 33, 100, 101, 1000, 1023, 1024, 1029, 4096, 12001, 16384])
 @pytest.mark.parametrize('kind', ['random', 'uniform', 'onehot', 'peaked', 'zerotail'])
 def test_conditional_indices_exact(N, kind):
     from fbs_b200.samplers.csmc import resamplings as R
