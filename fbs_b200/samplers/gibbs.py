@@ -58,10 +58,10 @@ def _gibbs_kernel_pipelined(key, x0, y0, bs_star, ts, fwd_sampler, sde, unpack, 
     views.  Chain b's numbers do not depend on the chunking (tests/test_gpu_csmc.py)."""
     from . import smc as _smc
     B = np.shape(key)[0]
-    nchunks = max(1, min(_smc.PIPELINE_CHUNKS, B // (_smc.PIPELINE_MIN_CHAINS // 2)))
+    bounds = _smc._chunk_bounds(B)
+    nchunks = len(bounds)
     while len(_smc._streams) < nchunks:
         _smc._streams.append(torch.cuda.Stream())
-    bounds = [(c * B // nchunks, (c + 1) * B // nchunks) for c in range(nchunks)]
 
     def host_t(x, dtype):
         if isinstance(x, torch.Tensor):

@@ -660,3 +660,27 @@ def test_pmcmc_filter_warp_per_chain_kernel(scheme, monkeypatch):
     monkeypatch.setenv('FBS_SWEEP_IMPL', 'v4')
     _check_pmcmc_filter(10, 64, 9, 21, scheme)
     _check_pmcmc_filter(8, 128, 4, 3, scheme)
+
+
+def test_gibbs_kernel_host_pipeline_equals_unchunked(monkeypatch):
+    """Host-buffer gibbs_kernel on many chains is chunked over CUDA streams (H2D / kernels / D2H overlapped, chunk sizes
+    rounded to whole waves of the sweep kernel); chains are independent, so the result equals the unchunked call bit for bit."""
+    from fbs_b200.samplers import gibbs_kernel
+    from fbs_b200.samplers import smc as psmc
+    d, N, K, B = 4, 16, 10, 100
+    p = gp_problem(d, K=K)
+    pm, sde = product_model(p)
+    keys = jr.split(jr.PRNGKey(5), B)
+    x0 = jr.normal(jr.PRNGKey(1), (B, d))
+    bs = np.stack([jr.randint(k, (K + 1,), 0, N) for k in jr.split(jr.PRNGKey(2), B)]).astype(np.int32)
+    args = (keys, x0, p['y0'], None, bs, p['ts'], pm.fwd_sampler, sde, pm.unpack, N, pm.transition_sampler, pm.transition_logpdf,
+            pm.likelihood_logpdf)
+    a = gibbs_kernel(*args)                                           # unchunked (also warms the model)
+    monkeypatch.setattr(psmc, 'PIPELINE_MIN_CHAINS', 32)
+    assert len(psmc._chunk_bounds(B)) > 1
+    b = gibbs_kernel(*args)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+    with pytest.raises(ValueError):
+        gibbs_kernel(keys, x0, p['y0'], None, bs + N, p['ts'], pm.fwd_sampler, sde, pm.unpack, N, pm.transition_sampler,
+                     pm.transition_logpdf, pm.likelihood_logpdf)   # stale reference indices are refused on the host
