@@ -58,6 +58,7 @@ def _gibbs_kernel_pipelined(key, x0, y0, bs_star, ts, fwd_sampler, sde, unpack, 
     views.  Chain b's numbers do not depend on the chunking (tests/test_gpu_csmc.py)."""
     from . import smc as _smc
     B = np.shape(key)[0]
+    _check_reference_indices(bs_star, int(nparticles) + 1 if explicit_final else int(nparticles))
     bounds = _smc._chunk_bounds(B)
     nchunks = len(bounds)
     while len(_smc._streams) < nchunks:
