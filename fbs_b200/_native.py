@@ -154,9 +154,25 @@ def _sync_env_options(handle):
 TIMED = {}
 
 
+# FBS_NVTX=1: every C-ABI call is wrapped in an NVTX range named after the entry point (per-phase ranges for
+# `ncu --nvtx` / Nsight timelines); off by default -- the push / pop are host-side calls on the launch path.
+NVTX = os.environ.get('FBS_NVTX', '') not in ('', '0')
+
+
 def call(name, *args):
     handle = lib()
     _sync_env_options(handle)
+    if NVTX:
+        import torch
+        torch.cuda.nvtx.range_push(name)
+        try:
+            return _call(handle, name, args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return _call(handle, name, args)
+
+
+def _call(handle, name, args):
     rec = TIMED.get(name)
     if rec is not None:
         import torch
