@@ -249,11 +249,19 @@ __global__ void __launch_bounds__(32 * WARPS, 1) sweep_warp_kernel(const SweepPa
     }
 
     // =============================== the K-step sweep ===============================
+    Key ka_l{0u, 0u}, kb_l{0u, 0u};  // the two keys of step (k & ~31) + lane, derived 32 steps at a time (one step per lane)
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
-      const Key key_k = split_key(kscan, (uint32_t)K, (uint32_t)k);  // csmc.py:157 / smc.py:154
+      if ((k & 31) == 0) {
+        const int kk = k + lane < K ? k + lane : K - 1;
+        const Key key_k = split_key(kscan, (uint32_t)K, (uint32_t)kk);  // csmc.py:157 / smc.py:154
+        split2(key_k, ka_l, kb_l);
+      }
       Key ka, kb;
-      split2(key_k, ka, kb);
+      ka.k0 = __shfl_sync(0xffffffffu, ka_l.k0, k & 31);
+      ka.k1 = __shfl_sync(0xffffffffu, ka_l.k1, k & 31);
+      kb.k0 = __shfl_sync(0xffffffffu, kb_l.k0, k & 31);
+      kb.k1 = __shfl_sync(0xffffffffu, kb_l.k1, k & 31);
       const Key kres = p.mode == MODE_CSMC ? ka : kb;  // csmc.py:136 (resampling, transition); smc.py:142 (proposal, resampling)
       const Key ktr = p.mode == MODE_CSMC ? kb : ka;
       drift_phase(k, k);
