@@ -33,6 +33,8 @@ struct SweepParams {
   int dup, dvp;
   // v3 only: tensor-core image of the step matrices (fbs_b200.h: MTc)
   const float* MTc;
+  // v3 only: optional phase time stamps of CTA 0 (fbs_debug_v3_timeline; NULL = off)
+  long long* dbg;
 };
 
 

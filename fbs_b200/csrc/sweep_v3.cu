@@ -326,6 +326,10 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // phase time stamps (profiling hook, scripts/v3_timeline.py): CTA 0, first chain pair, steps [DBG_K0, DBG_K0 + DBG_NS),
+  // lane 0 of one warp per role; layout dbg[role][step][stamp]
+  constexpr int DBG_K0 = 64, DBG_NS = 4, DBG_MAXS = 16;
+  const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
 
   // chains of this CTA: pair P = blockIdx.x + i * gridDim.x, group g runs chain 2 P + g
   const bool init_gemm = (p.mode == MODE_CSMC && p.init_mode == FBS_INIT_NORMAL);
@@ -387,6 +391,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           if (g == 1 && t >= G1) break;
           if (stages_flags & 0x200) mbar_wait_hint(ready + g, t & 1u); else mbar_wait(ready + g, t & 1u);
           tc_fence_after();
+          const int dbg_k = (int)(t % GP) - (init_gemm ? 1 : 0) - DBG_K0;  // the step this GEMM belongs to
+          const bool dbg_mma = dbg_cta && t < GP && dbg_k >= 0 && dbg_k < DBG_NS;
+          if (dbg_mma) p.dbg[(6 * DBG_NS + dbg_k) * DBG_MAXS + 2 * g] = clock64();
           const uint32_t a_hi0 = smem_u32(smem + L.A) + (uint32_t)g * 2u * L.a_bytes;
           const uint32_t d_tmem = tmem_base + (uint32_t)g * TMEM_COLS_PER_GROUP;
           for (int pass = 0; pass < npass; ++pass) {
@@ -418,6 +425,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             }
             umma_commit((pass == 0 ? accum : accum_u) + g);  // accumulator columns of this pass complete
           }
+          if (dbg_mma) p.dbg[(6 * DBG_NS + dbg_k) * DBG_MAXS + 2 * g + 1] = clock64();
         }
       }
     }
@@ -704,6 +712,11 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
 
       // =============================== the K-step sweep ===============================
       for (int k = 0; k < K; ++k) {
+        const int dbg_role = 3 * g + (gw == 0 ? 0 : (gw == 5 ? 1 : (gw == 4 ? 2 : -1)));
+        const bool dbg_on = dbg_cta && ci == 0 && dbg_role >= 3 * g && k >= DBG_K0 && k < DBG_K0 + DBG_NS;
+        long long* dbg_row = p.dbg + ((size_t)(dbg_on ? dbg_role : 0) * DBG_NS + (dbg_on ? k - DBG_K0 : 0)) * DBG_MAXS;
+#define FBS_STAMP(i) do { if (dbg_on) dbg_row[i] = clock64(); } while (0)
+        FBS_STAMP(0);
         if (is_noise) {
           // ---- noise on the CUDA cores || GEMM on the tensor core (first part) and || resampling (second part) ----
           if (is_E) load_cvs(k);
@@ -715,22 +728,29 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           const Key ktr = skeys[2 * (k & 1) + 1];
           const float sd = __ldg(p.sd + k);
           make_noise(ktr, sd, I_0{}, I_1{});
+          FBS_STAMP(1);
           if (is_E) {
             store_cvs();
             mbar_wait_sleep(accum + g, gcount & 1u);  // first pass: every v column
             tc_fence_after();
+            FBS_STAMP(2);
             bar_E();         // cvs visible to the four E warps
+            FBS_STAMP(3);
             epilogue_v(k);   // log-likelihood -> lwraw
             bar_ER_arrive(); // ... releases the resampling warp
           }
+          FBS_STAMP(4);
           make_noise(ktr, sd, I_1{}, I_2{});
+          FBS_STAMP(5);
           if (is_E) {
             if (L.nu_pass > 0) mbar_wait_sleep(accum_u + g, gcount & 1u);  // second pass: the u columns
             tc_fence_after();
             epilogue_u(k);   // means -> Alo
             tc_fence_before();
           }
+          FBS_STAMP(6);
           make_noise(ktr, sd, I_2{}, I_3{});
+          FBS_STAMP(7);
         } else {
           // ---- weights + ancestors (one warp) ----
           const bool fast = p.mode == MODE_PMCMC && (p.scheme == FBS_RESAMPLE_STRATIFIED || p.scheme == FBS_RESAMPLE_SYSTEMATIC);
@@ -776,7 +796,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             if (lane == 0) ub[2 * ROWS] = bits_to_unit(x0);
             __syncwarp();
           }
+          FBS_STAMP(1);
           bar_ER_sync();
+          FBS_STAMP(2);
           const Key kres = skeys[2 * (k & 1)];
           if (fastk) {
             // conditional killing (resamplings.py:40-88) + weights of the resampled parents (csmc.py:139-146), the warp's 4
@@ -984,7 +1006,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           }
         }
         ++gcount;
+        if (!is_noise) FBS_STAMP(7);
         bar_all();  // ancestors, means and noise complete
+        FBS_STAMP(8);
 
         if (is_noise) {
           // ---- children: gather the parents' means, add the noise (in the noise registers) ----
@@ -998,7 +1022,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
               nz[1][4 * i + 0] += m1.x; nz[1][4 * i + 1] += m1.y; nz[1][4 * i + 2] += m1.z; nz[1][4 * i + 3] += m1.w;
             }
           }
+          FBS_STAMP(9);
           bar_noise();  // every mean read before the operands are overwritten
+          FBS_STAMP(10);
           {
             const int bj = p.mode == MODE_CSMC ? reinterpret_cast<const int*>(pin)[du] : -1;
 #pragma unroll
@@ -1015,7 +1041,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             }
           }
           fence_proxy_async();  // the new particles are read by the tensor core (async proxy) next step
+          FBS_STAMP(11);
           bar_noise();
+          FBS_STAMP(12);
           if (nt == 0 && (k + 1 < K)) mbar_arrive(ready + g);
           // optional history
           if (p.mode == MODE_CSMC) {
@@ -1133,6 +1161,8 @@ int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8
   return check_launch("umma_selftest_kernel");
 }
 
+static long long* g_v3_dbg = nullptr;
+
 // Host: eligibility + launch.  p.MTc is the tensor-core image of the step matrices; p.ws the step-vector workspace.
 template <int NT>
 static cudaError_t launch_v3_nt(cudaStream_t st, int grid, size_t smem, const SweepParams& p, int stages) {
@@ -1163,6 +1193,7 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   }
   const int64_t pairs = (p.B + 1) / 2;
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+  p.dbg = g_v3_dbg;
   cudaError_t e;
   if (need <= 4) e = launch_v3_nt<4>(st, grid, L.total, p, stages | flags);
   else e = launch_v3_nt<8>(st, grid, L.total, p, stages | flags);
@@ -1174,3 +1205,11 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
 }
 
 }  // namespace fbs
+
+// Profiling hook: a device buffer of 7 x 4 x 16 int64 into which CTA 0 writes clock64() stamps of its phases for steps 64..67
+// of its first chain pair (roles: E / X / R warp of group 0, of group 1, MMA warp); NULL switches it off (default).
+// Not thread safe; for scripts/v3_timeline.py only.
+extern "C" int fbs_debug_v3_timeline(long long* dev_buf) {
+  fbs::g_v3_dbg = dev_buf;
+  return FBS_OK;
+}

@@ -150,6 +150,10 @@ int fbs_debug_umma_gemm(fbs_stream_t s, const float* A, const float* Bimg, int32
  * cycles it spends per phase (gather, barrier, noise, worker barrier, accumulator wait, epilogue, barrier, stores);
  * NULL switches it off (default).  Not thread safe; for scripts/step_tc_phases.py only. */
 int fbs_debug_step_tc_timers(long long* dev_buf);
+/* Profiling hook of the tcgen05 sweep kernel: a device buffer of 7 x 4 x 16 int64 into which CTA 0 writes clock64() stamps
+ * of its phases for steps 64..67 of its first chain pair (E / X / R warp of each group, MMA warp); NULL switches it off
+ * (default).  Not thread safe; for scripts/v3_timeline.py only. */
+int fbs_debug_v3_timeline(long long* dev_buf);
 
 /* Scratch the tiled sweep kernel needs for B chains (per-chain step vectors of all K steps); pass a device
  * buffer of at least this many bytes as `workspace` to fbs_csmc_forward_affine_f32 / fbs_pmcmc_filter_affine_f32.
