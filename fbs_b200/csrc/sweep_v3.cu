@@ -289,7 +289,7 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
   return lse;
 }
 
-template <int NT>
+template <int NT, bool DBG>
 __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages_flags) {
   const int stages = stages_flags & 0xFF;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
   // phase time stamps (profiling hook, scripts/v3_timeline.py): CTA 0, first chain pair, steps [DBG_K0, DBG_K0 + DBG_NS),
   // lane 0 of one warp per role; layout dbg[role][step][stamp]
   constexpr int DBG_K0 = 64, DBG_NS = 4, DBG_MAXS = 16;
-  const bool dbg_cta = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+  const bool dbg_cta = DBG && p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
 
   // chains of this CTA: pair P = blockIdx.x + i * gridDim.x, group g runs chain 2 P + g
   const bool init_gemm = (p.mode == MODE_CSMC && p.init_mode == FBS_INIT_NORMAL);
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         const int dbg_role = 3 * g + (gw == 0 ? 0 : (gw == 5 ? 1 : (gw == 4 ? 2 : -1)));
         const bool dbg_on = dbg_cta && ci == 0 && dbg_role >= 3 * g && k >= DBG_K0 && k < DBG_K0 + DBG_NS;
         long long* dbg_row = p.dbg + ((size_t)(dbg_on ? dbg_role : 0) * DBG_NS + (dbg_on ? k - DBG_K0 : 0)) * DBG_MAXS;
-#define FBS_STAMP(i) do { if (dbg_on) dbg_row[i] = clock64(); } while (0)
+#define FBS_STAMP(i) do { if (DBG && dbg_on) dbg_row[i] = clock64(); } while (0)
         FBS_STAMP(0);
         if (is_noise) {
           // ---- noise on the CUDA cores || GEMM on the tensor core (first part) and || resampling (second part) ----
@@ -820,8 +820,44 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
               }
             }
             const float w_max = warp_max(m);
+            // J_prob (:79) goes to the int scratch first so that its SUM (:81) rides in lane 1 of the serial pass that builds
+            // cumsum(w) in lane 0 -- one dependent chain of N additions less on the step's critical path (this warp is what
+            // the twelve noise warps wait for, scripts/v3_timeline.py); the order of every sum is unchanged
+            float* jpf = reinterpret_cast<float*>(tmp);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lane + 32 * j;
+              if (q < N) jpf[q] = (q == ci) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(wv[j], w_max)), fn);
+            }
             __syncwarp();
-            const float total = warp_seq_cumsum(w, cum, N, lane);
+            float sacc2 = 0.f;
+            if (lane < 2) {
+              const bool l0 = lane == 0;
+              const float* src = l0 ? w : jpf;
+              int i = 0;
+              for (; i + 8 <= N; i += 8) {
+                float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+                a.x = sacc2 = __fadd_rn(sacc2, a.x);
+                a.y = sacc2 = __fadd_rn(sacc2, a.y);
+                a.z = sacc2 = __fadd_rn(sacc2, a.z);
+                a.w = sacc2 = __fadd_rn(sacc2, a.w);
+                b.x = sacc2 = __fadd_rn(sacc2, b.x);
+                b.y = sacc2 = __fadd_rn(sacc2, b.y);
+                b.z = sacc2 = __fadd_rn(sacc2, b.z);
+                b.w = sacc2 = __fadd_rn(sacc2, b.w);
+                if (l0) {
+                  *reinterpret_cast<float4*>(cum + i) = a;
+                  *reinterpret_cast<float4*>(cum + i + 4) = b;
+                }
+              }
+              for (; i < N; ++i) {
+                sacc2 = __fadd_rn(sacc2, src[i]);
+                if (l0) cum[i] = sacc2;
+              }
+            }
+            __syncwarp();
+            const float total = __shfl_sync(0xffffffffu, sacc2, 0);
+            const float jsum = __shfl_sync(0xffffffffu, sacc2, 1);
             float r[4];
             int lo[4], hi[4];
 #pragma unroll
@@ -848,23 +884,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             for (int j = 0; j < 4; ++j) {
               const int q = lane + 32 * j;
               if (q < N) {
-                tmp[q] = lo[j];
-                cum[q] = (q == ci) ? 0.f : __fdiv_rn(__fsub_rn(1.0f, __fdiv_rn(wv[j], w_max)), fn);  // J_prob (:79)
+                cum[q] = (q == ci) ? fmaxf(__fsub_rn(1.0f, jsum), 0.f) : jpf[q];  // :80-82
+                tmp[q] = lo[j];  // (the same thread read jpf[q] = this word just above)
               }
-            }
-            __syncwarp();
-            if (lane == 0) {
-              float acc = 0.f;
-              int q = 0;
-              for (; q + 8 <= N; q += 8) {
-                float x[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) x[t] = cum[q + t];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, x[t]);
-              }
-              for (; q < N; ++q) acc = __fadd_rn(acc, cum[q]);
-              cum[ci] = fmaxf(__fsub_rn(1.0f, acc), 0.f);  // :80-82
             }
             __syncwarp();
             warp_seq_cumsum(cum, cum, N, lane);
@@ -1164,11 +1186,11 @@ int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8
 static long long* g_v3_dbg = nullptr;
 
 // Host: eligibility + launch.  p.MTc is the tensor-core image of the step matrices; p.ws the step-vector workspace.
-template <int NT>
+template <int NT, bool DBG>
 static cudaError_t launch_v3_nt(cudaStream_t st, int grid, size_t smem, const SweepParams& p, int stages) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  sweep_v3_kernel<NT><<<grid, NTHREADS, smem, st>>>(p, stages);
+  sweep_v3_kernel<NT, DBG><<<grid, NTHREADS, smem, st>>>(p, stages);
   return cudaSuccess;
 }
 
@@ -1195,8 +1217,9 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   p.dbg = g_v3_dbg;
   cudaError_t e;
-  if (need <= 4) e = launch_v3_nt<4>(st, grid, L.total, p, stages | flags);
-  else e = launch_v3_nt<8>(st, grid, L.total, p, stages | flags);
+  if (need <= 4) e = launch_v3_nt<4, false>(st, grid, L.total, p, stages | flags);
+  else if (p.dbg != nullptr) e = launch_v3_nt<8, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
+  else e = launch_v3_nt<8, false>(st, grid, L.total, p, stages | flags);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
