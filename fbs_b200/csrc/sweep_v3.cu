@@ -289,14 +289,15 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
   return lse;
 }
 
-template <int NT, bool DBG>
+// NE / NX: noise tasks per thread of the E (epilogue + noise) and X (noise only) warps (the two epilogues cost an E warp
+// about two tasks: <6, 8> at d = 100, N = 100).
+template <int NE, int NX, bool DBG>
 __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages_flags) {
   const int stages = stages_flags & 0xFF;
   extern __shared__ __align__(1024) unsigned char smem[];
-  // noise tasks per thread: X (noise only) warps NT, E (epilogue + noise) warps NE = NT - 2 (the epilogue costs about two
-  // tasks); an E warp generates NE1 of them in the shadow of the first GEMM pass, up to NE2 in the shadow of the second
+  // an E warp generates NE1 of its tasks in the shadow of the first GEMM pass, up to NE2 in the shadow of the second
   // pass (while the resampling warp works), the rest after its u-epilogue
-  constexpr int NE = NT - 2, NE1 = NE / 2, NE2 = NE > 0 ? NE - 1 : 0;
+  constexpr int NT = NE > NX ? NE : NX, NE1 = NE / 2, NE2 = NE > 0 ? NE - 1 : 0;
   const Layout L = make_layout(p.N, p.du, p.dv, stages_flags);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     for (int i = 0; i < NT; ++i) {
       int t = ntasks;
       if (is_E && i < NE) t = gt + 128 * i;
-      if (gw > 4) t = 128 * NE + xt + 64 * i;
+      if (gw > 4 && i < NX) t = 128 * NE + xt + 64 * i;
       task[i] = t < ntasks ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
     }
     float nz[2][4 * NT];  // noise, then the children, of the owned (rows, columns)
@@ -1186,11 +1187,11 @@ int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8
 static long long* g_v3_dbg = nullptr;
 
 // Host: eligibility + launch.  p.MTc is the tensor-core image of the step matrices; p.ws the step-vector workspace.
-template <int NT, bool DBG>
+template <int NE, int NX, bool DBG>
 static cudaError_t launch_v3_nt(cudaStream_t st, int grid, size_t smem, const SweepParams& p, int stages) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NE, NX, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  sweep_v3_kernel<NT, DBG><<<grid, NTHREADS, smem, st>>>(p, stages);
+  sweep_v3_kernel<NE, NX, DBG><<<grid, NTHREADS, smem, st>>>(p, stages);
   return cudaSuccess;
 }
 
@@ -1207,8 +1208,8 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   if (L.nout > TMEM_COLS_PER_GROUP || L.nkb < 1) return -1;
   const int ntasks = (p.N / 2) * L.ncg;
   if (((p.du + 7) / 8 * 8 + (p.dv + 7) / 8 * 8) > 2 * 128) return -1;  // cv_reg: 2 values per E thread
-  const int need = (ntasks + 256 + NOISE_THREADS - 1) / NOISE_THREADS;  // 128 (NT - 2) + 64 NT >= ntasks
-  if (need > 8) return -1;
+  // task capacity of a group: 128 NE (four E warps) + 64 NX (two X warps)
+  if (ntasks > 128 * 6 + 64 * 8) return -1;
   {
     const int rc = launch_stepvec(stream, p);
     if (rc) return rc;
@@ -1217,9 +1218,13 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   p.dbg = g_v3_dbg;
   cudaError_t e;
-  if (need <= 4) e = launch_v3_nt<4, false>(st, grid, L.total, p, stages | flags);
-  else if (p.dbg != nullptr) e = launch_v3_nt<8, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
-  else e = launch_v3_nt<8, false>(st, grid, L.total, p, stages | flags);
+  // v3_variant bit 1: the <7, 6> task split (A/B; measured 1 % SLOWER than <6, 8>: the E warps, which also run both
+  // epilogues, become the critical path and the X warps idle 15 k cycles before the barrier)
+  const bool alt_split = (debug_opt(OPT_V3_VARIANT) & 2) != 0;
+  if (ntasks <= 128 * 2 + 64 * 4) e = launch_v3_nt<2, 4, false>(st, grid, L.total, p, stages | flags);
+  else if (p.dbg != nullptr) e = launch_v3_nt<6, 8, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
+  else if (alt_split && ntasks <= 128 * 7 + 64 * 6) e = launch_v3_nt<7, 6, false>(st, grid, L.total, p, stages | flags);
+  else e = launch_v3_nt<6, 8, false>(st, grid, L.total, p, stages | flags);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
