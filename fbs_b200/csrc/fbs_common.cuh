@@ -58,6 +58,7 @@ enum DebugOpt {
   OPT_V3_TWOPASS,       // 1: two-pass GEMM in the tcgen05 sweep kernel
   OPT_EM_IMPL,          // 1: CTA-per-chain, 2: thread-per-chain Euler--Maruyama path kernel
   OPT_V3_VARIANT,       // experimental variants of the tcgen05 sweep kernel (A/B measurements)
+  OPT_CONV_IMPL,        // 1: per-tap activation boxes for every convolution (no haloed 3x3 path)
   OPT_COUNT
 };
 int debug_opt(DebugOpt which);

@@ -10,8 +10,9 @@
 //
 //   warp 0 : TMA producer (activation box + weight tile per K-block, ring of mbarrier-guarded stages)
 //   warp 1 : MMA issuer   (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 accumulator in tensor memory)
-//   warps 2..5 : epilogue (tcgen05.ld, + bias, + optional fp32 residual, fp32 and / or bf16 store; optional
-//                pixel-shuffle addressing 'b h w (h2 w2 c) -> b (h h2) (w w2) c')
+//   warps 2..5 : epilogue (tcgen05.ld, transpose through shared memory so that global stores are row-contiguous, + bias,
+//                + optional fp32 residual, fp32 and / or bf16 store; optional pixel-shuffle addressing
+//                'b h w (h2 w2 c) -> b (h h2) (w w2) c')
 //
 // Reference: flax.linen.Conv call sites of fbs/nn/unet.py (3x3 / 1x1 convolutions :50,68,70,97-124,165,183,205,219,242,
 // 317,351,363); the 4x4 stride-2 Downsample (:50) is run as a 2x2 convolution on a space-to-depth copy (nn_ops.cu).
@@ -26,8 +27,11 @@ namespace nnconv {
 constexpr int TILE_M = 128;
 constexpr int KBLK = 64;                       // bf16 channels per K-block = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * 128;    // 16 KB
-constexpr int NTHREADS = 192;
+constexpr int N_EPI_WARPS = 8;
+constexpr int NTHREADS = 32 * (2 + N_EPI_WARPS);
 constexpr int MAX_STAGES = 6;
+constexpr int STG_WARP_BYTES = 32 * 128;       // one epilogue warp's transpose buffer: 32 tile rows x 32 fp32 columns
+constexpr int RING_BUDGET = 192 * 1024;        // operand ring (+ resident weights); 227 KB - staging - barriers - alignment
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -116,36 +120,58 @@ struct Params {
   int C0, C1, Cout;   // source channels (multiples of 64; C1 = 0: one source), output channels
   int ntile;          // N tile: multiple of 16, <= 256, divides Cout
   int kh, kw, off_h, off_w;
-  int BW, BH, BNb;    // pixel box of one M tile: BW * BH * BNb <= 128, BW == W
+  int BW, BH, BNb;    // pixel box of one M tile: BW * BH * BNb <= 128; BW == W (per-tap boxes) or W + 2 (haloed box)
   int h_tiles, m_tiles, stages;
   int pixel_shuffle;
+  int halo;           // 1: haloed activation box + resident weights (3x3, stride 1, "same"), see the kernel comment
+  int halo_bo;        // debug: also set the descriptor's base-offset field from the shifted start address
+  uint32_t a_stage_bytes, a_tx_bytes;  // ring pitch / bytes one activation box load delivers
+  uint32_t wres_bytes;                  // resident weight image in front of the ring (halo mode)
   const float* bias;
   const float* residual;
   float* out_f32;
   __nv_bfloat16* out_bf16;
 };
 
+// Two operand schemes share the kernel.
+//
+// per-tap (any kernel size): K-block = (tap, 64-channel chunk); ring stage = activation box shifted by the tap + the weight tile.
+//
+// haloed (3x3 "same", <= 128 source channels, N tile 64): a 3x3 layer at 28x28 re-read its input nine times through L2 and its
+// weights once per M tile -- 198 KB per 128 x 64 tile, which bound the layer by the SM's L2 port, not by the tensor pipe.
+// Here the box carries a one-pixel halo (BH + 2 rows of W + 2 pixels: the row pitch in shared memory is W + 2 pixels) and
+// is loaded ONCE per 64-channel chunk; M row m = hh * (W + 2) + w, so that tap (ty, tx) is the SAME shared-memory image
+// read from (ty * (W + 2) + tx) rows further on -- an operand-descriptor start address, nothing moves (SWIZZLE_128B is a
+// function of the absolute address bits, which a whole-row shift preserves).  The w >= W rows of the tile are junk and never
+// stored.  The weights of the CTA's N tile (9 taps x <= 2 chunks x 8 KB) are loaded once per CTA and stay resident; a CTA keeps
+// its N tile for all its M tiles.
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const Params p) {
-  // Persistent: CTA c runs tiles c, c + gridDim.x, ...; the accumulator is double buffered in tensor memory so that the
-  // epilogue of tile i overlaps the TMA / MMA main loop of tile i + 1.
+  // Persistent: a CTA keeps N tile blockIdx.x % n_ntiles and runs M tiles blockIdx.x / n_ntiles, + gridDim.x / n_ntiles, ...;
+  // the accumulator is double buffered in tensor memory so that the epilogue of tile i overlaps the TMA / MMA main loop of
+  // tile i + 1.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t b_stage_bytes = (uint32_t)p.ntile * 128u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  unsigned char* ring = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * stage_bytes);
+  const uint32_t b_stage_bytes = p.halo ? 0u : (uint32_t)p.ntile * 128u;
+  const uint32_t stage_bytes = p.a_stage_bytes + b_stage_bytes;
+  unsigned char* wres = smem;                   // halo mode: [tap][chunk][64 x 128 bytes]
+  unsigned char* ring = smem + p.wres_bytes;
+  unsigned char* stg_base = ring + (size_t)p.stages * stage_bytes;  // epilogue staging: 8 warps x (32 rows x 128 bytes)
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + N_EPI_WARPS * STG_WARP_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* acc_full = empty + MAX_STAGES;   // [2]: accumulator buffer written by the MMA warp
-  uint64_t* acc_empty = acc_full + 2;        // [2]: ... drained by the four epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 2;        // [2]: ... drained by the epilogue warps
+  uint64_t* wbar = acc_empty + 2;            // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int ctot = p.C0 + p.C1;
-  const int kblocks = p.kh * p.kw * (ctot / KBLK);
+  const int cblocks = ctot / KBLK;
+  const int kblocks = p.kh * p.kw * cblocks;
   const int n_ntiles = p.Cout / p.ntile;
-  const int ntiles = p.m_tiles * n_ntiles;
+  const int nt = blockIdx.x % n_ntiles;
+  const int mt_first = blockIdx.x / n_ntiles, mt_step = gridDim.x / n_ntiles;  // host: gridDim.x % n_ntiles == 0
   uint32_t acc_cols = 32;  // columns of one accumulator buffer (power of two >= ntile)
   while (acc_cols < (uint32_t)p.ntile) acc_cols <<= 1;
 
@@ -158,8 +184,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(acc_full + i, 1);
-        mbar_init(acc_empty + i, 4);  // one arrival per epilogue warp
+        mbar_init(acc_empty + i, N_EPI_WARPS);  // one arrival per epilogue warp
       }
+      mbar_init(wbar, 1);
       fence_barrier_init();
     }
   }
@@ -170,26 +197,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)(KBLK * p.BW * p.BH * p.BNb) * 2u;
       uint32_t s = 0, ph = 1;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int mt = t / n_ntiles, nt = t - mt * n_ntiles;  // N tiles of one M tile are neighbours: the A boxes hit in L2
-        const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
-        int kcol = 0;  // column of this K-block in the weight matrix
-        for (int ty = 0; ty < p.kh; ++ty) {
-          for (int tx = 0; tx < p.kw; ++tx) {
-            for (int c = 0; c < ctot; c += KBLK, kcol += KBLK) {
-              mbar_wait(empty + s, ph);
-              unsigned char* dst = ring + (size_t)s * stage_bytes;
-              mbar_expect_tx(full + s, a_bytes + b_stage_bytes);
-              if (c < p.C0)
-                tma_load_4d(dst, &tmA0, full + s, c, p.off_w + tx, h0 + p.off_h + ty, n0);
-              else
-                tma_load_4d(dst, &tmA1, full + s, c - p.C0, p.off_w + tx, h0 + p.off_h + ty, n0);
-              tma_load_2d(dst + A_STAGE_BYTES, &tmB, full + s, kcol, nt * p.ntile);
-              if (++s == (uint32_t)p.stages) {
-                s = 0;
-                ph ^= 1u;
+      if (p.halo) {
+        mbar_expect_tx(wbar, p.wres_bytes);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int cb = 0; cb < cblocks; ++cb)
+            tma_load_2d(wres + (size_t)(tap * cblocks + cb) * (KBLK * 128), &tmB, wbar, tap * ctot + cb * KBLK, nt * p.ntile);
+        for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
+          const int n0 = mt / p.h_tiles, h0 = (mt % p.h_tiles) * p.BH;
+          for (int c = 0; c < ctot; c += KBLK) {
+            mbar_wait(empty + s, ph);
+            unsigned char* dst = ring + (size_t)s * stage_bytes;
+            mbar_expect_tx(full + s, p.a_tx_bytes);
+            if (c < p.C0)
+              tma_load_4d(dst, &tmA0, full + s, c, -1, h0 - 1, n0);
+            else
+              tma_load_4d(dst, &tmA1, full + s, c - p.C0, -1, h0 - 1, n0);
+            if (++s == (uint32_t)p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      } else {
+        for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
+          const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
+          int kcol = 0;  // column of this K-block in the weight matrix
+          for (int ty = 0; ty < p.kh; ++ty) {
+            for (int tx = 0; tx < p.kw; ++tx) {
+              for (int c = 0; c < ctot; c += KBLK, kcol += KBLK) {
+                mbar_wait(empty + s, ph);
+                unsigned char* dst = ring + (size_t)s * stage_bytes;
+                mbar_expect_tx(full + s, p.a_tx_bytes + b_stage_bytes);
+                if (c < p.C0)
+                  tma_load_4d(dst, &tmA0, full + s, c, p.off_w + tx, h0 + p.off_h + ty, n0);
+                else
+                  tma_load_4d(dst, &tmA1, full + s, c - p.C0, p.off_w + tx, h0 + p.off_h + ty, n0);
+                tma_load_2d(dst + p.a_stage_bytes, &tmB, full + s, kcol, nt * p.ntile);
+                if (++s == (uint32_t)p.stages) {
+                  s = 0;
+                  ph ^= 1u;
+                }
               }
             }
           }
@@ -203,23 +251,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       uint32_t s = 0, ph = 0;
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      if (p.halo) {
+        mbar_wait(wbar, 0);
+        tc_fence_after();
+      }
+      for (int mt = mt_first; mt < p.m_tiles; mt += mt_step, ++it) {
         const uint32_t buf = it & 1u;
         mbar_wait(acc_empty + buf, ((it >> 1) & 1u) ^ 1u);  // passes on a fresh barrier; then waits for the epilogue of tile it - 2
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * acc_cols;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full + s, ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
-          const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + A_STAGE_BYTES);
+        if (p.halo) {
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(full + s, ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t sa = a_addr + (uint32_t)((tap / 3) * p.BW + tap % 3) * 128u;  // whole-row shift of the haloed image
+              uint64_t da = make_desc_sw128(sa);
+              if (p.halo_bo) da |= (uint64_t)((sa >> 7) & 7u) << 49;
+              const uint64_t db = make_desc_sw128(smem_u32(wres + (size_t)(tap * cblocks + cb) * (KBLK * 128)));
 #pragma unroll
-          for (int k = 0; k < KBLK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row: +2 in the address field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(empty + s);
-          if (++s == (uint32_t)p.stages) {
-            s = 0;
-            ph ^= 1u;
+              for (int k = 0; k < KBLK / 16; ++k)
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cb | tap | k) ? 1u : 0u);
+            }
+            umma_commit(empty + s);
+            if (++s == (uint32_t)p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        } else {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(full + s, ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
+            const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + p.a_stage_bytes);
+#pragma unroll
+            for (int k = 0; k < KBLK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row: +2 in the address field
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(empty + s);
+            if (++s == (uint32_t)p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
         umma_commit(acc_full + buf);
@@ -227,67 +301,73 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else {
-    // epilogue: TMEM lane = tile row = pixel
+    // epilogue: TMEM lane = tile row = pixel.  A thread owns one ROW of the accumulator, so storing it directly would be 32
+    // scattered 16-byte requests per warp instruction (the store-request rate, not the bytes, bound the 1x1 layers); instead
+    // each warp transposes 32 rows x 32 columns through its own shared-memory buffer (16-byte pieces XOR-swizzled by the row:
+    // conflict-free both ways) and writes rows out with 8 lanes per 128-byte row segment.  Two warps share a TMEM lane
+    // quadrant (a warp may only read lanes 32 * (warp % 4) ...) and take alternate 32-column chunks: with one warp per
+    // scheduler the epilogue was bound by a single warp's dependent-issue latency.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = 32 * q + lane;
     const int w = r % p.BW, hh = (r / p.BW) % p.BH, nn = r / (p.BW * p.BH);
+    float* stg = reinterpret_cast<float*>(stg_base + (warp - 2) * STG_WARP_BYTES);
+    const int piece = lane & 7, sub = lane >> 3;
+    const int Cq = p.Cout >> 2;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int mt = t / n_ntiles, nt = t - mt * n_ntiles;
+    for (int mt = mt_first; mt < p.m_tiles; mt += mt_step, ++it) {
       const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
       const int h = h0 + hh, n = n0 + nn;
-      const bool valid = r < p.BW * p.BH * p.BNb && h < p.H && n < p.B;
+      const bool valid = r < p.BW * p.BH * p.BNb && w < p.W && h < p.H && n < p.B;
+      // row base in units of 4 elements, without the chunk's channel offset (Cout % 16 == 0)
+      uint32_t mybase = 0xFFFFFFFFu;
+      if (valid)
+        mybase = p.pixel_shuffle ? (uint32_t)(((((size_t)n * (2 * p.H) + 2 * h) * (2 * p.W) + 2 * w) * Cq) >> 2)
+                                 : (uint32_t)(((((size_t)n * p.H + h) * p.W + w) * p.Cout) >> 2);
+      uint32_t rowbase[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rowbase[i] = __shfl_sync(0xffffffffu, mybase, 4 * i + sub);
       const uint32_t buf = it & 1u;
       mbar_wait(acc_full + buf, (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + buf * acc_cols + ((uint32_t)(32 * q) << 16);
-      const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-      for (int c0 = 0; c0 < p.ntile; c0 += 32) {
+      for (int c0 = 32 * half; c0 < p.ntile; c0 += 64) {
         float acc[32];
         tmem_ld32(trow + c0, acc);
-        if (!valid) continue;
-        const int cg = nt * p.ntile + c0;  // first global output channel of this chunk
-        const int nc = min(32, p.ntile - c0);
-        if (p.bias) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < nc) acc[c] += __ldg(p.bias + cg + c);
-        }
-        size_t obase;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 32 + 4 * (j ^ (lane & 7))) =
+              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        const int cg = nt * p.ntile + c0;  // first global output channel of this chunk
+        const bool col_ok = 4 * piece < p.ntile - c0;
+        uint32_t coff = (uint32_t)cg;  // element offset of the chunk inside a row
         if (p.pixel_shuffle) {
           // channel = (h2 * 2 + w2) * Cq + cq  ->  pixel (2h + h2, 2w + w2), channel cq   (fbs/nn/utils.py:53-57)
-          const int Cq = p.Cout >> 2;
           const int blk = cg / Cq, cq = cg - blk * Cq;  // a 32-channel chunk never straddles a block (Cq % 32 == 0)
-          const int h2 = blk >> 1, w2 = blk & 1;
-          obase = (((size_t)n * (2 * p.H) + (2 * h + h2)) * (2 * p.W) + (2 * w + w2)) * Cq + cq;
-        } else {
-          obase = pix * p.Cout + cg;
+          coff = (uint32_t)((((blk >> 1) * 2 * p.W) + (blk & 1)) * Cq + cq);
         }
-        if (p.residual) {
+        const uint32_t col4 = (coff >> 2) + (uint32_t)piece;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cg + 4 * piece));
+        __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            if (c < nc) {
-              const float4 rv = *reinterpret_cast<const float4*>(p.residual + obase + c);
-              acc[c] += rv.x; acc[c + 1] += rv.y; acc[c + 2] += rv.z; acc[c + 3] += rv.w;
-            }
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + sub;
+          if (rowbase[i] == 0xFFFFFFFFu || !col_ok) continue;
+          float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + 4 * (piece ^ (row & 7)));
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          const size_t off = (size_t)(rowbase[i] + col4) << 2;
+          if (p.residual) {
+            const float4 rv = *reinterpret_cast<const float4*>(p.residual + off);
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          }
+          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = v;
+          if (p.out_bf16) {
+            __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(v.x, v.y), __floats2bfloat162_rn(v.z, v.w)};
+            *reinterpret_cast<uint2*>(p.out_bf16 + off) = *reinterpret_cast<const uint2*>(o);
           }
         }
-        if (p.out_f32) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            if (c < nc) *reinterpret_cast<float4*>(p.out_f32 + obase + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-        }
-        if (p.out_bf16) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            if (c < nc) {
-              __align__(16) __nv_bfloat162 v[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = __floats2bfloat162_rn(acc[c + 2 * j], acc[c + 2 * j + 1]);
-              *reinterpret_cast<uint4*>(p.out_bf16 + obase + c) = *reinterpret_cast<const uint4*>(v);
-            }
-          }
-        }
+        __syncwarp();
       }
       // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
       tc_fence_before();
@@ -360,13 +440,14 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   p.pixel_shuffle = a->pixel_shuffle;
   p.bias = a->bias; p.residual = a->residual; p.out_f32 = a->out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  const int Hin = a->Hin > 0 ? a->Hin : a->H, Win = a->Win > 0 ? a->Win : a->W;
+  const int ctot = a->C0 + a->C1;
   // N tile: the largest of 256 / 192 / 128 / 64 / ... that divides Cout
   int ntile = a->Cout;
   if (ntile > 256) {
     ntile = 256;
     while (a->Cout % ntile) ntile -= 16;
   }
-  p.ntile = ntile;
   if (p.pixel_shuffle) FBS_REQUIRE((a->Cout / 4) % 32 == 0, "nn_conv: pixel shuffle needs Cout / 4 to be a multiple of 32");
   // M tile: full rows; as many rows (then samples) as fit 128 pixels
   p.BW = a->W;
@@ -378,27 +459,59 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     if (p.BNb > a->B) p.BNb = a->B;
     if (p.BNb < 1) p.BNb = 1;
   }
+  // haloed scheme (kernel comment): 3x3 "same" layers whose N-tile weights fit beside two activation boxes, and whose tiles
+  // keep at least 3/4 of the pixels the per-tap tiling would have
+  p.halo = 0;
+  p.halo_bo = debug_opt(OPT_CONV_IMPL) == 2;
+  p.wres_bytes = 0;
+  const int PW = a->W + 2;
+  if (debug_opt(OPT_CONV_IMPL) != 1 && a->kh == 3 && a->kw == 3 && a->off_h == -1 && a->off_w == -1 && Hin == a->H && Win == a->W &&
+      a->Cout % 64 == 0 && PW <= TILE_M) {
+    int hBH = TILE_M / PW;
+    if (hBH > a->H) hBH = a->H;
+    const size_t a_box = (size_t)(hBH + 2) * PW * 128;
+    const size_t a_stage = (a_box + 1023) & ~(size_t)1023;
+    const size_t wres = (size_t)9 * (ctot / KBLK) * (64 * 128);
+    // rows an MMA may touch past the box (junk rows of the last taps) stay inside the staging area that follows the ring
+    // (compared at the un-capped samples-per-tile, so that the choice -- hence the summation order -- does not depend on B)
+    const int per_tap_pixels = p.BH == a->H ? a->W * a->H * (TILE_M / (a->W * a->H)) : a->W * p.BH;
+    if (hBH >= 1 && 4 * hBH * a->W >= 3 * per_tap_pixels && wres + 2 * a_stage <= (size_t)RING_BUDGET) {
+      p.halo = 1;
+      ntile = 64;
+      p.BW = PW; p.BH = hBH; p.BNb = 1;
+      p.a_stage_bytes = (uint32_t)a_stage;
+      p.a_tx_bytes = (uint32_t)a_box;
+      p.wres_bytes = (uint32_t)wres;
+    }
+  }
   p.h_tiles = (a->H + p.BH - 1) / p.BH;
   const int n_tiles = (a->B + p.BNb - 1) / p.BNb;
   p.m_tiles = n_tiles * p.h_tiles;
-  // few M tiles (the 7x7 / 14x14 levels): a CTA streams its K loop through ONE SM's L2 port, so prefer narrower N tiles
-  // until there are about two tiles per SM
-  while (ntile > 64 && ntile % 32 == 0 && (int64_t)p.m_tiles * (a->Cout / ntile) < 2 * sm_count()) ntile /= 2;
+  int stages;
+  if (p.halo) {
+    stages = (int)((RING_BUDGET - p.wres_bytes) / p.a_stage_bytes);
+  } else {
+    // few M tiles (the 7x7 / 14x14 levels): a CTA streams its K loop through ONE SM's L2 port, so prefer narrower N tiles
+    // until there are about two tiles per SM
+    while (ntile > 64 && ntile % 32 == 0 && (int64_t)p.m_tiles * (a->Cout / ntile) < 2 * sm_count()) ntile /= 2;
+    p.a_stage_bytes = A_STAGE_BYTES;
+    p.a_tx_bytes = (uint32_t)(KBLK * p.BW * p.BH * p.BNb) * 2u;
+    stages = (int)(RING_BUDGET / ((size_t)A_STAGE_BYTES + (size_t)ntile * 128));
+  }
   p.ntile = ntile;
-  const size_t stage = (size_t)A_STAGE_BYTES + (size_t)ntile * 128;
-  int stages = (int)((200 * 1024) / stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) {
     set_error("nn_conv: tile does not fit shared memory");
     return FBS_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage + (2 * MAX_STAGES + 4) * 8 + 16;
+  const size_t stage = (size_t)p.a_stage_bytes + (p.halo ? 0 : (size_t)ntile * 128);
+  const size_t smem = 1024 + p.wres_bytes + stages * stage + N_EPI_WARPS * STG_WARP_BYTES + (2 * MAX_STAGES + 5) * 8 + 16;
   CUtensorMap tmA0, tmA1, tmB;
-  const int Hin = a->Hin > 0 ? a->Hin : a->H, Win = a->Win > 0 ? a->Win : a->W;
-  int rc = make_act_map(&tmA0, a->in0, a->B, Hin, Win, a->C0, p.BW, p.BH, p.BNb);
-  if (!rc) rc = make_act_map(&tmA1, a->C1 ? a->in1 : a->in0, a->B, Hin, Win, a->C1 ? a->C1 : a->C0, p.BW, p.BH, p.BNb);
-  if (!rc) rc = make_w_map(&tmB, a->weight, a->kh * a->kw * (a->C0 + a->C1), a->Cout, ntile);
+  const int boxH = p.halo ? p.BH + 2 : p.BH;
+  int rc = make_act_map(&tmA0, a->in0, a->B, Hin, Win, a->C0, p.BW, boxH, p.BNb);
+  if (!rc) rc = make_act_map(&tmA1, a->C1 ? a->in1 : a->in0, a->B, Hin, Win, a->C1 ? a->C1 : a->C0, p.BW, boxH, p.BNb);
+  if (!rc) rc = make_w_map(&tmB, a->weight, a->kh * a->kw * ctot, a->Cout, ntile);
   if (rc) {
     set_error("nn_conv: cuTensorMapEncodeTiled failed with CUresult %d", rc);
     return FBS_ERR_CUDA;
@@ -408,8 +521,11 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     set_error("nn_conv: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
   }
-  const int64_t tiles = (int64_t)p.m_tiles * (a->Cout / ntile);
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const int n_ntiles = a->Cout / ntile;
+  const int64_t tiles = (int64_t)p.m_tiles * n_ntiles;
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  grid -= grid % n_ntiles;  // a CTA keeps one N tile (n_ntiles <= 16 <= the SM count)
+  if (grid < n_ntiles) grid = n_ntiles;
   conv_gemm_kernel<<<grid, NTHREADS, smem, as_stream(s)>>>(tmA0, tmA1, tmB, p);
   return check_launch("conv_gemm_kernel");
 }

@@ -30,7 +30,7 @@ int sm_count() {
 
 static std::atomic<int> g_opts[OPT_COUNT];
 static const char* const g_opt_names[OPT_COUNT] = {"sweep_impl", "sweep_verbose", "step_impl", "step_tc_warps", "stepvec_impl",
-                                                    "sweep_g", "v3_twopass", "em_impl", "v3_variant"};
+                                                    "sweep_g", "v3_twopass", "em_impl", "v3_variant", "conv_impl"};
 int debug_opt(DebugOpt which) { return g_opts[which].load(std::memory_order_relaxed); }
 
 enum { OUT_BITS = 0, OUT_UNIFORM = 1, OUT_NORMAL = 2 };

@@ -36,6 +36,11 @@ def _conv_ref(x, w, bias, pad, stride=1):
     (3, 28, 28, 64, 0, 384, 1),      # qkv projection: N tile 192, no bias
     (2, 16, 16, 64, 64, 64, 1),      # res_conv over a concatenation
     (1, 64, 64, 64, 0, 64, 3),       # CelebA-64 width: two full rows per tile
+    (1, 28, 28, 64, 0, 64, 3),       # haloed-box scheme: one sample (7 tiles)
+    (2, 28, 28, 64, 64, 64, 3),      # ... two sources, two resident weight chunks, two-stage ring
+    (5, 14, 14, 128, 0, 128, 3),     # ... two N tiles per M tile (a CTA keeps its N tile), ragged last row tile
+    (3, 32, 32, 64, 0, 192, 3),      # ... three N tiles, three rows of 34 per tile
+    (150, 14, 14, 64, 0, 64, 3),     # ... more tiles than SMs: CTAs loop, accumulator buffers and ring wrap
 ])
 def test_conv_matches_torch(B, H, W, C0, C1, Cout, k):
     from fbs_b200.nn import ops
