@@ -96,6 +96,108 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
 }
 
+// Same operation, one CTA of 1024 threads per SAMPLE (all groups): a (sample, group) slice is 32 bytes out of every 256-byte
+// pixel at 64 channels / 8 groups, so the per-group kernel above spends its time on 32-byte segments; here a warp reads and
+// writes whole pixels (512 contiguous bytes per instruction).  1024 % (C / 4) == 0 makes a thread's channel quad -- hence
+// its group and its affine constants -- fixed; group statistics are reduced by segmented shuffles, then over the warps in a
+// fixed order (deterministic).  Used for large samples when there are enough of them to fill the machine.
+template <bool STAGED, int NT>
+__global__ void __launch_bounds__(NT) gn_sample_kernel(const float* __restrict__ x, int P, int C, int groups,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ tss, const float* __restrict__ residual,
+                                                       float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, float eps) {
+  extern __shared__ float4 slice[];  // STAGED: the sample, read from global memory exactly once
+  constexpr int NW = NT / 32;
+  __shared__ float part[NW][17];
+  __shared__ float tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q4 = C >> 2, cpg = C / groups, L = cpg >> 2;  // float4 per pixel / per group inside a pixel (powers of two)
+  const int quad = tid % q4, g = quad / L;
+  const int n4 = P * q4;
+  const size_t base4 = (size_t)blockIdx.x * n4;
+  const float4* xb = reinterpret_cast<const float4*>(x) + base4;
+  const int Lw = L < 32 ? L : 32, qw = q4 < 32 ? q4 : 32;
+  const int GW = qw / Lw;                                       // groups one warp holds partial sums of
+  const int gf_lane = lane < NW ? ((lane * 32) % q4) / L : 0;   // first group warp `lane` holds
+  auto group_total = [&](float v) -> float {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+      if (o < L || o >= q4) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane < qw && (lane % Lw) == 0) part[warp][lane / Lw] = v;
+    __syncthreads();
+    // warp j adds up group j (j, j + NW, ...) over the warps that hold it: lane = source warp, fixed xor tree
+    for (int j = warp; j < groups; j += NW) {
+      float t = (lane < NW && j >= gf_lane && j < gf_lane + GW) ? part[lane][j - gf_lane] : 0.f;
+      t = warp_sum(t);
+      if (lane == 0) tot[j] = t;
+    }
+    __syncthreads();
+    return tot[g];
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = 0.f;
+  for (int e0 = tid; e0 < n4; e0 += 4 * NT) {  // four independent loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = e0 + u * NT < n4 ? xb[e0 + u * NT] : zero4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (STAGED && e0 + u * NT < n4) slice[e0 + u * NT] = v[u];
+      s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+  }
+  const float inv_n = 1.0f / (float)(P * cpg);
+  const float mean = group_total(s) * inv_n;
+  float ss = 0.f;
+  for (int e0 = tid; e0 < n4; e0 += 4 * NT) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = e0 + u * NT < n4 ? (STAGED ? slice[e0 + u * NT] : xb[e0 + u * NT]) : make_float4(mean, mean, mean, mean);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float a = v[u].x - mean, bq = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+      ss += (a * a + bq * bq) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(group_total(ss) * inv_n + eps);
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + quad), bt = __ldg(reinterpret_cast<const float4*>(beta) + quad);
+  float4 sc = zero4, sh = zero4;
+  if (tss) {
+    sc = __ldg(reinterpret_cast<const float4*>(tss) + quad);
+    sh = __ldg(reinterpret_cast<const float4*>(tss + C) + quad);
+  }
+  const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
+  const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+  for (int e0 = tid; e0 < n4; e0 += 4 * NT) {
+    float4 v[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * NT;
+      r[u] = (residual && e < n4) ? reinterpret_cast<const float4*>(residual)[base4 + e] : zero4;
+      v[u] = e < n4 ? (STAGED ? slice[e] : xb[e]) : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * NT;
+      if (e >= n4) continue;
+      float y[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const float rr[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = (y[j] - mean) * rstd * gmv[j] + btv[j];
+        if (tss) t = t * (1.0f + scv[j]) + shv[j];  // h * (1 + scale) + shift
+        y[j] = swishf(t) + rr[j];
+      }
+      if (out_f32) reinterpret_cast<float4*>(out_f32)[base4 + e] = make_float4(y[0], y[1], y[2], y[3]);
+      if (out_bf16) {
+        __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y[0], y[1]), __floats2bfloat162_rn(y[2], y[3])};
+        reinterpret_cast<uint2*>(out_bf16)[base4 + e] = *reinterpret_cast<const uint2*>(o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm over channels, scale only (+ residual): unet.py:243,258,264.  One warp per pixel.
 // ---------------------------------------------------------------------------------------------------------
@@ -132,6 +234,60 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       if (residual) y += residual[row * C + c];
       if (out_f32) out_f32[row * C + c] = y;
       if (out_bf16) out_bf16[row * C + c] = __float2bfloat16_rn(y);
+    }
+}
+
+// Same operation with 16-byte accesses: min(32, C / 4) lanes per pixel, C in {64, 128, 256, 512}.
+__global__ void __launch_bounds__(256) layernorm4_kernel(const float* __restrict__ x, int64_t R, int C,
+                                                         const float* __restrict__ gamma, const float* __restrict__ residual,
+                                                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q4 = C >> 2, LPR = q4 < 32 ? q4 : 32, per = q4 / LPR, rpw = 32 / LPR;
+  const int64_t row = ((int64_t)blockIdx.x * 8 + warp) * rpw + lane / LPR;
+  const int l = lane % LPR;
+  const bool active = row < R;
+  const float4* xr = reinterpret_cast<const float4*>(x) + row * q4;
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < per) {
+      v[j] = active ? xr[l + LPR * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    if (o < LPR) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < per) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    if (o < LPR) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / (float)C + eps);
+  if (!active) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < per) {
+      const int c4 = l + LPR * j;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      float4 y = make_float4((v[j].x - mean) * rstd * gm.x, (v[j].y - mean) * rstd * gm.y, (v[j].z - mean) * rstd * gm.z,
+                             (v[j].w - mean) * rstd * gm.w);
+      const size_t off = (size_t)row * q4 + c4;
+      if (residual) {
+        const float4 r = reinterpret_cast<const float4*>(residual)[off];
+        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+      }
+      if (out_f32) reinterpret_cast<float4*>(out_f32)[off] = y;
+      if (out_bf16) {
+        __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y.x, y.y), __floats2bfloat162_rn(y.z, y.w)};
+        reinterpret_cast<uint2*>(out_bf16)[off] = *reinterpret_cast<const uint2*>(o);
+      }
     }
 }
 
@@ -551,6 +707,78 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
   }
 }
 
+// Same convolution, thread = (4 horizontally adjacent pixels, 16 output channels): a tap's 16 weights (four 16-byte shared
+// loads) serve 64 FMAs instead of 16 -- the kernel above is bound by its shared-memory loads.  W % 4 == 0.
+__global__ void __launch_bounds__(256, 2) stem_conv4_kernel(const float* __restrict__ x, int B, int H, int W, int Cin, int Cout,
+                                                         const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  extern __shared__ float ws[];
+  const int nw = 49 * Cin * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wgt[i];
+  __syncthreads();
+  const int cgs = Cout / 16, wqs = W / 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * wqs * cgs) return;
+  const int cg = (int)(idx % cgs);
+  int64_t t = idx / cgs;
+  const int w0 = 4 * (int)(t % wqs);
+  t /= wqs;
+  const int h = (int)(t % H);
+  const int64_t b = t / H;
+  float acc[4][16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float bj = bias[16 * cg + j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][j] = bj;
+  }
+  for (int ty = 0; ty < 7; ++ty) {
+    const int hh = h + ty - 3;
+    if (hh < 0 || hh >= H) continue;
+    for (int c = 0; c < Cin; ++c) {
+      float xv[10];  // columns w0 - 3 .. w0 + 6 of this row / channel (zero outside the image)
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int ww = w0 - 3 + i;
+        xv[i] = (ww >= 0 && ww < W) ? __ldg(x + ((b * H + hh) * W + ww) * Cin + c) : 0.f;
+      }
+#pragma unroll
+      for (int tx = 0; tx < 7; ++tx) {
+        const float* wp = ws + ((ty * 7 + tx) * Cin + c) * Cout + 16 * cg;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp + j);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][j] = fmaf(xv[q + tx], wv.x, acc[q][j]);
+            acc[q][j + 1] = fmaf(xv[q + tx], wv.y, acc[q][j + 1]);
+            acc[q][j + 2] = fmaf(xv[q + tx], wv.z, acc[q][j + 2]);
+            acc[q][j + 3] = fmaf(xv[q + tx], wv.w, acc[q][j + 3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const size_t off = (((size_t)b * H + h) * W + w0 + q) * Cout + 16 * cg;
+    if (out_f32) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(out_f32 + off + j) = make_float4(acc[q][j], acc[q][j + 1], acc[q][j + 2], acc[q][j + 3]);
+    }
+    if (out_bf16) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 8) {
+        __align__(16) __nv_bfloat162 o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = __floats2bfloat162_rn(acc[q][j + 2 * u], acc[q][j + 2 * u + 1]);
+        *reinterpret_cast<uint4*>(out_bf16 + off + j) = *reinterpret_cast<const uint4*>(o);
+      }
+    }
+  }
+}
+
 // Last convolution: 1x1, 64 -> Cimg (unet.py:363).  One warp per pixel.
 __global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int64_t R, int C, int Cimg,
                                                         const float* __restrict__ wgt, const float* __restrict__ bias,
@@ -735,15 +963,36 @@ int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_
                                float* out_f32, void* out_bf16) {
   FBS_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), "groupnorm: null argument");
   FBS_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 4 == 0, "groupnorm: channels per group must be a multiple of 4");
+  const int q4 = C / 4, L = (C / groups) / 4;
+  const bool pow2 = (q4 & (q4 - 1)) == 0 && (L & (L - 1)) == 0;
+  if (pow2 && q4 <= 256 && groups <= 32 && (q4 < 32 ? q4 : 32) / (L < 32 ? L : 32) <= 17 && 2 * B >= sm_count() &&
+      (int64_t)P * q4 >= 8192) {
+    // large samples, enough of them for one CTA each: whole-pixel accesses (measured: 21.9 -> 16.3 us at 101 x 784 x 64; the
+    // per-group kernel stays ahead below ~8k float4 per sample, where its 8x more CTAs hide latency better)
+    const size_t sample_bytes = (size_t)P * C * sizeof(float);
+    const auto bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+#define FBS_GN_LAUNCH(STAGED, NT, SMEM)                                                                                     \
+  do {                                                                                                                       \
+    if ((SMEM) > 48 * 1024)                                                                                                  \
+      cudaFuncSetAttribute(gn_sample_kernel<STAGED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));          \
+    gn_sample_kernel<STAGED, NT><<<(unsigned)B, NT, (SMEM), as_stream(s)>>>(x, P, C, groups, gamma, beta, time_scale_shift, \
+                                                                            residual, out_f32, bf, eps);                    \
+  } while (0)
+    if (sample_bytes <= 200 * 1024) {
+      FBS_GN_LAUNCH(true, 1024, sample_bytes);
+    } else {
+      FBS_GN_LAUNCH(false, 1024, 0);
+    }
+#undef FBS_GN_LAUNCH
+    return check_launch("gn_sample_kernel");
+  }
   const size_t slice_bytes = (size_t)P * (C / groups) * sizeof(float);
   if (slice_bytes <= 160 * 1024) {
     if (slice_bytes > 48 * 1024)
       cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slice_bytes);
-    gn_apply_kernel<true><<<(unsigned)(B * groups), 256, slice_bytes, as_stream(s)>>>(
-        x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+    gn_apply_kernel<true><<<(unsigned)(B * groups), 256, slice_bytes, as_stream(s)>>>(x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
   } else {
-    gn_apply_kernel<false><<<(unsigned)(B * groups), 256, 0, as_stream(s)>>>(
-        x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+    gn_apply_kernel<false><<<(unsigned)(B * groups), 256, 0, as_stream(s)>>>(x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
   }
   return check_launch("gn_apply_kernel");
 }
@@ -752,8 +1001,13 @@ int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C
                          float eps, float* out_f32, void* out_bf16) {
   FBS_REQUIRE(x && gamma && (out_f32 || out_bf16), "layernorm: null argument");
   FBS_REQUIRE(C % 32 == 0 && C <= 512, "layernorm: C must be a multiple of 32, <= 512");
-  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(s)>>>(x, rows, C, gamma, residual, out_f32,
-                                                                         reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  if (C == 64 || C == 128 || C == 256 || C == 512) {
+    const int rows_per_cta = 8 * (32 / (C / 4 < 32 ? C / 4 : 32));
+    layernorm4_kernel<<<(unsigned)((rows + rows_per_cta - 1) / rows_per_cta), 256, 0, as_stream(s)>>>(x, rows, C, gamma, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  } else {
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(s)>>>(x, rows, C, gamma, residual, out_f32,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
+  }
   return check_launch("layernorm_kernel");
 }
 
@@ -789,6 +1043,13 @@ int fbs_nn_stem_conv_f32(fbs_stream_t s, const float* x, int64_t B, int32_t H, i
   FBS_REQUIRE(x && weight && bias && (out_f32 || out_bf16), "stem_conv: null argument");
   FBS_REQUIRE(Cout % 16 == 0 && (size_t)49 * Cin * Cout * 4 <= 96 * 1024, "stem_conv: weights must fit shared memory");
   const size_t smem = (size_t)49 * Cin * Cout * 4;
+  if (W % 4 == 0) {
+    cudaFuncSetAttribute(stem_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t n4 = B * H * (W / 4) * (Cout / 16);
+    stem_conv4_kernel<<<(unsigned)((n4 + 255) / 256), 256, smem, as_stream(s)>>>(x, (int)B, H, W, Cin, Cout, weight, bias, out_f32,
+                                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    return check_launch("stem_conv4_kernel");
+  }
   cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t n = B * H * W * (Cout / 16);
   stem_conv_kernel<<<(unsigned)((n + 255) / 256), 256, smem, as_stream(s)>>>(x, (int)B, H, W, Cin, Cout, weight, bias, out_f32,

@@ -139,6 +139,7 @@ class ScoreUNet:
         self._time_blocks = []       # resnet block name -> offset into the time table
         self._prepare(params)
         self.tval = torch.zeros((1,), dtype=F32, device=self.device)
+        self._side = torch.cuda.Stream(device=self.device)
 
     # ------------------------------------------------------------------ weights
     def _put(self, name, arr, dtype=F32):
@@ -250,11 +251,17 @@ class ScoreUNet:
         w, dim = self._w, self.dim
         H, W = self.H, self.W
         nres = len(self.dim_mults)
-        ops.time_mlp(self.tval, self.dt, dim, w['time.dense_0.w'], w['time.dense_0.bias'], w['time.dense_1.w'],
-                     w['time.dense_1.bias'], w['time.Wcat'], w['time.bcat'], self.table)
+        # the time-embedding table does not depend on x: it runs beside the first convolution (a fork / join of the stream,
+        # which a CUDA-graph capture records as a parallel branch)
+        cur = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            ops.time_mlp(self.tval, self.dt, dim, w['time.dense_0.w'], w['time.dense_0.bias'], w['time.dense_1.w'],
+                         w['time.dense_1.bias'], w['time.Wcat'], w['time.bcat'], self.table)
         h_f32 = self._buf(B, 'h0_f32', (B, H, W, dim), F32)
         h_bf = self._buf(B, 'h0_bf16', (B, H, W, dim), BF16)
         ops.stem_conv(x, w['init.conv_0.w'], w['init.conv_0.bias'], out_f32=h_f32, out_bf16=h_bf)
+        cur.wait_stream(self._side)
         skips = [h_bf]
         c = dim
         for ind in range(nres):

@@ -90,6 +90,35 @@ def test_conv_pixel_shuffle_and_stride2():
     np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize('B,P,C', [(80, 784, 64), (76, 196, 128), (75, 49, 256), (74, 4096, 64), (3, 100, 512)])
+def test_norm_kernels_for_full_batches(B, P, C):
+    """The one-CTA-per-sample GroupNorm (batches that fill the machine; (74, 4096, 64) does not fit shared memory and re-reads)
+    and the 16-byte LayerNorm against the oracle pieces, with and without the optional operands."""
+    from fbs_b200.nn import ops
+    g = torch.Generator().manual_seed(B + P)
+    x = torch.randn(B, P, 1, C, generator=g) * 1.5 - 0.3
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    tss = torch.randn(2 * C, generator=g) * 0.3
+    res = torch.randn(B, P, 1, C, generator=g)
+    Pm = ou._P({'n.scale': gamma.numpy(), 'n.bias': beta.numpy()})
+    out = torch.empty_like(x, device='cuda')
+    out16 = torch.empty(x.shape, device='cuda', dtype=torch.bfloat16)
+    want = ou._swish(ou._group_norm(Pm, 'n', x) * (1 + tss[:C]) + tss[C:]) + res
+    ops.groupnorm_swish(x.cuda(), gamma.cuda(), beta.cuda(), 8, tss=tss.cuda(), residual=res.cuda(), out_f32=out, out_bf16=out16)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
+    want = ou._swish(ou._group_norm(Pm, 'n', x))
+    ops.groupnorm_swish(x.cuda(), gamma.cuda(), beta.cuda(), 8, out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=3e-5, atol=3e-5)
+    want = ou._layer_norm(Pm, 'n', x) + res
+    ops.layernorm(x.cuda(), gamma.cuda(), residual=res.cuda(), out_f32=out, out_bf16=out16)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=1e-2)
+    want = ou._layer_norm(Pm, 'n', x)
+    ops.layernorm(x.cuda(), gamma.cuda(), out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=3e-5, atol=3e-5)
+
+
 def test_norms_and_attention_match_oracle_pieces():
     from fbs_b200.nn import ops
     g = torch.Generator().manual_seed(3)
