@@ -58,6 +58,7 @@ SIGNATURES = {
     'fbs_debug_umma_gemm': ([_p, _p, _p, _i32, _i32, _p], _int),
     'fbs_debug_step_tc_timers': ([_p], _int),
     'fbs_debug_v3_timeline': ([_p], _int),
+    'fbs_debug_conv_timeline': ([_p], _int),
     'fbs_sweep_workspace_bytes': ([_M, _i64], C.c_size_t),
     'fbs_csmc_forward_affine_f32': ([_p, _M, _p, _p, _p, _p, _int, _f32, _int, _i64, _i64, _p, _p, _p, _p, _p, _p,
                                      C.c_size_t], _int),

@@ -28,6 +28,7 @@ constexpr int TILE_M = 128;
 constexpr int KBLK = 64;                       // bf16 channels per K-block = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = TILE_M * 128;    // 16 KB
 constexpr int N_EPI_WARPS = 8;
+constexpr int MAX_ACC = 4;                     // accumulator buffers in tensor memory (even: buffer b belongs to epilogue group b & 1)
 constexpr int NTHREADS = 32 * (2 + N_EPI_WARPS);
 constexpr int MAX_STAGES = 6;
 constexpr int STG_WARP_BYTES = 32 * 128;       // one epilogue warp's transpose buffer: 32 tile rows x 32 fp32 columns
@@ -55,6 +56,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// explicit shared-window accesses for the epilogue's transpose buffer (through the carved-up dynamic buffer the compiler only
+// sees generic pointers: LD.E / ST.E on the global path, ~200 cycles per dependent round trip)
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -94,8 +116,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 columns of the accumulator -> 32 registers per thread; asynchronous until tmem_ld_wait, which takes the
+// registers as in/out operands so that the compiler cannot read (or copy) them before the wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -106,9 +129,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B (8 rows x 128 bytes atoms, SBO = 1024), version 1 (Blackwell)
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -131,20 +160,53 @@ struct Params {
   const float* residual;
   float* out_f32;
   __nv_bfloat16* out_bf16;
+  long long* dbg;     // profiling hook (fbs_debug_conv_timeline): CTA 0 stamps clock64() at its phase boundaries; NULL = off
 };
+
+#define CONV_STAMP(i)                                                                                        \
+  do {                                                                                                       \
+    if (DBG && p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < 256) p.dbg[(i)] = clock64(); \
+  } while (0)
+
+// Copy-out of one 32-column chunk: this lane's 16-byte pieces of rows 4 i + sub (+ bias, + optional fp32 residual), as fp32
+// and / or bf16.  Specialised on the outputs: with run-time pointers every store dragged its own null tests, predicated
+// address arithmetic and parameter loads along, and the epilogue -- ~540 instructions per chunk and warp -- was plainly
+// instruction bound.
+template <bool F32, bool BF16, bool RES>
+__device__ __forceinline__ void store_rows(const float4 (&v)[8], const uint32_t (&rowbase)[8], uint32_t col4, bool col_ok, float4 b4,
+                                           const float* __restrict__ res_p, float* __restrict__ out32_p,
+                                           __nv_bfloat16* __restrict__ out16_p) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (rowbase[i] != 0xFFFFFFFFu && col_ok) {
+      const uint32_t e4 = rowbase[i] + col4;  // in units of 4 elements
+      float4 y = make_float4(v[i].x + b4.x, v[i].y + b4.y, v[i].z + b4.z, v[i].w + b4.w);
+      if (RES) {
+        const float4 rv = reinterpret_cast<const float4*>(res_p)[e4];
+        y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+      }
+      if (F32) reinterpret_cast<float4*>(out32_p)[e4] = y;
+      if (BF16) {
+        __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y.x, y.y), __floats2bfloat162_rn(y.z, y.w)};
+        reinterpret_cast<uint2*>(out16_p)[e4] = *reinterpret_cast<const uint2*>(o);
+      }
+    }
+  }
+}
 
 // Two operand schemes share the kernel.
 //
 // per-tap (any kernel size): K-block = (tap, 64-channel chunk); ring stage = activation box shifted by the tap + the weight tile.
 //
-// haloed (3x3 "same", <= 128 source channels, N tile 64): a 3x3 layer at 28x28 re-read its input nine times through L2 and its
+// haloed (3x3 "same", resident weights of an N tile of 64 or 32): a 3x3 layer at 28x28 re-read its input nine times through L2 and its
 // weights once per M tile -- 198 KB per 128 x 64 tile, which bound the layer by the SM's L2 port, not by the tensor pipe.
 // Here the box carries a one-pixel halo (BH + 2 rows of W + 2 pixels: the row pitch in shared memory is W + 2 pixels) and
 // is loaded ONCE per 64-channel chunk; M row m = hh * (W + 2) + w, so that tap (ty, tx) is the SAME shared-memory image
 // read from (ty * (W + 2) + tx) rows further on -- an operand-descriptor start address, nothing moves (SWIZZLE_128B is a
 // function of the absolute address bits, which a whole-row shift preserves).  The w >= W rows of the tile are junk and never
-// stored.  The weights of the CTA's N tile (9 taps x <= 2 chunks x 8 KB) are loaded once per CTA and stay resident; a CTA keeps
+// stored.  The weights of the CTA's N tile (9 taps x chunks x 8 or 4 KB) are loaded once per CTA and stay resident; a CTA keeps
 // its N tile for all its M tiles.
+template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -153,7 +215,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // tile i + 1.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform for the compiler, so that the role branches below are uniform
+  // control flow and the TMA / MMA operands can be kept in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) CONV_STAMP(0);
   const uint32_t b_stage_bytes = p.halo ? 0u : (uint32_t)p.ntile * 128u;
   const uint32_t stage_bytes = p.a_stage_bytes + b_stage_bytes;
   unsigned char* wres = smem;                   // halo mode: [tap][chunk][64 x 128 bytes]
@@ -161,9 +226,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   unsigned char* stg_base = ring + (size_t)p.stages * stage_bytes;  // epilogue staging: 8 warps x (32 rows x 128 bytes)
   uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + N_EPI_WARPS * STG_WARP_BYTES);
   uint64_t* empty = full + MAX_STAGES;
-  uint64_t* acc_full = empty + MAX_STAGES;   // [2]: accumulator buffer written by the MMA warp
-  uint64_t* acc_empty = acc_full + 2;        // [2]: ... drained by the epilogue warps
-  uint64_t* wbar = acc_empty + 2;            // resident weights have landed
+  uint64_t* acc_full = empty + MAX_STAGES;    // [MAX_ACC]: accumulator buffer written by the MMA warp
+  uint64_t* acc_empty = acc_full + MAX_ACC;   // [MAX_ACC]: ... drained by the four epilogue warps of the buffer's group
+  uint64_t* wbar = acc_empty + MAX_ACC;       // resident weights have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int ctot = p.C0 + p.C1;
@@ -174,17 +239,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int mt_first = blockIdx.x / n_ntiles, mt_step = gridDim.x / n_ntiles;  // host: gridDim.x % n_ntiles == 0
   uint32_t acc_cols = 32;  // columns of one accumulator buffer (power of two >= ntile)
   while (acc_cols < (uint32_t)p.ntile) acc_cols <<= 1;
+  // accumulator buffers in tensor memory (512 columns): the MMA warp runs up to nacc tiles ahead of the epilogue
+  const uint32_t nacc = 512u / acc_cols < (uint32_t)MAX_ACC ? 512u / acc_cols : (uint32_t)MAX_ACC;
 
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 2 * acc_cols);
+    tmem_alloc(tmem_slot, nacc * acc_cols);
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(full + s, 1);
         mbar_init(empty + s, 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < MAX_ACC; ++i) {
         mbar_init(acc_full + i, 1);
-        mbar_init(acc_empty + i, N_EPI_WARPS);  // one arrival per epilogue warp
+        mbar_init(acc_empty + i, N_EPI_WARPS / 2);  // one arrival per epilogue warp of the group that owns the buffer
       }
       mbar_init(wbar, 1);
       fence_barrier_init();
@@ -193,51 +260,70 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (threadIdx.x == 0) CONV_STAMP(1);
 
+  // The producer and the MMA issuer run their loops with ALL lanes of their warp and predicate only the asynchronous
+  // instructions on one lane: addresses and descriptors then live in uniform registers.  (Inside an `if (lane == 0)` region
+  // every TMA / MMA operand was moved vector -> uniform register with its own scoreboard wait: ~70 cycles per MMA issued,
+  // twice the 32 cycles the tensor pipe needs for a 128 x 64 x 16 MMA -- the 3x3 layers were bound by that.)
+  const bool leader = elect_one();  // (evaluated by every warp in converged code; only warps 0 and 1 use it)
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t s = 0, ph = 1;
-      if (p.halo) {
-        mbar_expect_tx(wbar, p.wres_bytes);
-        for (int tap = 0; tap < 9; ++tap)
-          for (int cb = 0; cb < cblocks; ++cb)
-            tma_load_2d(wres + (size_t)(tap * cblocks + cb) * (KBLK * 128), &tmB, wbar, tap * ctot + cb * KBLK, nt * p.ntile);
-        for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
-          const int n0 = mt / p.h_tiles, h0 = (mt % p.h_tiles) * p.BH;
-          for (int c = 0; c < ctot; c += KBLK) {
-            mbar_wait(empty + s, ph);
-            unsigned char* dst = ring + (size_t)s * stage_bytes;
+    uint32_t s = 0, ph = 1;
+    int dbg_it = 0;
+    if (p.halo) {
+      if (leader) mbar_expect_tx(wbar, p.wres_bytes);
+      const uint32_t wtile = (uint32_t)p.ntile * 128u;
+      for (int tap = 0; tap < 9; ++tap)
+        for (int cb = 0; cb < cblocks; ++cb)
+          if (leader) tma_load_2d(wres + (size_t)(tap * cblocks + cb) * wtile, &tmB, wbar, tap * ctot + cb * KBLK, nt * p.ntile);
+      CONV_STAMP(2);
+      for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
+        const int n0 = mt / p.h_tiles, h0 = (mt % p.h_tiles) * p.BH;
+        for (int c = 0; c < ctot; c += KBLK) {
+          mbar_wait(empty + s, ph);
+          if (c == 0) {
+            CONV_STAMP(8 + 8 * dbg_it);
+            ++dbg_it;
+          }
+          unsigned char* dst = ring + (size_t)s * stage_bytes;
+          if (leader) {
             mbar_expect_tx(full + s, p.a_tx_bytes);
             if (c < p.C0)
               tma_load_4d(dst, &tmA0, full + s, c, -1, h0 - 1, n0);
             else
               tma_load_4d(dst, &tmA1, full + s, c - p.C0, -1, h0 - 1, n0);
-            if (++s == (uint32_t)p.stages) {
-              s = 0;
-              ph ^= 1u;
-            }
+          }
+          if (++s == (uint32_t)p.stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
-      } else {
-        for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
-          const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
-          int kcol = 0;  // column of this K-block in the weight matrix
-          for (int ty = 0; ty < p.kh; ++ty) {
-            for (int tx = 0; tx < p.kw; ++tx) {
-              for (int c = 0; c < ctot; c += KBLK, kcol += KBLK) {
-                mbar_wait(empty + s, ph);
-                unsigned char* dst = ring + (size_t)s * stage_bytes;
+      }
+    } else {
+      for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
+        const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
+        int kcol = 0;  // column of this K-block in the weight matrix
+        for (int ty = 0; ty < p.kh; ++ty) {
+          for (int tx = 0; tx < p.kw; ++tx) {
+            for (int c = 0; c < ctot; c += KBLK, kcol += KBLK) {
+              mbar_wait(empty + s, ph);
+              if (kcol == 0) {
+                CONV_STAMP(8 + 8 * dbg_it);
+                ++dbg_it;
+              }
+              unsigned char* dst = ring + (size_t)s * stage_bytes;
+              if (leader) {
                 mbar_expect_tx(full + s, p.a_tx_bytes + b_stage_bytes);
                 if (c < p.C0)
                   tma_load_4d(dst, &tmA0, full + s, c, p.off_w + tx, h0 + p.off_h + ty, n0);
                 else
                   tma_load_4d(dst, &tmA1, full + s, c - p.C0, p.off_w + tx, h0 + p.off_h + ty, n0);
                 tma_load_2d(dst + p.a_stage_bytes, &tmB, full + s, kcol, nt * p.ntile);
-                if (++s == (uint32_t)p.stages) {
-                  s = 0;
-                  ph ^= 1u;
-                }
+              }
+              if (++s == (uint32_t)p.stages) {
+                s = 0;
+                ph ^= 1u;
               }
             }
           }
@@ -246,76 +332,104 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D fp32, A / B bf16, both K-major, N, M
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-      uint32_t s = 0, ph = 0;
-      uint32_t it = 0;
+    // instruction descriptor: D fp32, A / B bf16, both K-major, N, M
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    uint32_t s = 0, ph = 0;
+    uint32_t it = 0;
+    if (p.halo) {
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+    }
+    CONV_STAMP(3);
+    const uint32_t ring_u = smem_u32(ring), wres_u = smem_u32(wres);
+    const uint32_t wtile16 = (uint32_t)p.ntile * 8u;  // one resident weight tile, in descriptor units of 16 bytes
+    for (int mt = mt_first; mt < p.m_tiles; mt += mt_step, ++it) {
+      const uint32_t buf = it % nacc;
+      mbar_wait(acc_empty + buf, ((it / nacc) & 1u) ^ 1u);  // passes on a fresh barrier; then waits for the epilogue of tile it - nacc
+      tc_fence_after();
+      CONV_STAMP(8 + 8 * it + 1);
+      const uint32_t d_tmem = tmem_base + buf * acc_cols;
       if (p.halo) {
-        mbar_wait(wbar, 0);
-        tc_fence_after();
-      }
-      for (int mt = mt_first; mt < p.m_tiles; mt += mt_step, ++it) {
-        const uint32_t buf = it & 1u;
-        mbar_wait(acc_empty + buf, ((it >> 1) & 1u) ^ 1u);  // passes on a fresh barrier; then waits for the epilogue of tile it - 2
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * acc_cols;
-        if (p.halo) {
-          for (int cb = 0; cb < cblocks; ++cb) {
-            mbar_wait(full + s, ph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t sa = a_addr + (uint32_t)((tap / 3) * p.BW + tap % 3) * 128u;  // whole-row shift of the haloed image
-              uint64_t da = make_desc_sw128(sa);
-              if (p.halo_bo) da |= (uint64_t)((sa >> 7) & 7u) << 49;
-              const uint64_t db = make_desc_sw128(smem_u32(wres + (size_t)(tap * cblocks + cb) * (KBLK * 128)));
+        for (int cb = 0; cb < cblocks; ++cb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          if (cb == 0) CONV_STAMP(8 + 8 * it + 2);
+          // descriptors differ from a base one only in the 14-bit start-address field (no carry: shared memory < 256 KB)
+          const uint64_t da0 = make_desc_sw128(ring_u + s * stage_bytes);
+          const uint64_t db0 = make_desc_sw128(wres_u) + (uint64_t)((uint32_t)cb * wtile16);
+          uint32_t acc_flag = cb ? 1u : 0u;
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k)
-                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cb | tap | k) ? 1u : 0u);
-            }
-            umma_commit(empty + s);
-            if (++s == (uint32_t)p.stages) {
-              s = 0;
-              ph ^= 1u;
+          for (int ty = 0; ty < 3; ++ty) {
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) {
+              // tap (ty, tx) = the haloed image read (ty * pitch + tx) rows further on: + 8 descriptor units per row
+              const uint64_t da = da0 + (uint64_t)((uint32_t)(ty * p.BW + tx) * 8u);
+              const uint64_t db = db0 + (uint64_t)((uint32_t)((ty * 3 + tx) * cblocks) * wtile16);
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k) {
+                if (leader) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc_flag);
+                acc_flag = 1u;
+              }
             }
           }
-        } else {
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(full + s, ph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(ring + (size_t)s * stage_bytes);
-            const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + p.a_stage_bytes);
-#pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row: +2 in the address field
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-            umma_commit(empty + s);
-            if (++s == (uint32_t)p.stages) {
-              s = 0;
-              ph ^= 1u;
-            }
+          if (leader) umma_commit(empty + s);
+          if (++s == (uint32_t)p.stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
-        umma_commit(acc_full + buf);
+      } else {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          if (kb == 0) CONV_STAMP(8 + 8 * it + 2);
+          const uint32_t a_addr = ring_u + s * stage_bytes;
+          const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + p.a_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes along the swizzled row: +2 in the address field
+            if (leader) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          if (leader) umma_commit(empty + s);
+          if (++s == (uint32_t)p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
       }
+      if (leader) umma_commit(acc_full + buf);
+      CONV_STAMP(8 + 8 * it + 3);
     }
     __syncwarp();
   } else {
     // epilogue: TMEM lane = tile row = pixel.  A thread owns one ROW of the accumulator, so storing it directly would be 32
     // scattered 16-byte requests per warp instruction (the store-request rate, not the bytes, bound the 1x1 layers); instead
     // each warp transposes 32 rows x 32 columns through its own shared-memory buffer (16-byte pieces XOR-swizzled by the row:
-    // conflict-free both ways) and writes rows out with 8 lanes per 128-byte row segment.  Two warps share a TMEM lane
-    // quadrant (a warp may only read lanes 32 * (warp % 4) ...) and take alternate 32-column chunks: with one warp per
-    // scheduler the epilogue was bound by a single warp's dependent-issue latency.
+    // conflict-free both ways) and writes rows out with 8 lanes per 128-byte row segment.
+    // Two groups of four warps (a warp may only read TMEM lanes 32 * (warp % 4) ...) take alternate tiles, so that one group's
+    // tensor-memory reads (64 bytes per cycle per SM: 512 cycles for a 128 x 64 tile) overlap the other's stores; inside a
+    // warp the tcgen05.ld of the next 32-column chunk is in flight while the current one is written out.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;
+    // the output pointers in registers: left in the parameter bank they cost two or three dependent constant loads in front
+    // of EVERY store (the loop below is predicated, the compiler does not hoist them): ~230 cycles per 16-byte row piece
+    const float* const res_p = p.residual;
+    float* const out32_p = p.out_f32;
+    __nv_bfloat16* const out16_p = p.out_bf16;
+    const float* const bias_p = p.bias;
+    const int ntile = p.ntile;
     const int r = 32 * q + lane;
     const int w = r % p.BW, hh = (r / p.BW) % p.BH, nn = r / (p.BW * p.BH);
-    float* stg = reinterpret_cast<float*>(stg_base + (warp - 2) * STG_WARP_BYTES);
+    const uint32_t stg = smem_u32(stg_base + (warp - 2) * STG_WARP_BYTES);
     const int piece = lane & 7, sub = lane >> 3;
     const int Cq = p.Cout >> 2;
-    uint32_t it = 0;
-    for (int mt = mt_first; mt < p.m_tiles; mt += mt_step, ++it) {
+    // byte offsets inside the transpose buffer: own row (written), rows 4 i + sub (read); pieces XOR-swizzled by row & 7
+    uint32_t st_addr[8];  // own row, pieces XOR-swizzled
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st_addr[j] = stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+    const int out_mode = (out32_p ? 1 : 0) | (out16_p ? 2 : 0) | (res_p ? 4 : 0);
+    const uint32_t ld_even = stg + (uint32_t)sub * 128u + (uint32_t)((piece ^ sub) << 4);        // rows 8 j + sub
+    const uint32_t ld_odd = stg + (uint32_t)(4 + sub) * 128u + (uint32_t)((piece ^ (4 + sub)) << 4);  // rows 8 j + 4 + sub
+    for (uint32_t it = (uint32_t)grp; mt_first + (int)it * mt_step < p.m_tiles; it += 2) {
+      const int mt = mt_first + (int)it * mt_step;
       const int n0 = (mt / p.h_tiles) * p.BNb, h0 = (mt % p.h_tiles) * p.BH;
       const int h = h0 + hh, n = n0 + nn;
       const bool valid = r < p.BW * p.BH * p.BNb && w < p.W && h < p.H && n < p.B;
@@ -327,19 +441,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t rowbase[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rowbase[i] = __shfl_sync(0xffffffffu, mybase, 4 * i + sub);
-      const uint32_t buf = it & 1u;
-      mbar_wait(acc_full + buf, (it >> 1) & 1u);
+      const uint32_t buf = it % nacc;
+      mbar_wait(acc_full + buf, (it / nacc) & 1u);
       tc_fence_after();
+      if (q == 2 && lane == 0) CONV_STAMP(8 + 8 * it + 4);
       const uint32_t trow = tmem_base + buf * acc_cols + ((uint32_t)(32 * q) << 16);
-      for (int c0 = 32 * half; c0 < p.ntile; c0 += 64) {
-        float acc[32];
-        tmem_ld32(trow + c0, acc);
+      uint32_t acc[32];
+      tmem_ld32_issue(trow, acc);
+      for (int c0 = 0; c0 < ntile; c0 += 32) {
+        tmem_ld_wait(acc);
+        if (q == 2 && c0 == 0) CONV_STAMP(8 + 8 * it + 6);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 32 + 4 * (j ^ (lane & 7))) =
-              make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        const int cg = nt * p.ntile + c0;  // first global output channel of this chunk
-        const bool col_ok = 4 * piece < p.ntile - c0;
+        for (int j = 0; j < 8; ++j) sts_v4(st_addr[j], acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        if (c0 + 32 < ntile) tmem_ld32_issue(trow + c0 + 32, acc);  // (the stores above have read their registers)
+        const int cg = nt * ntile + c0;  // first global output channel of this chunk
+        const bool col_ok = 4 * piece < ntile - c0;
         uint32_t coff = (uint32_t)cg;  // element offset of the chunk inside a row
         if (p.pixel_shuffle) {
           // channel = (h2 * 2 + w2) * Cq + cq  ->  pixel (2h + h2, 2w + w2), channel cq   (fbs/nn/utils.py:53-57)
@@ -348,37 +464,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         const uint32_t col4 = (coff >> 2) + (uint32_t)piece;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cg + 4 * piece));
+        if (bias_p && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias_p + cg + 4 * piece));
         __syncwarp();
+        float4 v[8];  // all eight row pieces first: independent shared loads, then the stores
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + sub;
-          if (rowbase[i] == 0xFFFFFFFFu || !col_ok) continue;
-          float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + 4 * (piece ^ (row & 7)));
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          const size_t off = (size_t)(rowbase[i] + col4) << 2;
-          if (p.residual) {
-            const float4 rv = *reinterpret_cast<const float4*>(p.residual + off);
-            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-          }
-          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = v;
-          if (p.out_bf16) {
-            __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(v.x, v.y), __floats2bfloat162_rn(v.z, v.w)};
-            *reinterpret_cast<uint2*>(p.out_bf16 + off) = *reinterpret_cast<const uint2*>(o);
-          }
+        for (int i = 0; i < 8; ++i) v[i] = lds_v4(((i & 1) ? ld_odd : ld_even) + (uint32_t)(i >> 1) * 1024u);
+        switch (out_mode) {
+          case 1: store_rows<true, false, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
+          case 2: store_rows<false, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
+          case 3: store_rows<true, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
+          case 5: store_rows<true, false, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
+          case 6: store_rows<false, true, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
+          default: store_rows<true, true, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
         }
+        if (q == 2 && c0 == 0) CONV_STAMP(8 + 8 * it + 7);
         __syncwarp();
       }
-      // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
+      // this warp's TMEM reads of the buffer are complete (the last tmem_ld_wait): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + buf);
+      if (q == 2 && lane == 0) CONV_STAMP(8 + 8 * it + 5);
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) CONV_STAMP(4);
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * acc_cols);
+    tmem_dealloc(tmem_base, nacc * acc_cols);
   }
 }
 
@@ -421,6 +534,16 @@ static int make_w_map(CUtensorMap* tm, const void* base, int K, int Cout, int nt
 
 using namespace fbs;
 
+static long long* g_conv_dbg = nullptr;
+// Profiling hook: a device buffer of 256 int64 into which CTA 0 of every following convolution launch writes clock64()
+// stamps ([0] entry, [1] prologue done, [2] weights issued, [3] weights landed, [4] exit; per tile i at 8 + 8 i: producer
+// first load, MMA got the accumulator, first operands landed, all MMAs issued, epilogue start, epilogue end); NULL = off.
+// Not thread safe; for scripts/conv_timeline.py only.
+extern "C" int fbs_debug_conv_timeline(long long* dev_buf) {
+  g_conv_dbg = dev_buf;
+  return FBS_OK;
+}
+
 extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   using namespace fbs::nnconv;
   FBS_REQUIRE(a != nullptr && a->in0 != nullptr && a->weight != nullptr, "nn_conv: null argument");
@@ -440,6 +563,7 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   p.pixel_shuffle = a->pixel_shuffle;
   p.bias = a->bias; p.residual = a->residual; p.out_f32 = a->out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.dbg = g_conv_dbg;
   const int Hin = a->Hin > 0 ? a->Hin : a->H, Win = a->Win > 0 ? a->Win : a->W;
   const int ctot = a->C0 + a->C1;
   // N tile: the largest of 256 / 192 / 128 / 64 / ... that divides Cout
@@ -459,29 +583,32 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     if (p.BNb > a->B) p.BNb = a->B;
     if (p.BNb < 1) p.BNb = 1;
   }
-  // haloed scheme (kernel comment): 3x3 "same" layers whose N-tile weights fit beside two activation boxes, and whose tiles
-  // keep at least 3/4 of the pixels the per-tap tiling would have
+  // haloed scheme (kernel comment): 3x3 "same" layers whose N-tile weights (N tile 64, else 32) fit beside two activation
+  // boxes.  The tiles may hold fewer pixels than the per-tap tiling (7x7: one sample with its halo = 49 of 128 rows, against
+  // two samples = 98): these layers are bound by the bytes an SM pulls through its L2 port, not by the tensor pipe
   p.halo = 0;
   p.halo_bo = debug_opt(OPT_CONV_IMPL) == 2;
   p.wres_bytes = 0;
   const int PW = a->W + 2;
   if (debug_opt(OPT_CONV_IMPL) != 1 && a->kh == 3 && a->kw == 3 && a->off_h == -1 && a->off_w == -1 && Hin == a->H && Win == a->W &&
-      a->Cout % 64 == 0 && PW <= TILE_M) {
+      a->Cout % 32 == 0 && PW <= TILE_M) {
     int hBH = TILE_M / PW;
     if (hBH > a->H) hBH = a->H;
     const size_t a_box = (size_t)(hBH + 2) * PW * 128;
     const size_t a_stage = (a_box + 1023) & ~(size_t)1023;
-    const size_t wres = (size_t)9 * (ctot / KBLK) * (64 * 128);
-    // rows an MMA may touch past the box (junk rows of the last taps) stay inside the staging area that follows the ring
     // (compared at the un-capped samples-per-tile, so that the choice -- hence the summation order -- does not depend on B)
     const int per_tap_pixels = p.BH == a->H ? a->W * a->H * (TILE_M / (a->W * a->H)) : a->W * p.BH;
-    if (hBH >= 1 && 4 * hBH * a->W >= 3 * per_tap_pixels && wres + 2 * a_stage <= (size_t)RING_BUDGET) {
+    int hnt = 0;
+    for (int cand = 64; cand >= 32 && !hnt; cand /= 2)
+      if (a->Cout % cand == 0 && (size_t)9 * (ctot / KBLK) * cand * 128 + 2 * a_stage <= (size_t)RING_BUDGET) hnt = cand;
+    // rows an MMA may touch past the box (junk rows of the last taps) stay inside the staging area that follows the ring
+    if (hBH >= 1 && 8 * hBH * a->W >= 3 * per_tap_pixels && hnt) {
       p.halo = 1;
-      ntile = 64;
+      ntile = hnt;
       p.BW = PW; p.BH = hBH; p.BNb = 1;
       p.a_stage_bytes = (uint32_t)a_stage;
       p.a_tx_bytes = (uint32_t)a_box;
-      p.wres_bytes = (uint32_t)wres;
+      p.wres_bytes = (uint32_t)((size_t)9 * (ctot / KBLK) * hnt * 128);
     }
   }
   p.h_tiles = (a->H + p.BH - 1) / p.BH;
@@ -506,7 +633,7 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   }
   p.stages = stages;
   const size_t stage = (size_t)p.a_stage_bytes + (p.halo ? 0 : (size_t)ntile * 128);
-  const size_t smem = 1024 + p.wres_bytes + stages * stage + N_EPI_WARPS * STG_WARP_BYTES + (2 * MAX_STAGES + 5) * 8 + 16;
+  const size_t smem = 1024 + p.wres_bytes + stages * stage + N_EPI_WARPS * STG_WARP_BYTES + (2 * MAX_STAGES + 2 * MAX_ACC + 1) * 8 + 16;
   CUtensorMap tmA0, tmA1, tmB;
   const int boxH = p.halo ? p.BH + 2 : p.BH;
   int rc = make_act_map(&tmA0, a->in0, a->B, Hin, Win, a->C0, p.BW, boxH, p.BNb);
@@ -516,7 +643,8 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     set_error("nn_conv: cuTensorMapEncodeTiled failed with CUresult %d", rc);
     return FBS_ERR_CUDA;
   }
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && p.dbg) e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("nn_conv: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
@@ -526,6 +654,9 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   grid -= grid % n_ntiles;  // a CTA keeps one N tile (n_ntiles <= 16 <= the SM count)
   if (grid < n_ntiles) grid = n_ntiles;
-  conv_gemm_kernel<<<grid, NTHREADS, smem, as_stream(s)>>>(tmA0, tmA1, tmB, p);
+  if (p.dbg)
+    conv_gemm_kernel<true><<<grid, NTHREADS, smem, as_stream(s)>>>(tmA0, tmA1, tmB, p);
+  else
+    conv_gemm_kernel<false><<<grid, NTHREADS, smem, as_stream(s)>>>(tmA0, tmA1, tmB, p);
   return check_launch("conv_gemm_kernel");
 }

@@ -155,6 +155,12 @@ int fbs_debug_step_tc_timers(long long* dev_buf);
  * (default).  Not thread safe; for scripts/v3_timeline.py only. */
 int fbs_debug_v3_timeline(long long* dev_buf);
 
+/* Profiling hook of conv_gemm_kernel: a device buffer of 256 int64 receiving CTA 0's clock64() stamps ([0] entry, [1] prologue
+ * done, [2] weights issued, [3] weights landed, [4] exit; per tile i at 8 + 8 i: producer's first load, MMA warp got the
+ * accumulator buffer, first operands landed, all MMAs issued, epilogue start, epilogue end); NULL switches it off (default).
+ * Not thread safe; for scripts/conv_timeline.py only. */
+int fbs_debug_conv_timeline(long long* dev_buf);
+
 /* Scratch the tiled sweep kernel needs for B chains (per-chain step vectors of all K steps); pass a device
  * buffer of at least this many bytes as `workspace` to fbs_csmc_forward_affine_f32 / fbs_pmcmc_filter_affine_f32.
  * With workspace == NULL (or too small) the general kernel runs instead. */
