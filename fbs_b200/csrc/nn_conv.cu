@@ -583,9 +583,11 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     if (p.BNb > a->B) p.BNb = a->B;
     if (p.BNb < 1) p.BNb = 1;
   }
-  // haloed scheme (kernel comment): 3x3 "same" layers whose N-tile weights (N tile 64, else 32) fit beside two activation
-  // boxes.  The tiles may hold fewer pixels than the per-tap tiling (7x7: one sample with its halo = 49 of 128 rows, against
-  // two samples = 98): these layers are bound by the bytes an SM pulls through its L2 port, not by the tensor pipe
+  // haloed scheme (kernel comment): 3x3 "same" layers with up to 128 output channels whose N-tile weights (N tile 64) fit
+  // beside two activation boxes, and whose tiles keep at least 3/4 of the pixels the per-tap tiling would have.  Measured
+  // (101 samples, us, haloed / per-tap): 28x28 64->64 12.0 / 14.7, 128->64 16.5 / 21.2; 14x14 128->128 12.1 / 14.4; but
+  // 14x14 128->512 18.4 / 16.3 (per-tap runs N tiles of 128: a 128 x 64 x 16 MMA is bound by its shared-memory operand reads,
+  // 48 cycles for 32 cycles of tensor work), and 7x7 256->256 with N tile 32 and one sample per tile 25.8 / 14.7
   p.halo = 0;
   p.halo_bo = debug_opt(OPT_CONV_IMPL) == 2;
   p.wres_bytes = 0;
@@ -598,11 +600,9 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
     const size_t a_stage = (a_box + 1023) & ~(size_t)1023;
     // (compared at the un-capped samples-per-tile, so that the choice -- hence the summation order -- does not depend on B)
     const int per_tap_pixels = p.BH == a->H ? a->W * a->H * (TILE_M / (a->W * a->H)) : a->W * p.BH;
-    int hnt = 0;
-    for (int cand = 64; cand >= 32 && !hnt; cand /= 2)
-      if (a->Cout % cand == 0 && (size_t)9 * (ctot / KBLK) * cand * 128 + 2 * a_stage <= (size_t)RING_BUDGET) hnt = cand;
+    const int hnt = (a->Cout % 64 == 0 && a->Cout <= 128 && (size_t)9 * (ctot / KBLK) * 64 * 128 + 2 * a_stage <= (size_t)RING_BUDGET) ? 64 : 0;
     // rows an MMA may touch past the box (junk rows of the last taps) stay inside the staging area that follows the ring
-    if (hBH >= 1 && 8 * hBH * a->W >= 3 * per_tap_pixels && hnt) {
+    if (hBH >= 1 && 4 * hBH * a->W >= 3 * per_tap_pixels && hnt) {
       p.halo = 1;
       ntile = hnt;
       p.BW = PW; p.BH = hBH; p.BNb = 1;
