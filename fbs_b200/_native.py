@@ -31,7 +31,7 @@ _M = C.POINTER(AffineModelStruct)
 class NNConvStruct(C.Structure):
     _fields_ = [('B', _i32), ('H', _i32), ('W', _i32), ('Hin', _i32), ('Win', _i32), ('C0', _i32), ('C1', _i32), ('Cout', _i32),
                 ('kh', _i32), ('kw', _i32), ('off_h', _i32), ('off_w', _i32), ('pixel_shuffle', _i32), ('reserved', _i32),
-                ('in0', _p), ('in1', _p), ('weight', _p), ('bias', _p), ('residual', _p), ('out_f32', _p), ('out_bf16', _p)]
+                ('in0', _p), ('in1', _p), ('weight', _p), ('bias', _p), ('residual', _p), ('out_f32', _p), ('out_bf16', _p), ('gn_partials', _p)]
 
 
 _CV = C.POINTER(NNConvStruct)
@@ -73,6 +73,8 @@ SIGNATURES = {
     'fbs_mh_accept_f32': ([_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _p], _int),
     'fbs_gaussian_ref_sample_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p], _int),
     'fbs_nn_conv_bf16': ([_p, _CV], _int),
+    'fbs_nn_conv_gn_layout': ([_CV, _p], _int),
+    'fbs_nn_groupnorm_swish_stats': ([_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p], _int),
     'fbs_nn_groupnorm_swish_f32': ([_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p], _int),
     'fbs_nn_layernorm_f32': ([_p, _p, _i64, _i32, _p, _p, _f32, _p, _p], _int),
     'fbs_nn_linear_attention_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),

@@ -153,13 +153,13 @@ struct Params {
   int h_tiles, m_tiles, stages;
   int pixel_shuffle;
   int halo;           // 1: haloed activation box + resident weights (3x3, stride 1, "same"), see the kernel comment
-  int halo_bo;        // debug: also set the descriptor's base-offset field from the shifted start address
   uint32_t a_stage_bytes, a_tx_bytes;  // ring pitch / bytes one activation box load delivers
   uint32_t wres_bytes;                  // resident weight image in front of the ring (halo mode)
   const float* bias;
   const float* residual;
   float* out_f32;
   __nv_bfloat16* out_bf16;
+  float* gn_partials;  // GroupNorm partial sums of the output (host: only single-sample tiles, no residual / pixel shuffle), or NULL
   long long* dbg;     // profiling hook (fbs_debug_conv_timeline): CTA 0 stamps clock64() at its phase boundaries; NULL = off
 };
 
@@ -172,15 +172,23 @@ struct Params {
 // and / or bf16.  Specialised on the outputs: with run-time pointers every store dragged its own null tests, predicated
 // address arithmetic and parameter loads along, and the epilogue -- ~540 instructions per chunk and warp -- was plainly
 // instruction bound.
-template <bool F32, bool BF16, bool RES>
+// STATS: also the sums and sums of squares of this lane's four columns over the warp's valid rows -- the statistics of the
+// GroupNorm that follows the convolution (flax's GroupNorm forms var = E[x^2] - E[x]^2 from exactly these two means) -- reduced
+// over the warp's rows and written to part[colq] (float2 per channel quad); fixed order: deterministic.
+template <bool F32, bool BF16, bool RES, bool STATS>
 __device__ __forceinline__ void store_rows(const float4 (&v)[8], const uint32_t (&rowbase)[8], uint32_t col4, bool col_ok, float4 b4,
                                            const float* __restrict__ res_p, float* __restrict__ out32_p,
-                                           __nv_bfloat16* __restrict__ out16_p) {
+                                           __nv_bfloat16* __restrict__ out16_p, float2* __restrict__ part, int lane) {
+  float s = 0.f, ss = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (rowbase[i] != 0xFFFFFFFFu && col_ok) {
       const uint32_t e4 = rowbase[i] + col4;  // in units of 4 elements
       float4 y = make_float4(v[i].x + b4.x, v[i].y + b4.y, v[i].z + b4.z, v[i].w + b4.w);
+      if (STATS) {
+        s += (y.x + y.y) + (y.z + y.w);
+        ss += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+      }
       if (RES) {
         const float4 rv = reinterpret_cast<const float4*>(res_p)[e4];
         y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
@@ -191,6 +199,14 @@ __device__ __forceinline__ void store_rows(const float4 (&v)[8], const uint32_t 
         reinterpret_cast<uint2*>(out16_p)[e4] = *reinterpret_cast<const uint2*>(o);
       }
     }
+  }
+  if (STATS) {
+    // lanes sub = 0..3 hold rows 4 i + sub of the same four columns
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    if (lane < 8 && col_ok) part[lane] = make_float2(s, ss);
   }
 }
 
@@ -415,6 +431,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     float* const out32_p = p.out_f32;
     __nv_bfloat16* const out16_p = p.out_bf16;
     const float* const bias_p = p.bias;
+    float* const gn_p = p.gn_partials;
     const int ntile = p.ntile;
     const int r = 32 * q + lane;
     const int w = r % p.BW, hh = (r / p.BW) % p.BH, nn = r / (p.BW * p.BH);
@@ -441,6 +458,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint32_t rowbase[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rowbase[i] = __shfl_sync(0xffffffffu, mybase, 4 * i + sub);
+      // GroupNorm partials of this (sample, row tile, lane quadrant): [sample][slot = 4 row tile + q][Cout / 4] float2
+      float2* const part_tile =
+          gn_p ? reinterpret_cast<float2*>(gn_p) + ((size_t)(mt / p.h_tiles) * (4 * p.h_tiles) + 4 * (mt % p.h_tiles) + q) * (size_t)Cq : nullptr;
       const uint32_t buf = it % nacc;
       mbar_wait(acc_full + buf, (it / nacc) & 1u);
       tc_fence_after();
@@ -469,13 +489,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         float4 v[8];  // all eight row pieces first: independent shared loads, then the stores
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = lds_v4(((i & 1) ? ld_odd : ld_even) + (uint32_t)(i >> 1) * 1024u);
-        switch (out_mode) {
-          case 1: store_rows<true, false, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
-          case 2: store_rows<false, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
-          case 3: store_rows<true, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
-          case 5: store_rows<true, false, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
-          case 6: store_rows<false, true, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
-          default: store_rows<true, true, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p); break;
+        float2* const part = part_tile ? part_tile + (cg >> 2) : nullptr;  // this chunk's channel quads
+        switch (part_tile ? 8 + out_mode : out_mode) {
+          case 1: store_rows<true, false, false, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 2: store_rows<false, true, false, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 3: store_rows<true, true, false, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 5: store_rows<true, false, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 6: store_rows<false, true, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 7: store_rows<true, true, true, false>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 9: store_rows<true, false, false, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          case 10: store_rows<false, true, false, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
+          default: store_rows<true, true, false, true>(v, rowbase, col4, col_ok, b4, res_p, out32_p, out16_p, part, lane); break;
         }
         if (q == 2 && c0 == 0) CONV_STAMP(8 + 8 * it + 7);
         __syncwarp();
@@ -544,7 +568,8 @@ extern "C" int fbs_debug_conv_timeline(long long* dev_buf) {
   return FBS_OK;
 }
 
-extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
+// Validation and tiling of one convolution call (shared by the launch and by fbs_nn_conv_gn_layout).
+static int plan_conv(const fbs_nn_conv_t* a, fbs::nnconv::Params& p, size_t& smem_out) {
   using namespace fbs::nnconv;
   FBS_REQUIRE(a != nullptr && a->in0 != nullptr && a->weight != nullptr, "nn_conv: null argument");
   FBS_REQUIRE(a->C0 > 0 && a->C0 % KBLK == 0 && a->C1 >= 0 && a->C1 % KBLK == 0, "nn_conv: source channels must be multiples of 64");
@@ -552,11 +577,6 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   FBS_REQUIRE(a->Cout % 16 == 0 && a->Cout >= 16, "nn_conv: Cout must be a multiple of 16");
   FBS_REQUIRE(a->W >= 1 && a->W <= TILE_M && a->H >= 1 && a->B >= 1, "nn_conv: need 1 <= W <= 128");
   FBS_REQUIRE(a->out_f32 != nullptr || a->out_bf16 != nullptr, "nn_conv: no output");
-  if (encode_fn() == nullptr) {
-    set_error("nn_conv: cuTensorMapEncodeTiled is not available from this driver");
-    return FBS_ERR_CUDA;
-  }
-  Params p;
   p.B = a->B; p.H = a->H; p.W = a->W;
   p.C0 = a->C0; p.C1 = a->C1; p.Cout = a->Cout;
   p.kh = a->kh; p.kw = a->kw; p.off_h = a->off_h; p.off_w = a->off_w;
@@ -564,6 +584,7 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   p.bias = a->bias; p.residual = a->residual; p.out_f32 = a->out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
   p.dbg = g_conv_dbg;
+  p.gn_partials = a->gn_partials;
   const int Hin = a->Hin > 0 ? a->Hin : a->H, Win = a->Win > 0 ? a->Win : a->W;
   const int ctot = a->C0 + a->C1;
   // N tile: the largest of 256 / 192 / 128 / 64 / ... that divides Cout
@@ -589,7 +610,6 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   // 14x14 128->512 18.4 / 16.3 (per-tap runs N tiles of 128: a 128 x 64 x 16 MMA is bound by its shared-memory operand reads,
   // 48 cycles for 32 cycles of tensor work), and 7x7 256->256 with N tile 32 and one sample per tile 25.8 / 14.7
   p.halo = 0;
-  p.halo_bo = debug_opt(OPT_CONV_IMPL) == 2;
   p.wres_bytes = 0;
   const int PW = a->W + 2;
   if (debug_opt(OPT_CONV_IMPL) != 1 && a->kh == 3 && a->kw == 3 && a->off_h == -1 && a->off_w == -1 && Hin == a->H && Win == a->W &&
@@ -633,7 +653,43 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   }
   p.stages = stages;
   const size_t stage = (size_t)p.a_stage_bytes + (p.halo ? 0 : (size_t)ntile * 128);
-  const size_t smem = 1024 + p.wres_bytes + stages * stage + N_EPI_WARPS * STG_WARP_BYTES + (2 * MAX_STAGES + 2 * MAX_ACC + 1) * 8 + 16;
+  smem_out = 1024 + p.wres_bytes + stages * stage + N_EPI_WARPS * STG_WARP_BYTES + (2 * MAX_STAGES + 2 * MAX_ACC + 1) * 8 + 16;
+  if (p.gn_partials != nullptr)
+    FBS_REQUIRE(p.BNb == 1 && !p.pixel_shuffle && p.residual == nullptr,
+                "nn_conv: GroupNorm partials need single-sample tiles, no residual and no pixel shuffle (fbs_nn_conv_gn_layout)");
+  return FBS_OK;
+}
+
+extern "C" int fbs_nn_conv_gn_layout(const fbs_nn_conv_t* a, int32_t* slots_per_sample) {
+  using namespace fbs::nnconv;
+  FBS_REQUIRE(a != nullptr && slots_per_sample != nullptr, "nn_conv_gn_layout: null argument");
+  fbs_nn_conv_t b = *a;
+  b.gn_partials = nullptr;
+  Params p;
+  size_t smem;
+  const int rc = plan_conv(&b, p, smem);
+  if (rc != FBS_OK) return rc;
+  // (the answer must not depend on the batch size: a per-tap tiling that WOULD pack two samples per tile says no even for B = 1)
+  const bool packs_samples = !p.halo && 2 * a->H * a->W <= TILE_M;
+  *slots_per_sample = (p.BNb == 1 && !packs_samples && !p.pixel_shuffle && p.residual == nullptr) ? 4 * p.h_tiles : 0;
+  return FBS_OK;
+}
+
+extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
+  using namespace fbs::nnconv;
+  if (encode_fn() == nullptr) {
+    set_error("nn_conv: cuTensorMapEncodeTiled is not available from this driver");
+    return FBS_ERR_CUDA;
+  }
+  Params p;
+  size_t smem;
+  {
+    const int rc = plan_conv(a, p, smem);
+    if (rc != FBS_OK) return rc;
+  }
+  const int Hin = a->Hin > 0 ? a->Hin : a->H, Win = a->Win > 0 ? a->Win : a->W;
+  const int ctot = a->C0 + a->C1;
+  const int ntile = p.ntile;
   CUtensorMap tmA0, tmA1, tmB;
   const int boxH = p.halo ? p.BH + 2 : p.BH;
   int rc = make_act_map(&tmA0, a->in0, a->B, Hin, Win, a->C0, p.BW, boxH, p.BNb);

@@ -198,6 +198,100 @@ __global__ void __launch_bounds__(NT) gn_sample_kernel(const float* __restrict__
   }
 }
 
+// GroupNorm + swish with the statistics handed over by the convolution that produced x (nn_conv.cu, `gn_partials`:
+// [B][slots][C / 4] float2 = sum, sum of squares per (sample, slot, channel quad)): one streaming pass over the activations,
+// CTA = (sample, pixel chunk), a thread keeps one channel quad (blockDim % (C / 4) == 0).  var = E[x^2] - E[x]^2 is flax's
+// own formula (flax.linen.normalization._compute_stats, use_fast_variance = True).
+template <bool IN16>
+__global__ void __launch_bounds__(256) gn_stats_apply_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
+                                                             const float2* __restrict__ partials, int slots, int P, int C, int groups,
+                                                             int pchunks, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ tss,
+                                                             const float* __restrict__ residual, float* __restrict__ out_f32,
+                                                             __nv_bfloat16* __restrict__ out_bf16, float eps) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / pchunks, pc = blockIdx.x % pchunks;
+  const int q4 = C >> 2, cpg = C / groups, L = cpg >> 2;
+  // group statistics: warp w adds up groups w, w + 8, ... (lanes stride over the (slot, quad) partials; fixed xor tree)
+  const float2* pb = partials + (size_t)b * slots * q4;
+  for (int g = warp; g < groups; g += 8) {
+    float s = 0.f, ss = 0.f;
+    for (int e = lane; e < slots * L; e += 32) {
+      const float2 t = __ldg(pb + (size_t)(e / L) * q4 + g * L + e % L);
+      s += t.x;
+      ss += t.y;
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      const float inv_n = 1.0f / (float)(P * cpg);
+      const float mean = s * inv_n;
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+    }
+  }
+  __syncthreads();
+  const int quad = tid % q4, g = quad / L;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + quad), bt = __ldg(reinterpret_cast<const float4*>(beta) + quad);
+  float4 sc = zero4, sh = zero4;
+  if (tss) {
+    sc = __ldg(reinterpret_cast<const float4*>(tss) + quad);
+    sh = __ldg(reinterpret_cast<const float4*>(tss + C) + quad);
+  }
+  // y = swish(x * A + Bc): the affine parts folded per channel
+  float A[4], Bc[4];
+  {
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = rstd * gmv[j], b0 = btv[j] - mean * a0;
+      A[j] = a0 * (1.0f + scv[j]);
+      Bc[j] = b0 * (1.0f + scv[j]) + shv[j];
+    }
+  }
+  const int n4 = P * q4;
+  const int per = ((P + pchunks - 1) / pchunks) * q4;  // whole pixels per chunk
+  const int e_begin = pc * per, e_end = min(n4, e_begin + per);
+  const size_t base4 = (size_t)b * n4;
+  for (int e0 = e_begin + tid; e0 < e_end; e0 += 4 * 256) {
+    float4 v[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      const bool ok = e < e_end;
+      if (IN16) {
+        uint2 raw = make_uint2(0u, 0u);
+        if (ok) raw = reinterpret_cast<const uint2*>(x16)[base4 + e];
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        const float2 fl = __bfloat1622float2(lo), fh = __bfloat1622float2(hi);
+        v[u] = make_float4(fl.x, fl.y, fh.x, fh.y);
+      } else {
+        v[u] = ok ? reinterpret_cast<const float4*>(x32)[base4 + e] : zero4;
+      }
+      r[u] = (residual && ok) ? reinterpret_cast<const float4*>(residual)[base4 + e] : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256;
+      if (e >= e_end) continue;
+      float4 y;
+      y.x = swishf(fmaf(v[u].x, A[0], Bc[0])) + r[u].x;
+      y.y = swishf(fmaf(v[u].y, A[1], Bc[1])) + r[u].y;
+      y.z = swishf(fmaf(v[u].z, A[2], Bc[2])) + r[u].z;
+      y.w = swishf(fmaf(v[u].w, A[3], Bc[3])) + r[u].w;
+      if (out_f32) reinterpret_cast<float4*>(out_f32)[base4 + e] = y;
+      if (out_bf16) {
+        __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y.x, y.y), __floats2bfloat162_rn(y.z, y.w)};
+        reinterpret_cast<uint2*>(out_bf16)[base4 + e] = *reinterpret_cast<const uint2*>(o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm over channels, scale only (+ residual): unet.py:243,258,264.  One warp per pixel.
 // ---------------------------------------------------------------------------------------------------------
@@ -995,6 +1089,30 @@ int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_
     gn_apply_kernel<false><<<(unsigned)(B * groups), 256, 0, as_stream(s)>>>(x, P, C, groups, gamma, beta, time_scale_shift, residual, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), eps);
   }
   return check_launch("gn_apply_kernel");
+}
+
+int fbs_nn_groupnorm_swish_stats(fbs_stream_t s, const float* x_f32, const void* x_bf16, const float* partials, int32_t slots,
+                                 int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma, const float* beta,
+                                 const float* time_scale_shift, const float* residual, float eps, float* out_f32, void* out_bf16) {
+  FBS_REQUIRE(((x_f32 != nullptr) != (x_bf16 != nullptr)) && partials && gamma && beta && (out_f32 || out_bf16),
+              "groupnorm_stats: null argument (exactly one of x_f32 / x_bf16)");
+  FBS_REQUIRE(groups > 0 && groups <= 32 && C % groups == 0 && (C / groups) % 4 == 0 && slots > 0,
+              "groupnorm_stats: channels per group must be a multiple of 4, at most 32 groups");
+  FBS_REQUIRE(256 % (C / 4) == 0, "groupnorm_stats: C / 4 must divide 256");
+  // about five CTAs per SM's worth of (sample, pixel chunk) items, at least 16 pixels each
+  int64_t pch = (5 * (int64_t)sm_count() + B - 1) / B;
+  if (pch > P / 16) pch = P / 16;
+  if (pch < 1) pch = 1;
+  const auto bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  const auto pt = reinterpret_cast<const float2*>(partials);
+  if (x_bf16)
+    gn_stats_apply_kernel<true><<<(unsigned)(B * pch), 256, 0, as_stream(s)>>>(nullptr, reinterpret_cast<const __nv_bfloat16*>(x_bf16), pt,
+                                                                              slots, P, C, groups, (int)pch, gamma, beta, time_scale_shift,
+                                                                              residual, out_f32, bf, eps);
+  else
+    gn_stats_apply_kernel<false><<<(unsigned)(B * pch), 256, 0, as_stream(s)>>>(x_f32, nullptr, pt, slots, P, C, groups, (int)pch, gamma,
+                                                                               beta, time_scale_shift, residual, out_f32, bf, eps);
+  return check_launch("gn_stats_apply_kernel");
 }
 
 int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, const float* gamma, const float* residual,

@@ -406,7 +406,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_gather_rows, GatherRowsImpl, FBS_BIND_STRE
 // flax.linen.Conv call sites of unet.py as implicit GEMMs on tcgen05 -> (out_f32, out_bf16); either result may be empty
 static ffi::Error NnConvImpl(cudaStream_t stream, BufH in0, BufH in1, BufH weight, BufF bias, BufF residual, int32_t kh, int32_t kw,
                              int32_t off_h, int32_t off_w, int32_t pixel_shuffle, int32_t H, int32_t W, int32_t Cout, ResF out_f32,
-                             ResH out_bf16) {
+                             ResH out_bf16, ResF gn_partials) {
   auto d = in0.dimensions();  // [B, Hin, Win, C0]
   fbs_nn_conv_t a{};
   a.B = (int32_t)d[0]; a.H = H; a.W = W; a.Hin = (int32_t)d[1]; a.Win = (int32_t)d[2];
@@ -414,12 +414,26 @@ static ffi::Error NnConvImpl(cudaStream_t stream, BufH in0, BufH in1, BufH weigh
   a.kh = kh; a.kw = kw; a.off_h = off_h; a.off_w = off_w; a.pixel_shuffle = pixel_shuffle;
   a.in0 = in0.untyped_data(); a.in1 = opt_raw(in1); a.weight = weight.untyped_data();
   a.bias = opt(bias); a.residual = opt(residual); a.out_f32 = opt(*out_f32); a.out_bf16 = opt_raw(*out_bf16);
+  a.gn_partials = opt(*gn_partials);  // [B, slots, Cout / 4, 2] (slots: fbs_nn_conv_gn_layout, evaluated at trace time) or empty
   return as_error(fbs_nn_conv_bf16(stream, &a));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_nn_conv, NnConvImpl,
                               FBS_BIND_STREAM().Arg<BufH>().Arg<BufH>().Arg<BufH>().Arg<BufF>().Arg<BufF>().Attr<int32_t>("kh")
                                   .Attr<int32_t>("kw").Attr<int32_t>("off_h").Attr<int32_t>("off_w").Attr<int32_t>("pixel_shuffle")
-                                  .Attr<int32_t>("H").Attr<int32_t>("W").Attr<int32_t>("Cout").Ret<BufF>().Ret<BufH>());
+                                  .Attr<int32_t>("H").Attr<int32_t>("W").Attr<int32_t>("Cout").Ret<BufF>().Ret<BufH>().Ret<BufF>());
+
+// GroupNorm + swish with the statistics of the producing convolution (x: fp32 or bf16, the other one empty)
+static ffi::Error NnGroupNormStatsImpl(cudaStream_t stream, BufF x_f32, BufH x_bf16, BufF partials, BufF gamma, BufF beta,
+                                       BufF time_scale_shift, BufF residual, int32_t groups, float eps, ResF out_f32, ResH out_bf16) {
+  auto d = x_f32.element_count() ? x_f32.dimensions() : x_bf16.dimensions();  // [B, P, C]
+  return as_error(fbs_nn_groupnorm_swish_stats(stream, opt(x_f32), opt_raw(x_bf16), partials.typed_data(),
+                                               (int32_t)partials.dimensions()[1], d[0], (int32_t)d[1], (int32_t)d[2], groups,
+                                               gamma.typed_data(), beta.typed_data(), opt(time_scale_shift), opt(residual), eps,
+                                               opt(*out_f32), opt_raw(*out_bf16)));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_nn_groupnorm_swish_stats, NnGroupNormStatsImpl,
+                              FBS_BIND_STREAM().Arg<BufF>().Arg<BufH>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>()
+                                  .Attr<int32_t>("groups").Attr<float>("eps").Ret<BufF>().Ret<BufH>());
 
 static ffi::Error NnGroupNormImpl(cudaStream_t stream, BufF x, BufF gamma, BufF beta, BufF time_scale_shift, BufF residual,
                                   int32_t groups, float eps, ResF out_f32, ResH out_bf16) {

@@ -9,9 +9,8 @@ from .._tensor import ptr, stream
 BF16, F32 = torch.bfloat16, torch.float32
 
 
-def conv(in0, weight, Cout, kh, kw, off, H, W, in1=None, bias=None, residual=None, out_f32=None, out_bf16=None,
-         pixel_shuffle=False):
-    """in0 / in1: bf16 [B, Hin, Win, C]; weight: bf16 [Cout, kh * kw * (C0 + C1)]; H, W: output pixels."""
+def _conv_args(in0, weight, Cout, kh, kw, off, H, W, in1=None, bias=None, residual=None, out_f32=None, out_bf16=None,
+               pixel_shuffle=False, gn_partials=None):
     a = nat.NNConvStruct()
     B, Hin, Win, C0 = in0.shape
     a.B, a.H, a.W, a.Hin, a.Win = B, H, W, Hin, Win
@@ -20,7 +19,32 @@ def conv(in0, weight, Cout, kh, kw, off, H, W, in1=None, bias=None, residual=Non
     a.pixel_shuffle, a.reserved = int(pixel_shuffle), 0
     a.in0, a.in1, a.weight = ptr(in0), ptr(in1), ptr(weight)
     a.bias, a.residual, a.out_f32, a.out_bf16 = ptr(bias), ptr(residual), ptr(out_f32), ptr(out_bf16)
+    a.gn_partials = ptr(gn_partials)
+    return a
+
+
+def conv(in0, weight, Cout, kh, kw, off, H, W, **kw_args):
+    """in0 / in1: bf16 [B, Hin, Win, C]; weight: bf16 [Cout, kh * kw * (C0 + C1)]; H, W: output pixels.
+    ``gn_partials`` (fp32 [B, slots, Cout / 4, 2], slots from :func:`conv_gn_slots`): GroupNorm statistics of the output."""
+    a = _conv_args(in0, weight, Cout, kh, kw, off, H, W, **kw_args)
     nat.call('fbs_nn_conv_bf16', stream(), C.byref(a))
+
+
+def conv_gn_slots(in0, weight, Cout, kh, kw, off, H, W, **kw_args):
+    """Slots per sample of the ``gn_partials`` this convolution call would write (0: it cannot)."""
+    a = _conv_args(in0, weight, Cout, kh, kw, off, H, W, **kw_args)
+    n = C.c_int32(0)
+    nat.call('fbs_nn_conv_gn_layout', C.byref(a), C.byref(n))
+    return int(n.value)
+
+
+def groupnorm_swish_stats(x, partials, gamma, beta, groups=8, tss=None, residual=None, out_f32=None, out_bf16=None, eps=1e-6):
+    """GroupNorm + swish of ``x`` (fp32 or bf16 [B, ..., C]) with the statistics from the producing convolution's partials."""
+    B, Cc = x.shape[0], x.shape[-1]
+    P = x.numel() // (B * Cc)
+    x32, x16 = (ptr(x), None) if x.dtype == F32 else (None, ptr(x))
+    nat.call('fbs_nn_groupnorm_swish_stats', stream(), x32, x16, ptr(partials), partials.shape[1], B, P, Cc, groups, ptr(gamma),
+             ptr(beta), ptr(tss), ptr(residual), float(eps), ptr(out_f32), ptr(out_bf16))
 
 
 def groupnorm_swish(x, gamma, beta, groups=8, tss=None, residual=None, out_f32=None, out_bf16=None, eps=1e-6):

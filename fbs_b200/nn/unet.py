@@ -136,6 +136,8 @@ class ScoreUNet:
         self._w = {}
         self._bufs = {}
         self._graphs = {}
+        self._gn_slots = {}
+        self.gn_input_bf16 = False    # GroupNorm inputs (convolution outputs) kept in fp32
         self._time_blocks = []       # resnet block name -> offset into the time table
         self._prepare(params)
         self.tval = torch.zeros((1,), dtype=F32, device=self.device)
@@ -205,22 +207,40 @@ class ScoreUNet:
         w = self._w
         in0, in1 = srcs[0], (srcs[1] if len(srcs) > 1 else None)
         cin = sum(s.shape[-1] for s in srcs)
-        t_f32 = self._buf(B, f'tmp_f32_{H}x{d}', (B, H, W, d), F32)
         t_bf = self._buf(B, f'tmp_bf16_{H}x{d}', (B, H, W, d), BF16)
-        ops.conv(in0, w[name + '.conv_0.w'], d, 3, 3, -1, H, W, in1=in1, bias=w[name + '.conv_0.bias'], out_f32=t_f32)
         o, dd = self._toff[name]
-        ops.groupnorm_swish(t_f32, w[name + '.norm_0.scale'], w[name + '.norm_0.bias'], self.groups, tss=self.table[o:o + 2 * dd],
-                            out_bf16=t_bf)
-        ops.conv(t_bf, w[name + '.conv_1.w'], d, 3, 3, -1, H, W, bias=w[name + '.conv_1.bias'], out_f32=t_f32)
+        # conv -> GroupNorm pairs: the convolution's epilogue hands the GroupNorm its statistics (sum / sum of squares per row
+        # tile and channel quad), so the normalisation is one streaming pass; where the tiling cannot (several samples per tile:
+        # the 7x7 level) the stand-alone GroupNorm kernel computes them itself
+        t_in = self._buf(B, f'tmp_gnin_{H}x{d}', (B, H, W, d), BF16 if self.gn_input_bf16 else F32)
+        tkw = {'out_bf16': t_in} if self.gn_input_bf16 else {'out_f32': t_in}
+
+        def conv_gn(src0, src1, wname, bname, gamma, beta, tss, residual, o32, o16):
+            args = (src0, w[wname], d, 3, 3, -1, H, W)
+            key = (B, wname)
+            slots = self._gn_slots.get(key)
+            if slots is None:
+                slots = self._gn_slots[key] = ops.conv_gn_slots(*args, in1=src1, bias=w[bname], **tkw)
+            if slots and 256 % (d // 4) == 0:
+                part = self._buf(B, f'gn_part_{H}x{d}', (B, slots, d // 4, 2), F32)
+                ops.conv(*args, in1=src1, bias=w[bname], gn_partials=part, **tkw)
+                ops.groupnorm_swish_stats(t_in, part, gamma, beta, self.groups, tss=tss, residual=residual, out_f32=o32, out_bf16=o16)
+            else:
+                t_f32 = self._buf(B, f'tmp_f32_{H}x{d}', (B, H, W, d), F32)
+                ops.conv(*args, in1=src1, bias=w[bname], out_f32=t_f32)
+                ops.groupnorm_swish(t_f32, gamma, beta, self.groups, tss=tss, residual=residual, out_f32=o32, out_bf16=o16)
+
         if cin != d:
             res = self._buf(B, f'res_f32_{H}x{d}', (B, H, W, d), F32)
             ops.conv(in0, w[name + '.res_conv_0.w'], d, 1, 1, 0, H, W, in1=in1, bias=w[name + '.res_conv_0.bias'], out_f32=res)
         else:
             res = x_f32
+        conv_gn(in0, in1, name + '.conv_0.w', name + '.conv_0.bias', w[name + '.norm_0.scale'], w[name + '.norm_0.bias'],
+                self.table[o:o + 2 * dd], None, None, t_bf)
         out_f32 = self._buf(B, tag + '_f32', (B, H, W, d), F32)
         out_bf = self._buf(B, tag + '_bf16', (B, H, W, d), BF16)
-        ops.groupnorm_swish(t_f32, w[name + '.norm_1.scale'], w[name + '.norm_1.bias'], self.groups, residual=res, out_f32=out_f32,
-                            out_bf16=out_bf)
+        conv_gn(t_bf, None, name + '.conv_1.w', name + '.conv_1.bias', w[name + '.norm_1.scale'], w[name + '.norm_1.bias'],
+                None, res, out_f32, out_bf)
         return out_f32, out_bf
 
     def _attnblock(self, B, name, x_f32, H, W, C, tag, linear=True):

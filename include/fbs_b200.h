@@ -309,14 +309,25 @@ typedef struct {
   const float* residual; /* fp32, same layout as the output, or NULL */
   float* out_f32;        /* either output may be NULL */
   void* out_bf16;
+  float* gn_partials;    /* NULL, or [B][slots][Cout / 4][2]: sums and sums of squares of the output per (sample, slot, channel
+                          * quad) for the GroupNorm that follows (fbs_nn_groupnorm_swish_stats); slots: fbs_nn_conv_gn_layout */
 } fbs_nn_conv_t;
 int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* args);
+/* Slots per sample of `gn_partials` for this call's tiling, or 0 when the call cannot produce them (tiles that hold several
+ * samples, a residual, pixel shuffle).  Host-side only, no launch. */
+int fbs_nn_conv_gn_layout(const fbs_nn_conv_t* args, int32_t* slots_per_sample);
 
 /* swish(GroupNorm(x) * gamma + beta [* (1 + scale) + shift]) [+ residual]   (unet.py:144-155,159-160,172).
  * x fp32 [B, P, C]; time_scale_shift: [2 C] = (scale | shift) shared by the batch, or NULL. */
 int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma,
                                const float* beta, const float* time_scale_shift, const float* residual, float eps,
                                float* out_f32, void* out_bf16);
+/* The same with the statistics taken from the producing convolution's `gn_partials` (flax forms var = E[x^2] - E[x]^2 from
+ * the two means, flax.linen.normalization._compute_stats with use_fast_variance): one streaming pass, no reduction over the
+ * activations.  x: fp32 [B, P, C] (x_f32) or bf16 (x_bf16); exactly one of the two is non-NULL. */
+int fbs_nn_groupnorm_swish_stats(fbs_stream_t s, const float* x_f32, const void* x_bf16, const float* partials, int32_t slots,
+                                 int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma, const float* beta,
+                                 const float* time_scale_shift, const float* residual, float eps, float* out_f32, void* out_bf16);
 /* LayerNorm over channels, scale only (unet.py:243,258) [+ residual (unet.py:264)].  x fp32 [rows, C]. */
 int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, const float* gamma, const float* residual,
                          float eps, float* out_f32, void* out_bf16);

@@ -64,6 +64,49 @@ def test_conv_matches_torch(B, H, W, C0, C1, Cout, k):
     np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize('B,H,W,C0,C1,Cout', [(3, 28, 28, 64, 0, 64), (5, 14, 14, 128, 64, 128), (2, 32, 32, 64, 0, 128),
+                                              (150, 14, 14, 64, 0, 64), (2, 16, 16, 128, 0, 256)])
+def test_conv_hands_groupnorm_its_statistics(B, H, W, C0, C1, Cout):
+    """conv -> GroupNorm pair: the statistics come from the convolution's epilogue (`gn_partials`), the normalisation is one
+    streaming pass (fp32 or bf16 activations); against the oracle GroupNorm of the fp32 convolution output."""
+    from fbs_b200.nn import ops
+    g = torch.Generator().manual_seed(7)
+    x0 = _bf(torch.randn(B, H, W, C0, generator=g))
+    x1 = _bf(torch.randn(B, H, W, C1, generator=g)) if C1 else None
+    w = _bf(torch.randn(3, 3, C0 + C1, Cout, generator=g) / math.sqrt(9 * (C0 + C1)))
+    bias = torch.randn(Cout, generator=g)
+    gamma, beta = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    tss = torch.randn(2 * Cout, generator=g) * 0.3
+    res = torch.randn(B, H, W, Cout, generator=g)
+    wp = w.float().reshape(9 * (C0 + C1), Cout).t().contiguous().to(torch.bfloat16).cuda()
+    kw = dict(in1=None if x1 is None else x1.cuda(), bias=bias.cuda())
+    args = (x0.cuda(), wp, Cout, 3, 3, -1, H, W)
+    t32 = torch.empty(B, H, W, Cout, device='cuda')
+    t16 = torch.empty(B, H, W, Cout, device='cuda', dtype=torch.bfloat16)
+    slots = ops.conv_gn_slots(*args, out_f32=t32, **kw)
+    assert slots > 0
+    part = torch.full((B, slots, Cout // 4, 2), float('nan'), device='cuda')     # every entry must be written
+    ops.conv(*args, out_f32=t32, out_bf16=t16, gn_partials=part, **kw)
+    torch.cuda.synchronize()
+    y = t32.cpu()
+    np.testing.assert_allclose(part[..., 0].sum(dim=(1, 2)).cpu().numpy(), y.sum(dim=(1, 2, 3)).numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(part[..., 1].sum(dim=(1, 2)).cpu().numpy(), (y * y).sum(dim=(1, 2, 3)).numpy(), rtol=1e-4)
+    Pm = ou._P({'n.scale': gamma.numpy(), 'n.bias': beta.numpy()})
+    want = ou._swish(ou._group_norm(Pm, 'n', y) * (1 + tss[:Cout]) + tss[Cout:]) + res
+    out = torch.empty_like(t32)
+    out16 = torch.empty_like(t16)
+    ops.groupnorm_swish_stats(t32, part, gamma.cuda(), beta.cuda(), 8, tss=tss.cuda(), residual=res.cuda(), out_f32=out, out_bf16=out16)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-2)
+    ops.groupnorm_swish_stats(t16, part, gamma.cuda(), beta.cuda(), 8, tss=tss.cuda(), residual=res.cuda(), out_f32=out)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-2, atol=4e-2)   # bf16 activations
+    # tilings that pack several samples into a tile, residuals and pixel shuffle cannot: the query says so, the call refuses
+    assert ops.conv_gn_slots(_bf(torch.randn(4, 7, 7, 256)).cuda(), _bf(torch.randn(256, 9 * 256)).cuda(), 256, 3, 3, -1, 7, 7,
+                             out_f32=torch.empty(4, 7, 7, 256, device='cuda')) == 0
+    with pytest.raises(ValueError):
+        ops.conv(*args, out_f32=t32, residual=res.cuda(), gn_partials=part, **kw)
+
+
 def test_conv_pixel_shuffle_and_stride2():
     from fbs_b200.nn import ops
     from fbs_b200.nn.unet import _pack, _pack_stride2

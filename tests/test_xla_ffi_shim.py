@@ -20,7 +20,7 @@ CUDA_INC = '/usr/local/cuda/include'
 # every entry point a jitted reference driver needs -> must be wrapped (host-side IPC plumbing, debug hooks and the
 # bookkeeping calls are not XLA custom calls)
 NOT_WRAPPED = {'fbs_version', 'fbs_last_error', 'fbs_launch_count', 'fbs_reset_launch_count', 'fbs_debug_set_option',
-               'fbs_debug_umma_gemm', 'fbs_debug_step_tc_timers', 'fbs_debug_v3_timeline', 'fbs_debug_conv_timeline', 'fbs_sweep_workspace_bytes', 'fbs_ipc_export', 'fbs_ipc_import',
+               'fbs_debug_umma_gemm', 'fbs_debug_step_tc_timers', 'fbs_debug_v3_timeline', 'fbs_debug_conv_timeline', 'fbs_nn_conv_gn_layout', 'fbs_sweep_workspace_bytes', 'fbs_ipc_export', 'fbs_ipc_import',
                'fbs_ipc_release', 'fbs_gather_rows_peer_f32', 'fbs_nn_f32_to_bf16'}
 
 
