@@ -131,7 +131,7 @@ _ENV_OPTS = {
     'FBS_V3_TWOPASS': ('v3_twopass', None),
     'FBS_EM_IMPL': ('em_impl', {'cta': 1, 'tpc': 2}),
     'FBS_V3_VARIANT': ('v3_variant', None),
-    'FBS_CONV_IMPL': ('conv_impl', {'taps': 1, 'halo_bo': 2}),
+    'FBS_CONV_IMPL': ('conv_impl', {'taps': 1}),
 }
 _env_seen = {}
 
