@@ -121,6 +121,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -300,7 +311,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
   constexpr int NT = NE > NX ? NE : NX, NE1 = NE / 2, NE2 = NE > 0 ? NE - 1 : 0;
   const Layout L = make_layout(p.N, p.du, p.dv, stages_flags);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (warp index through a shuffle: provably warp-uniform, so that the role branches are uniform control flow and the MMA / TMA
+  // warps' descriptors and addresses stay in uniform registers)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   unsigned char* ring = smem + L.ring;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + MAX_STAGES;
@@ -326,7 +339,8 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const bool leader = elect_one();  // the one lane of the MMA / TMA warps that issues the asynchronous instructions
   // phase time stamps (profiling hook, scripts/v3_timeline.py): CTA 0, first chain pair, steps [DBG_K0, DBG_K0 + DBG_NS),
   // lane 0 of one warp per role; layout dbg[role][step][stamp]
   constexpr int DBG_K0 = 64, DBG_NS = 4, DBG_MAXS = 16;
@@ -350,7 +364,8 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
   if (warp == NWARPS - 1) {
     // =============================== TMA producer warp ===============================
     // streams the K-blocks of the step matrices, in the order the MMA warp consumes them, through the ring
-    if (lane == 0) {
+    // all lanes run the loop (uniform registers for the addresses); the copies are issued by one elected lane
+    {
       uint32_t ps = 0, pph = 1;  // slot, parity of its "empty" barrier (1: passes on a fresh barrier)
       fence_proxy_async();
       for (uint32_t t = 0; t < G0; ++t) {
@@ -367,10 +382,12 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             for (int kb = 0; kb < L.nkb; ++kb, src += L.img_bytes) {
               if (stages_flags & 0x200) mbar_wait_hint(empty + ps, pph); else mbar_wait(empty + ps, pph);
               unsigned char* dst = ring + (size_t)ps * L.stage_bytes;
-              mbar_expect_tx(full + ps, 4u * run);
+              if (leader) {
+                mbar_expect_tx(full + ps, 4u * run);
 #pragma unroll
-              for (uint32_t c = 0; c < 4; ++c)  // (hi, chunk 0) (hi, chunk 1) (lo, chunk 0) (lo, chunk 1)
-                bulk_g2s(dst + c * run, src + (size_t)c * L.b_lbo, run, full + ps);
+                for (uint32_t c = 0; c < 4; ++c)  // (hi, chunk 0) (hi, chunk 1) (lo, chunk 0) (lo, chunk 1)
+                  bulk_g2s(dst + c * run, src + (size_t)c * L.b_lbo, run, full + ps);
+              }
               if (++ps == (uint32_t)stages) {
                 ps = 0;
                 pph ^= 1u;
@@ -383,7 +400,9 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
     __syncwarp();
   } else if (warp == 0) {
     // =============================== MMA warp ===============================
-    if (lane == 0) {
+    // all lanes run the loop, one elected lane issues: inside an `if (lane == 0)` region every descriptor was moved from a
+    // vector to a uniform register in front of each tcgen05.mma (measured on conv_gemm_kernel: ~75 cycles per MMA issued)
+    {
       uint32_t cs = 0, cph = 0;  // slot, parity of its "full" barrier
       const uint32_t ring16 = smem_u32(ring) >> 4, stage16 = L.stage_bytes >> 4;
       const uint64_t desc_hi_A = ((uint64_t)((L.a_lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
@@ -413,10 +432,12 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
               tc_fence_after();
               const uint64_t dBh = desc_hi_B | (uint64_t)((ring16 + cs * stage16) & 0x3FFFu);
               const uint64_t dBl = dBh + b_lo_off;
-              umma_tf32(dt, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
-              umma_tf32(dt, dAl, dBh, idesc, 1u);
-              umma_tf32(dt, dAh, dBl, idesc, 1u);
-              umma_commit(empty + cs);  // slot free once these MMAs have read it
+              if (leader) {
+                umma_tf32(dt, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
+                umma_tf32(dt, dAl, dBh, idesc, 1u);
+                umma_tf32(dt, dAh, dBl, idesc, 1u);
+                umma_commit(empty + cs);  // slot free once these MMAs have read it
+              }
               dAh += a_inc;
               dAl += a_inc;
               if (++cs == (uint32_t)stages) {
@@ -424,7 +445,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
                 cph ^= 1u;
               }
             }
-            umma_commit((pass == 0 ? accum : accum_u) + g);  // accumulator columns of this pass complete
+            if (leader) umma_commit((pass == 0 ? accum : accum_u) + g);  // accumulator columns of this pass complete
           }
           if (dbg_mma) p.dbg[(6 * DBG_NS + dbg_k) * DBG_MAXS + 2 * g + 1] = clock64();
         }
