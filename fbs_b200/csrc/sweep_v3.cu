@@ -301,7 +301,7 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
 }
 
 // NE / NX: noise tasks per thread of the E (epilogue + noise) and X (noise only) warps (the two epilogues cost an E warp
-// about two tasks: <6, 8> at d = 100, N = 100).
+// about two tasks: <7, 6> at d = 100, N = 100).
 template <int NE, int NX, bool DBG>
 __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages_flags) {
   const int stages = stages_flags & 0xFF;
@@ -1239,13 +1239,14 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   p.dbg = g_v3_dbg;
   cudaError_t e;
-  // v3_variant bit 1: the <7, 6> task split (A/B; measured 1 % SLOWER than <6, 8>: the E warps, which also run both
-  // epilogues, become the critical path and the X warps idle 15 k cycles before the barrier)
-  const bool alt_split = (debug_opt(OPT_V3_VARIANT) & 2) != 0;
+  // noise tasks per E / X warp: <7, 6> (capacity 128 * 7 + 64 * 6 = 1280 tasks, as <6, 8>).  Measured at the benchmarked shape
+  // after the MMA-issue fix (ms per Gibbs sweep): <7, 6> 52.8, <7, 7> 53.1, <6, 8> 56.3, <5, 10> 62.4, <8, 4> 63.8 -- before it
+  // <6, 8> was 1 % ahead.  v3_variant bit 1 selects <6, 8> (A/B).
+  const bool old_split = (debug_opt(OPT_V3_VARIANT) & 2) != 0;
   if (ntasks <= 128 * 2 + 64 * 4) e = launch_v3_nt<2, 4, false>(st, grid, L.total, p, stages | flags);
-  else if (p.dbg != nullptr) e = launch_v3_nt<6, 8, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
-  else if (alt_split && ntasks <= 128 * 7 + 64 * 6) e = launch_v3_nt<7, 6, false>(st, grid, L.total, p, stages | flags);
-  else e = launch_v3_nt<6, 8, false>(st, grid, L.total, p, stages | flags);
+  else if (p.dbg != nullptr) e = launch_v3_nt<7, 6, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
+  else if (old_split) e = launch_v3_nt<6, 8, false>(st, grid, L.total, p, stages | flags);
+  else e = launch_v3_nt<7, 6, false>(st, grid, L.total, p, stages | flags);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
