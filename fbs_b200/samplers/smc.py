@@ -95,14 +95,14 @@ def pcn_proposal(key, delta: float, x, mean, sampler):
 
 
 PIPELINE_MIN_CHAINS = 512     # host-buffer calls with at least this many chains are chunked over CUDA streams
-PIPELINE_CHUNKS = int(__import__('os').environ.get('FBS_PIPELINE_CHUNKS', '8'))
+PIPELINE_CHUNKS = int(__import__('os').environ.get('FBS_PIPELINE_CHUNKS', '4'))   # measured: 8 -> 59.8, 4 -> 56.6, 2 -> 57.3 ms per host-buffer Gibbs sweep (4144 chains)
 _streams = []
 
 
 def _chunk_bounds(B: int):
     """Chunks of chains for the host-buffer pipeline.  The sweep kernels run two chains per CTA on every SM, so a chunk
     that is not a multiple of 2 x (number of SMs) chains ends in a partly empty wave; chunk sizes are rounded up to whole waves
-    (4144 chains on 148 SMs: 7 chunks of 592 instead of 8 chunks of 518 = 1.75 waves each)."""
+    (4144 chains on 148 SMs: chunks of 1184 = four waves, the last one 592)."""
     wave = 2 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     nchunks = max(1, min(PIPELINE_CHUNKS, B // (PIPELINE_MIN_CHAINS // 2)))
     size = -(-B // nchunks)
