@@ -74,7 +74,7 @@ SIGNATURES = {
     'fbs_gaussian_ref_sample_f32': ([_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p], _int),
     'fbs_nn_conv_bf16': ([_p, _CV], _int),
     'fbs_nn_conv_gn_layout': ([_CV, _p], _int),
-    'fbs_nn_groupnorm_swish_stats': ([_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p], _int),
+    'fbs_nn_groupnorm_swish_stats': ([_p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p, _p, _f32, _p], _int),
     'fbs_nn_groupnorm_swish_f32': ([_p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _f32, _p, _p], _int),
     'fbs_nn_layernorm_f32': ([_p, _p, _i64, _i32, _p, _p, _f32, _p, _p], _int),
     'fbs_nn_linear_attention_bf16': ([_p, _p, _i64, _i32, _i32, _i32, _p], _int),

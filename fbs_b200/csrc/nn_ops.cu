@@ -202,13 +202,18 @@ __global__ void __launch_bounds__(NT) gn_sample_kernel(const float* __restrict__
 // [B][slots][C / 4] float2 = sum, sum of squares per (sample, slot, channel quad)): one streaming pass over the activations,
 // CTA = (sample, pixel chunk), a thread keeps one channel quad (blockDim % (C / 4) == 0).  var = E[x^2] - E[x]^2 is flax's
 // own formula (flax.linen.normalization._compute_stats, use_fast_variance = True).
-template <bool IN16>
+// LN: the attention block that follows normalises the block output once more over the channels (LayerNorm, scale only,
+// unet.py:258); a pixel's C / 4 channel quads sit in C / 4 <= 32 adjacent lanes, so that second normalisation is two shuffle
+// reductions on values already in registers and one more bf16 store -- it saves a launch and a pass over the fp32 tensor.
+template <bool IN16, bool LN>
 __global__ void __launch_bounds__(256) gn_stats_apply_kernel(const float* __restrict__ x32, const __nv_bfloat16* __restrict__ x16,
                                                              const float2* __restrict__ partials, int slots, int P, int C, int groups,
                                                              int pchunks, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ tss,
                                                              const float* __restrict__ residual, float* __restrict__ out_f32,
-                                                             __nv_bfloat16* __restrict__ out_bf16, float eps) {
+                                                             __nv_bfloat16* __restrict__ out_bf16, float eps,
+                                                             const float* __restrict__ ln_gamma, float ln_eps,
+                                                             __nv_bfloat16* __restrict__ ln_out) {
   __shared__ float s_mean[32], s_rstd[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / pchunks, pc = blockIdx.x % pchunks;
@@ -257,7 +262,10 @@ __global__ void __launch_bounds__(256) gn_stats_apply_kernel(const float* __rest
   const int per = ((P + pchunks - 1) / pchunks) * q4;  // whole pixels per chunk
   const int e_begin = pc * per, e_end = min(n4, e_begin + per);
   const size_t base4 = (size_t)b * n4;
-  for (int e0 = e_begin + tid; e0 < e_end; e0 += 4 * 256) {
+  float4 lg = zero4;
+  if (LN) lg = __ldg(reinterpret_cast<const float4*>(ln_gamma) + quad);
+  for (int eb = e_begin; eb < e_end; eb += 4 * 256) {  // (the same trip count for every thread: the LN shuffles are warp-wide)
+    const int e0 = eb + tid;
     float4 v[4], r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -277,16 +285,38 @@ __global__ void __launch_bounds__(256) gn_stats_apply_kernel(const float* __rest
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int e = e0 + u * 256;
-      if (e >= e_end) continue;
+      const bool ok = e < e_end;
+      if (!LN && !ok) continue;
       float4 y;
       y.x = swishf(fmaf(v[u].x, A[0], Bc[0])) + r[u].x;
       y.y = swishf(fmaf(v[u].y, A[1], Bc[1])) + r[u].y;
       y.z = swishf(fmaf(v[u].z, A[2], Bc[2])) + r[u].z;
       y.w = swishf(fmaf(v[u].w, A[3], Bc[3])) + r[u].w;
-      if (out_f32) reinterpret_cast<float4*>(out_f32)[base4 + e] = y;
-      if (out_bf16) {
-        __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y.x, y.y), __floats2bfloat162_rn(y.z, y.w)};
-        reinterpret_cast<uint2*>(out_bf16)[base4 + e] = *reinterpret_cast<const uint2*>(o);
+      if (ok) {
+        if (out_f32) reinterpret_cast<float4*>(out_f32)[base4 + e] = y;
+        if (out_bf16) {
+          __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(y.x, y.y), __floats2bfloat162_rn(y.z, y.w)};
+          reinterpret_cast<uint2*>(out_bf16)[base4 + e] = *reinterpret_cast<const uint2*>(o);
+        }
+      }
+      if (LN) {
+        // the q4 lanes of this pixel: mean, then the variance about it (the stand-alone LayerNorm's two passes)
+        float sm = (y.x + y.y) + (y.z + y.w);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+          if (o < q4) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        const float mu = sm / (float)C;
+        const float a = y.x - mu, bq = y.y - mu, c = y.z - mu, d = y.w - mu;
+        float sq = (a * a + bq * bq) + (c * c + d * d);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+          if (o < q4) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rs = rsqrtf(sq / (float)C + ln_eps);
+        if (ok) {
+          __align__(8) __nv_bfloat162 o[2] = {__floats2bfloat162_rn(a * rs * lg.x, bq * rs * lg.y),
+                                              __floats2bfloat162_rn(c * rs * lg.z, d * rs * lg.w)};
+          reinterpret_cast<uint2*>(ln_out)[base4 + e] = *reinterpret_cast<const uint2*>(o);
+        }
       }
     }
   }
@@ -1093,25 +1123,33 @@ int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_
 
 int fbs_nn_groupnorm_swish_stats(fbs_stream_t s, const float* x_f32, const void* x_bf16, const float* partials, int32_t slots,
                                  int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma, const float* beta,
-                                 const float* time_scale_shift, const float* residual, float eps, float* out_f32, void* out_bf16) {
+                                 const float* time_scale_shift, const float* residual, float eps, float* out_f32, void* out_bf16,
+                                 const float* ln_gamma, float ln_eps, void* ln_out_bf16) {
   FBS_REQUIRE(((x_f32 != nullptr) != (x_bf16 != nullptr)) && partials && gamma && beta && (out_f32 || out_bf16),
               "groupnorm_stats: null argument (exactly one of x_f32 / x_bf16)");
   FBS_REQUIRE(groups > 0 && groups <= 32 && C % groups == 0 && (C / groups) % 4 == 0 && slots > 0,
               "groupnorm_stats: channels per group must be a multiple of 4, at most 32 groups");
   FBS_REQUIRE(256 % (C / 4) == 0, "groupnorm_stats: C / 4 must divide 256");
+  FBS_REQUIRE((ln_gamma != nullptr) == (ln_out_bf16 != nullptr), "groupnorm_stats: ln_gamma and ln_out_bf16 go together");
+  FBS_REQUIRE(ln_gamma == nullptr || C <= 128, "groupnorm_stats: the fused LayerNorm needs C <= 128 (a pixel inside one warp)");
   // about five CTAs per SM's worth of (sample, pixel chunk) items, at least 16 pixels each
   int64_t pch = (5 * (int64_t)sm_count() + B - 1) / B;
   if (pch > P / 16) pch = P / 16;
   if (pch < 1) pch = 1;
   const auto bf = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  const auto lnb = reinterpret_cast<__nv_bfloat16*>(ln_out_bf16);
+  const auto x16 = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
   const auto pt = reinterpret_cast<const float2*>(partials);
-  if (x_bf16)
-    gn_stats_apply_kernel<true><<<(unsigned)(B * pch), 256, 0, as_stream(s)>>>(nullptr, reinterpret_cast<const __nv_bfloat16*>(x_bf16), pt,
-                                                                              slots, P, C, groups, (int)pch, gamma, beta, time_scale_shift,
-                                                                              residual, out_f32, bf, eps);
-  else
-    gn_stats_apply_kernel<false><<<(unsigned)(B * pch), 256, 0, as_stream(s)>>>(x_f32, nullptr, pt, slots, P, C, groups, (int)pch, gamma,
-                                                                               beta, time_scale_shift, residual, out_f32, bf, eps);
+#define FBS_GNS_LAUNCH(IN16, LN)                                                                                                \
+  gn_stats_apply_kernel<IN16, LN><<<(unsigned)(B * pch), 256, 0, as_stream(s)>>>(x_f32, x16, pt, slots, P, C, groups, (int)pch, gamma, \
+                                                                                 beta, time_scale_shift, residual, out_f32, bf, eps,  \
+                                                                                 ln_gamma, ln_eps, lnb)
+  if (x_bf16) {
+    if (ln_gamma) FBS_GNS_LAUNCH(true, true); else FBS_GNS_LAUNCH(true, false);
+  } else {
+    if (ln_gamma) FBS_GNS_LAUNCH(false, true); else FBS_GNS_LAUNCH(false, false);
+  }
+#undef FBS_GNS_LAUNCH
   return check_launch("gn_stats_apply_kernel");
 }
 

@@ -424,16 +424,18 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_nn_conv, NnConvImpl,
 
 // GroupNorm + swish with the statistics of the producing convolution (x: fp32 or bf16, the other one empty)
 static ffi::Error NnGroupNormStatsImpl(cudaStream_t stream, BufF x_f32, BufH x_bf16, BufF partials, BufF gamma, BufF beta,
-                                       BufF time_scale_shift, BufF residual, int32_t groups, float eps, ResF out_f32, ResH out_bf16) {
+                                       BufF time_scale_shift, BufF residual, BufF ln_gamma, int32_t groups, float eps, float ln_eps,
+                                       ResF out_f32, ResH out_bf16, ResH ln_out_bf16) {
   auto d = x_f32.element_count() ? x_f32.dimensions() : x_bf16.dimensions();  // [B, P, C]
   return as_error(fbs_nn_groupnorm_swish_stats(stream, opt(x_f32), opt_raw(x_bf16), partials.typed_data(),
                                                (int32_t)partials.dimensions()[1], d[0], (int32_t)d[1], (int32_t)d[2], groups,
                                                gamma.typed_data(), beta.typed_data(), opt(time_scale_shift), opt(residual), eps,
-                                               opt(*out_f32), opt_raw(*out_bf16)));
+                                               opt(*out_f32), opt_raw(*out_bf16), opt(ln_gamma), ln_eps, opt_raw(*ln_out_bf16)));
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fbs_xla_nn_groupnorm_swish_stats, NnGroupNormStatsImpl,
                               FBS_BIND_STREAM().Arg<BufF>().Arg<BufH>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>().Arg<BufF>()
-                                  .Attr<int32_t>("groups").Attr<float>("eps").Ret<BufF>().Ret<BufH>());
+                                  .Arg<BufF>().Attr<int32_t>("groups").Attr<float>("eps").Attr<float>("ln_eps").Ret<BufF>()
+                                  .Ret<BufH>().Ret<BufH>());
 
 static ffi::Error NnGroupNormImpl(cudaStream_t stream, BufF x, BufF gamma, BufF beta, BufF time_scale_shift, BufF residual,
                                   int32_t groups, float eps, ResF out_f32, ResH out_bf16) {

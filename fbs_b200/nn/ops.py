@@ -38,13 +38,16 @@ def conv_gn_slots(in0, weight, Cout, kh, kw, off, H, W, **kw_args):
     return int(n.value)
 
 
-def groupnorm_swish_stats(x, partials, gamma, beta, groups=8, tss=None, residual=None, out_f32=None, out_bf16=None, eps=1e-6):
-    """GroupNorm + swish of ``x`` (fp32 or bf16 [B, ..., C]) with the statistics from the producing convolution's partials."""
+def groupnorm_swish_stats(x, partials, gamma, beta, groups=8, tss=None, residual=None, out_f32=None, out_bf16=None, eps=1e-6,
+                          ln_gamma=None, ln_out_bf16=None, ln_eps=1e-5):
+    """GroupNorm + swish of ``x`` (fp32 or bf16 [B, ..., C]) with the statistics from the producing convolution's partials;
+    ``ln_gamma`` / ``ln_out_bf16``: also ``LayerNorm(result) * ln_gamma`` (C <= 128)."""
     B, Cc = x.shape[0], x.shape[-1]
     P = x.numel() // (B * Cc)
     x32, x16 = (ptr(x), None) if x.dtype == F32 else (None, ptr(x))
     nat.call('fbs_nn_groupnorm_swish_stats', stream(), x32, x16, ptr(partials), partials.shape[1], B, P, Cc, groups, ptr(gamma),
-             ptr(beta), ptr(tss), ptr(residual), float(eps), ptr(out_f32), ptr(out_bf16))
+             ptr(beta), ptr(tss), ptr(residual), float(eps), ptr(out_f32), ptr(out_bf16), ptr(ln_gamma), float(ln_eps),
+             ptr(ln_out_bf16))
 
 
 def groupnorm_swish(x, gamma, beta, groups=8, tss=None, residual=None, out_f32=None, out_bf16=None, eps=1e-6):

@@ -202,8 +202,10 @@ class ScoreUNet:
         return t
 
     # ------------------------------------------------------------------ blocks
-    def _resblock(self, B, name, srcs, x_f32, H, W, d, tag):
-        """ResnetBlock (unet.py:127-172).  srcs: bf16 tensors whose channel concatenation is the block input."""
+    def _resblock(self, B, name, srcs, x_f32, H, W, d, tag, ln=None):
+        """ResnetBlock (unet.py:127-172).  srcs: bf16 tensors whose channel concatenation is the block input.
+        ``ln = (gamma, out_bf16)``: the attention block that follows wants ``LayerNorm(output) * gamma`` (unet.py:258); where the
+        one-pass GroupNorm runs (and C <= 128) it writes that too and the method returns ``(out_f32, out_bf16, True)``."""
         w = self._w
         in0, in1 = srcs[0], (srcs[1] if len(srcs) > 1 else None)
         cin = sum(s.shape[-1] for s in srcs)
@@ -215,7 +217,7 @@ class ScoreUNet:
         t_in = self._buf(B, f'tmp_gnin_{H}x{d}', (B, H, W, d), BF16 if self.gn_input_bf16 else F32)
         tkw = {'out_bf16': t_in} if self.gn_input_bf16 else {'out_f32': t_in}
 
-        def conv_gn(src0, src1, wname, bname, gamma, beta, tss, residual, o32, o16):
+        def conv_gn(src0, src1, wname, bname, gamma, beta, tss, residual, o32, o16, ln=None):
             args = (src0, w[wname], d, 3, 3, -1, H, W)
             key = (B, wname)
             slots = self._gn_slots.get(key)
@@ -224,11 +226,15 @@ class ScoreUNet:
             if slots and 256 % (d // 4) == 0:
                 part = self._buf(B, f'gn_part_{H}x{d}', (B, slots, d // 4, 2), F32)
                 ops.conv(*args, in1=src1, bias=w[bname], gn_partials=part, **tkw)
-                ops.groupnorm_swish_stats(t_in, part, gamma, beta, self.groups, tss=tss, residual=residual, out_f32=o32, out_bf16=o16)
+                fuse_ln = ln is not None and d <= 128
+                ops.groupnorm_swish_stats(t_in, part, gamma, beta, self.groups, tss=tss, residual=residual, out_f32=o32, out_bf16=o16,
+                                          ln_gamma=ln[0] if fuse_ln else None, ln_out_bf16=ln[1] if fuse_ln else None)
+                return fuse_ln
             else:
                 t_f32 = self._buf(B, f'tmp_f32_{H}x{d}', (B, H, W, d), F32)
                 ops.conv(*args, in1=src1, bias=w[bname], out_f32=t_f32)
                 ops.groupnorm_swish(t_f32, gamma, beta, self.groups, tss=tss, residual=residual, out_f32=o32, out_bf16=o16)
+                return False
 
         if cin != d:
             res = self._buf(B, f'res_f32_{H}x{d}', (B, H, W, d), F32)
@@ -239,11 +245,15 @@ class ScoreUNet:
                 self.table[o:o + 2 * dd], None, None, t_bf)
         out_f32 = self._buf(B, tag + '_f32', (B, H, W, d), F32)
         out_bf = self._buf(B, tag + '_bf16', (B, H, W, d), BF16)
-        conv_gn(t_bf, None, name + '.conv_1.w', name + '.conv_1.bias', w[name + '.norm_1.scale'], w[name + '.norm_1.bias'],
-                None, res, out_f32, out_bf)
-        return out_f32, out_bf
+        ln_done = conv_gn(t_bf, None, name + '.conv_1.w', name + '.conv_1.bias', w[name + '.norm_1.scale'], w[name + '.norm_1.bias'],
+                          None, res, out_f32, out_bf, ln=ln)
+        return (out_f32, out_bf, ln_done) if ln is not None else (out_f32, out_bf)
 
-    def _attnblock(self, B, name, x_f32, H, W, C, tag, linear=True):
+    def _attn_ln(self, B, name, H, W, C):
+        """(scale, output buffer) of the LayerNorm in front of attention block ``name`` -- the buffer `_attnblock` reads."""
+        return self._w[name + '.norm.scale'], self._buf(B, f'attn_norm_{H}x{C}', (B, H, W, C), BF16)
+
+    def _attnblock(self, B, name, x_f32, H, W, C, tag, linear=True, normed=False):
         """AttnBlock (unet.py:248-264) around LinearAttention (:209-245) or Attention (:175-206)."""
         w = self._w
         hd = self.heads * self.dim_head
@@ -252,7 +262,8 @@ class ScoreUNet:
         ao = self._buf(B, f'attn_out_{H}', (B, H, W, hd), BF16)
         out_f32 = self._buf(B, tag + '_f32', (B, H, W, C), F32)
         out_bf = self._buf(B, tag + '_bf16', (B, H, W, C), BF16)
-        ops.layernorm(x_f32, w[name + '.norm.scale'], out_bf16=n_bf)
+        if not normed:   # (else the preceding ResnetBlock's GroupNorm kernel has written attn_norm already)
+            ops.layernorm(x_f32, w[name + '.norm.scale'], out_bf16=n_bf)
         ops.conv(n_bf, w[name + '.attn.to_qkv.conv_0.w'], 3 * hd, 1, 1, 0, H, W, out_bf16=qkv)
         if linear:
             ops.linear_attention(qkv, ao, self.heads, self.dim_head)
@@ -287,8 +298,9 @@ class ScoreUNet:
         for ind in range(nres):
             h_f32, h_bf = self._resblock(B, f'down_{ind}.resblock_0', [h_bf], h_f32, H, W, c, f'd{ind}r0')
             skips.append(h_bf)
-            h_f32, h_bf = self._resblock(B, f'down_{ind}.resblock_1', [h_bf], h_f32, H, W, c, f'd{ind}r1')
-            h_f32, h_bf = self._attnblock(B, f'down_{ind}.attnblock_0', h_f32, H, W, c, f'd{ind}a')
+            h_f32, h_bf, nd = self._resblock(B, f'down_{ind}.resblock_1', [h_bf], h_f32, H, W, c, f'd{ind}r1',
+                                             ln=self._attn_ln(B, f'down_{ind}.attnblock_0', H, W, c))
+            h_f32, h_bf = self._attnblock(B, f'down_{ind}.attnblock_0', h_f32, H, W, c, f'd{ind}a', normed=nd)
             skips.append(h_bf)
             if ind < nres - 1:
                 cout = dim * self.dim_mults[ind]
@@ -312,8 +324,9 @@ class ScoreUNet:
             dim_in = dim * self.dim_mults[ind]
             dim_out = dim * self.dim_mults[ind - 1] if ind > 0 else dim
             h_f32, h_bf = self._resblock(B, f'up_{ind}.resblock_0', [h_bf, skips.pop()], None, H, W, dim_in, f'u{ind}r0')
-            h_f32, h_bf = self._resblock(B, f'up_{ind}.resblock_1', [h_bf, skips.pop()], None, H, W, dim_in, f'u{ind}r1')
-            h_f32, h_bf = self._attnblock(B, f'up_{ind}.attnblock_0', h_f32, H, W, dim_in, f'u{ind}a')
+            h_f32, h_bf, nd = self._resblock(B, f'up_{ind}.resblock_1', [h_bf, skips.pop()], None, H, W, dim_in, f'u{ind}r1',
+                                             ln=self._attn_ln(B, f'up_{ind}.attnblock_0', H, W, dim_in))
+            h_f32, h_bf = self._attnblock(B, f'up_{ind}.attnblock_0', h_f32, H, W, dim_in, f'u{ind}a', normed=nd)
             if ind > 0:
                 ps = self._buf(B, f'u{ind}ps_bf16', (B, 2 * H, 2 * W, dim_in), BF16)
                 ops.conv(h_bf, w[f'up_{ind}.upsample_0.conv_0.w'], 4 * dim_in, 3, 3, -1, H, W,

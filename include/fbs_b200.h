@@ -324,10 +324,13 @@ int fbs_nn_groupnorm_swish_f32(fbs_stream_t s, const float* x, int64_t B, int32_
                                float* out_f32, void* out_bf16);
 /* The same with the statistics taken from the producing convolution's `gn_partials` (flax forms var = E[x^2] - E[x]^2 from
  * the two means, flax.linen.normalization._compute_stats with use_fast_variance): one streaming pass, no reduction over the
- * activations.  x: fp32 [B, P, C] (x_f32) or bf16 (x_bf16); exactly one of the two is non-NULL. */
+ * activations.  x: fp32 [B, P, C] (x_f32) or bf16 (x_bf16); exactly one of the two is non-NULL.
+ * ln_gamma / ln_out_bf16 (both or neither; C <= 128): also LayerNorm(result) * ln_gamma as bf16 -- the pre-normalisation of the
+ * attention block that follows a ResnetBlock (unet.py:258), from the values already in registers. */
 int fbs_nn_groupnorm_swish_stats(fbs_stream_t s, const float* x_f32, const void* x_bf16, const float* partials, int32_t slots,
                                  int64_t B, int32_t P, int32_t C, int32_t groups, const float* gamma, const float* beta,
-                                 const float* time_scale_shift, const float* residual, float eps, float* out_f32, void* out_bf16);
+                                 const float* time_scale_shift, const float* residual, float eps, float* out_f32, void* out_bf16,
+                                 const float* ln_gamma, float ln_eps, void* ln_out_bf16);
 /* LayerNorm over channels, scale only (unet.py:243,258) [+ residual (unet.py:264)].  x fp32 [rows, C]. */
 int fbs_nn_layernorm_f32(fbs_stream_t s, const float* x, int64_t rows, int32_t C, const float* gamma, const float* residual,
                          float eps, float* out_f32, void* out_bf16);

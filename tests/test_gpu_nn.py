@@ -100,6 +100,14 @@ def test_conv_hands_groupnorm_its_statistics(B, H, W, C0, C1, Cout):
     np.testing.assert_allclose(out16.float().cpu().numpy(), want.numpy(), rtol=1e-2, atol=2e-2)
     ops.groupnorm_swish_stats(t16, part, gamma.cuda(), beta.cuda(), 8, tss=tss.cuda(), residual=res.cuda(), out_f32=out)
     np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-2, atol=4e-2)   # bf16 activations
+    if Cout <= 128:   # ... and the LayerNorm of the attention block that follows, from the same registers
+        lg = torch.randn(Cout, generator=g)
+        ln16 = torch.empty_like(t16)
+        ops.groupnorm_swish_stats(t32, part, gamma.cuda(), beta.cuda(), 8, tss=tss.cuda(), residual=res.cuda(), out_f32=out,
+                                  ln_gamma=lg.cuda(), ln_out_bf16=ln16)
+        np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+        want_ln = ou._layer_norm(ou._P({'n.scale': lg.numpy()}), 'n', want)
+        np.testing.assert_allclose(ln16.float().cpu().numpy(), want_ln.numpy(), rtol=1e-2, atol=2e-2)
     # tilings that pack several samples into a tile, residuals and pixel shuffle cannot: the query says so, the call refuses
     assert ops.conv_gn_slots(_bf(torch.randn(4, 7, 7, 256)).cuda(), _bf(torch.randn(256, 9 * 256)).cuda(), 256, 3, 3, -1, 7, 7,
                              out_f32=torch.empty(4, 7, 7, 256, device='cuda')) == 0
