@@ -225,16 +225,18 @@ __global__ void __launch_bounds__(64) em_affine_path_tpc_kernel(
 // The same integrator with a chain split over T = 2 or 4 adjacent lanes (lane t owns coordinates [t DO, (t + 1) DO),
 // DO = D / T <= 8): T times as many warps for the same number of chains -- what the serial sub-step chain needs to
 // hide its latencies when there are only tens of thousands of chains.  The matvec exchanges the state by warp shuffles.
-template <int T>
+// DOC: the coordinates per lane D / T as a compile-time constant (0: run time, loops padded to 8) -- with it the 8-wide
+// predicated loops of the matvec (64 FMA slots per exchanged lane for 25 products at D = 20, T = 4) shrink to the products.
+template <int T, int DOC>
 __global__ void __launch_bounds__(128) em_affine_path_split_kernel(
     const uint32_t* __restrict__ keys, const float* __restrict__ x0, int x0_batched, const float* __restrict__ AT,
     const float* __restrict__ a, const float* __restrict__ ddt, const float* __restrict__ disp, int64_t B, int K, int m,
     int D, int du, int rev, float* __restrict__ out_u, float* __restrict__ out_v) {
-  constexpr int DOT = 8;
+  constexpr int DOT = DOC ? DOC : 8;
   extern __shared__ __align__(16) float sm[];
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31;
   const int cpc = nt / T, cl = tid / T, t = tid % T, lbase = lane & ~(T - 1);
-  const int DO = D / T;
+  const int DO = DOC ? DOC : D / T;
   const uint32_t n = (uint32_t)m * D, h = (n + 1u) >> 1;
   const int per_k = m * D * D, per_ka = m * D, per_buf = (per_k + per_ka + 3) & ~3;
   float* mat = sm;                   // [2][per_buf]
@@ -602,17 +604,17 @@ int fbs_em_affine_path_f32(fbs_stream_t s, const uint32_t* keys, const float* x0
       const size_t smem_sp = (2 * per_buf + (size_t)((m * D + 1) / 2) * (cpc + 1)) * sizeof(float);
       if (smem_sp <= 100 * 1024) {
         const int grid_sp = (int)((B + cpc - 1) / cpc);
-        if (T == 4) {
-          if (smem_sp > 48 * 1024)
-            cudaFuncSetAttribute(em_affine_path_split_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
-          em_affine_path_split_kernel<4><<<grid_sp, 128, smem_sp, as_stream(s)>>>(keys, x0, x0_batched, AT, a, ddt, disp, B, (int)K,
-                                                                                (int)m, (int)D, (int)du, rev, out_u, out_v);
-        } else {
-          if (smem_sp > 48 * 1024)
-            cudaFuncSetAttribute(em_affine_path_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);
-          em_affine_path_split_kernel<2><<<grid_sp, 128, smem_sp, as_stream(s)>>>(keys, x0, x0_batched, AT, a, ddt, disp, B, (int)K,
-                                                                                (int)m, (int)D, (int)du, rev, out_u, out_v);
-        }
+#define FBS_EM_SPLIT(TT, DD)                                                                                                   \
+  do {                                                                                                                        \
+    if (smem_sp > 48 * 1024)                                                                                                  \
+      cudaFuncSetAttribute(em_affine_path_split_kernel<TT, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp);   \
+    em_affine_path_split_kernel<TT, DD><<<grid_sp, 128, smem_sp, as_stream(s)>>>(keys, x0, x0_batched, AT, a, ddt, disp, B, (int)K, \
+                                                                                 (int)m, (int)D, (int)du, rev, out_u, out_v); \
+  } while (0)
+        if (T == 4 && D == 20) FBS_EM_SPLIT(4, 5);        // the Gaussian Schroedinger bridge (sb/gibbs.py: d = 10, state 2 d)
+        else if (T == 4) FBS_EM_SPLIT(4, 0);
+        else FBS_EM_SPLIT(2, 0);
+#undef FBS_EM_SPLIT
         return check_launch("em_affine_path_split_kernel");
       }
     }
