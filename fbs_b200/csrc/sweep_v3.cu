@@ -301,14 +301,17 @@ __device__ __forceinline__ float warp_normalise_v3(float* lw, int n, int lane) {
 }
 
 // NE / NX: noise tasks per thread of the E (epilogue + noise) and X (noise only) warps (the two epilogues cost an E warp
-// about two tasks: <7, 6> at d = 100, N = 100).
-template <int NE, int NX, bool DBG>
+// about two tasks: <6, 7, 2> at d = 100, N = 100).
+template <int NE, int NX, int NR, bool DBG>
 __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepParams p, const int stages_flags) {
   const int stages = stages_flags & 0xFF;
   extern __shared__ __align__(1024) unsigned char smem[];
   // an E warp generates NE1 of its tasks in the shadow of the first GEMM pass, up to NE2 in the shadow of the second
   // pass (while the resampling warp works), the rest after its u-epilogue
-  constexpr int NT = NE > NX ? NE : NX, NE1 = NE / 2, NE2 = NE > 0 ? NE - 1 : 0;
+  constexpr int NT0 = NE > NX ? NE : NX, NT = NT0 > NR ? NT0 : NR, NE1 = NE / 2, NE2 = NE > 0 ? NE - 1 : 0;
+  // NR > 0: the resampling warp generates NR tasks per lane too, in the window in which it otherwise waits for the weights,
+  // and takes part in the gather / operand stores with them
+  constexpr int TASK_THREADS = NR > 0 ? GTHREADS : NOISE_THREADS;
   const Layout L = make_layout(p.N, p.du, p.dv, stages_flags);
   const int du = p.du, dv = p.dv, N = p.N, K = p.K, half = N / 2;
   // (warp index through a shuffle: provably warp-uniform, so that the role branches are uniform control flow and the MMA / TMA
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
 
     // named barriers of this group
     auto bar_all = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GTHREADS) : "memory"); };
-    auto bar_noise = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "n"(NOISE_THREADS) : "memory"); };
+    auto bar_noise = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(3 + g), "n"(TASK_THREADS) : "memory"); };
     auto bar_E = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(5 + g), "n"(128) : "memory"); };
     auto bar_ER_arrive = [&]() { asm volatile("bar.arrive %0, %1;" ::"r"(7 + g), "n"(160) : "memory"); };
     auto bar_ER_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(7 + g), "n"(160) : "memory"); };
@@ -505,6 +508,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
       int t = ntasks;
       if (is_E && i < NE) t = gt + 128 * i;
       if (gw > 4 && i < NX) t = 128 * NE + xt + 64 * i;
+      if (is_R && i < NR) t = 128 * NE + 64 * NX + lane + 32 * i;
       task[i] = t < ntasks ? ((uint32_t)(t % half) | ((uint32_t)(t / half) << 16)) : 0xFFFFFFFFu;
     }
     float nz[2][4 * NT];  // noise, then the children, of the owned (rows, columns)
@@ -818,6 +822,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
             if (lane == 0) ub[2 * ROWS] = bits_to_unit(x0);
             __syncwarp();
           }
+          if (NR > 0) make_noise(skeys[2 * (k & 1) + 1], __ldg(p.sd + k), I_0{}, std::integral_constant<int, NR>{});
           FBS_STAMP(1);
           bar_ER_sync();
           FBS_STAMP(2);
@@ -1054,7 +1059,7 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
         bar_all();  // ancestors, means and noise complete
         FBS_STAMP(8);
 
-        if (is_noise) {
+        if (is_noise || NR > 0) {
           // ---- children: gather the parents' means, add the noise (in the noise registers) ----
 #pragma unroll
           for (int i = 0; i < NT; ++i) {
@@ -1088,12 +1093,14 @@ __global__ void __launch_bounds__(v3::NTHREADS, 1) sweep_v3_kernel(const SweepPa
           FBS_STAMP(11);
           bar_noise();
           FBS_STAMP(12);
-          if (nt == 0 && (k + 1 < K)) mbar_arrive(ready + g);
+          if (is_noise && nt == 0 && (k + 1 < K)) mbar_arrive(ready + g);
           // optional history
-          if (p.mode == MODE_CSMC) {
-            if (p.uss) store_particles(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du, nt, NOISE_THREADS);
-          } else {
-            if (p.us_hist) store_particles(p.us_hist + ((size_t)chain * K + k) * N * du, nt, NOISE_THREADS);
+          if (is_noise) {
+            if (p.mode == MODE_CSMC) {
+              if (p.uss) store_particles(p.uss + ((size_t)chain * (K + 1) + k + 1) * N * du, nt, NOISE_THREADS);
+            } else {
+              if (p.us_hist) store_particles(p.us_hist + ((size_t)chain * K + k) * N * du, nt, NOISE_THREADS);
+            }
           }
         }
       }
@@ -1208,11 +1215,11 @@ int launch_umma_selftest(void* stream, const float* A, const float* Bimg, int K8
 static long long* g_v3_dbg = nullptr;
 
 // Host: eligibility + launch.  p.MTc is the tensor-core image of the step matrices; p.ws the step-vector workspace.
-template <int NE, int NX, bool DBG>
+template <int NE, int NX, int NR, bool DBG>
 static cudaError_t launch_v3_nt(cudaStream_t st, int grid, size_t smem, const SweepParams& p, int stages) {
-  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NE, NX, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(sweep_v3_kernel<NE, NX, NR, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  sweep_v3_kernel<NE, NX, DBG><<<grid, NTHREADS, smem, st>>>(p, stages);
+  sweep_v3_kernel<NE, NX, NR, DBG><<<grid, NTHREADS, smem, st>>>(p, stages);
   return cudaSuccess;
 }
 
@@ -1239,14 +1246,16 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   p.dbg = g_v3_dbg;
   cudaError_t e;
-  // noise tasks per E / X warp: <7, 6> (capacity 128 * 7 + 64 * 6 = 1280 tasks, as <6, 8>).  Measured at the benchmarked shape
-  // after the MMA-issue fix (ms per Gibbs sweep): <7, 6> 52.8, <7, 7> 53.1, <6, 8> 56.3, <5, 10> 62.4, <8, 4> 63.8 -- before it
-  // <6, 8> was 1 % ahead.  v3_variant bit 1 selects <6, 8> (A/B).
-  const bool old_split = (debug_opt(OPT_V3_VARIANT) & 2) != 0;
-  if (ntasks <= 128 * 2 + 64 * 4) e = launch_v3_nt<2, 4, false>(st, grid, L.total, p, stages | flags);
-  else if (p.dbg != nullptr) e = launch_v3_nt<7, 6, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
-  else if (old_split) e = launch_v3_nt<6, 8, false>(st, grid, L.total, p, stages | flags);
-  else e = launch_v3_nt<7, 6, false>(st, grid, L.total, p, stages | flags);
+  // noise tasks per lane of the E / X / resampling warps: <6, 7, 2> (capacity 128 * 6 + 64 * 7 + 32 * 2 = 1280 tasks).  The
+  // resampling warp generates its two tasks while it would otherwise wait for the weights, which takes one task off every E
+  // thread -- the E warps (noise + both epilogues) are the step's critical path.  Measured at the benchmarked shape after the
+  // MMA-issue fix (ms per Gibbs sweep): <6, 7, 2> 50.8, <7, 6, 0> 52.8, <7, 7, 0> 53.1, <6, 8, 0> 56.3 (eight tasks per thread
+  // push the noise registers into local memory), <5, 10, 0> 62.4, <8, 4, 0> 63.8.  v3_variant bit 1 selects <7, 6, 0> (A/B).
+  const bool no_r_noise = (debug_opt(OPT_V3_VARIANT) & 2) != 0;
+  if (ntasks <= 128 * 2 + 64 * 4) e = launch_v3_nt<2, 4, 0, false>(st, grid, L.total, p, stages | flags);
+  else if (p.dbg != nullptr) e = launch_v3_nt<6, 7, 2, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
+  else if (no_r_noise) e = launch_v3_nt<7, 6, 0, false>(st, grid, L.total, p, stages | flags);
+  else e = launch_v3_nt<6, 7, 2, false>(st, grid, L.total, p, stages | flags);
   if (e != cudaSuccess) {
     set_error("sweep_v3: cudaFuncSetAttribute(%u B) failed: %s", L.total, cudaGetErrorString(e));
     return FBS_ERR_CUDA;
