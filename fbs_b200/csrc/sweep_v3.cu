@@ -1251,7 +1251,8 @@ int launch_sweep_v3(void* stream, SweepParams& p) {
   // thread -- the E warps (noise + both epilogues) are the step's critical path.  Measured at the benchmarked shape after the
   // MMA-issue fix (ms per Gibbs sweep): <6, 7, 2> 50.8, <7, 6, 0> 52.8, <7, 7, 0> 53.1, <6, 8, 0> 56.3 (eight tasks per thread
   // push the noise registers into local memory), <5, 10, 0> 62.4, <8, 4, 0> 63.8.  v3_variant bit 1 selects <7, 6, 0> (A/B).
-  const bool no_r_noise = (debug_opt(OPT_V3_VARIANT) & 2) != 0;
+  // (the pMCMC sweep -- stratified resampling, a shorter resampling phase -- measured 25.0 ms with <7, 6, 0>, 25.6 ms with <6, 7, 2>)
+  const bool no_r_noise = (debug_opt(OPT_V3_VARIANT) & 2) != 0 || p.mode != MODE_CSMC;
   if (ntasks <= 128 * 2 + 64 * 4) e = launch_v3_nt<2, 4, 0, false>(st, grid, L.total, p, stages | flags);
   else if (p.dbg != nullptr) e = launch_v3_nt<6, 7, 2, true>(st, grid, L.total, p, stages | flags);  // time-stamped build (profiling hook)
   else if (no_r_noise) e = launch_v3_nt<7, 6, 0, false>(st, grid, L.total, p, stages | flags);
