@@ -49,3 +49,37 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(_native.NativeError):
         _native.lib()
+
+
+def test_conv_gn_layout_is_host_logic(lib_path):
+    """fbs_nn_conv_gn_layout (no launch): slots per sample of the GroupNorm partials a convolution call would write -- four lane
+    quadrants per row tile where a tile holds one sample, 0 where the tiling packs samples, with a residual or pixel shuffle; the
+    answer must not depend on the batch size (the summation order of a network evaluation must not)."""
+    import ctypes as C
+    from fbs_b200 import _native as nat
+    handle = nat.lib()
+
+    def slots(B, H, W, C0, Cout, k=3, **over):
+        a = nat.NNConvStruct()
+        a.B, a.H, a.W, a.Hin, a.Win = B, H, W, H, W
+        a.C0, a.C1, a.Cout = C0, 0, Cout
+        a.kh = a.kw = k
+        a.off_h = a.off_w = -(k // 2)
+        a.in0 = a.weight = a.out_f32 = 4096          # never dereferenced by the layout query
+        for key, val in over.items():
+            setattr(a, key, val)
+        n = C.c_int32(-1)
+        rc = handle.fbs_nn_conv_gn_layout(C.byref(a), C.byref(n))
+        assert rc == 0, handle.fbs_last_error()
+        return n.value
+
+    assert slots(101, 28, 28, 64, 64) == 4 * 7          # haloed tiles of four image rows
+    assert slots(101, 14, 14, 128, 128) == 4 * 2
+    assert slots(101, 28, 28, 64, 64, k=1) == 4 * 7     # per-tap tiling, four rows of 28 per tile
+    assert slots(101, 7, 7, 256, 256) == 0              # two samples per tile
+    assert slots(1, 7, 7, 256, 256) == 0                # ... whatever the batch
+    assert slots(101, 28, 28, 64, 64, residual=4096) == 0
+    assert slots(101, 14, 14, 128, 512, pixel_shuffle=1) == 0
+    assert slots(1, 28, 28, 64, 64) == slots(808, 28, 28, 64, 64)
+    a = nat.NNConvStruct()
+    assert handle.fbs_nn_conv_gn_layout(C.byref(a), None) != 0   # null argument: an error code, not a crash
