@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -290,9 +297,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.halo) {
       if (leader) mbar_expect_tx(wbar, p.wres_bytes);
       const uint32_t wtile = (uint32_t)p.ntile * 128u;
-      for (int tap = 0; tap < 9; ++tap)
-        for (int cb = 0; cb < cblocks; ++cb)
-          if (leader) tma_load_2d(wres + (size_t)(tap * cblocks + cb) * wtile, &tmB, wbar, tap * ctot + cb * KBLK, nt * p.ntile);
+      // the weight map is 3-D here, (channel, output channel, tap): ONE copy per 64-channel chunk delivers all nine taps as
+      // [tap][N tile][64 channels] (nine 2-D copies cost ~180 cycles of issue each at the head of every launch)
+      for (int cb = 0; cb < cblocks; ++cb)
+        if (leader) tma_load_3d(wres + (size_t)cb * 9u * wtile, &tmB, wbar, cb * KBLK, nt * p.ntile, 0);
       CONV_STAMP(2);
       for (int mt = mt_first; mt < p.m_tiles; mt += mt_step) {
         const int n0 = mt / p.h_tiles, h0 = (mt % p.h_tiles) * p.BH;
@@ -372,7 +380,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (cb == 0) CONV_STAMP(8 + 8 * it + 2);
           // descriptors differ from a base one only in the 14-bit start-address field (no carry: shared memory < 256 KB)
           const uint64_t da0 = make_desc_sw128(ring_u + s * stage_bytes);
-          const uint64_t db0 = make_desc_sw128(wres_u) + (uint64_t)((uint32_t)cb * wtile16);
+          const uint64_t db0 = make_desc_sw128(wres_u) + (uint64_t)((uint32_t)cb * 9u * wtile16);  // resident weights: [chunk][tap]
           uint32_t acc_flag = cb ? 1u : 0u;
 #pragma unroll
           for (int ty = 0; ty < 3; ++ty) {
@@ -380,7 +388,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int tx = 0; tx < 3; ++tx) {
               // tap (ty, tx) = the haloed image read (ty * pitch + tx) rows further on: + 8 descriptor units per row
               const uint64_t da = da0 + (uint64_t)((uint32_t)(ty * p.BW + tx) * 8u);
-              const uint64_t db = db0 + (uint64_t)((uint32_t)((ty * 3 + tx) * cblocks) * wtile16);
+              const uint64_t db = db0 + (uint64_t)((uint32_t)(ty * 3 + tx) * wtile16);
 #pragma unroll
               for (int k = 0; k < KBLK / 16; ++k) {
                 if (leader) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, acc_flag);
@@ -539,6 +547,17 @@ static int make_act_map(CUtensorMap* tm, const void* base, int B, int H, int W, 
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+// halo mode: the weight matrix [Cout][9 taps x ctot] seen as (channel, output channel, tap); box = 64 channels x N tile x 9 taps
+static int make_w_map3(CUtensorMap* tm, const void* base, int ctot, int Cout, int ntile) {
+  const cuuint64_t dims[3] = {(cuuint64_t)ctot, (cuuint64_t)Cout, 9};
+  const cuuint64_t strides[2] = {(cuuint64_t)9 * ctot * 2, (cuuint64_t)ctot * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)KBLK, (cuuint32_t)ntile, 9};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
@@ -709,7 +728,7 @@ extern "C" int fbs_nn_conv_bf16(fbs_stream_t s, const fbs_nn_conv_t* a) {
   const int boxH = p.halo ? p.BH + 2 : p.BH;
   int rc = make_act_map(&tmA0, a->in0, a->B, Hin, Win, a->C0, p.BW, boxH, p.BNb);
   if (!rc) rc = make_act_map(&tmA1, a->C1 ? a->in1 : a->in0, a->B, Hin, Win, a->C1 ? a->C1 : a->C0, p.BW, boxH, p.BNb);
-  if (!rc) rc = make_w_map(&tmB, a->weight, a->kh * a->kw * ctot, a->Cout, ntile);
+  if (!rc) rc = p.halo ? make_w_map3(&tmB, a->weight, ctot, a->Cout, ntile) : make_w_map(&tmB, a->weight, a->kh * a->kw * ctot, a->Cout, ntile);
   if (rc) {
     set_error("nn_conv: cuTensorMapEncodeTiled failed with CUresult %d", rc);
     return FBS_ERR_CUDA;
