@@ -833,14 +833,15 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 
 // Same convolution, thread = (4 horizontally adjacent pixels, 16 output channels): a tap's 16 weights (four 16-byte shared
 // loads) serve 64 FMAs instead of 16 -- the kernel above is bound by its shared-memory loads.  W % 4 == 0.
-__global__ void __launch_bounds__(256, 2) stem_conv4_kernel(const float* __restrict__ x, int B, int H, int W, int Cin, int Cout,
+template <int CPT>  // output channels per thread: 16, or 8 (twice the threads, half the accumulators: three CTAs per SM)
+__global__ void __launch_bounds__(256, CPT == 8 ? 3 : 2) stem_conv4_kernel(const float* __restrict__ x, int B, int H, int W, int Cin, int Cout,
                                                          const float* __restrict__ wgt, const float* __restrict__ bias,
                                                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
   extern __shared__ float ws[];
   const int nw = 49 * Cin * Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wgt[i];
   __syncthreads();
-  const int cgs = Cout / 16, wqs = W / 4;
+  const int cgs = Cout / CPT, wqs = W / 4;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * H * wqs * cgs) return;
   const int cg = (int)(idx % cgs);
@@ -849,10 +850,10 @@ __global__ void __launch_bounds__(256, 2) stem_conv4_kernel(const float* __restr
   t /= wqs;
   const int h = (int)(t % H);
   const int64_t b = t / H;
-  float acc[4][16];
+  float acc[4][CPT];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float bj = bias[16 * cg + j];
+  for (int j = 0; j < CPT; ++j) {
+    const float bj = bias[CPT * cg + j];
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q][j] = bj;
   }
@@ -868,9 +869,9 @@ __global__ void __launch_bounds__(256, 2) stem_conv4_kernel(const float* __restr
       }
 #pragma unroll
       for (int tx = 0; tx < 7; ++tx) {
-        const float* wp = ws + ((ty * 7 + tx) * Cin + c) * Cout + 16 * cg;
+        const float* wp = ws + ((ty * 7 + tx) * Cin + c) * Cout + CPT * cg;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
+        for (int j = 0; j < CPT; j += 4) {
           const float4 wv = *reinterpret_cast<const float4*>(wp + j);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -885,15 +886,15 @@ __global__ void __launch_bounds__(256, 2) stem_conv4_kernel(const float* __restr
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const size_t off = (((size_t)b * H + h) * W + w0 + q) * Cout + 16 * cg;
+    const size_t off = (((size_t)b * H + h) * W + w0 + q) * Cout + CPT * cg;
     if (out_f32) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
+      for (int j = 0; j < CPT; j += 4)
         *reinterpret_cast<float4*>(out_f32 + off + j) = make_float4(acc[q][j], acc[q][j + 1], acc[q][j + 2], acc[q][j + 3]);
     }
     if (out_bf16) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 8) {
+      for (int j = 0; j < CPT; j += 8) {
         __align__(16) __nv_bfloat162 o[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) o[u] = __floats2bfloat162_rn(acc[q][j + 2 * u], acc[q][j + 2 * u + 1]);
@@ -1200,10 +1201,11 @@ int fbs_nn_stem_conv_f32(fbs_stream_t s, const float* x, int64_t B, int32_t H, i
   FBS_REQUIRE(Cout % 16 == 0 && (size_t)49 * Cin * Cout * 4 <= 96 * 1024, "stem_conv: weights must fit shared memory");
   const size_t smem = (size_t)49 * Cin * Cout * 4;
   if (W % 4 == 0) {
-    cudaFuncSetAttribute(stem_conv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t n4 = B * H * (W / 4) * (Cout / 16);
-    stem_conv4_kernel<<<(unsigned)((n4 + 255) / 256), 256, smem, as_stream(s)>>>(x, (int)B, H, W, Cin, Cout, weight, bias, out_f32,
-                                                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    // 8 channels per thread: the 16-channel variant needs 128 registers, and 101 x 28 x 28 then misses one resident wave by 4 %
+    cudaFuncSetAttribute(stem_conv4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t n4 = B * H * (W / 4) * (Cout / 8);
+    stem_conv4_kernel<8><<<(unsigned)((n4 + 255) / 256), 256, smem, as_stream(s)>>>(x, (int)B, H, W, Cin, Cout, weight, bias, out_f32,
+                                                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16));
     return check_launch("stem_conv4_kernel");
   }
   cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
