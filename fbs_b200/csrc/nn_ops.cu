@@ -668,26 +668,27 @@ __global__ void __launch_bounds__(256) linear_attention_kernel(const __nv_bfloat
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int P, int heads, float scale,
                                                         __nv_bfloat16* __restrict__ out) {
-  __shared__ float ks[128][33], vs[128][33];
+  __shared__ __align__(16) float ks[128][36], vs[128][36];  // rows of 32 (+ 4: 16-byte aligned, conflict-free broadcasts)
   __shared__ float qn[32], kn[32];
   __shared__ float part[4][32];
-  const int qblocks = (P + 127) / 128;
+  const int qblocks = (P + (int)blockDim.x - 1) / (int)blockDim.x;
   const int b = blockIdx.x / (heads * qblocks), rem = blockIdx.x % (heads * qblocks);
   const int hd = rem / qblocks, qb = rem % qblocks;
   const int HD = heads * 32, ld = 3 * HD;
   const __nv_bfloat16* q = qkv + (size_t)b * P * ld + hd * 32;
   const __nv_bfloat16* k = q + HD;
   const __nv_bfloat16* v = k + HD;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;  // 64 or 128 threads
   // column norms over the tokens
   {
     float sq = 0.f, sk = 0.f;
-    for (int n = w; n < P; n += 4) {
+    for (int n = w; n < P; n += nw) {
       const float a = __bfloat162float(q[(size_t)n * ld + lane]), c = __bfloat162float(k[(size_t)n * ld + lane]);
       sq = fmaf(a, a, sq);
       sk = fmaf(c, c, sk);
     }
     part[w][lane] = sq;
+    if (w + 2 < 4 && nw == 2) part[w + 2][lane] = 0.f;
     __syncthreads();
     if (w == 0) qn[lane] = 1.0f / fmaxf(sqrtf(part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]), 1e-12f);
     __syncthreads();
@@ -696,33 +697,68 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
     if (w == 0) kn[lane] = 1.0f / fmaxf(sqrtf(part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane]), 1e-12f);
     __syncthreads();
   }
-  const int i = qb * 128 + threadIdx.x;  // this thread's query
+  const int i = qb * nthr + threadIdx.x;  // this thread's query
   float qi[32], acc[32];
+  auto load8 = [&](const __nv_bfloat16* src, float (&f)[8]) {  // 16-byte load of 8 bf16
+    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-  for (int dd = 0; dd < 32; ++dd) {
-    qi[dd] = i < P ? __bfloat162float(q[(size_t)i * ld + dd]) * qn[dd] * scale : 0.f;
-    acc[dd] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h2[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
+    }
+  };
+#pragma unroll
+  for (int d8 = 0; d8 < 4; ++d8) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (i < P) load8(q + (size_t)i * ld + 8 * d8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      qi[8 * d8 + j] = f[j] * qn[8 * d8 + j] * scale;
+      acc[8 * d8 + j] = 0.f;
+    }
   }
   float mx = -INFINITY, den = 0.f;
   for (int j0 = 0; j0 < P; j0 += 128) {
+    const int jn = min(128, P - j0);
     __syncthreads();
-    for (int t = threadIdx.x; t < 128 * 32; t += 128) {
-      const int j = t >> 5, dd = t & 31;
-      const bool ok = j0 + j < P;
-      ks[j][dd] = ok ? __bfloat162float(k[(size_t)(j0 + j) * ld + dd]) * kn[dd] : 0.f;
-      vs[j][dd] = ok ? __bfloat162float(v[(size_t)(j0 + j) * ld + dd]) : 0.f;
+    for (int t = threadIdx.x; t < jn * 4; t += nthr) {  // only the rows that exist; 8 channels per thread and load
+      const int j = t >> 2, d8 = t & 3;
+      float fk[8], fv[8];
+      load8(k + (size_t)(j0 + j) * ld + 8 * d8, fk);
+      load8(v + (size_t)(j0 + j) * ld + 8 * d8, fv);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        ks[j][8 * d8 + c] = fk[c] * kn[8 * d8 + c];
+        vs[j][8 * d8 + c] = fv[c];
+      }
     }
     __syncthreads();
-    const int jn = min(128, P - j0);
     for (int j = 0; j < jn; ++j) {
-      float sdot = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four partial sums: the 32-deep dependent chain was the key loop's latency
 #pragma unroll
-      for (int dd = 0; dd < 32; ++dd) sdot = fmaf(qi[dd], ks[j][dd], sdot);
+      for (int dd = 0; dd < 32; dd += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(&ks[j][dd]);
+        s0 = fmaf(qi[dd], kk.x, s0);
+        s1 = fmaf(qi[dd + 1], kk.y, s1);
+        s2 = fmaf(qi[dd + 2], kk.z, s2);
+        s3 = fmaf(qi[dd + 3], kk.w, s3);
+      }
+      const float sdot = (s0 + s1) + (s2 + s3);
       const float nm = fmaxf(mx, sdot);
       const float corr = __expf(mx - nm), pj = __expf(sdot - nm);
       den = den * corr + pj;
 #pragma unroll
-      for (int dd = 0; dd < 32; ++dd) acc[dd] = fmaf(acc[dd], corr, pj * vs[j][dd]);
+      for (int dd = 0; dd < 32; dd += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&vs[j][dd]);
+        acc[dd] = fmaf(acc[dd], corr, pj * vv.x);
+        acc[dd + 1] = fmaf(acc[dd + 1], corr, pj * vv.y);
+        acc[dd + 2] = fmaf(acc[dd + 2], corr, pj * vv.z);
+        acc[dd + 3] = fmaf(acc[dd + 3], corr, pj * vv.w);
+      }
       mx = nm;
     }
   }
@@ -1181,8 +1217,9 @@ int fbs_nn_attention_bf16(fbs_stream_t s, const void* qkv, int64_t B, int32_t P,
                           void* out_bf16) {
   FBS_REQUIRE(qkv && out_bf16, "attention: null argument");
   FBS_REQUIRE(dim_head == 32 && heads >= 1, "attention: dim_head must be 32");
-  const int qblocks = (P + 127) / 128;
-  attention_kernel<<<(unsigned)(B * heads * qblocks), 128, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), P, heads, scale,
+  const int nthr = P <= 64 ? 64 : 128;  // one query per thread: 49 tokens leave 79 of 128 threads idle in the key loop
+  const int qblocks = (P + nthr - 1) / nthr;
+  attention_kernel<<<(unsigned)(B * heads * qblocks), nthr, 0, as_stream(s)>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), P, heads, scale,
                                                                              reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return check_launch("attention_kernel");
 }
