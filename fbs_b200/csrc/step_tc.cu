@@ -162,13 +162,26 @@ __host__ __device__ inline Layout make_layout(int du, int dv, int stages) {
   return L;
 }
 
+__device__ __forceinline__ bool elect_one_lane() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 template <int WW, bool PRE>
 __global__ void __launch_bounds__(32 * WW + 64, 1) step_transition_tc_kernel(const Params p) {
   constexpr int WORKERS = 32 * WW, NTHREADS = WORKERS + 64, HS = WW / 4, QSLOTS = 4 * WW;
   extern __shared__ __align__(1024) unsigned char smem[];
   const Layout L = make_layout(p.du, p.dv, p.stages);
   const int du = p.du, dv = p.dv, N = p.N, half = N / 2, D = du + dv;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (warp index through a shuffle: provably warp-uniform, so that the MMA / TMA warps' descriptors stay in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   unsigned char* Ahi = smem + L.Ahi;
   unsigned char* Alo = smem + L.Alo;
   float* nz = reinterpret_cast<float*>(smem + L.nz);
@@ -194,7 +207,8 @@ __global__ void __launch_bounds__(32 * WW + 64, 1) step_transition_tc_kernel(con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = misc[0];
+  const uint32_t tbase = __shfl_sync(0xffffffffu, misc[0], 0);
+  const bool leader = elect_one_lane();  // the lane of the MMA / TMA warps that issues the asynchronous instructions
   const float dt = p.dt[p.k], sd = p.sd[p.k], lognorm = p.lognorm[p.k];
   const float inv_s2 = 1.0f / (sd * sd);
   const float* MTk = p.MT + (size_t)p.k * D * D;
@@ -223,11 +237,12 @@ __global__ void __launch_bounds__(32 * WW + 64, 1) step_transition_tc_kernel(con
   if (warp == 1) {
     // ---- TMA producer (free running, synchronised with the MMA warp through the ring's mbarriers only): the K-blocks
     //      of the step matrix once per tile, in consumption order
-    if (lane == 0) {
-      for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
-        for (int kb = 0; kb < L.nkb; ++kb, ++g) {
-          const uint32_t slot = g % (uint32_t)p.stages, use = g / (uint32_t)p.stages;
-          if (use > 0) mbar_wait_sleep(empty + slot, (use - 1) & 1u);
+    // (all lanes run the loop, one elected lane issues)
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+      for (int kb = 0; kb < L.nkb; ++kb, ++g) {
+        const uint32_t slot = g % (uint32_t)p.stages, use = g / (uint32_t)p.stages;
+        if (use > 0) mbar_wait_sleep(empty + slot, (use - 1) & 1u);
+        if (leader) {
           mbar_expect_tx(full + slot, L.stage_bytes);
           bulk_g2s(ring + slot * L.stage_bytes, img + (size_t)kb * L.stage_bytes, L.stage_bytes, full + slot);
         }
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(32 * WW + 64, 1) step_transition_tc_kernel(con
 
     if (warp == 0) {
       // ---- MMA issuer
-      if (lane == 0) {
+      {
         uint32_t gm = g;
         for (int kb = 0; kb < L.nkb; ++kb, ++gm) {
           const uint32_t slot = gm % (uint32_t)p.stages, use = gm / (uint32_t)p.stages;
@@ -356,12 +371,14 @@ __global__ void __launch_bounds__(32 * WW + 64, 1) step_transition_tc_kernel(con
           const uint32_t b_hi = smem_u32(ring + slot * L.stage_bytes), b_lo = b_hi + L.blk_bytes;
           const uint64_t dAh = make_desc(a_hi, A_LBO, 128), dAl = make_desc(a_lo, A_LBO, 128);
           const uint64_t dBh = make_desc(b_hi, L.b_lbo, 128), dBl = make_desc(b_lo, L.b_lbo, 128);
-          umma_tf32(tbase, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
-          umma_tf32(tbase, dAl, dBh, idesc, 1u);
-          umma_tf32(tbase, dAh, dBl, idesc, 1u);
-          umma_commit(empty + slot);
+          if (leader) {
+            umma_tf32(tbase, dAh, dBh, idesc, kb > 0 ? 1u : 0u);
+            umma_tf32(tbase, dAl, dBh, idesc, 1u);
+            umma_tf32(tbase, dAh, dBl, idesc, 1u);
+            umma_commit(empty + slot);
+          }
         }
-        umma_commit(acc_full);
+        if (leader) umma_commit(acc_full);
       }
       g += (uint32_t)L.nkb;
     } else if (warp >= 2) {
