@@ -41,6 +41,8 @@ def _conv_ref(x, w, bias, pad, stride=1):
     (5, 14, 14, 128, 0, 128, 3),     # ... two N tiles per M tile (a CTA keeps its N tile), ragged last row tile
     (3, 32, 32, 64, 0, 192, 3),      # ... three N tiles, three rows of 34 per tile
     (150, 14, 14, 64, 0, 64, 3),     # ... more tiles than SMs: CTAs loop, accumulator buffers and ring wrap
+    (200, 28, 28, 64, 0, 64, 3),     # ... ~9.5 tiles per CTA: the four accumulator buffers and both epilogue groups wrap twice
+    (200, 28, 28, 64, 0, 64, 1),     # the same for the per-tap scheme (1x1)
     (5, 7, 7, 256, 0, 256, 3),       # ... N tile 32 (four resident weight chunks), one sample with its halo per tile
     (3, 14, 14, 128, 64, 128, 3),    # ... N tile 32, two sources
 ])
